@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE ONLY -- Python face of the CPU oracle (oracle/wol_oracle.c).
+
+Function names and argument order follow the reference's per-frame API
+(structureLibs/water_properties.py:210-391) so the parity tests read like calls into the reference.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module; nothing under ``waterorderlib_b200/`` does.
+
+Pinned by: tests/test_oracle_vs_reference.py (live reference, build container only) and
+tests/test_oracle_golden.py (committed fixtures generated from the live reference by
+tests/golden/make_golden.py).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_lp = ctypes.POINTER(ctypes.c_int64)
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libwol_oracle.so")
+        if not os.path.exists(path):
+            from . import build_oracle
+            build_oracle.build(verbose=False)
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _c(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _pos(a):
+    a = _c(a)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("positions must be (n,3)")
+    return a
+
+
+def _box(b):
+    b = _c(b).reshape(-1)
+    if b.size != 3:
+        raise ValueError("box must hold 3 values")
+    return b
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def histogram(x, nbins=500, lo=0.0, hi=180.0):
+    """np.histogram(x, bins=nbins, range=[lo, hi]) counts, restated (numpy uniform-bin rule)."""
+    x = _c(x).reshape(-1)
+    h = np.zeros(nbins, dtype=np.int64)
+    _lib().wol_oracle_histogram(_ptr(x, _dp), ctypes.c_int64(x.size), ctypes.c_double(lo), ctypes.c_double(hi),
+                                ctypes.c_int(nbins), _ptr(h, _lp))
+    return h
+
+
+def three_body(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413, nBins=500, binRange=(0.0, 180.0),
+               materialize=True):
+    """getCosAngs + the integer/sum parts of tetrahedralMetrics in one pass.
+    Returns dict(angVals, numAngs (int32 neighbour counts), hist (int64), tet (count, sum cos, sum cos^2),
+    n_angles)."""
+    sub, pos, box = _pos(subPos), _pos(Pos), _box(BoxDims)
+    m, n = sub.shape[0], pos.shape[0]
+    ncount = np.zeros(m, dtype=np.int32)
+    hist = np.zeros(nBins, dtype=np.int64)
+    tet = np.zeros(3, dtype=np.float64)
+    n_ang = ctypes.c_int64(0)
+    lib = _lib()
+
+    def run(buf, cap):
+        hist[:] = 0
+        tet[:] = 0
+        rc = lib.wol_oracle_three_body(
+            _ptr(sub, _dp), m, _ptr(pos, _dp), n, _ptr(box, _dp), ctypes.c_double(lowCut),
+            ctypes.c_double(highCut), _ptr(ncount, _ip), _ptr(buf, _dp), ctypes.c_int64(cap),
+            ctypes.byref(n_ang), _ptr(hist, _lp), nBins, ctypes.c_double(binRange[0]),
+            ctypes.c_double(binRange[1]), _ptr(tet, _dp))
+        if rc != 0:
+            raise RuntimeError("oracle three_body failed rc=%d" % rc)
+
+    ang = None
+    if materialize:
+        cap = max(16 * m, 1024)
+        ang = np.zeros(cap, dtype=np.float64)
+        run(ang, cap)
+        if n_ang.value > cap:
+            cap = n_ang.value
+            ang = np.zeros(cap, dtype=np.float64)
+            run(ang, cap)
+        ang = ang[: n_ang.value].copy()
+    else:
+        run(None, 0)
+    return {"angVals": ang, "numAngs": ncount, "hist": hist, "tet": tet, "n_angles": int(n_ang.value)}
+
+
+def getCosAngs(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413):
+    """structureLibs/water_properties.py:210-250 -> (angVals f64, numAngs f64 neighbour counts)."""
+    r = three_body(subPos, Pos, BoxDims, lowCut, highCut)
+    return r["angVals"], r["numAngs"].astype(np.float64)
+
+
+def order_param_q(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
+    """getOrderParamq plus the selection it implies -> (q f64 (m,), nn4 int32 (m,4) -1 padded, ncount int32)."""
+    sub, pos, box = _pos(subPos), _pos(Pos), _box(BoxDims)
+    m, n = sub.shape[0], pos.shape[0]
+    q = np.zeros(m, dtype=np.float64)
+    nn4 = np.zeros((m, 4), dtype=np.int32)
+    ncount = np.zeros(m, dtype=np.int32)
+    rc = _lib().wol_oracle_order_param_q(_ptr(sub, _dp), m, _ptr(pos, _dp), n, _ptr(box, _dp),
+                                         ctypes.c_double(lowCut), ctypes.c_double(highCut), _ptr(q, _dp),
+                                         _ptr(nn4, _ip), _ptr(ncount, _ip))
+    if rc != 0:
+        raise RuntimeError("oracle order_param_q failed rc=%d" % rc)
+    return q, nn4, ncount
+
+
+def getOrderParamq(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
+    """structureLibs/water_properties.py:344-391."""
+    return order_param_q(subPos, Pos, BoxDims, lowCut, highCut)[0]
+
+
+def tetrahedralMetrics(angVals, nBins=500, binRange=(0.0, 180.0)):
+    """structureLibs/water_properties.py:314-342 with the histogram restated."""
+    angVals = _c(angVals).reshape(-1)
+    angDist = histogram(angVals, nBins, binRange[0], binRange[1])
+    bins = np.linspace(binRange[0], binRange[1], nBins + 1)
+    angTet = angVals[(angVals >= 100.0) & (angVals <= 120.0)]
+    fracTet = float(len(angTet)) / float(len(angVals))
+    c = np.cos(angTet * np.pi / 180.0)
+    avgCos, varCos = np.mean(c), np.var(c)
+    dens = angDist / float(np.sum(angDist))
+    dens = dens[dens != 0]
+    entropy = -np.sum(dens * np.log(dens))
+    return angDist, bins, fracTet, avgCos, varCos, entropy
+
+
+def neighbor_matrix(subPos, Pos, BoxDims, lowCut, highCut):
+    """nearNeighbors / allNearNeighbors (fortran/waterlib.f90:710-743, :830-862) -> (m,n) int32."""
+    sub, pos, box = _pos(subPos), _pos(Pos), _box(BoxDims)
+    mat = np.zeros((sub.shape[0], pos.shape[0]), dtype=np.int32)
+    _lib().wol_oracle_neighbor_matrix(_ptr(sub, _dp), sub.shape[0], _ptr(pos, _dp), pos.shape[0], _ptr(box, _dp),
+                                      ctypes.c_double(lowCut), ctypes.c_double(highCut), _ptr(mat, _ip))
+    return mat
+
+
+def shell_mask(solPos, watPos, BoxDims, cutoff=4.0, lowCut=0.0):
+    """structureLibs/orderParam_lib.py:495-498 -> int32 mask over waters."""
+    sol, wat, box = _pos(solPos), _pos(watPos), _box(BoxDims)
+    mask = np.zeros(wat.shape[0], dtype=np.int32)
+    _lib().wol_oracle_shell_mask(_ptr(sol, _dp), sol.shape[0], _ptr(wat, _dp), wat.shape[0], _ptr(box, _dp),
+                                 ctypes.c_double(lowCut), ctypes.c_double(cutoff), _ptr(mask, _ip))
+    return mask
+
+
+def hbonds(accPos, donPos, donHPos, BoxDims, distCut=3.5, angCut=150.0, dense=False):
+    """generalHbonds (fortran/waterlib.f90:1156-1210) -> (acc_count, don_count[, matrix])."""
+    acc, don, donh, box = _pos(accPos), _pos(donPos), _pos(donHPos), _box(BoxDims)
+    if don.shape[0] != donh.shape[0]:
+        raise ValueError("donor heavy atoms and hydrogens differ in number")
+    na, nd = acc.shape[0], don.shape[0]
+    ac = np.zeros(na, dtype=np.int32)
+    dc = np.zeros(nd, dtype=np.int32)
+    mat = np.zeros((na, nd), dtype=np.int32) if dense else None
+    _lib().wol_oracle_hbonds(_ptr(acc, _dp), na, _ptr(don, _dp), _ptr(donh, _dp), nd, _ptr(box, _dp),
+                             ctypes.c_double(distCut), ctypes.c_double(angCut), _ptr(ac, _ip), _ptr(dc, _ip),
+                             _ptr(mat, _ip))
+    return (ac, dc, mat) if dense else (ac, dc)

@@ -2,11 +2,11 @@
 
   oracle/libwol_oracle.so      the C restatement (oracle/wol_oracle.c), OpenMP, no FMA contraction
   oracle/_ref/libgfortran.so.3 the stub runtime the reference's prebuilt f2py module needs
-  oracle/_ref/<reference files> staged only while /root/reference is visible (build container):
-        the reference's prebuilt waterlib f2py module and its water_properties.py, so that the real
-        reference can also run on a GPU box where /root/reference does not exist.  oracle/_ref/ is
-        git-ignored (never enters history) but travels with the gpurun snapshot, exactly like the
-        `pip install --target baseline/_ref` staging the bench contract describes.
+  oracle/_ref/waterlib.cpython-37m-x86_64-linux-gnu.so   staged only while /root/reference is visible
+        (build container): the reference's own prebuilt BINARY of fortran/waterlib.f90 (gfortran is not
+        in this image, so it cannot be recompiled), so that the reference's compiled arithmetic can also
+        run on a GPU box where /root/reference does not exist.  No reference source text is staged.
+        oracle/_ref/ is git-ignored (never enters history) but travels with the gpurun snapshot.
 
 Run: python oracle/build_oracle.py
 """
@@ -20,7 +20,6 @@ REF = os.path.join(HERE, "_ref")
 REFERENCE_ROOT = "/root/reference"
 STAGED = (
     (os.path.join("fortran", "waterlib.cpython-37m-x86_64-linux-gnu.so"), "waterlib.cpython-37m-x86_64-linux-gnu.so"),
-    (os.path.join("structureLibs", "water_properties.py"), "water_properties.py"),
 )
 
 

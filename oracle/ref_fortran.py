@@ -18,8 +18,10 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / `
 legs may use this module.  Nothing under ``waterorderlib_b200/`` imports it.
 
 Where the reference lives: ``/root/reference`` in the build container; on a GPU box only the
-git-ignored staging directory ``oracle/_ref/`` (filled by ``oracle/build_oracle.py`` while
-``/root/reference`` is visible) exists.
+prebuilt Fortran binary staged into the git-ignored ``oracle/_ref/`` (by ``oracle/build_oracle.py``
+while ``/root/reference`` is visible) exists -- the Python bodies are then supplied by the
+restatement in ``oracle/ref_driver.py`` (pinned against the live bodies by
+tests/test_oracle_vs_reference.py).
 """
 import ast
 import ctypes
@@ -44,11 +46,16 @@ def _find(rel_in_reference, staged_name):
 
 
 def reference_available():
+    """True when the reference's compiled Fortran can be loaded (build container or staged binary)."""
     return (
         os.path.exists(os.path.join(_REF_DIR, "libgfortran.so.3"))
         and _find(os.path.join("fortran", _SO_NAME), _SO_NAME) is not None
-        and _find(os.path.join("structureLibs", "water_properties.py"), "water_properties.py") is not None
     )
+
+
+def reference_python_available():
+    """True only where the reference's Python source is visible (the build container)."""
+    return os.path.exists(os.path.join("/root/reference", "structureLibs", "water_properties.py"))
 
 
 def _f64(a):
@@ -197,9 +204,9 @@ _WP_FUNCS = ("getCosAngs", "getOrderParamq", "tetrahedralMetrics", "getLSI", "HB
 def load_reference_functions(names=_WP_FUNCS, wl=None):
     """Return {name: function} built from the reference's own source text
     (structureLibs/water_properties.py:210-391, :681-719), executed with a RefWaterlib as `wl`."""
-    src_path = _find(os.path.join("structureLibs", "water_properties.py"), "water_properties.py")
-    if src_path is None:
-        raise RuntimeError("reference water_properties.py not found (neither /root/reference nor oracle/_ref)")
+    src_path = os.path.join("/root/reference", "structureLibs", "water_properties.py")
+    if not os.path.exists(src_path):
+        raise RuntimeError("reference water_properties.py not visible (only in the build container)")
     with open(src_path) as fh:
         tree = ast.parse(fh.read())
     wl = wl if wl is not None else RefWaterlib()

@@ -1,0 +1,92 @@
+"""Pins the C oracle on the LIVE reference (compiled Fortran via ctypes + AST-extracted Python bodies).
+Only runs where /root/reference exists (the build container); the GPU box relies on tests/golden."""
+import numpy as np
+import pytest
+
+from oracle import port, ref_fortran
+from waterorderlib_b200 import synth
+
+pytestmark = pytest.mark.live_reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import build_oracle
+    build_oracle.build(verbose=False)
+    wl = ref_fortran.RefWaterlib()
+    return wl, ref_fortran.load_reference_functions(wl=wl)
+
+
+@pytest.mark.parametrize("m,sigma,seed", [(2, 0.3, 1), (3, 0.6, 2), (4, 0.25, 1234), (5, 0.45, 9)])
+def test_q_bit_exact(ref, m, sigma, seed):
+    wl, fn = ref
+    pos, box = synth.water_box(m, sigma=sigma, seed=seed)
+    highq = min(10.0, 0.49 * box.min())
+    assert np.array_equal(port.getOrderParamq(pos, pos, box, 0.0, highq), fn["getOrderParamq"](pos, pos, box, 0.0, highq))
+
+
+@pytest.mark.parametrize("m,sigma,seed,high", [(2, 0.3, 1, 3.413), (4, 0.6, 2, 3.413), (4, 0.25, 3, 3.7), (6, 0.5, 4, 3.0)])
+def test_three_body_bit_exact(ref, m, sigma, seed, high):
+    wl, fn = ref
+    pos, box = synth.water_box(m, sigma=sigma, seed=seed)
+    a_ref, n_ref = fn["getCosAngs"](pos, pos, box, 0.0, high)
+    a, n = port.getCosAngs(pos, pos, box, 0.0, high)
+    assert np.array_equal(a, a_ref) and np.array_equal(n, n_ref)
+    r = port.three_body(pos, pos, box, 0.0, high)
+    assert np.array_equal(r["hist"], fn["tetrahedralMetrics"](a_ref)[0])
+
+
+def test_neighbor_matrix_and_subpop(ref):
+    wl, fn = ref
+    rng = np.random.default_rng(5)
+    box = np.array([13.0, 15.0, 11.5])
+    pos = rng.random((300, 3)) * box * 3.0 - box  # unwrapped
+    sub = rng.random((37, 3)) * box
+    assert np.array_equal(port.neighbor_matrix(pos, pos, box, 0.0, 3.5), wl.allnearneighbors(pos, box, 0.0, 3.5))
+    assert np.array_equal(port.neighbor_matrix(sub, pos, box, 1.0, 4.5), wl.nearneighbors(sub, pos, box, 1.0, 4.5))
+    assert np.array_equal(port.getOrderParamq(sub, pos, box, 0.0, 5.0), fn["getOrderParamq"](sub, pos, box, 0.0, 5.0))
+    a_ref, n_ref = fn["getCosAngs"](sub, pos, box, 0.5, 4.0)
+    a, n = port.getCosAngs(sub, pos, box, 0.5, 4.0)
+    assert np.array_equal(a, a_ref) and np.array_equal(n, n_ref)
+
+
+def test_hbonds_and_shell(ref):
+    wl, fn = ref
+    opos, box = synth.water_box(3, sigma=0.35, seed=11)
+    hpos = synth.add_hydrogens(opos, seed=11)
+    don = np.repeat(opos, 2, axis=0)
+    mat = wl.generalhbonds(opos, don, hpos, box, 3.5, 120.0)
+    ac, dc, m2 = port.hbonds(opos, don, hpos, box, 3.5, 120.0, dense=True)
+    assert np.array_equal(m2, mat)
+    assert np.array_equal(ac, mat.sum(axis=1)) and np.array_equal(dc, mat.sum(axis=0))
+    sol = synth.solute_grid(box, n_side=2)
+    ref_mask = wl.nearneighbors(sol, opos, box, 0.0, 4.0).any(axis=0)
+    assert np.array_equal(port.shell_mask(sol, opos, box, 4.0).astype(bool), ref_mask)
+
+
+def test_angle_quirks(ref):
+    wl, _ = ref
+    assert wl.cosangle3([1, 0, 0], [0, 0, 0], [-1, 0, 0]) == -180.0
+    assert wl.cosangle3([1, 0, 0], [0, 0, 0], [2, 0, 0]) == 0.0
+    # collinear simple-cubic neighbours: the -180 angles drop out of np.histogram, in the oracle too
+    g = np.arange(4) * 3.0
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    box = np.array([12.0, 12.0, 12.0])
+    r = port.three_body(pos, pos, box, 0.0, 3.2)
+    assert np.all(r["numAngs"] == 6) and r["n_angles"] == 64 * 15
+    assert (r["angVals"] == -180.0).sum() == 64 * 3
+    assert r["hist"].sum() == 64 * 12
+
+
+def test_ref_driver_matches_live(ref):
+    """oracle/ref_driver.py (used for the CPU baseline on the GPU box) == the live reference bodies."""
+    from oracle import ref_driver
+    wl, fn = ref
+    pos, box = synth.water_box(4, sigma=0.5, seed=21)
+    assert np.array_equal(ref_driver.get_order_param_q(wl, pos, pos, box), fn["getOrderParamq"](pos, pos, box))
+    a, n = ref_driver.get_cos_angs(wl, pos, pos, box)
+    a_ref, n_ref = fn["getCosAngs"](pos, pos, box)
+    assert np.array_equal(a, a_ref) and np.array_equal(n, n_ref)
+    sub = pos[5:60:3] + 0.125
+    assert np.array_equal(ref_driver.get_order_param_q(wl, sub, pos, box, 0.0, 7.0),
+                          fn["getOrderParamq"](sub, pos, box, 0.0, 7.0))

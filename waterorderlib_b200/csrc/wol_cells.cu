@@ -1,0 +1,235 @@
+// K1: cell-list build for a batch of frames (sm_100a).
+//
+//   cell_count  : one thread per atom; positions are staged through shared memory with 16-byte
+//                 vector loads, converted to periodic fixed point, binned; the atomicAdd that counts
+//                 the cell also hands the atom its rank ("slot") inside the cell.
+//   scan_*      : exclusive prefix sum over all F*ncell counters (reduce / scan-of-sums / apply, the
+//                 in-block part is a warp shuffle scan).
+//   cell_scatter: each atom writes its 16-byte record to cell_start[cell] + slot.
+//
+// The reference has no counterpart: its neighbour search is the O(N^2) double loop of
+// fortran/waterlib.f90:846-861 writing an N x N logical matrix.
+#include "wol_device.cuh"
+#include "wol_internal.h"
+#include "wol_workspace.h"
+
+namespace wol {
+
+constexpr int kBuildThreads = 256;
+
+// Stage `n_elems` consecutive position components (3 per atom) of a tile into shared memory.
+// 16-byte vector loads when the tile base is 16-byte aligned, scalar (still coalesced) otherwise.
+template <typename T>
+__device__ __forceinline__ void stage_tile(const T *__restrict__ src, int n_elems, T *smem) {
+    constexpr int kVec = 16 / sizeof(T);
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const int n_vec = n_elems / kVec;
+        const int4 *src4 = reinterpret_cast<const int4 *>(src);
+        int4 *dst4 = reinterpret_cast<int4 *>(smem);
+        for (int i = tid; i < n_vec; i += blockDim.x) dst4[i] = __ldg(src4 + i);
+        for (int i = n_vec * kVec + tid; i < n_elems; i += blockDim.x) smem[i] = src[i];
+    } else {
+        for (int i = tid; i < n_elems; i += blockDim.x) smem[i] = src[i];
+    }
+}
+
+struct BuildParams {
+    const void *pos;
+    const double *box;
+    int n_frames, n_pos;
+    int nc0, nc1, nc2;
+    int tiles_per_frame;
+    uint32_t *cell_start;
+    uint32_t *cell_id;
+    uint32_t *slot;
+    Rec *recs;
+};
+
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p) {
+    __shared__ __align__(16) T s_pos[kBuildThreads * 3];
+    __shared__ double s_iL[3];
+    const int f = blockIdx.x / p.tiles_per_frame;
+    const int tile = blockIdx.x - f * p.tiles_per_frame;
+    const int a0 = tile * kBuildThreads;
+    const int n_here = min(kBuildThreads, p.n_pos - a0);
+    const size_t frame_atom0 = (size_t)f * p.n_pos;
+    if (threadIdx.x < 3) {
+        double L = p.box[(size_t)f * 3 + threadIdx.x];
+        s_iL[threadIdx.x] = 1.0 / L;
+    }
+    stage_tile(reinterpret_cast<const T *>(p.pos) + (frame_atom0 + a0) * 3, n_here * 3, s_pos);
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= n_here) return;
+    const uint32_t xf = to_fixed((double)s_pos[3 * t + 0], s_iL[0]);
+    const uint32_t yf = to_fixed((double)s_pos[3 * t + 1], s_iL[1]);
+    const uint32_t zf = to_fixed((double)s_pos[3 * t + 2], s_iL[2]);
+    const size_t ga = frame_atom0 + a0 + t;
+    const size_t ncell = (size_t)p.nc0 * p.nc1 * p.nc2;
+    if (!SCATTER) {
+        const int cx = cell_coord(xf, p.nc0), cy = cell_coord(yf, p.nc1), cz = cell_coord(zf, p.nc2);
+        const uint32_t c = (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx);
+        p.cell_id[ga] = c;
+        p.slot[ga] = atomicAdd(&p.cell_start[(size_t)f * ncell + c], 1u);
+    } else {
+        const uint32_t c = p.cell_id[ga];
+        const uint32_t dst = p.cell_start[(size_t)f * ncell + c] + p.slot[ga];
+        Rec r;
+        r.x = xf;
+        r.y = yf;
+        r.z = zf;
+        r.idx = a0 + t;
+        *reinterpret_cast<int4 *>(&p.recs[dst]) = *reinterpret_cast<const int4 *>(&r);
+    }
+}
+
+// ---- exclusive scan over n uint32 values, in place ------------------------------------------
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t *__restrict__ data, size_t n,
+                                                                  uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t sum = 0;
+    if (base + kScanItems <= n && ((reinterpret_cast<uintptr_t>(data + base) & 15u) == 0)) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(data + base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(data + base + 4);
+        sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i)
+            if (base + i < n) sum += data[base + i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < kScanThreads / 32; ++i) s += s_warp[i];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of block_sums[0..nb) in place
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *__restrict__ block_sums, int nb) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = (i < nb) ? block_sums[i] : 0u;
+        uint32_t inc = warp_inclusive_scan(v, lane);
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane];
+            uint32_t winc = warp_inclusive_scan(w, lane);
+            s_warp[lane] = winc - w;  // exclusive offset of each warp
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[wid] + inc - v;
+        if (i < nb) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, size_t n,
+                                                                 const uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    const bool vec = base + kScanItems <= n && ((reinterpret_cast<uintptr_t>(data + base) & 15u) == 0);
+    if (vec) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(data + base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < n) ? data[base + i] : 0u;
+    }
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) tsum += v[i];
+    const uint32_t inc = warp_inclusive_scan(tsum, lane);
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = (lane < kScanThreads / 32) ? s_warp[lane] : 0u;
+        uint32_t winc = warp_inclusive_scan(w, lane);
+        if (lane < kScanThreads / 32) s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = block_sums[blockIdx.x] + s_warp[wid] + inc - tsum;
+    uint32_t o[kScanItems];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        o[i] = run;
+        run += v[i];
+    }
+    if (vec) {
+        *reinterpret_cast<uint4 *>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i)
+            if (base + i < n) data[base + i] = o[i];
+    }
+}
+
+int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_frames, int n_pos, const int32_t nc[3],
+                      void *workspace, const WorkspaceLayout &lay, cudaStream_t stream, int *launches) {
+    char *ws = reinterpret_cast<char *>(workspace);
+    BuildParams p;
+    p.pos = pos;
+    p.box = box;
+    p.n_frames = n_frames;
+    p.n_pos = n_pos;
+    p.nc0 = nc[0];
+    p.nc1 = nc[1];
+    p.nc2 = nc[2];
+    p.tiles_per_frame = (n_pos + kBuildThreads - 1) / kBuildThreads;
+    p.cell_start = reinterpret_cast<uint32_t *>(ws + lay.off_cell_start);
+    p.cell_id = reinterpret_cast<uint32_t *>(ws + lay.off_cell_id);
+    p.slot = reinterpret_cast<uint32_t *>(ws + lay.off_slot);
+    p.recs = reinterpret_cast<Rec *>(ws + lay.off_recs);
+    uint32_t *block_sums = reinterpret_cast<uint32_t *>(ws + lay.off_block_sums);
+    const size_t n_scan = (size_t)lay.n_cells_total + 1;
+
+    cudaError_t e = cudaMemsetAsync(p.cell_start, 0, n_scan * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell counters)", e);
+    const long long blocks = (long long)p.tiles_per_frame * n_frames;
+    if (blocks > 0x7fffffffLL) return set_error(WOL_ERR_RANGE, "too many atom tiles for one launch");
+    if (blocks > 0) {
+        if (pos_dtype == WOL_F64)
+            cell_pass_kernel<double, false><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
+        else
+            cell_pass_kernel<float, false><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
+        ++*launches;
+    }
+    scan_reduce_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, lay.scan_blocks);
+    scan_apply_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
+    *launches += 3;
+    if (blocks > 0) {
+        if (pos_dtype == WOL_F64)
+            cell_pass_kernel<double, true><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
+        else
+            cell_pass_kernel<float, true><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
+        ++*launches;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("cell build launch", e);
+    return WOL_OK;
+}
+
+}  // namespace wol

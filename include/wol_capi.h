@@ -14,8 +14,8 @@
  *   - arrays are dense row-major: positions [n_frames][n][3], boxes [n_frames][3] (orthorhombic edge
  *     lengths, what the reference takes from frame.box.values[:3], orderParam_lib.py:1315).
  *   - the caller owns every buffer including scratch (`wol_workspace_bytes`); the library never
- *     allocates device memory, never synchronises the host and keeps no state besides a
- *     thread-local error string.  All work is enqueued on `stream`.
+ *     allocates device memory, never synchronises the host (except wol_status, which exists to do so)
+ *     and keeps no state besides a thread-local error string.  All work is enqueued on `stream`.
  *   - return value: WOL_OK or a negative WOL_ERR_* code; wol_last_error() describes the failure.
  *     Nothing aborts the process (the reference's Fortran `stop`s do, waterlib.f90:1171-1174).
  *   - indices are 0-based int32; "no neighbour" is -1.
@@ -38,7 +38,8 @@ enum {
     WOL_ERR_UNSUPPORTED = -2, /* valid in the reference but not implemented here (e.g. BoxL <= 0)  */
     WOL_ERR_WORKSPACE = -3,   /* workspace too small                                                */
     WOL_ERR_CUDA = -4,        /* a CUDA runtime call failed; message holds cudaGetErrorString       */
-    WOL_ERR_RANGE = -5        /* sizes overflow the 32-bit indexing of the kernels                  */
+    WOL_ERR_RANGE = -5,       /* sizes overflow the 32-bit indexing of the kernels                  */
+    WOL_ERR_CAPACITY = -6     /* a device-side list overflowed (reported by wol_status)             */
 };
 
 enum { WOL_F64 = 0, WOL_F32 = 1 };            /* storage dtype of a position array               */
@@ -57,31 +58,54 @@ enum {
     WOL_STAT_N_NEIGH = 7    /* sum of 3-body neighbour counts                          */
 };
 
+/* Extra doubles that follow the nbins + 1 thresholds of an angle-bin table (wol_angle_table). */
+#define WOL_TABLE_EXTRA 8
+
 const char *wol_version(void);
 const char *wol_last_error(void);
 int wol_abi_version(void);
 
 /*
- * Cell-grid plan for a batch of frames.  Picks nc[3] (cells per axis, identical for all frames of the
- * batch) such that every frame's cell edge L/nc is >= r_cell, and reports the stencil half-width
- * `w_out` for which w*edge >= r_complete on every axis.  Host-only, cheap.
- * Replaces nothing in the reference (its search is O(N^2), waterlib.f90:846-861).
+ * Cell-grid plan for a batch of frames (host-only, cheap).  Picks nc[3] (cells per axis, identical
+ * for all frames of the batch) such that every frame's cell edge L/nc is >= r_cell (1 + 1e-9), and
+ * reports the smallest cell edge of the batch, which the evaluation kernels use as the radius inside
+ * which a 27-cell sweep is complete.  Replaces nothing in the reference (its search is the O(N^2)
+ * double loop of waterlib.f90:846-861).
  */
-int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, double r_complete,
-                  int32_t nc_out[3], int32_t *w_out);
+int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3],
+                  double *edge_min_out);
 
 /* Bytes of scratch needed by wol_cell_build + the evaluation kernels for this batch shape.
- * n_centres_max = the largest number of centres any later call on this workspace will pass. */
+ * n_centres_max = the largest number of centres per frame any later call on this workspace passes. */
 size_t wol_workspace_bytes(int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3]);
 
 /*
- * K1: cell-list build (counting sort of atoms by cell, fixed-point periodic coordinates).
+ * K1: cell-list build (counting sort of atoms by cell).
  *   pos        [n_frames][n_pos][3] of pos_dtype
  *   box        [n_frames][3] double, all > 0
+ *   precision  WOL_PREC_FP64: 32-byte records (x, y, z double + index + cell)
+ *              WOL_PREC_FP32: 16-byte records (x, y, z float + index)
  * Afterwards `workspace` holds the cell list consumed by the entry points below.
  */
 int wol_cell_build(const void *pos, int32_t pos_dtype, const double *box, int32_t n_frames, int32_t n_pos,
-                   const int32_t nc[3], void *workspace, size_t workspace_bytes, void *stream);
+                   const int32_t nc[3], int32_t precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Angle-bin table (host-only).  The reference bins the angle acos(c) in degrees with np.histogram
+ * (water_properties.py:328, CosAngle3 waterlib.f90:696-702).  Because that chain is monotone in the
+ * clamped cosine c, bin membership is decided on the device by comparing c with nbins + 1 thresholds
+ * that this routine finds by bisection over the doubles with the host libm -- the same acos the
+ * reference's Fortran calls -- so no device transcendental sits between c and its bin.
+ *   table_host[k], k = 0..nbins : largest c whose angle lies at or beyond bin k (k = nbins: beyond hi)
+ *   table_host[nbins+1]         : bin position of the angle the reference returns for c == -1 (-180)
+ *   table_host[nbins+2]         : bin position of a 0-degree angle (coincident-position rule, :690)
+ *   table_host[nbins+3..+4]     : largest c with angle >= tet_lo, smallest c with angle <= tet_hi
+ *   table_host[nbins+5]         : 1.0 if the table passed its monotonicity self-check
+ * The caller uploads the nbins + 1 + WOL_TABLE_EXTRA doubles to the device and passes them as
+ * wol_q3b_args.angle_table.
+ */
+int wol_angle_table(double hist_lo, double hist_hi, int32_t nbins, double tet_lo, double tet_hi,
+                    double *table_host);
 
 /*
  * K2: fused neighbour sweep -> 4 nearest neighbours -> tetrahedral q, plus all three-body angles among
@@ -101,34 +125,32 @@ int wol_cell_build(const void *pos, int32_t pos_dtype, const double *box, int32_
  *   nn_idx      [n_frames][n_centres][4] int32, indices into pos of the selected neighbours in
  *               selection order (distance, then index), -1 padded
  *   n3          [n_frames][n_centres] int32 neighbour count inside (low3, high3]  (== numAngs)
- *   ang_hist    [n_frames][nbins] int64, ACCUMULATED (+=): np.histogram(angles, nbins, [hist_lo, hist_hi])
- *   q_hist      [n_frames][q_nbins] int64, ACCUMULATED: np.histogram(q, q_nbins, [0, 1])
+ *   ang_hist    [n_frames or 1][nbins] int64, ACCUMULATED (+=): np.histogram(angles, nbins, [hist_lo, hist_hi])
+ *   q_hist      [n_frames or 1][q_nbins] int64, ACCUMULATED: np.histogram(q, q_nbins, [0, 1])
  *   frame_stats [n_frames][WOL_NSTATS] double, ACCUMULATED
- * `hist_frame_stride0` = 1 keeps one histogram row per frame; 0 folds all frames into row 0.
  */
 typedef struct wol_q3b_args {
     uint32_t struct_size; /* sizeof(wol_q3b_args), for forward compatibility */
-    int32_t precision;    /* WOL_PREC_FP64 | WOL_PREC_FP32 */
-    const void *pos;
-    int32_t pos_dtype;
+    int32_t precision;    /* WOL_PREC_FP64 | WOL_PREC_FP32; must match wol_cell_build */
     int32_t n_frames;
     int32_t n_pos;
     int32_t n_centres; /* ignored when centres == NULL (then n_centres = n_pos) */
-    const void *centres;
     int32_t centre_dtype;
-    int32_t hist_per_frame; /* 1: one histogram row per frame, 0: a single shared row */
+    const void *centres;
     const double *box;
-    const void *workspace; /* as filled by wol_cell_build for the same pos/box/nc */
+    void *workspace; /* as filled by wol_cell_build for the same pos/box/nc */
     size_t workspace_bytes;
     int32_t nc[3];
-    int32_t stencil_w; /* from wol_plan_grid */
-    double low3, high3; /* getCosAngs lowCut/highCut (default 0, 3.413) */
-    double lowq, highq; /* getOrderParamq lowCut/highCut (default 0, 10) */
-    int32_t do_q;       /* evaluate the q branch */
-    int32_t do_3body;   /* evaluate the three-body branch */
-    int32_t nbins;      /* angle histogram bins (default 500) */
-    int32_t q_nbins;    /* q histogram bins (default 500) */
-    double hist_lo, hist_hi; /* angle histogram range (default 0, 180) */
+    int32_t hist_per_frame; /* 1: one histogram row per frame, 0: a single shared row */
+    double edge_min;        /* from wol_plan_grid */
+    double low3, high3;     /* getCosAngs lowCut/highCut (default 0, 3.413) */
+    double lowq, highq;     /* getOrderParamq lowCut/highCut (default 0, 10) */
+    int32_t do_q;           /* evaluate the q branch */
+    int32_t do_3body;       /* evaluate the three-body branch */
+    int32_t nbins;          /* angle histogram bins (default 500) */
+    int32_t q_nbins;        /* q histogram bins (default 500) */
+    double hist_lo, hist_hi; /* angle histogram range (default 0, 180); must match angle_table */
+    const double *angle_table; /* device copy of wol_angle_table output; required when do_3body */
     void *q;
     int32_t *nn_idx;
     int32_t *n3;
@@ -138,6 +160,18 @@ typedef struct wol_q3b_args {
 } wol_q3b_args;
 
 int wol_q3b_frames(const wol_q3b_args *args, void *stream);
+
+/*
+ * Device-side status of the last evaluation on this workspace (same shape arguments as
+ * wol_workspace_bytes).  Synchronises `stream`.
+ *   status_host[0]  number of centres that took the widened-search path (q with < 4 neighbours in 27 cells)
+ *   status_host[1]  number of centres whose neighbour list overflowed the fast path
+ *   status_host[2]  non-zero: a neighbour list overflowed even the large-capacity path -> results invalid
+ *   status_host[3]  reserved
+ * Returns WOL_ERR_CAPACITY when status_host[2] != 0.
+ */
+int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3],
+               void *stream, int32_t status_host[4]);
 
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);

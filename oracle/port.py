@@ -175,3 +175,11 @@ def hbonds(accPos, donPos, donHPos, BoxDims, distCut=3.5, angCut=150.0, dense=Fa
                              ctypes.c_double(distCut), ctypes.c_double(angCut), _ptr(ac, _ip), _ptr(dc, _ip),
                              _ptr(mat, _ip))
     return (ac, dc, mat) if dense else (ac, dc)
+
+
+def angles_from_cos(c):
+    """CosAngle3's clamp/acos/mod/degrees tail (fortran/waterlib.f90:698-702) for an array of cosines."""
+    c = _c(c).reshape(-1)
+    out = np.zeros_like(c)
+    _lib().wol_oracle_angles_from_cos(_ptr(c, _dp), ctypes.c_int64(c.size), _ptr(out, _dp))
+    return out

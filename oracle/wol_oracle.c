@@ -464,3 +464,15 @@ int wol_oracle_hbonds(const double *acc, int na, const double *don, const double
     cells_free(&cl);
     return 0;
 }
+
+/* The tail of CosAngle3 (waterlib.f90:698-702) for an array of already-formed cosine ratios: clamp,
+ * acos, the mod/branch, degrees.  Used to pin the device's threshold-table binning. */
+int wol_oracle_angles_from_cos(const double *c, int64_t n, double *ang) {
+    for (int64_t i = 0; i < n; ++i) {
+        double phi = acos(fmin(1.0, fmax(-1.0, c[i])));
+        double a = fmod(phi + kPi, kTwoPi) - kPi;
+        if (a < -kPi) a += kTwoPi;
+        ang[i] = a * kDegPerRad;
+    }
+    return 0;
+}

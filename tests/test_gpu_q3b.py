@@ -1,0 +1,116 @@
+"""Parity of the CUDA fused q / three-body path (through the C ABI) against the golden fixtures (outputs of
+the reference's compiled Fortran + Python) and against the CPU oracle on seeded inputs.
+
+fp64 mode: neighbour indices, counts and histogram bins bit-exact; q within 1e-6 relative (in fact ~1e-15).
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import port  # noqa: E402  (the checker)
+from waterorderlib_b200 import engine, synth  # noqa: E402
+
+Q_RTOL = 1e-6  # north_star tolerance for fp64 mode
+CASES = ["cfg1_n512_ice", "cfg1_n512_liq", "lattice_n216", "random_n160_noncubic", "subpop_n512_m97",
+         "cfg2_n4096_frame0"]
+
+
+def run(sub, pos, box, same, **kw):
+    r = engine.q3b_frames(pos, box, None if same else sub, **kw)
+    torch.cuda.synchronize()
+    return r
+
+
+def assert_q_close(q, q_ref):
+    assert np.allclose(q, q_ref, rtol=Q_RTOL, atol=1e-9), float(np.abs(q - q_ref).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_against_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    same = np.array_equal(g["sub"], g["pos"])
+    r = run(g["sub"], g["pos"], g["box"], same, low3=float(g["low3"]), high3=float(g["high3"]),
+            lowq=float(g["lowq"]), highq=float(g["highq"]))
+    assert np.array_equal(r.n3.cpu().numpy()[0], g["n3"])
+    assert np.array_equal(r.ang_hist.cpu().numpy()[0], g["hist"])
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], g["nn4"])
+    assert_q_close(r.q.cpu().numpy()[0], g["q"])
+    assert np.array_equal(r.q_hist.cpu().numpy()[0], np.histogram(g["q"], bins=500, range=[0.0, 1.0])[0])
+    st = r.frame_stats.cpu().numpy()[0]
+    assert st[6] == int(g["n_angles"]) and st[7] == g["n3"].sum() and st[2] == g["q"].size
+    assert st[3] == round(float(g["fracTet"]) * int(g["n_angles"]))
+    assert abs(st[4] / st[3] - float(g["avgCos"])) < 1e-12
+    assert abs(st[0] - g["q"].sum()) < 1e-9 * max(1.0, abs(g["q"].sum()))
+
+
+@pytest.mark.parametrize("m,sigma,seed", [(6, 0.25, 11), (6, 0.6, 12), (10, 0.45, 13)])
+def test_against_oracle_batched(m, sigma, seed):
+    """Several frames in one call, per-frame histograms, float32 storage of (float32-representable) inputs."""
+    pos, box = synth.trajectory(m, 3, sigma=sigma, seed0=seed)
+    r = run(None, pos.astype(np.float32), box, True, hist_per_frame=True)
+    for f in range(3):
+        q, nn4, _ = port.order_param_q(pos[f], pos[f], box[f])
+        tb = port.three_body(pos[f], pos[f], box[f], materialize=False)
+        assert np.array_equal(r.nn_idx.cpu().numpy()[f], nn4)
+        assert np.array_equal(r.n3.cpu().numpy()[f], tb["numAngs"])
+        assert np.array_equal(r.ang_hist.cpu().numpy()[f], tb["hist"])
+        assert_q_close(r.q.cpu().numpy()[f], q)
+
+
+def test_unwrapped_and_noncubic_vs_oracle():
+    rng = np.random.default_rng(17)
+    box = np.array([31.0, 24.5, 40.25])
+    n = 1200
+    pos = rng.random((n, 3)) * box + box * rng.integers(-3, 4, size=(n, 3))
+    r = run(None, pos, box, True, high3=3.7, highq=9.0)
+    q, nn4, _ = port.order_param_q(pos, pos, box, 0.0, 9.0)
+    tb = port.three_body(pos, pos, box, 0.0, 3.7, materialize=False)
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)
+    assert np.array_equal(r.n3.cpu().numpy()[0], tb["numAngs"])
+    assert np.array_equal(r.ang_hist.cpu().numpy()[0], tb["hist"])
+    assert_q_close(r.q.cpu().numpy()[0], q)
+    assert r.n_widened > 0  # dilute random gas: the widened search is exercised
+
+
+def test_dense_cluster_overflow_path():
+    """More neighbours than the fast list holds -> large-capacity pass; still exact."""
+    rng = np.random.default_rng(23)
+    box = np.array([30.0, 30.0, 30.0])
+    pos = np.concatenate([rng.random((300, 3)) * 4.0 + 10.0, rng.random((500, 3)) * box])
+    r = run(None, pos, box, True, high3=3.413, highq=8.0)
+    q, nn4, _ = port.order_param_q(pos, pos, box, 0.0, 8.0)
+    tb = port.three_body(pos, pos, box, 0.0, 3.413, materialize=False)
+    assert r.n_overflow > 0
+    assert np.array_equal(r.n3.cpu().numpy()[0], tb["numAngs"])
+    assert np.array_equal(r.ang_hist.cpu().numpy()[0], tb["hist"])
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)
+    assert_q_close(r.q.cpu().numpy()[0], q)
+
+
+def test_collinear_minus_180_quirk():
+    g = np.arange(4) * 3.0
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    box = np.array([12.0, 12.0, 12.0])
+    r = run(None, pos, box, True, high3=3.2, highq=5.0)
+    tb = port.three_body(pos, pos, box, 0.0, 3.2, materialize=False)
+    assert np.array_equal(r.ang_hist.cpu().numpy()[0], tb["hist"])
+    assert r.ang_hist.sum().item() == 64 * 12 and r.frame_stats[0, 6].item() == 64 * 15
+    q, nn4, _ = port.order_param_q(pos, pos, box, 0.0, 5.0)
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)  # six equidistant neighbours: ties by index
+    assert_q_close(r.q.cpu().numpy()[0], q)
+
+
+def test_few_neighbours_padding_and_empty():
+    box = np.array([40.0, 40.0, 40.0])
+    pos = np.array([[1.0, 1.0, 1.0], [3.0, 1.0, 1.0],            # pair: 1 neighbour each
+                    [20.0, 20.0, 20.0], [22.0, 20.0, 20.0], [20.0, 22.5, 20.0],  # triple
+                    [10.0, 30.0, 5.0]])                            # isolated
+    r = run(None, pos, box, True, highq=5.0)
+    q, nn4, _ = port.order_param_q(pos, pos, box, 0.0, 5.0)
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)
+    assert_q_close(r.q.cpu().numpy()[0], q)
+    assert r.q[0, 5].item() == 0.0 and abs(r.q[0, 0].item()) < 1e-12

@@ -1,11 +1,12 @@
 // K1: cell-list build for a batch of frames (sm_100a).
 //
 //   cell_count  : one thread per atom; positions are staged through shared memory with 16-byte
-//                 vector loads, converted to periodic fixed point, binned; the atomicAdd that counts
-//                 the cell also hands the atom its rank ("slot") inside the cell.
+//                 vector loads and binned; the atomicAdd that counts the cell also hands the atom its
+//                 rank ("slot") inside the cell.
 //   scan_*      : exclusive prefix sum over all F*ncell counters (reduce / scan-of-sums / apply, the
 //                 in-block part is a warp shuffle scan).
-//   cell_scatter: each atom writes its 16-byte record to cell_start[cell] + slot.
+//   cell_scatter: each atom writes its record (original coordinates, index, cell) to
+//                 cell_start[cell] + slot with 16-byte stores.
 //
 // The reference has no counterpart: its neighbour search is the O(N^2) double loop of
 // fortran/waterlib.f90:846-861 writing an N x N logical matrix.
@@ -43,10 +44,13 @@ struct BuildParams {
     uint32_t *cell_start;
     uint32_t *cell_id;
     uint32_t *slot;
-    Rec *recs;
+    void *recs;
 };
 
-template <typename T, bool SCATTER>
+// T = storage type of the input positions, R = record type (RecD keeps doubles, RecF floats).
+// SCATTER = false: bin + count (the counting atomic also hands the atom its slot inside the cell);
+// SCATTER = true : write the record at cell_start[cell] + slot.
+template <typename T, typename R, bool SCATTER>
 __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p) {
     __shared__ __align__(16) T s_pos[kBuildThreads * 3];
     __shared__ double s_iL[3];
@@ -56,32 +60,51 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     const int n_here = min(kBuildThreads, p.n_pos - a0);
     const size_t frame_atom0 = (size_t)f * p.n_pos;
     if (threadIdx.x < 3) {
-        double L = p.box[(size_t)f * 3 + threadIdx.x];
-        s_iL[threadIdx.x] = 1.0 / L;
+        const double L = p.box[(size_t)f * 3 + threadIdx.x];
+        s_iL[threadIdx.x] = __ddiv_rn(1.0, L);
     }
     stage_tile(reinterpret_cast<const T *>(p.pos) + (frame_atom0 + a0) * 3, n_here * 3, s_pos);
     __syncthreads();
     const int t = threadIdx.x;
     if (t >= n_here) return;
-    const uint32_t xf = to_fixed((double)s_pos[3 * t + 0], s_iL[0]);
-    const uint32_t yf = to_fixed((double)s_pos[3 * t + 1], s_iL[1]);
-    const uint32_t zf = to_fixed((double)s_pos[3 * t + 2], s_iL[2]);
+    const T x = s_pos[3 * t + 0], y = s_pos[3 * t + 1], z = s_pos[3 * t + 2];
     const size_t ga = frame_atom0 + a0 + t;
     const size_t ncell = (size_t)p.nc0 * p.nc1 * p.nc2;
     if (!SCATTER) {
-        const int cx = cell_coord(xf, p.nc0), cy = cell_coord(yf, p.nc1), cz = cell_coord(zf, p.nc2);
+        double xd = (double)x, yd = (double)y, zd = (double)z;
+        if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
+            xd = (double)(float)x;
+            yd = (double)(float)y;
+            zd = (double)(float)z;
+        }
+        const int cx = cell_coord(xd, s_iL[0], p.nc0);
+        const int cy = cell_coord(yd, s_iL[1], p.nc1);
+        const int cz = cell_coord(zd, s_iL[2], p.nc2);
         const uint32_t c = (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx);
         p.cell_id[ga] = c;
         p.slot[ga] = atomicAdd(&p.cell_start[(size_t)f * ncell + c], 1u);
     } else {
         const uint32_t c = p.cell_id[ga];
         const uint32_t dst = p.cell_start[(size_t)f * ncell + c] + p.slot[ga];
-        Rec r;
-        r.x = xf;
-        r.y = yf;
-        r.z = zf;
-        r.idx = a0 + t;
-        *reinterpret_cast<int4 *>(&p.recs[dst]) = *reinterpret_cast<const int4 *>(&r);
+        if (sizeof(R) == sizeof(RecD)) {
+            RecD r;
+            r.x = (double)x;
+            r.y = (double)y;
+            r.z = (double)z;
+            r.idx = a0 + t;
+            r.cell = (int32_t)c;
+            int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst);
+            const int4 *s4 = reinterpret_cast<const int4 *>(&r);
+            d4[0] = s4[0];
+            d4[1] = s4[1];
+        } else {
+            RecF r;
+            r.x = (float)x;
+            r.y = (float)y;
+            r.z = (float)z;
+            r.idx = a0 + t;
+            *reinterpret_cast<int4 *>(reinterpret_cast<RecF *>(p.recs) + dst) = *reinterpret_cast<const int4 *>(&r);
+        }
     }
 }
 
@@ -186,8 +209,27 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__re
     }
 }
 
+template <typename T, typename R>
+static void launch_passes(const BuildParams &p, unsigned blocks, bool scatter, cudaStream_t stream) {
+    if (scatter)
+        cell_pass_kernel<T, R, true><<<blocks, kBuildThreads, 0, stream>>>(p);
+    else
+        cell_pass_kernel<T, R, false><<<blocks, kBuildThreads, 0, stream>>>(p);
+}
+
+static void launch_pass(const BuildParams &p, unsigned blocks, bool scatter, int pos_dtype, int precision,
+                        cudaStream_t stream) {
+    if (pos_dtype == WOL_F64) {
+        if (precision == WOL_PREC_FP64) launch_passes<double, RecD>(p, blocks, scatter, stream);
+        else launch_passes<double, RecF>(p, blocks, scatter, stream);
+    } else {
+        if (precision == WOL_PREC_FP64) launch_passes<float, RecD>(p, blocks, scatter, stream);
+        else launch_passes<float, RecF>(p, blocks, scatter, stream);
+    }
+}
+
 int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_frames, int n_pos, const int32_t nc[3],
-                      void *workspace, const WorkspaceLayout &lay, cudaStream_t stream, int *launches) {
+                      int precision, void *workspace, const WorkspaceLayout &lay, cudaStream_t stream) {
     char *ws = reinterpret_cast<char *>(workspace);
     BuildParams p;
     p.pos = pos;
@@ -201,7 +243,7 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     p.cell_start = reinterpret_cast<uint32_t *>(ws + lay.off_cell_start);
     p.cell_id = reinterpret_cast<uint32_t *>(ws + lay.off_cell_id);
     p.slot = reinterpret_cast<uint32_t *>(ws + lay.off_slot);
-    p.recs = reinterpret_cast<Rec *>(ws + lay.off_recs);
+    p.recs = ws + lay.off_recs;
     uint32_t *block_sums = reinterpret_cast<uint32_t *>(ws + lay.off_block_sums);
     const size_t n_scan = (size_t)lay.n_cells_total + 1;
 
@@ -210,22 +252,16 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     const long long blocks = (long long)p.tiles_per_frame * n_frames;
     if (blocks > 0x7fffffffLL) return set_error(WOL_ERR_RANGE, "too many atom tiles for one launch");
     if (blocks > 0) {
-        if (pos_dtype == WOL_F64)
-            cell_pass_kernel<double, false><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
-        else
-            cell_pass_kernel<float, false><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
-        ++*launches;
+        launch_pass(p, (unsigned)blocks, false, pos_dtype, precision, stream);
+        add_launches(1);
     }
     scan_reduce_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, lay.scan_blocks);
     scan_apply_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
-    *launches += 3;
+    add_launches(3);
     if (blocks > 0) {
-        if (pos_dtype == WOL_F64)
-            cell_pass_kernel<double, true><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
-        else
-            cell_pass_kernel<float, true><<<(unsigned)blocks, kBuildThreads, 0, stream>>>(p);
-        ++*launches;
+        launch_pass(p, (unsigned)blocks, true, pos_dtype, precision, stream);
+        add_launches(1);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("cell build launch", e);

@@ -1,0 +1,864 @@
+// K2: fused neighbour-cell sweep -> neighbour list -> {three-body angle histogram, 4-nearest selection
+// -> tetrahedral q}, for a batch of frames (sm_100a).
+//
+// Work decomposition: a GROUP of G lanes (G = 8 in the fast pass, a whole warp in the large-capacity
+// pass) owns one centre.
+//   phase 1  the lanes walk the flattened candidate list of the centre's cell stencil (contiguous
+//            x-runs of the cell-sorted records), evaluate the reference's minimum-image arithmetic
+//            exactly and append accepted candidates to the group's shared-memory list with a
+//            ballot/popc prefix (three-body neighbours from the front, q-only candidates from the back);
+//   phase 2  per list entry: the reimaged difference vector the reference's angle code sees, its
+//            squared norm, and a per-lane register top-4 by (distance, atom index);
+//   phase 3a the K(K-1)/2 neighbour pairs are spread over the lanes: clamped cosine in reference
+//            operation order, bin by threshold-table compare (no device acos), shared-memory histogram;
+//   phase 3b the group merges its lanes' top-4 with shuffles, and six lanes evaluate the pair cosines
+//            of the four winners -> q.
+// Centres whose 4th neighbour is not certainly inside the 27-cell stencil, or whose list overflows the
+// fast capacity, are queued and redone by the same code instantiated with G = 32, a 1024-entry list
+// and a stencil that widens until the search is provably complete.
+//
+// Reference arithmetic being reproduced (relative to /root/reference):
+//   cutoff test            fortran/waterlib.f90:733-741, :851-859
+//   reimage                fortran/waterlib.f90:43-45
+//   tetraCosAng/CosAngle3  fortran/waterlib.f90:878-893, :690-702
+//   4-NN selection         structureLibs/water_properties.py:372-374
+//   q and padding          structureLibs/water_properties.py:379-388
+//   angle histogram        structureLibs/water_properties.py:328
+#include <limits.h>
+
+#include "wol_device.cuh"
+#include "wol_internal.h"
+#include "wol_workspace.h"
+
+namespace wol {
+
+template <typename T>
+struct alignas(16) Vec4 {
+    T x, y, z, w;
+};
+
+struct Q3bParams {
+    const void *recs;
+    const uint32_t *cell_start;
+    const double *box;
+    const void *centres;  // nullptr: every atom is a centre (visited in cell order)
+    int centre_dtype;
+    int n_frames, n_pos, n_centres;
+    int nc0, nc1, nc2;
+    double low3sq, high3sq, lowqsq, highqsq;
+    double highq;
+    double rc1;   // radius inside which a half-width-1 stencil is complete
+    int wq_max;   // half-width at which the q search is complete whatever it finds
+    int do_q, do_3b;
+    int nbins, q_nbins;
+    double hist_lo, hist_hi;
+    const double *table;
+    void *q;
+    int32_t *nn_idx;
+    int32_t *n3;
+    unsigned long long *ang_hist;
+    unsigned long long *q_hist;
+    double *stats;
+    int hist_per_frame;
+    uint32_t *counters;
+    uint32_t *fb_list;
+    int tiles_per_frame;
+    long long total_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+
+template <typename T>
+struct RecTraits;
+template <>
+struct RecTraits<double> {
+    typedef RecD Rec;
+    static __device__ __forceinline__ void load(const void *recs, size_t j, double &x, double &y, double &z, int &idx) {
+        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + j);
+        const int4 a = __ldg(p), b = __ldg(p + 1);
+        x = __hiloint2double(a.y, a.x);
+        y = __hiloint2double(a.w, a.z);
+        z = __hiloint2double(b.y, b.x);
+        idx = b.z;
+    }
+    static __device__ __forceinline__ int cell(const void *recs, size_t j) {
+        return reinterpret_cast<const RecD *>(recs)[j].cell;
+    }
+};
+template <>
+struct RecTraits<float> {
+    typedef RecF Rec;
+    static __device__ __forceinline__ void load(const void *recs, size_t j, float &x, float &y, float &z, int &idx) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const RecF *>(recs) + j));
+        x = __int_as_float(a.x);
+        y = __int_as_float(a.y);
+        z = __int_as_float(a.z);
+        idx = a.w;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ bool key_less(T d0, int i0, T d1, int i1) {
+    return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+// Per-lane sorted top-4 by (distance, atom index); payload = where the candidate can be found again.
+template <typename T>
+struct Top4 {
+    T d[4];
+    int i[4];
+    int p[4];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d[k] = Ops<T>::inf();
+            i[k] = INT_MAX;
+            p[k] = -1;
+        }
+    }
+    __device__ __forceinline__ void insert(T dd, int ii, int pp) {
+        if (key_less(dd, ii, d[3], i[3])) {
+            d[3] = dd;
+            i[3] = ii;
+            p[3] = pp;
+#pragma unroll
+            for (int k = 3; k > 0; --k) {
+                if (key_less(d[k], i[k], d[k - 1], i[k - 1])) {
+                    const T td = d[k]; d[k] = d[k - 1]; d[k - 1] = td;
+                    const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+                    const int tp = p[k]; p[k] = p[k - 1]; p[k - 1] = tp;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void pop() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            d[k] = d[k + 1];
+            i[k] = i[k + 1];
+            p[k] = p[k + 1];
+        }
+        d[3] = Ops<T>::inf();
+        i[3] = INT_MAX;
+        p[3] = -1;
+    }
+};
+
+__device__ __forceinline__ double shfl_xor_t(double v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
+__device__ __forceinline__ float shfl_xor_t(float v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
+__device__ __forceinline__ double shfl_t(double v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
+__device__ __forceinline__ float shfl_t(float v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
+
+// Position of the angle belonging to clamped cosine c on the histogram axis: -1 below the range,
+// 0..nbins-1 a bin, nbins above the range.  tab[k] (decreasing in k) is the largest c whose angle sits
+// at or beyond bin k, so the position is the largest k with c <= tab[k]; the float acos only seeds
+// the search.
+__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
+    if (c == -1.0) return (int)tab[nbins + 1];
+    const float th = acosf((float)c) * 57.29577951308232f;
+    int k = (int)(((double)th - lo) * inv_width);
+    k = min(max(k, 0), nbins);
+    while (k < nbins && c <= tab[k + 1]) ++k;
+    while (k >= 0 && !(c <= tab[k])) --k;
+    return k;
+}
+
+struct LaneStats {
+    double q_sum, q_sumsq, tet_cos, tet_cossq;
+    unsigned n_centres, tet_count, n_angles, n_neigh;
+    __device__ __forceinline__ void reset() {
+        q_sum = q_sumsq = tet_cos = tet_cossq = 0.0;
+        n_centres = tet_count = n_angles = n_neigh = 0u;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// One centre, one group.  Every lane of the WARP executes this function in lock step (the loops are
+// bounded with warp votes); lanes of groups without work pass valid = false.
+
+template <typename T, int G, int CAP, int MAXSEG, bool EXACT, bool LISTMODE>
+struct GroupWorker {
+    // per-group shared memory
+    struct Smem {
+        Vec4<T> ent[CAP];
+        int eidx[CAP];
+        int segj0[MAXSEG];
+        int segpref[MAXSEG + 1];
+        Vec4<T> win[4];
+    };
+
+    const Q3bParams &P;
+    Smem &S;
+    const int gl;          // lane inside the group
+    const unsigned gshift;  // first warp lane of the group
+    const unsigned gmask;
+
+    __device__ GroupWorker(const Q3bParams &p, Smem &s)
+        : P(p), S(s), gl((threadIdx.x & 31) & (G - 1)), gshift((threadIdx.x & 31) & ~(G - 1)),
+          gmask(G == 32 ? 0xffffffffu : ((1u << G) - 1u)) {}
+
+    __device__ __forceinline__ unsigned group_ballot(bool pred) const {
+        return (__ballot_sync(kFullMask, pred) >> gshift) & gmask;
+    }
+    __device__ __forceinline__ int group_sum(int v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o, G);
+        return v;
+    }
+
+    // Builds the group's segment table for half-width w; returns the candidate total.
+    __device__ int build_segments(bool valid, int f, int cx, int cy, int cz, int w) {
+        const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
+        const int span = 2 * w + 1;
+        const bool fullx = span >= nc0, fully = span >= nc1, fullz = span >= nc2;
+        const int cntx = fullx ? nc0 : span, cnty = fully ? nc1 : span, cntz = fullz ? nc2 : span;
+        const int xs = fullx ? 0 : (cx - w + nc0) % nc0;
+        const int ys = fully ? 0 : (cy - w + nc1) % nc1;
+        const int zs = fullz ? 0 : (cz - w + nc2) % nc2;
+        const int npieces = (xs + cntx > nc0) ? 2 : 1;
+        const int nseg = valid ? cntz * cnty * npieces : 0;
+        const size_t cell_base = (size_t)f * nc0 * nc1 * nc2;
+        int carry = 0;
+        const int nseg_max = __reduce_max_sync(kFullMask, nseg);
+        for (int base = 0; base < nseg_max; base += G) {
+            const int seg = base + gl;
+            int len = 0;
+            if (seg < nseg) {
+                const int piece = seg % npieces;
+                const int rest = seg / npieces;
+                const int iy = rest % cnty, iz = rest / cnty;
+                int y = ys + iy;
+                if (y >= nc1) y -= nc1;
+                int z = zs + iz;
+                if (z >= nc2) z -= nc2;
+                int x0, x1;
+                if (piece == 0) {
+                    x0 = xs;
+                    x1 = min(xs + cntx, nc0);
+                } else {
+                    x0 = 0;
+                    x1 = xs + cntx - nc0;
+                }
+                const size_t row = cell_base + ((size_t)z * nc1 + y) * nc0;
+                const int j0 = (int)__ldg(P.cell_start + row + x0);
+                const int j1 = (int)__ldg(P.cell_start + row + x1);
+                S.segj0[seg] = j0;
+                len = j1 - j0;
+            }
+            // inclusive scan of len inside the group
+            int inc = len;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const int n = __shfl_up_sync(kFullMask, inc, o, G);
+                if (gl >= o) inc += n;
+            }
+            if (seg < nseg) S.segpref[seg + 1] = carry + inc;
+            carry += __shfl_sync(kFullMask, inc, G - 1, G);
+        }
+        if (gl == 0) S.segpref[0] = 0;
+        __syncwarp();
+        return valid ? carry : 0;
+    }
+
+    // Everything for one centre.  flags: bit0 = do three-body, bit1 = do q.  w_start: first stencil
+    // half-width of the q search (the three-body sweep always uses half-width 1).
+    __device__ void run(bool valid, int f, T rx, T ry, T rz, int cx, int cy, int cz, size_t out_index, bool do3,
+                        bool doq, int w_start, uint32_t fb_id, unsigned *s_hist, const double *tab, LaneStats &st) {
+        const T Lx = (T)P.box[(size_t)f * 3 + 0], Ly = (T)P.box[(size_t)f * 3 + 1], Lz = (T)P.box[(size_t)f * 3 + 2];
+        const T iLx = Ops<T>::div((T)1, Lx), iLy = Ops<T>::div((T)1, Ly), iLz = Ops<T>::div((T)1, Lz);
+        const T low3sq = (T)P.low3sq, high3sq = (T)P.high3sq, lowqsq = (T)P.lowqsq, highqsq = (T)P.highqsq;
+        const double inv_width = (double)P.nbins / (P.hist_hi - P.hist_lo);
+        __syncwarp();  // the previous centre's shared-memory reads are over
+
+        Top4<T> top;
+        top.reset();
+        int n_sel = 0;          // q-eligible candidates inside the selection radius
+        bool q_done = !doq;
+        bool q_from_list = false;
+        int K3 = 0, Kb = 0;
+        bool overflow = false;
+
+        // ---------------- sweep at half-width 1: three-body list (+ q candidates) -----------------
+        const bool sweep1 = valid && (do3 || (doq && w_start <= 1));
+        const bool q_in_sweep1 = doq && w_start <= 1;
+        // selection radius at half-width 1
+        const bool full1 = (3 >= P.nc0) && (3 >= P.nc1) && (3 >= P.nc2);
+        const bool last1 = full1 || P.wq_max <= 1;
+        T selsq1;
+        {
+            const double r = last1 ? P.highq : fmin(P.highq, P.rc1);
+            selsq1 = last1 ? highqsq : (T)fmin((double)highqsq, r * r);
+        }
+        {
+            const int total = build_segments(sweep1, f, cx, cy, cz, 1);
+            int seg = 0;
+            for (int t0 = 0; __any_sync(kFullMask, t0 < total); t0 += G) {
+                const int t = t0 + gl;
+                const bool act = t < total;
+                bool in3 = false, inq = false;
+                T dx = 0, dy = 0, dz = 0, s = 0;
+                int idx = -1;
+                if (act) {
+                    while (t >= S.segpref[seg + 1]) ++seg;
+                    const size_t j = (size_t)(S.segj0[seg] + (t - S.segpref[seg]));
+                    T px, py, pz;
+                    RecTraits<T>::load(P.recs, j, px, py, pz, idx);
+                    dx = min_image_1<T, EXACT>(px, rx, Lx, iLx);
+                    dy = min_image_1<T, EXACT>(py, ry, Ly, iLy);
+                    dz = min_image_1<T, EXACT>(pz, rz, Lz, iLz);
+                    s = sumsq3<T>(dx, dy, dz);
+                    in3 = do3 && (s > low3sq) && (s <= high3sq);
+                    inq = q_in_sweep1 && (s > lowqsq) && (s <= selsq1);
+                }
+                const unsigned b3 = group_ballot(in3);
+                const unsigned bq = group_ballot(inq && !in3);
+                const unsigned lt = (1u << gl) - 1u;
+                const int n3new = __popc(b3), nbnew = __popc(bq);
+                if (K3 + Kb + n3new + nbnew > CAP) overflow = true;
+                if (!overflow) {
+                    int slot = -1;
+                    if (in3) slot = K3 + __popc(b3 & lt);
+                    else if (inq) slot = CAP - 1 - (Kb + __popc(bq & lt));
+                    if (slot >= 0) {
+                        Vec4<T> v;
+                        v.x = dx; v.y = dy; v.z = dz; v.w = s;
+                        S.ent[slot] = v;
+                        S.eidx[slot] = idx;
+                    }
+                    K3 += n3new;
+                    Kb += nbnew;
+                }
+            }
+            __syncwarp();
+        }
+
+        if (overflow) {
+            if (!LISTMODE) {
+                // hand the whole centre to the large-capacity pass
+                if (gl == 0) {
+                    const uint32_t at = atomicAdd(P.counters + kCntFallback, 1u);
+                    P.fb_list[at] = fb_id | (do3 ? kFbNeed3b : 0u) | (doq ? kFbNeedQ : 0u);
+                    atomicAdd(P.counters + kCntOverflow, 1u);
+                }
+            } else if (gl == 0) {
+                atomicAdd(P.counters + kCntFatal, 1u);
+            }
+            valid = false;
+            do3 = false;
+            doq = false;
+            q_done = true;
+            K3 = Kb = 0;
+        }
+
+        // ---------------- phase 2: reimaged vectors, norms, top-4 over the list --------------------
+        {
+            const int nent = valid ? K3 + Kb : 0;
+            for (int m0 = 0; __any_sync(kFullMask, m0 < nent); m0 += G) {
+                const int m = m0 + gl;
+                if (m < nent) {
+                    const int slot = (m < K3) ? m : CAP - 1 - (m - K3);
+                    Vec4<T> v = S.ent[slot];
+                    const T s = v.w;
+                    // ReimagedPos = RefPos + distvec (waterlib.f90:45); Vec = Pos - RefPos (:694-695)
+                    const T ex = Ops<T>::sub(Ops<T>::add(rx, v.x), rx);
+                    const T ey = Ops<T>::sub(Ops<T>::add(ry, v.y), ry);
+                    const T ez = Ops<T>::sub(Ops<T>::add(rz, v.z), rz);
+                    const T ne = sumsq3<T>(ex, ey, ez);
+                    v.x = ex; v.y = ey; v.z = ez; v.w = ne;
+                    S.ent[slot] = v;
+                    if (q_in_sweep1 && (s > lowqsq) && (s <= selsq1)) {
+                        ++n_sel;
+                        top.insert(Ops<T>::sqrt(ne), S.eidx[slot], slot);
+                    }
+                }
+            }
+            __syncwarp();
+            if (q_in_sweep1) {
+                n_sel = group_sum(n_sel);
+                q_from_list = true;
+                if (n_sel >= 4 || last1) q_done = true;
+            }
+        }
+
+        // ---------------- phase 3a: three-body pair angles ----------------------------------------
+        if (__any_sync(kFullMask, valid && do3)) {
+            const int K = (valid && do3) ? K3 : 0;
+            const int npairs = K * (K - 1) / 2;
+            for (int p0 = 0; __any_sync(kFullMask, p0 < npairs); p0 += G) {
+                const int p = p0 + gl;
+                if (p < npairs) {
+                    // p = b (b - 1) / 2 + a, a < b
+                    int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                    while (b * (b - 1) / 2 > p) --b;
+                    while ((b + 1) * b / 2 <= p) ++b;
+                    const int a = p - b * (b - 1) / 2;
+                    const Vec4<T> va = S.ent[a], vb = S.ent[b];
+                    int pos;
+                    double c;
+                    if (va.w == (T)0 || vb.w == (T)0) {  // coincident positions: CosAngle3 returns 0 (:690-693)
+                        pos = (int)tab[P.nbins + 2];
+                        c = 1.0;
+                    } else {
+                        const T dot = dot3<T>(va.x, va.y, va.z, vb.x, vb.y, vb.z);
+                        c = (double)clamped_cos<T>(dot, va.w, vb.w);
+                        pos = angle_position(c, tab, P.nbins, P.hist_lo, inv_width);
+                        if (c != -1.0 && c <= tab[P.nbins + 3] && c >= tab[P.nbins + 4]) {
+                            st.tet_count += 1u;
+                            st.tet_cos += c;
+                            st.tet_cossq += c * c;
+                        }
+                    }
+                    st.n_angles += 1u;
+                    if (pos >= 0 && pos < P.nbins) {
+                        if (s_hist) atomicAdd(s_hist + pos, 1u);
+                        else if (P.ang_hist)
+                            atomicAdd(P.ang_hist + (size_t)(P.hist_per_frame ? f : 0) * P.nbins + pos, 1ull);
+                    }
+                }
+            }
+            if (valid && do3 && gl == 0) {
+                if (P.n3) P.n3[out_index] = K3;
+                st.n_neigh += (unsigned)K3;
+            }
+        }
+
+        // ---------------- q search beyond the list: widen until provably complete -----------------
+        // (large-capacity pass only; the fast pass queues the centre instead)
+        if (__any_sync(kFullMask, valid && doq && !q_done)) {
+            if (!LISTMODE) {
+                if (valid && doq && !q_done && gl == 0) {
+                    const uint32_t at = atomicAdd(P.counters + kCntFallback, 1u);
+                    P.fb_list[at] = fb_id | kFbNeedQ;
+                    atomicAdd(P.counters + kCntWidened, 1u);
+                }
+                if (!q_done) doq = false;
+            } else {
+                int w = max(w_start, 2);
+                while (__any_sync(kFullMask, valid && doq && !q_done)) {
+                    const bool go = valid && doq && !q_done;
+                    const bool full = (2 * w + 1 >= P.nc0) && (2 * w + 1 >= P.nc1) && (2 * w + 1 >= P.nc2);
+                    const bool last = full || w >= P.wq_max;
+                    const double rsel = last ? P.highq : fmin(P.highq, (double)w * P.rc1);
+                    const T selsq = last ? highqsq : (T)fmin((double)highqsq, rsel * rsel);
+                    if (go) {
+                        top.reset();
+                        n_sel = 0;
+                        q_from_list = false;
+                    }
+                    const int total = build_segments(go, f, cx, cy, cz, w);
+                    int seg = 0;
+                    for (int t0 = 0; __any_sync(kFullMask, t0 < total); t0 += G) {
+                        const int t = t0 + gl;
+                        if (t < total) {
+                            while (t >= S.segpref[seg + 1]) ++seg;
+                            const size_t j = (size_t)(S.segj0[seg] + (t - S.segpref[seg]));
+                            T px, py, pz;
+                            int idx;
+                            RecTraits<T>::load(P.recs, j, px, py, pz, idx);
+                            const T dx = min_image_1<T, EXACT>(px, rx, Lx, iLx);
+                            const T dy = min_image_1<T, EXACT>(py, ry, Ly, iLy);
+                            const T dz = min_image_1<T, EXACT>(pz, rz, Lz, iLz);
+                            const T s = sumsq3<T>(dx, dy, dz);
+                            if ((s > lowqsq) && (s <= selsq)) {
+                                ++n_sel;
+                                const T ex = Ops<T>::sub(Ops<T>::add(rx, dx), rx);
+                                const T ey = Ops<T>::sub(Ops<T>::add(ry, dy), ry);
+                                const T ez = Ops<T>::sub(Ops<T>::add(rz, dz), rz);
+                                top.insert(Ops<T>::sqrt(sumsq3<T>(ex, ey, ez)), idx, (int)j);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const int n_all = group_sum(n_sel);
+                    if (go) {
+                        n_sel = n_all;
+                        if (n_all >= 4 || last) q_done = true;
+                    }
+                    ++w;
+                }
+            }
+        }
+
+        // ---------------- phase 3b: merge top-4, winners' vectors, q ------------------------------
+        if (__any_sync(kFullMask, valid && doq)) {
+            const bool go = valid && doq;
+            int win_idx[4], win_pay[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                T hd = top.d[0];
+                int hi = top.i[0], hp = top.p[0], owner = gl;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    const T od = shfl_xor_t(hd, o, G);
+                    const int oi = __shfl_xor_sync(kFullMask, hi, o, G);
+                    const int op = __shfl_xor_sync(kFullMask, hp, o, G);
+                    const int oo = __shfl_xor_sync(kFullMask, owner, o, G);
+                    const bool take = key_less(od, oi, hd, hi) || (od == hd && oi == hi && oo < owner);
+                    if (take) {
+                        hd = od; hi = oi; hp = op; owner = oo;
+                    }
+                }
+                win_idx[r] = hi;
+                win_pay[r] = hp;
+                if (owner == gl) top.pop();
+            }
+            const int n_found = go ? min(n_sel, 4) : 0;
+            // winners' vectors as tetraCosAng sees them: it is handed the already reimaged position and
+            // reimages it again (waterlib.f90:880-883) before CosAngle3 subtracts the centre (:694-695)
+            if (go && gl < n_found) {
+                T ex, ey, ez;
+                const int pay = (gl == 0) ? win_pay[0] : (gl == 1 ? win_pay[1] : (gl == 2 ? win_pay[2] : win_pay[3]));
+                if (q_from_list) {
+                    const Vec4<T> v = S.ent[pay];
+                    ex = v.x; ey = v.y; ez = v.z;
+                } else {
+                    T px, py, pz;
+                    int idx;
+                    RecTraits<T>::load(P.recs, (size_t)pay, px, py, pz, idx);
+                    const T dx = min_image_1<T, EXACT>(px, rx, Lx, iLx);
+                    const T dy = min_image_1<T, EXACT>(py, ry, Ly, iLy);
+                    const T dz = min_image_1<T, EXACT>(pz, rz, Lz, iLz);
+                    ex = Ops<T>::sub(Ops<T>::add(rx, dx), rx);
+                    ey = Ops<T>::sub(Ops<T>::add(ry, dy), ry);
+                    ez = Ops<T>::sub(Ops<T>::add(rz, dz), rz);
+                }
+                // second reimage of (img - ref): always the exact anint, it is only 4 per centre
+                const T d2x = Ops<T>::sub(ex, Ops<T>::mul(Lx, anint_exact<T>(Ops<T>::mul(ex, iLx))));
+                const T d2y = Ops<T>::sub(ey, Ops<T>::mul(Ly, anint_exact<T>(Ops<T>::mul(ey, iLy))));
+                const T d2z = Ops<T>::sub(ez, Ops<T>::mul(Lz, anint_exact<T>(Ops<T>::mul(ez, iLz))));
+                Vec4<T> v;
+                v.x = Ops<T>::sub(Ops<T>::add(rx, d2x), rx);
+                v.y = Ops<T>::sub(Ops<T>::add(ry, d2y), ry);
+                v.z = Ops<T>::sub(Ops<T>::add(rz, d2z), rz);
+                v.w = sumsq3<T>(v.x, v.y, v.z);
+                S.win[gl] = v;
+            }
+            __syncwarp();
+            // The six terms (cos + 1/3)^2 in the order of the reference's angle array: the real angles
+            // in triu order, then the 180-degree padding (cos = -1) it appends when the centre has fewer
+            // than four neighbours (water_properties.py:379-384); summed left to right like np.sum.
+            double term = 0.0;
+            if (go && gl < 6) {
+                int pa = -1, pb = -1;
+                if (n_found == 4) {
+                    pa = (gl < 3) ? 0 : (gl < 5 ? 1 : 2);
+                    pb = (gl < 3) ? gl + 1 : (gl < 5 ? gl - 1 : 3);
+                } else if (n_found == 3) {
+                    if (gl < 3) {
+                        pa = (gl == 2) ? 1 : 0;
+                        pb = (gl == 0) ? 1 : 2;
+                    }
+                } else if (n_found == 2) {
+                    if (gl == 0) {
+                        pa = 0;
+                        pb = 1;
+                    }
+                }
+                double c = -1.0;
+                if (pa >= 0) {
+                    const Vec4<T> va = S.win[pa], vb = S.win[pb];
+                    if (va.w == (T)0 || vb.w == (T)0) c = 1.0;
+                    else c = (double)clamped_cos<T>(dot3<T>(va.x, va.y, va.z, vb.x, vb.y, vb.z), va.w, vb.w);
+                }
+                const double u = c + (1.0 / 3.0);
+                term = u * u;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc += shfl_t(term, k, G);
+            if (go && gl == 0) {
+                const double qv = (n_found == 0) ? 0.0 : 1.0 - (3.0 / 8.0) * acc;
+                if (P.q) {
+                    if (sizeof(T) == 8) reinterpret_cast<double *>(P.q)[out_index] = qv;
+                    else reinterpret_cast<float *>(P.q)[out_index] = (float)qv;
+                }
+                if (P.nn_idx) {
+                    int4 o;
+                    o.x = (n_found > 0) ? win_idx[0] : -1;
+                    o.y = (n_found > 1) ? win_idx[1] : -1;
+                    o.z = (n_found > 2) ? win_idx[2] : -1;
+                    o.w = (n_found > 3) ? win_idx[3] : -1;
+                    reinterpret_cast<int4 *>(P.nn_idx)[out_index] = o;
+                }
+                if (P.q_hist) {
+                    const HistSpec hs = hist_spec(0.0, 1.0, P.q_nbins);
+                    const int b = hist_bin(hs, qv);
+                    if (b >= 0) atomicAdd(P.q_hist + (size_t)(P.hist_per_frame ? f : 0) * P.q_nbins + b, 1ull);
+                }
+                st.q_sum += qv;
+                st.q_sumsq += qv * qv;
+                st.n_centres += 1u;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void flush_stats(const Q3bParams &P, int f, LaneStats &st) {
+    double v[8];
+    v[WOL_STAT_Q_SUM] = st.q_sum;
+    v[WOL_STAT_Q_SUMSQ] = st.q_sumsq;
+    v[WOL_STAT_N_CENTRES] = (double)st.n_centres;
+    v[WOL_STAT_TET_COUNT] = (double)st.tet_count;
+    v[WOL_STAT_TET_COS] = st.tet_cos;
+    v[WOL_STAT_TET_COSSQ] = st.tet_cossq;
+    v[WOL_STAT_N_ANGLES] = (double)st.n_angles;
+    v[WOL_STAT_N_NEIGH] = (double)st.n_neigh;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double s = warp_sum(v[k]);
+        if (P.stats && (threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(P.stats + (size_t)f * WOL_NSTATS + k, s);
+    }
+    st.reset();
+}
+
+template <typename T>
+__device__ __forceinline__ void load_centre(const Q3bParams &P, int f, int m, T &rx, T &ry, T &rz) {
+    const size_t o = ((size_t)f * P.n_centres + m) * 3;
+    if (P.centre_dtype == WOL_F64) {
+        const double *c = reinterpret_cast<const double *>(P.centres);
+        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
+    } else {
+        const float *c = reinterpret_cast<const float *>(P.centres);
+        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
+    }
+}
+
+constexpr int kFastThreads = 128;
+constexpr int kFastG = 8;
+constexpr int kFastCap = 32;
+constexpr int kFastMaxSeg = 18;
+constexpr int kBigThreads = 64;
+constexpr int kBigCap = 1024;
+constexpr int kBigMaxSeg = 512;
+constexpr int kMaxSmemBins = 4096;
+
+// Fast pass: every centre once.  Persistent blocks walk contiguous tiles of kFastThreads / G centres so
+// that the block histogram is flushed once per frame the block touches.
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(kFastThreads) q3b_fast_kernel(const __grid_constant__ Q3bParams P) {
+    typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> Worker;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kGroups = kFastThreads / kFastG;
+    typename Worker::Smem *gs = reinterpret_cast<typename Worker::Smem *>(smem_raw);
+    unsigned char *after = smem_raw + sizeof(typename Worker::Smem) * kGroups;
+    const bool smem_hist = P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins;
+    double *s_tab = reinterpret_cast<double *>(after);
+    const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
+    const bool smem_tab = P.nbins <= kMaxSmemBins;
+    unsigned *s_hist = reinterpret_cast<unsigned *>(after + (smem_tab ? sizeof(double) * tab_len : 0));
+    if (smem_tab)
+        for (int i = threadIdx.x; i < tab_len; i += blockDim.x) s_tab[i] = P.table[i];
+    if (smem_hist)
+        for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const double *tab = smem_tab ? s_tab : P.table;
+
+    const int group = threadIdx.x / kFastG;
+    Worker worker(P, gs[group]);
+    LaneStats st;
+    st.reset();
+
+    const long long chunk = (P.total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t_begin = chunk * blockIdx.x;
+    const long long t_end = min(P.total_tiles, t_begin + chunk);
+    int cur_f = -1;
+    const int ncell_xy = P.nc0 * P.nc1;
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        const int f = (int)(tile / P.tiles_per_frame);
+        const int m = (int)(tile - (long long)f * P.tiles_per_frame) * kGroups + group;
+        if (f != cur_f) {
+            if (cur_f >= 0) {
+                flush_stats(P, cur_f, st);
+                if (smem_hist && P.hist_per_frame) {
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) {
+                        const unsigned v = s_hist[i];
+                        if (v) atomicAdd(P.ang_hist + (size_t)cur_f * P.nbins + i, (unsigned long long)v);
+                        s_hist[i] = 0u;
+                    }
+                    __syncthreads();
+                }
+            }
+            cur_f = f;
+        }
+        const bool valid = m < P.n_centres;
+        T rx = 0, ry = 0, rz = 0;
+        int cx = 0, cy = 0, cz = 0;
+        size_t out_index = 0;
+        uint32_t fb_id = 0;
+        if (valid) {
+            if (P.centres == nullptr) {
+                const size_t j = (size_t)f * P.n_pos + m;  // m-th atom of the frame in cell order
+                int idx;
+                RecTraits<T>::load(P.recs, j, rx, ry, rz, idx);
+                out_index = (size_t)f * P.n_pos + idx;
+                fb_id = (uint32_t)j;
+            } else {
+                load_centre<T>(P, f, m, rx, ry, rz);
+                out_index = (size_t)f * P.n_centres + m;
+                fb_id = (uint32_t)out_index;
+            }
+            const double *bx = P.box + (size_t)f * 3;
+            cx = cell_coord((double)rx, __ddiv_rn(1.0, bx[0]), P.nc0);
+            cy = cell_coord((double)ry, __ddiv_rn(1.0, bx[1]), P.nc1);
+            cz = cell_coord((double)rz, __ddiv_rn(1.0, bx[2]), P.nc2);
+        }
+        (void)ncell_xy;
+        worker.run(valid, f, rx, ry, rz, cx, cy, cz, out_index, P.do_3b != 0, P.do_q != 0, 1, fb_id,
+                   smem_hist ? s_hist : nullptr, tab, st);
+    }
+    if (cur_f >= 0) flush_stats(P, cur_f, st);
+    if (smem_hist) {
+        __syncthreads();
+        if (cur_f >= 0)
+            for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) {
+                const unsigned v = s_hist[i];
+                if (v) atomicAdd(P.ang_hist + (size_t)(P.hist_per_frame ? cur_f : 0) * P.nbins + i, (unsigned long long)v);
+            }
+    }
+}
+
+// Large-capacity pass over the queued centres: one warp per centre.
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_constant__ Q3bParams P) {
+    typedef GroupWorker<T, 32, kBigCap, kBigMaxSeg, EXACT, true> Worker;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename Worker::Smem *gs = reinterpret_cast<typename Worker::Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    Worker worker(P, gs[warp]);
+    LaneStats st;
+    const uint32_t n_items = P.counters[kCntFallback];
+    const uint32_t warps_total = gridDim.x * (kBigThreads / 32);
+    for (uint32_t it = blockIdx.x * (kBigThreads / 32) + warp; it < n_items; it += warps_total) {
+        st.reset();
+        const uint32_t e = P.fb_list[it];
+        const uint32_t id = e & kFbIdMask;
+        const bool do3 = (e & kFbNeed3b) != 0, doq = (e & kFbNeedQ) != 0;
+        T rx, ry, rz;
+        size_t out_index;
+        int f;
+        if (P.centres == nullptr) {
+            f = (int)(id / (uint32_t)P.n_pos);
+            int idx;
+            RecTraits<T>::load(P.recs, (size_t)id, rx, ry, rz, idx);
+            out_index = (size_t)f * P.n_pos + idx;
+        } else {
+            f = (int)(id / (uint32_t)P.n_centres);
+            load_centre<T>(P, f, (int)(id - (uint32_t)f * P.n_centres), rx, ry, rz);
+            out_index = id;
+        }
+        const double *bx = P.box + (size_t)f * 3;
+        const int cx = cell_coord((double)rx, __ddiv_rn(1.0, bx[0]), P.nc0);
+        const int cy = cell_coord((double)ry, __ddiv_rn(1.0, bx[1]), P.nc1);
+        const int cz = cell_coord((double)rz, __ddiv_rn(1.0, bx[2]), P.nc2);
+        // a centre queued only for q already failed at half-width 1; an overflowed one starts over
+        worker.run(true, f, rx, ry, rz, cx, cy, cz, out_index, do3, doq, do3 ? 1 : 2, id, nullptr, P.table, st);
+        flush_stats(P, f, st);
+    }
+}
+
+__global__ void reset_counters_kernel(uint32_t *counters) {
+    if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0u;
+}
+
+template <typename T, bool EXACT>
+static int launch_typed(const Q3bParams &P, cudaStream_t stream) {
+    typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> FastWorker;
+    typedef GroupWorker<T, 32, kBigCap, kBigMaxSeg, EXACT, true> BigWorker;
+    const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
+    size_t fast_smem = sizeof(typename FastWorker::Smem) * (kFastThreads / kFastG);
+    if (P.nbins <= kMaxSmemBins) fast_smem += sizeof(double) * tab_len;
+    if (P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins) fast_smem += sizeof(unsigned) * P.nbins;
+    const size_t big_smem = sizeof(typename BigWorker::Smem) * (kBigThreads / 32);
+    cudaError_t e;
+    e = cudaFuncSetAttribute(q3b_fast_kernel<T, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(fast)", e);
+    e = cudaFuncSetAttribute(q3b_big_kernel<T, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(big)", e);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3b_fast_kernel<T, EXACT>, kFastThreads, fast_smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int sms = sm_count();
+    long long grid = (long long)sms * per_sm;
+    if (grid > P.total_tiles) grid = P.total_tiles;
+    reset_counters_kernel<<<1, 32, 0, stream>>>(P.counters);
+    add_launches(1);
+    if (grid > 0) {
+        q3b_fast_kernel<T, EXACT><<<(unsigned)grid, kFastThreads, fast_smem, stream>>>(P);
+        add_launches(1);
+        int big_per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&big_per_sm, q3b_big_kernel<T, EXACT>, kBigThreads, big_smem);
+        if (e != cudaSuccess || big_per_sm < 1) big_per_sm = 1;
+        q3b_big_kernel<T, EXACT><<<(unsigned)(sms * big_per_sm), kBigThreads, big_smem, stream>>>(P);
+        add_launches(1);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("q3b launch", e);
+    return WOL_OK;
+}
+
+int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t stream) {
+    char *ws = reinterpret_cast<char *>(a.workspace);
+    Q3bParams P;
+    P.recs = ws + lay.off_recs;
+    P.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
+    P.box = a.box;
+    P.centres = a.centres;
+    P.centre_dtype = a.centre_dtype;
+    P.n_frames = a.n_frames;
+    P.n_pos = a.n_pos;
+    P.n_centres = a.centres ? a.n_centres : a.n_pos;
+    P.nc0 = a.nc[0];
+    P.nc1 = a.nc[1];
+    P.nc2 = a.nc[2];
+    P.low3sq = a.low3 * a.low3;
+    P.high3sq = a.high3 * a.high3;
+    P.lowqsq = a.lowq * a.lowq;
+    P.highqsq = a.highq * a.highq;
+    P.highq = a.highq;
+    P.rc1 = a.edge_min * (1.0 - 1e-9);
+    int wq = 1;
+    while ((double)wq * P.rc1 < a.highq && wq < 64) ++wq;
+    P.wq_max = wq;
+    P.do_q = a.do_q;
+    P.do_3b = a.do_3body;
+    P.nbins = a.nbins;
+    P.q_nbins = a.q_nbins;
+    P.hist_lo = a.hist_lo;
+    P.hist_hi = a.hist_hi;
+    P.table = a.angle_table;
+    P.q = a.q;
+    P.nn_idx = a.nn_idx;
+    P.n3 = a.n3;
+    P.ang_hist = reinterpret_cast<unsigned long long *>(a.ang_hist);
+    P.q_hist = reinterpret_cast<unsigned long long *>(a.q_hist);
+    P.stats = a.frame_stats;
+    P.hist_per_frame = a.hist_per_frame;
+    P.counters = reinterpret_cast<uint32_t *>(ws + lay.off_counters);
+    P.fb_list = reinterpret_cast<uint32_t *>(ws + lay.off_fb_list);
+    const int groups = kFastThreads / kFastG;
+    P.tiles_per_frame = (P.n_centres + groups - 1) / groups;
+    P.total_tiles = (long long)P.tiles_per_frame * a.n_frames;
+
+    // widest stencil the q search can need must fit the segment table of the large-capacity pass
+    {
+        int w = P.wq_max;
+        const int cz = (2 * w + 1 >= P.nc2) ? P.nc2 : 2 * w + 1;
+        const int cy = (2 * w + 1 >= P.nc1) ? P.nc1 : 2 * w + 1;
+        if ((long long)cz * cy * 2 > kBigMaxSeg && a.do_q)
+            return set_error(WOL_ERR_UNSUPPORTED,
+                             "q cutoff %.3f needs a stencil of half-width %d cells; plan the grid with a larger r_cell",
+                             a.highq, w);
+    }
+    // exact anint only matters when a cutoff can reach L/2 (see min_image_1)
+    const double reach = fmax(a.do_3body ? a.high3 : 0.0, a.do_q ? a.highq : 0.0);
+    const bool exact = reach > 0.49 * a.edge_min * (double)(P.nc0 < P.nc1 ? (P.nc0 < P.nc2 ? P.nc0 : P.nc2)
+                                                                          : (P.nc1 < P.nc2 ? P.nc1 : P.nc2));
+    if (a.precision == WOL_PREC_FP64)
+        return exact ? launch_typed<double, true>(P, stream) : launch_typed<double, false>(P, stream);
+    return exact ? launch_typed<float, true>(P, stream) : launch_typed<float, false>(P, stream);
+}
+
+}  // namespace wol

@@ -11,25 +11,46 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-// Sorted per-atom record: periodic fixed-point coordinates + original atom index.  16 bytes, loaded
-// as one int4.
-struct alignas(16) Rec {
-    uint32_t x, y, z;
+// Sorted per-atom records, grouped by (frame, cell).
+// FP64 mode: original coordinates (bit-identical to the input, the reference arithmetic needs them),
+// original atom index and the cell id.  32 bytes = two 16-byte loads.
+struct alignas(16) RecD {
+    double x, y, z;
+    int32_t idx;
+    int32_t cell;
+};
+// FP32 mode: 16 bytes = one load.
+struct alignas(16) RecF {
+    float x, y, z;
     int32_t idx;
 };
+
+// Device counters (uint32) at off_counters.
+enum {
+    kCntFallback = 0,  // entries in the fallback list
+    kCntWidened = 1,   // centres whose q search had to be widened
+    kCntOverflow = 2,  // centres whose list overflowed the fast path
+    kCntFatal = 3,     // centres whose list overflowed the large-capacity path
+    kNumCounters = 8
+};
+
+// Fallback list entry: centre id (frame * n_centres + centre) in the low 30 bits, flags above.
+constexpr uint32_t kFbNeedQ = 1u << 30;
+constexpr uint32_t kFbNeed3b = 1u << 31;
+constexpr uint32_t kFbIdMask = (1u << 30) - 1u;
 
 struct WorkspaceLayout {
     size_t off_cell_start;  // uint32[F*ncell + 1]  counts during the build, exclusive starts afterwards
     size_t off_block_sums;  // uint32[scan blocks + 1]
     size_t off_cell_id;     // uint32[F*N]
     size_t off_slot;        // uint32[F*N]  rank of the atom inside its cell
-    size_t off_recs;        // Rec[F*N]     atoms grouped by (frame, cell)
-    size_t off_counters;    // uint32[8]    [0] q-fallback count, [1] three-body overflow count
-    size_t off_fb_list;     // uint32[F*M]  centres whose 4-NN search must be widened
-    size_t off_ov_list;     // uint32[F*M]  centres with more three-body neighbours than the fast path holds
+    size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
+    size_t off_counters;    // uint32[kNumCounters]
+    size_t off_fb_list;     // uint32[F*M]  centres the fast path handed to the large-capacity path
     size_t total;
     int64_t n_cells_total;
     int64_t n_atoms_total;
+    int64_t n_centres_total;
     int32_t scan_blocks;
 };
 
@@ -41,7 +62,7 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
     w.n_cells_total = ncell * n_frames;
     w.n_atoms_total = (int64_t)n_pos * n_frames;
-    int64_t n_centres_total = (int64_t)(n_centres_max > n_pos ? n_centres_max : n_pos) * n_frames;
+    w.n_centres_total = (int64_t)(n_centres_max > n_pos ? n_centres_max : n_pos) * n_frames;
     w.scan_blocks = (int32_t)((w.n_cells_total + 1 + kScanTile - 1) / kScanTile);
     size_t o = 0;
     w.off_cell_start = o;
@@ -53,13 +74,11 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     w.off_slot = o;
     o = align_up(o + (size_t)w.n_atoms_total * 4, 256);
     w.off_recs = o;
-    o = align_up(o + (size_t)w.n_atoms_total * sizeof(Rec), 256);
+    o = align_up(o + (size_t)w.n_atoms_total * sizeof(RecD), 256);
     w.off_counters = o;
-    o = align_up(o + 8 * 4, 256);
+    o = align_up(o + kNumCounters * 4, 256);
     w.off_fb_list = o;
-    o = align_up(o + (size_t)n_centres_total * 4, 256);
-    w.off_ov_list = o;
-    o = align_up(o + (size_t)n_centres_total * 4, 256);
+    o = align_up(o + (size_t)w.n_centres_total * 4, 256);
     w.total = o;
     return w;
 }

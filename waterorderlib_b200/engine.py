@@ -1,0 +1,211 @@
+"""Host side of the fused q / three-body path: owns the device buffers (PyTorch tensors), plans the cell
+grid, and calls the C ABI (include/wol_capi.h) on the current CUDA stream.
+
+PyTorch is plumbing only here: device memory, streams, host<->device copies.  Every number comes out of
+libwol.so's sm_100a kernels; nothing in this module computes on the CPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import WOL_F32, WOL_F64, WOL_NSTATS, WOL_PREC_FP32, WOL_PREC_FP64, WOL_TABLE_EXTRA, Q3bArgs, check, lib
+
+_I3 = ctypes.c_int32 * 3
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float64:
+        return WOL_F64
+    if t.dtype == torch.float32:
+        return WOL_F32
+    raise ValueError("positions must be float64 or float32, got %s" % t.dtype)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def as_device_positions(a, device):
+    """(F,N,3) or (N,3) array/tensor -> contiguous (F,N,3) CUDA tensor, dtype kept if float32/float64."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        arr = np.asarray(a)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3 or t.shape[-1] != 3:
+        raise ValueError("positions must have shape (n,3) or (frames,n,3), got %s" % (tuple(t.shape),))
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def as_host_boxes(box, n_frames):
+    """BoxDims as the reference accepts it ((3,), (1,3), or per frame (F,3)) -> float64 (F,3) numpy."""
+    if isinstance(box, torch.Tensor):
+        box = box.detach().cpu().numpy()
+    b = np.asarray(box, dtype=np.float64)
+    if b.size == 3:
+        b = np.broadcast_to(b.reshape(1, 3), (n_frames, 3))
+    b = np.ascontiguousarray(b.reshape(-1, 3))
+    if b.shape[0] != n_frames:
+        raise ValueError("need one box per frame: %d boxes for %d frames" % (b.shape[0], n_frames))
+    return b
+
+
+_TABLE_CACHE = {}
+
+
+def angle_table(hist_lo, hist_hi, nbins, device, tet_lo=100.0, tet_hi=120.0):
+    """Device copy of wol_angle_table for this histogram spec (cached per device)."""
+    key = (float(hist_lo), float(hist_hi), int(nbins), float(tet_lo), float(tet_hi), str(device))
+    t = _TABLE_CACHE.get(key)
+    if t is None:
+        host = np.zeros(nbins + 1 + WOL_TABLE_EXTRA, dtype=np.float64)
+        check(lib().wol_angle_table(hist_lo, hist_hi, nbins, tet_lo, tet_hi, host.ctypes.data_as(ctypes.c_void_p)),
+              "wol_angle_table")
+        t = torch.from_numpy(host).to(device)
+        _TABLE_CACHE[key] = t
+    return t
+
+
+def plan_grid(box_host, r_cell):
+    nc = _I3()
+    edge = ctypes.c_double(0.0)
+    check(lib().wol_plan_grid(box_host.ctypes.data_as(ctypes.c_void_p), box_host.shape[0], float(r_cell),
+                              ctypes.byref(nc), ctypes.byref(edge)), "wol_plan_grid")
+    return nc, edge.value
+
+
+class Q3bResult(dict):
+    """Outputs of one fused call (torch tensors on the device) plus launch bookkeeping."""
+    __getattr__ = dict.__getitem__
+
+
+class Workspace:
+    """Caller-owned scratch, grown on demand and reused between calls."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        off = (-self.buf.data_ptr()) % 256
+        return self.buf.data_ptr() + off, self.buf.numel() - off
+
+
+def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, high3=3.413, lowq=0.0, highq=10.0,
+               nbins=500, bin_range=(0.0, 180.0), q_nbins=500, precision="fp64", hist_per_frame=False, r_cell=None,
+               want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), out=None, workspace=None,
+               device=None, check_status=True):
+    """Fused tetrahedral q + three-body angle histogram for a batch of frames.
+
+    pos      (F,N,3) positions of all atoms that can be neighbours (reference: `Pos`)
+    box      (3,), (1,3) or (F,3) orthorhombic box edges (reference: `BoxDims`)
+    centres  None = every atom of pos is a centre (reference: subPos is Pos); else (F,M,3) (`subPos`)
+    out      optional dict of preallocated output tensors to accumulate into / overwrite
+    Returns a Q3bResult of device tensors; histograms and frame_stats ACCUMULATE into `out` if given.
+    """
+    if device is None:
+        device = pos.device if isinstance(pos, torch.Tensor) and pos.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    L = lib()
+    pos_d = as_device_positions(pos, device)
+    F, N = int(pos_d.shape[0]), int(pos_d.shape[1])
+    box_h = as_host_boxes(box, F)
+    box_d = torch.from_numpy(box_h).to(device)
+    cen_d = None
+    M = N
+    if centres is not None:
+        cen_d = as_device_positions(centres, device)
+        if cen_d.shape[0] != F:
+            raise ValueError("centres and pos must hold the same number of frames")
+        M = int(cen_d.shape[1])
+    prec = {"fp64": WOL_PREC_FP64, "fp32": WOL_PREC_FP32}[precision]
+    if r_cell is None:
+        r_cell = default_r_cell(do_q, do_3body, high3, highq)
+    nc, edge_min = plan_grid(box_h, r_cell)
+    ws = workspace if workspace is not None else Workspace(device)
+    need = L.wol_workspace_bytes(F, N, M, ctypes.byref(nc))
+    ws_ptr, ws_bytes = ws.get(need)
+    stream = _stream_ptr()
+    launches = 0
+    with torch.cuda.device(device):
+        check(L.wol_cell_build(_ptr(pos_d), _dtype_code(pos_d), _ptr(box_d), F, N, ctypes.byref(nc), prec,
+                               ctypes.c_void_p(ws_ptr), ws_bytes, stream), "wol_cell_build")
+        launches += L.wol_last_launch_count()
+        res = Q3bResult()
+        out = out or {}
+        qdtype = torch.float64 if prec == WOL_PREC_FP64 else torch.float32
+        H = F if hist_per_frame else 1
+
+        def buf(name, shape, dtype, zero):
+            if name not in want:
+                return None
+            t = out.get(name)
+            if t is None:
+                t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            res[name] = t
+            return t
+
+        q = buf("q", (F, M), qdtype, True) if do_q else None
+        nn = buf("nn_idx", (F, M, 4), torch.int32, False) if do_q else None
+        n3 = buf("n3", (F, M), torch.int32, True) if do_3body else None
+        ah = buf("ang_hist", (H, nbins), torch.int64, True) if do_3body else None
+        qh = buf("q_hist", (H, q_nbins), torch.int64, True) if do_q else None
+        fs = buf("frame_stats", (F, WOL_NSTATS), torch.float64, True)
+        table = angle_table(bin_range[0], bin_range[1], nbins, device) if do_3body else None
+
+        a = Q3bArgs()
+        a.struct_size = ctypes.sizeof(Q3bArgs)
+        a.precision = prec
+        a.n_frames, a.n_pos, a.n_centres = F, N, M
+        a.centre_dtype = _dtype_code(cen_d) if cen_d is not None else WOL_F64
+        a.centres = cen_d.data_ptr() if cen_d is not None else None
+        a.box = box_d.data_ptr()
+        a.workspace, a.workspace_bytes = ws_ptr, ws_bytes
+        a.nc = nc
+        a.hist_per_frame = 1 if hist_per_frame else 0
+        a.edge_min = edge_min
+        a.low3, a.high3, a.lowq, a.highq = float(low3), float(high3), float(lowq), float(highq)
+        a.do_q, a.do_3body = int(bool(do_q)), int(bool(do_3body))
+        a.nbins, a.q_nbins = int(nbins), int(q_nbins)
+        a.hist_lo, a.hist_hi = float(bin_range[0]), float(bin_range[1])
+        a.angle_table = table.data_ptr() if table is not None else None
+        for name, t in (("q", q), ("nn_idx", nn), ("n3", n3), ("ang_hist", ah), ("q_hist", qh), ("frame_stats", fs)):
+            setattr(a, name, t.data_ptr() if t is not None else None)
+        check(L.wol_q3b_frames(ctypes.byref(a), stream), "wol_q3b_frames")
+        launches += L.wol_last_launch_count()
+        res["launches"] = launches
+        res["nc"] = tuple(nc)
+        res["edge_min"] = edge_min
+        if check_status:
+            st = (ctypes.c_int32 * 4)()
+            check(L.wol_status(ctypes.c_void_p(ws_ptr), F, N, M, ctypes.byref(nc), stream, ctypes.byref(st)), "wol_status")
+            res["n_widened"], res["n_overflow"] = int(st[0]), int(st[1])
+    # keep inputs alive until the stream has consumed them
+    res["_keep"] = (pos_d, box_d, cen_d, ws, table)
+    return res
+
+
+def default_r_cell(do_q, do_3body, high3, highq):
+    """Cell edge request: at least the three-body cutoff (the 27-cell sweep must contain it).  For q the
+    4 nearest oxygens of liquid water sit inside ~3.5 A, so a cell of that size makes the widened search
+    rare without inflating the candidate count."""
+    r = 0.0
+    if do_3body:
+        r = max(r, float(high3))
+    if do_q:
+        r = max(r, min(float(highq), 3.5))
+    return max(r, 1e-3)

@@ -69,11 +69,11 @@ int wol_abi_version(void);
  * Cell-grid plan for a batch of frames (host-only, cheap).  Picks nc[3] (cells per axis, identical
  * for all frames of the batch) such that every frame's cell edge L/nc is >= r_cell (1 + 1e-9), and
  * reports the smallest cell edge of the batch, which the evaluation kernels use as the radius inside
- * which a 27-cell sweep is complete.  Replaces nothing in the reference (its search is the O(N^2)
+ * which a 27-cell sweep is complete, and the largest box edge.  Replaces nothing in the reference (its search is the O(N^2)
  * double loop of waterlib.f90:846-861).
  */
 int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3],
-                  double *edge_min_out);
+                  double *edge_min_out, double *box_max_out);
 
 /* Bytes of scratch needed by wol_cell_build + the evaluation kernels for this batch shape.
  * n_centres_max = the largest number of centres per frame any later call on this workspace passes. */
@@ -143,6 +143,7 @@ typedef struct wol_q3b_args {
     int32_t nc[3];
     int32_t hist_per_frame; /* 1: one histogram row per frame, 0: a single shared row */
     double edge_min;        /* from wol_plan_grid */
+    double box_max;         /* from wol_plan_grid: largest box edge of the batch (bounds float rounding) */
     double low3, high3;     /* getCosAngs lowCut/highCut (default 0, 3.413) */
     double lowq, highq;     /* getOrderParamq lowCut/highCut (default 0, 10) */
     int32_t do_q;           /* evaluate the q branch */

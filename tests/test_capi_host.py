@@ -36,14 +36,14 @@ def test_plan_grid(L):
     box = np.array([[49.655, 49.655, 49.655], [49.0, 50.0, 24.83]])
     nc = (ctypes.c_int32 * 3)()
     edge = ctypes.c_double()
-    _capi.check(L.wol_plan_grid(box.ctypes.data_as(ctypes.c_void_p), 2, 3.413, ctypes.byref(nc), ctypes.byref(edge)), "plan")
+    _capi.check(L.wol_plan_grid(box.ctypes.data_as(ctypes.c_void_p), 2, 3.413, ctypes.byref(nc), ctypes.byref(edge), None), "plan")
     assert tuple(nc) == (14, 14, 7)
     assert edge.value >= 3.413 * (1 + 1e-9) and abs(edge.value - 49.0 / 14) < 1e-12
     tiny = np.array([[5.0, 5.0, 5.0]])
-    _capi.check(L.wol_plan_grid(tiny.ctypes.data_as(ctypes.c_void_p), 1, 3.413, ctypes.byref(nc), ctypes.byref(edge)), "plan")
+    _capi.check(L.wol_plan_grid(tiny.ctypes.data_as(ctypes.c_void_p), 1, 3.413, ctypes.byref(nc), ctypes.byref(edge), None), "plan")
     assert tuple(nc) == (1, 1, 1)
     bad = np.array([[10.0, -1.0, 10.0]])
-    rc = L.wol_plan_grid(bad.ctypes.data_as(ctypes.c_void_p), 1, 3.4, ctypes.byref(nc), ctypes.byref(edge))
+    rc = L.wol_plan_grid(bad.ctypes.data_as(ctypes.c_void_p), 1, 3.4, ctypes.byref(nc), ctypes.byref(edge), None)
     assert rc == -2 and b"non-periodic" in L.wol_last_error()
     with pytest.raises(ValueError):
         _capi.check(rc, "plan")

@@ -23,7 +23,7 @@ class Q3bArgs(ctypes.Structure):
         ("struct_size", ctypes.c_uint32), ("precision", c_i32), ("n_frames", c_i32), ("n_pos", c_i32),
         ("n_centres", c_i32), ("centre_dtype", c_i32), ("centres", c_vp), ("box", c_vp), ("workspace", c_vp),
         ("workspace_bytes", ctypes.c_size_t), ("nc", c_i32 * 3), ("hist_per_frame", c_i32),
-        ("edge_min", ctypes.c_double), ("low3", ctypes.c_double), ("high3", ctypes.c_double),
+        ("edge_min", ctypes.c_double), ("box_max", ctypes.c_double), ("low3", ctypes.c_double), ("high3", ctypes.c_double),
         ("lowq", ctypes.c_double), ("highq", ctypes.c_double), ("do_q", c_i32), ("do_3body", c_i32),
         ("nbins", c_i32), ("q_nbins", c_i32), ("hist_lo", ctypes.c_double), ("hist_hi", ctypes.c_double),
         ("angle_table", c_vp), ("q", c_vp), ("nn_idx", c_vp), ("n3", c_vp), ("ang_hist", c_vp), ("q_hist", c_vp),
@@ -37,7 +37,8 @@ SIGNATURES = {
     "wol_last_error": (ctypes.c_char_p, []),
     "wol_abi_version": (ctypes.c_int, []),
     "wol_last_launch_count": (ctypes.c_int, []),
-    "wol_plan_grid": (ctypes.c_int, [c_vp, c_i32, ctypes.c_double, ctypes.POINTER(c_i32 * 3), ctypes.POINTER(ctypes.c_double)]),
+    "wol_plan_grid": (ctypes.c_int, [c_vp, c_i32, ctypes.c_double, ctypes.POINTER(c_i32 * 3), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_double)]),
     "wol_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, ctypes.POINTER(c_i32 * 3)]),
     "wol_cell_build": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_i32, c_vp, ctypes.c_size_t, c_vp]),
     "wol_angle_table": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, c_i32, ctypes.c_double, ctypes.c_double, c_vp]),

@@ -107,10 +107,11 @@ const char *wol_last_error(void) { return g_error; }
 int wol_abi_version(void) { return WOL_ABI_VERSION; }
 int wol_last_launch_count(void) { return g_launches; }
 
-int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3], double *edge_min_out) {
+int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3], double *edge_min_out,
+                  double *box_max_out) {
     if (!box_host || !nc_out || n_frames < 1) return set_error(WOL_ERR_INVALID, "wol_plan_grid: null argument or no frames");
     if (!(r_cell > 0.0)) return set_error(WOL_ERR_INVALID, "wol_plan_grid: r_cell must be positive");
-    double lmin[3];
+    double lmin[3], lmax = 0.0;
     for (int k = 0; k < 3; ++k) lmin[k] = INFINITY;
     for (int f = 0; f < n_frames; ++f)
         for (int k = 0; k < 3; ++k) {
@@ -119,6 +120,7 @@ int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32
                 return set_error(WOL_ERR_UNSUPPORTED,
                                  "frame %d: box edge %d is %g; non-periodic (negative) or empty axes are not supported", f, k, L);
             if (L < lmin[k]) lmin[k] = L;
+            if (L > lmax) lmax = L;
         }
     double emin = INFINITY;
     for (int k = 0; k < 3; ++k) {
@@ -130,6 +132,7 @@ int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32
         if (e < emin) emin = e;
     }
     if (edge_min_out) *edge_min_out = emin;
+    if (box_max_out) *box_max_out = lmax;
     return WOL_OK;
 }
 

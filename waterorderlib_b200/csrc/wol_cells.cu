@@ -45,6 +45,7 @@ struct BuildParams {
     uint32_t *cell_id;
     uint32_t *slot;
     void *recs;
+    float4 *wrapped;
 };
 
 // T = storage type of the input positions, R = record type (RecD keeps doubles, RecF floats).
@@ -54,6 +55,7 @@ template <typename T, typename R, bool SCATTER>
 __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p) {
     __shared__ __align__(16) T s_pos[kBuildThreads * 3];
     __shared__ double s_iL[3];
+    __shared__ double s_L[3];
     const int f = blockIdx.x / p.tiles_per_frame;
     const int tile = blockIdx.x - f * p.tiles_per_frame;
     const int a0 = tile * kBuildThreads;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     if (threadIdx.x < 3) {
         const double L = p.box[(size_t)f * 3 + threadIdx.x];
         s_iL[threadIdx.x] = __ddiv_rn(1.0, L);
+        s_L[threadIdx.x] = L;
     }
     stage_tile(reinterpret_cast<const T *>(p.pos) + (frame_atom0 + a0) * 3, n_here * 3, s_pos);
     __syncthreads();
@@ -92,11 +95,21 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
             r.y = (double)y;
             r.z = (double)z;
             r.idx = a0 + t;
-            r.cell = (int32_t)c;
+            const int cxy = (int)(c % (uint32_t)(p.nc0 * p.nc1));
+            r.cell = (cxy % p.nc0) | ((cxy / p.nc0) << 10) | ((int)(c / (uint32_t)(p.nc0 * p.nc1)) << 20);
             int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst);
             const int4 *s4 = reinterpret_cast<const int4 *>(&r);
             d4[0] = s4[0];
             d4[1] = s4[1];
+            if (p.wrapped) {
+                // box-wrapped coordinates for the float prefilter of the sweep: frac(x / L) * L
+                float4 w;
+                w.x = wrapped_coord((double)x, s_L[0], s_iL[0]);
+                w.y = wrapped_coord((double)y, s_L[1], s_iL[1]);
+                w.z = wrapped_coord((double)z, s_L[2], s_iL[2]);
+                w.w = __int_as_float(a0 + t);
+                p.wrapped[dst] = w;
+            }
         } else {
             RecF r;
             r.x = (float)x;
@@ -244,6 +257,7 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     p.cell_id = reinterpret_cast<uint32_t *>(ws + lay.off_cell_id);
     p.slot = reinterpret_cast<uint32_t *>(ws + lay.off_slot);
     p.recs = ws + lay.off_recs;
+    p.wrapped = (precision == WOL_PREC_FP64) ? reinterpret_cast<float4 *>(ws + lay.off_wrapped) : nullptr;
     uint32_t *block_sums = reinterpret_cast<uint32_t *>(ws + lay.off_block_sums);
     const size_t n_scan = (size_t)lay.n_cells_total + 1;
 

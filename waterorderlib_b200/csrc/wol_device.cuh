@@ -140,6 +140,14 @@ __device__ __forceinline__ int cell_coord(double x, double iL, int nc) {
     return min(max(c, 0), nc - 1);
 }
 
+// Box-wrapped coordinate frac(x / L) * L as a float, for the prefilter of the sweep.  Same frac as
+// cell_coord, so an atom's wrapped coordinate lies inside its cell (up to float rounding).
+__device__ __forceinline__ float wrapped_coord(double x, double L, double iL) {
+    double f = __dmul_rn(x, iL);
+    f = __dsub_rn(f, floor(f));
+    return (float)__dmul_rn(f, L);
+}
+
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

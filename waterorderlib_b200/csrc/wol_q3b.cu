@@ -24,153 +24,12 @@
 //   4-NN selection         structureLibs/water_properties.py:372-374
 //   q and padding          structureLibs/water_properties.py:379-388
 //   angle histogram        structureLibs/water_properties.py:328
-#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
 
-#include "wol_device.cuh"
-#include "wol_internal.h"
-#include "wol_workspace.h"
+#include "wol_q3b_common.cuh"
 
 namespace wol {
-
-template <typename T>
-struct alignas(16) Vec4 {
-    T x, y, z, w;
-};
-
-struct Q3bParams {
-    const void *recs;
-    const uint32_t *cell_start;
-    const double *box;
-    const void *centres;  // nullptr: every atom is a centre (visited in cell order)
-    int centre_dtype;
-    int n_frames, n_pos, n_centres;
-    int nc0, nc1, nc2;
-    double low3sq, high3sq, lowqsq, highqsq;
-    double highq;
-    double rc1;   // radius inside which a half-width-1 stencil is complete
-    int wq_max;   // half-width at which the q search is complete whatever it finds
-    int do_q, do_3b;
-    int nbins, q_nbins;
-    double hist_lo, hist_hi;
-    const double *table;
-    void *q;
-    int32_t *nn_idx;
-    int32_t *n3;
-    unsigned long long *ang_hist;
-    unsigned long long *q_hist;
-    double *stats;
-    int hist_per_frame;
-    uint32_t *counters;
-    uint32_t *fb_list;
-    int tiles_per_frame;
-    long long total_tiles;
-};
-
-// ------------------------------------------------------------------------------------------------
-
-template <typename T>
-struct RecTraits;
-template <>
-struct RecTraits<double> {
-    typedef RecD Rec;
-    static __device__ __forceinline__ void load(const void *recs, size_t j, double &x, double &y, double &z, int &idx) {
-        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + j);
-        const int4 a = __ldg(p), b = __ldg(p + 1);
-        x = __hiloint2double(a.y, a.x);
-        y = __hiloint2double(a.w, a.z);
-        z = __hiloint2double(b.y, b.x);
-        idx = b.z;
-    }
-    static __device__ __forceinline__ int cell(const void *recs, size_t j) {
-        return reinterpret_cast<const RecD *>(recs)[j].cell;
-    }
-};
-template <>
-struct RecTraits<float> {
-    typedef RecF Rec;
-    static __device__ __forceinline__ void load(const void *recs, size_t j, float &x, float &y, float &z, int &idx) {
-        const int4 a = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const RecF *>(recs) + j));
-        x = __int_as_float(a.x);
-        y = __int_as_float(a.y);
-        z = __int_as_float(a.z);
-        idx = a.w;
-    }
-};
-
-template <typename T>
-__device__ __forceinline__ bool key_less(T d0, int i0, T d1, int i1) {
-    return d0 < d1 || (d0 == d1 && i0 < i1);
-}
-
-// Per-lane sorted top-4 by (distance, atom index); payload = where the candidate can be found again.
-template <typename T>
-struct Top4 {
-    T d[4];
-    int i[4];
-    int p[4];
-    __device__ __forceinline__ void reset() {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            d[k] = Ops<T>::inf();
-            i[k] = INT_MAX;
-            p[k] = -1;
-        }
-    }
-    __device__ __forceinline__ void insert(T dd, int ii, int pp) {
-        if (key_less(dd, ii, d[3], i[3])) {
-            d[3] = dd;
-            i[3] = ii;
-            p[3] = pp;
-#pragma unroll
-            for (int k = 3; k > 0; --k) {
-                if (key_less(d[k], i[k], d[k - 1], i[k - 1])) {
-                    const T td = d[k]; d[k] = d[k - 1]; d[k - 1] = td;
-                    const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
-                    const int tp = p[k]; p[k] = p[k - 1]; p[k - 1] = tp;
-                }
-            }
-        }
-    }
-    __device__ __forceinline__ void pop() {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            d[k] = d[k + 1];
-            i[k] = i[k + 1];
-            p[k] = p[k + 1];
-        }
-        d[3] = Ops<T>::inf();
-        i[3] = INT_MAX;
-        p[3] = -1;
-    }
-};
-
-__device__ __forceinline__ double shfl_xor_t(double v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
-__device__ __forceinline__ float shfl_xor_t(float v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
-__device__ __forceinline__ double shfl_t(double v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
-__device__ __forceinline__ float shfl_t(float v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
-
-// Position of the angle belonging to clamped cosine c on the histogram axis: -1 below the range,
-// 0..nbins-1 a bin, nbins above the range.  tab[k] (decreasing in k) is the largest c whose angle sits
-// at or beyond bin k, so the position is the largest k with c <= tab[k]; the float acos only seeds
-// the search.
-__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
-    if (c == -1.0) return (int)tab[nbins + 1];
-    const float th = acosf((float)c) * 57.29577951308232f;
-    int k = (int)(((double)th - lo) * inv_width);
-    k = min(max(k, 0), nbins);
-    while (k < nbins && c <= tab[k + 1]) ++k;
-    while (k >= 0 && !(c <= tab[k])) --k;
-    return k;
-}
-
-struct LaneStats {
-    double q_sum, q_sumsq, tet_cos, tet_cossq;
-    unsigned n_centres, tet_count, n_angles, n_neigh;
-    __device__ __forceinline__ void reset() {
-        q_sum = q_sumsq = tet_cos = tet_cossq = 0.0;
-        n_centres = tet_count = n_angles = n_neigh = 0u;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // One centre, one group.  Every lane of the WARP executes this function in lock step (the loops are
@@ -595,44 +454,14 @@ struct GroupWorker {
 
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void flush_stats(const Q3bParams &P, int f, LaneStats &st) {
-    double v[8];
-    v[WOL_STAT_Q_SUM] = st.q_sum;
-    v[WOL_STAT_Q_SUMSQ] = st.q_sumsq;
-    v[WOL_STAT_N_CENTRES] = (double)st.n_centres;
-    v[WOL_STAT_TET_COUNT] = (double)st.tet_count;
-    v[WOL_STAT_TET_COS] = st.tet_cos;
-    v[WOL_STAT_TET_COSSQ] = st.tet_cossq;
-    v[WOL_STAT_N_ANGLES] = (double)st.n_angles;
-    v[WOL_STAT_N_NEIGH] = (double)st.n_neigh;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const double s = warp_sum(v[k]);
-        if (P.stats && (threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(P.stats + (size_t)f * WOL_NSTATS + k, s);
-    }
-    st.reset();
-}
-
-template <typename T>
-__device__ __forceinline__ void load_centre(const Q3bParams &P, int f, int m, T &rx, T &ry, T &rz) {
-    const size_t o = ((size_t)f * P.n_centres + m) * 3;
-    if (P.centre_dtype == WOL_F64) {
-        const double *c = reinterpret_cast<const double *>(P.centres);
-        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
-    } else {
-        const float *c = reinterpret_cast<const float *>(P.centres);
-        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
-    }
-}
-
 constexpr int kFastThreads = 128;
 constexpr int kFastG = 8;
 constexpr int kFastCap = 32;
 constexpr int kFastMaxSeg = 18;
 constexpr int kBigThreads = 64;
 constexpr int kBigCap = 1024;
+constexpr int kLightCap = 32;
 constexpr int kBigMaxSeg = 512;
-constexpr int kMaxSmemBins = 4096;
 
 // Fast pass: every centre once.  Persistent blocks walk contiguous tiles of kFastThreads / G centres so
 // that the block histogram is flushed once per frame the block touches.
@@ -721,9 +550,11 @@ __global__ void __launch_bounds__(kFastThreads) q3b_fast_kernel(const __grid_con
 }
 
 // Large-capacity pass over the queued centres: one warp per centre.
-template <typename T, bool EXACT>
+// CAP = kBigCap handles the centres that need their three-body list redone (overflow of the fast path);
+// CAP = kLightCap handles the q-only ones (the common case) with a small footprint and high occupancy.
+template <typename T, bool EXACT, int CAP>
 __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_constant__ Q3bParams P) {
-    typedef GroupWorker<T, 32, kBigCap, kBigMaxSeg, EXACT, true> Worker;
+    typedef GroupWorker<T, 32, CAP, kBigMaxSeg, EXACT, true> Worker;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Worker::Smem *gs = reinterpret_cast<typename Worker::Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5;
@@ -736,6 +567,7 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
         const uint32_t e = P.fb_list[it];
         const uint32_t id = e & kFbIdMask;
         const bool do3 = (e & kFbNeed3b) != 0, doq = (e & kFbNeedQ) != 0;
+        if (do3 != (CAP == kBigCap)) continue;
         T rx, ry, rz;
         size_t out_index;
         int f;
@@ -763,38 +595,51 @@ __global__ void reset_counters_kernel(uint32_t *counters) {
     if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0u;
 }
 
-template <typename T, bool EXACT>
-static int launch_typed(const Q3bParams &P, cudaStream_t stream) {
-    typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> FastWorker;
-    typedef GroupWorker<T, 32, kBigCap, kBigMaxSeg, EXACT, true> BigWorker;
-    const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
-    size_t fast_smem = sizeof(typename FastWorker::Smem) * (kFastThreads / kFastG);
-    if (P.nbins <= kMaxSmemBins) fast_smem += sizeof(double) * tab_len;
-    if (P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins) fast_smem += sizeof(unsigned) * P.nbins;
+template <typename T, bool EXACT, int CAP>
+static int launch_big(const Q3bParams &P, cudaStream_t stream) {
+    typedef GroupWorker<T, 32, CAP, kBigMaxSeg, EXACT, true> BigWorker;
     const size_t big_smem = sizeof(typename BigWorker::Smem) * (kBigThreads / 32);
-    cudaError_t e;
-    e = cudaFuncSetAttribute(q3b_fast_kernel<T, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem);
-    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(fast)", e);
-    e = cudaFuncSetAttribute(q3b_big_kernel<T, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem);
+    cudaError_t e = cudaFuncSetAttribute(q3b_big_kernel<T, EXACT, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(big)", e);
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3b_fast_kernel<T, EXACT>, kFastThreads, fast_smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3b_big_kernel<T, EXACT, CAP>, kBigThreads, big_smem);
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int sms = sm_count();
-    long long grid = (long long)sms * per_sm;
-    if (grid > P.total_tiles) grid = P.total_tiles;
+    q3b_big_kernel<T, EXACT, CAP><<<(unsigned)(sm_count() * per_sm), kBigThreads, big_smem, stream>>>(P);
+    add_launches(1);
+    return WOL_OK;
+}
+
+template <typename T, bool EXACT>
+static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
+    typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> FastWorker;
     reset_counters_kernel<<<1, 32, 0, stream>>>(P.counters);
     add_launches(1);
-    if (grid > 0) {
-        q3b_fast_kernel<T, EXACT><<<(unsigned)grid, kFastThreads, fast_smem, stream>>>(P);
-        add_launches(1);
-        int big_per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&big_per_sm, q3b_big_kernel<T, EXACT>, kBigThreads, big_smem);
-        if (e != cudaSuccess || big_per_sm < 1) big_per_sm = 1;
-        q3b_big_kernel<T, EXACT><<<(unsigned)(sms * big_per_sm), kBigThreads, big_smem, stream>>>(P);
-        add_launches(1);
+    if (use_tpc) {
+        int rc = q3b_tpc_launch(P, stream, EXACT);
+        if (rc != WOL_OK) return rc;
+    } else {
+        const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
+        size_t fast_smem = sizeof(typename FastWorker::Smem) * (kFastThreads / kFastG);
+        if (P.nbins <= kMaxSmemBins) fast_smem += sizeof(double) * tab_len;
+        if (P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins) fast_smem += sizeof(unsigned) * P.nbins;
+        cudaError_t e = cudaFuncSetAttribute(q3b_fast_kernel<T, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem);
+        if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(fast)", e);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3b_fast_kernel<T, EXACT>, kFastThreads, fast_smem);
+        if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+        long long grid = (long long)sm_count() * per_sm;
+        if (grid > P.total_tiles) grid = P.total_tiles;
+        if (grid > 0) {
+            q3b_fast_kernel<T, EXACT><<<(unsigned)grid, kFastThreads, fast_smem, stream>>>(P);
+            add_launches(1);
+        }
     }
-    e = cudaGetLastError();
+    // queued centres: q-only ones in the light instantiation, list overflows in the large-capacity one
+    int rc = WOL_OK;
+    if (P.do_q) rc = launch_big<T, EXACT, kLightCap>(P, stream);
+    if (rc == WOL_OK) rc = launch_big<T, EXACT, kBigCap>(P, stream);
+    if (rc != WOL_OK) return rc;
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("q3b launch", e);
     return WOL_OK;
 }
@@ -856,9 +701,25 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     const double reach = fmax(a.do_3body ? a.high3 : 0.0, a.do_q ? a.highq : 0.0);
     const bool exact = reach > 0.49 * a.edge_min * (double)(P.nc0 < P.nc1 ? (P.nc0 < P.nc2 ? P.nc0 : P.nc2)
                                                                           : (P.nc1 < P.nc2 ? P.nc1 : P.nc2));
+    // thread-per-centre fast path: fp64 mode, >= 4 cells per axis
+    P.wrapped = (a.precision == WOL_PREC_FP64) ? reinterpret_cast<const float4 *>(ws + lay.off_wrapped) : nullptr;
+    P.skip_q_only = 0;
+    {
+        double lmax = 0.0;  // upper bound of the box edges: every cell edge is < 2 * edge of the smallest frame ... use nc * edge bound
+        // edge_min * nc underestimates L for the larger frames of an NPT batch; the caller-provided
+        // box_max (>= every edge of every frame) is what the margin needs
+        lmax = a.box_max > 0.0 ? a.box_max : 0.0;
+        const bool last1 = P.wq_max <= 1;
+        const double rsel = a.do_q ? (last1 ? a.highq : fmin(a.highq, P.rc1)) : 0.0;
+        const double rthr = fmax(a.do_3body ? a.high3 : 0.0, rsel);
+        const double margin = 16.0 * ldexp(1.0, -24) * lmax;
+        const double thr2 = (rthr + margin) * (rthr + margin) * (1.0 + 1e-6);
+        P.pre_thr2 = nextafterf((float)thr2, INFINITY);
+    }
+    const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
     if (a.precision == WOL_PREC_FP64)
-        return exact ? launch_typed<double, true>(P, stream) : launch_typed<double, false>(P, stream);
-    return exact ? launch_typed<float, true>(P, stream) : launch_typed<float, false>(P, stream);
+        return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);
+    return exact ? launch_typed<float, true>(P, stream, false) : launch_typed<float, false>(P, stream, false);
 }
 
 }  // namespace wol

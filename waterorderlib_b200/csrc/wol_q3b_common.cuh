@@ -1,0 +1,200 @@
+// Pieces shared by the evaluation kernels (group-per-centre generic path and thread-per-centre fast path).
+#pragma once
+#include <limits.h>
+
+#include "wol_device.cuh"
+#include "wol_internal.h"
+#include "wol_workspace.h"
+
+namespace wol {
+
+template <typename T>
+struct alignas(16) Vec4 {
+    T x, y, z, w;
+};
+
+struct Q3bParams {
+    const void *recs;
+    const uint32_t *cell_start;
+    const double *box;
+    const void *centres;  // nullptr: every atom is a centre (visited in cell order)
+    int centre_dtype;
+    int n_frames, n_pos, n_centres;
+    int nc0, nc1, nc2;
+    double low3sq, high3sq, lowqsq, highqsq;
+    double highq;
+    double rc1;   // radius inside which a half-width-1 stencil is complete
+    int wq_max;   // half-width at which the q search is complete whatever it finds
+    int do_q, do_3b;
+    int nbins, q_nbins;
+    double hist_lo, hist_hi;
+    const double *table;
+    void *q;
+    int32_t *nn_idx;
+    int32_t *n3;
+    unsigned long long *ang_hist;
+    unsigned long long *q_hist;
+    double *stats;
+    int hist_per_frame;
+    uint32_t *counters;
+    uint32_t *fb_list;
+    int tiles_per_frame;
+    long long total_tiles;
+    // thread-per-centre fast path
+    const float4 *wrapped;  // box-wrapped float coordinates in record order (nullptr: not built)
+    float pre_thr2;         // prefilter acceptance threshold on the float squared distance
+    int skip_q_only;        // large-capacity pass: 1 = leave q-only items to the light instantiation
+};
+
+// ------------------------------------------------------------------------------------------------
+
+template <typename T>
+struct RecTraits;
+template <>
+struct RecTraits<double> {
+    typedef RecD Rec;
+    static __device__ __forceinline__ void load(const void *recs, size_t j, double &x, double &y, double &z, int &idx) {
+        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + j);
+        const int4 a = __ldg(p), b = __ldg(p + 1);
+        x = __hiloint2double(a.y, a.x);
+        y = __hiloint2double(a.w, a.z);
+        z = __hiloint2double(b.y, b.x);
+        idx = b.z;
+    }
+    static __device__ __forceinline__ int cell(const void *recs, size_t j) {
+        return reinterpret_cast<const RecD *>(recs)[j].cell;
+    }
+};
+template <>
+struct RecTraits<float> {
+    typedef RecF Rec;
+    static __device__ __forceinline__ void load(const void *recs, size_t j, float &x, float &y, float &z, int &idx) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const RecF *>(recs) + j));
+        x = __int_as_float(a.x);
+        y = __int_as_float(a.y);
+        z = __int_as_float(a.z);
+        idx = a.w;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ bool key_less(T d0, int i0, T d1, int i1) {
+    return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+// Per-lane sorted top-4 by (distance, atom index); payload = where the candidate can be found again.
+template <typename T>
+struct Top4 {
+    T d[4];
+    int i[4];
+    int p[4];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d[k] = Ops<T>::inf();
+            i[k] = INT_MAX;
+            p[k] = -1;
+        }
+    }
+    __device__ __forceinline__ void insert(T dd, int ii, int pp) {
+        if (key_less(dd, ii, d[3], i[3])) {
+            d[3] = dd;
+            i[3] = ii;
+            p[3] = pp;
+#pragma unroll
+            for (int k = 3; k > 0; --k) {
+                if (key_less(d[k], i[k], d[k - 1], i[k - 1])) {
+                    const T td = d[k]; d[k] = d[k - 1]; d[k - 1] = td;
+                    const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+                    const int tp = p[k]; p[k] = p[k - 1]; p[k - 1] = tp;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void pop() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            d[k] = d[k + 1];
+            i[k] = i[k + 1];
+            p[k] = p[k + 1];
+        }
+        d[3] = Ops<T>::inf();
+        i[3] = INT_MAX;
+        p[3] = -1;
+    }
+};
+
+__device__ __forceinline__ double shfl_xor_t(double v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
+__device__ __forceinline__ float shfl_xor_t(float v, int o, int w) { return __shfl_xor_sync(kFullMask, v, o, w); }
+__device__ __forceinline__ double shfl_t(double v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
+__device__ __forceinline__ float shfl_t(float v, int src, int w) { return __shfl_sync(kFullMask, v, src, w); }
+
+// Position of the angle belonging to clamped cosine c on the histogram axis: -1 below the range,
+// 0..nbins-1 a bin, nbins above the range.  tab[k] (decreasing in k) is the largest c whose angle sits
+// at or beyond bin k, so the position is the largest k with c <= tab[k]; the float acos only seeds
+// the search.
+__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
+    if (c == -1.0) return (int)tab[nbins + 1];
+    const float th = acosf((float)c) * 57.29577951308232f;
+    int k = (int)(((double)th - lo) * inv_width);
+    k = min(max(k, 0), nbins);
+    while (k < nbins && c <= tab[k + 1]) ++k;
+    while (k >= 0 && !(c <= tab[k])) --k;
+    return k;
+}
+
+struct LaneStats {
+    double q_sum, q_sumsq, tet_cos, tet_cossq;
+    unsigned n_centres, tet_count, n_angles, n_neigh;
+    __device__ __forceinline__ void reset() {
+        q_sum = q_sumsq = tet_cos = tet_cossq = 0.0;
+        n_centres = tet_count = n_angles = n_neigh = 0u;
+    }
+};
+
+__device__ __forceinline__ void flush_stats(const Q3bParams &P, int f, LaneStats &st) {
+    double v[8];
+    v[WOL_STAT_Q_SUM] = st.q_sum;
+    v[WOL_STAT_Q_SUMSQ] = st.q_sumsq;
+    v[WOL_STAT_N_CENTRES] = (double)st.n_centres;
+    v[WOL_STAT_TET_COUNT] = (double)st.tet_count;
+    v[WOL_STAT_TET_COS] = st.tet_cos;
+    v[WOL_STAT_TET_COSSQ] = st.tet_cossq;
+    v[WOL_STAT_N_ANGLES] = (double)st.n_angles;
+    v[WOL_STAT_N_NEIGH] = (double)st.n_neigh;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double s = warp_sum(v[k]);
+        if (P.stats && (threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(P.stats + (size_t)f * WOL_NSTATS + k, s);
+    }
+    st.reset();
+}
+
+template <typename T>
+__device__ __forceinline__ void load_centre(const Q3bParams &P, int f, int m, T &rx, T &ry, T &rz) {
+    const size_t o = ((size_t)f * P.n_centres + m) * 3;
+    if (P.centre_dtype == WOL_F64) {
+        const double *c = reinterpret_cast<const double *>(P.centres);
+        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
+    } else {
+        const float *c = reinterpret_cast<const float *>(P.centres);
+        rx = (T)c[o]; ry = (T)c[o + 1]; rz = (T)c[o + 2];
+    }
+}
+
+
+constexpr int kMaxSmemBins = 4096;
+
+// flush of a block's shared-memory angle histogram into the global int64 bins
+__device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist, int f, bool clear) {
+    for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) {
+        const unsigned v = s_hist[i];
+        if (v) atomicAdd(P.ang_hist + (size_t)(P.hist_per_frame ? f : 0) * P.nbins + i, (unsigned long long)v);
+        if (clear) s_hist[i] = 0u;
+    }
+}
+
+int q3b_tpc_launch(const Q3bParams &P, cudaStream_t stream, bool exact);
+bool q3b_tpc_supported(const Q3bParams &P);
+
+}  // namespace wol

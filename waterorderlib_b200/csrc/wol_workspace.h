@@ -13,7 +13,8 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 // Sorted per-atom records, grouped by (frame, cell).
 // FP64 mode: original coordinates (bit-identical to the input, the reference arithmetic needs them),
-// original atom index and the cell id.  32 bytes = two 16-byte loads.
+// original atom index and the cell coordinates packed 10 bits per axis (cx | cy << 10 | cz << 20).
+// 32 bytes = two 16-byte loads.
 struct alignas(16) RecD {
     double x, y, z;
     int32_t idx;
@@ -45,6 +46,7 @@ struct WorkspaceLayout {
     size_t off_cell_id;     // uint32[F*N]
     size_t off_slot;        // uint32[F*N]  rank of the atom inside its cell
     size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
+    size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates + atom index, same order as recs
     size_t off_counters;    // uint32[kNumCounters]
     size_t off_fb_list;     // uint32[F*M]  centres the fast path handed to the large-capacity path
     size_t total;
@@ -75,6 +77,8 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     o = align_up(o + (size_t)w.n_atoms_total * 4, 256);
     w.off_recs = o;
     o = align_up(o + (size_t)w.n_atoms_total * sizeof(RecD), 256);
+    w.off_wrapped = o;
+    o = align_up(o + (size_t)w.n_atoms_total * 16, 256);
     w.off_counters = o;
     o = align_up(o + kNumCounters * 4, 256);
     w.off_fb_list = o;

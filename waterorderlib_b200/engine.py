@@ -81,9 +81,10 @@ def angle_table(hist_lo, hist_hi, nbins, device, tet_lo=100.0, tet_hi=120.0):
 def plan_grid(box_host, r_cell):
     nc = _I3()
     edge = ctypes.c_double(0.0)
+    bmax = ctypes.c_double(0.0)
     check(lib().wol_plan_grid(box_host.ctypes.data_as(ctypes.c_void_p), box_host.shape[0], float(r_cell),
-                              ctypes.byref(nc), ctypes.byref(edge)), "wol_plan_grid")
-    return nc, edge.value
+                              ctypes.byref(nc), ctypes.byref(edge), ctypes.byref(bmax)), "wol_plan_grid")
+    return nc, edge.value, bmax.value
 
 
 class Q3bResult(dict):
@@ -124,7 +125,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     pos_d = as_device_positions(pos, device)
     F, N = int(pos_d.shape[0]), int(pos_d.shape[1])
     box_h = as_host_boxes(box, F)
-    box_d = torch.from_numpy(box_h).to(device)
+    box_d = torch.from_numpy(box_h.copy()).to(device)
     cen_d = None
     M = N
     if centres is not None:
@@ -135,7 +136,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     prec = {"fp64": WOL_PREC_FP64, "fp32": WOL_PREC_FP32}[precision]
     if r_cell is None:
         r_cell = default_r_cell(do_q, do_3body, high3, highq)
-    nc, edge_min = plan_grid(box_h, r_cell)
+    nc, edge_min, box_max = plan_grid(box_h, r_cell)
     ws = workspace if workspace is not None else Workspace(device)
     need = L.wol_workspace_bytes(F, N, M, ctypes.byref(nc))
     ws_ptr, ws_bytes = ws.get(need)
@@ -178,6 +179,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
         a.nc = nc
         a.hist_per_frame = 1 if hist_per_frame else 0
         a.edge_min = edge_min
+        a.box_max = box_max
         a.low3, a.high3, a.lowq, a.highq = float(low3), float(high3), float(lowq), float(highq)
         a.do_q, a.do_3body = int(bool(do_q)), int(bool(do_3body))
         a.nbins, a.q_nbins = int(nbins), int(q_nbins)

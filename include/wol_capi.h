@@ -158,6 +158,10 @@ typedef struct wol_q3b_args {
     int64_t *ang_hist;
     int64_t *q_hist;
     double *frame_stats;
+    /* Optional cudaEvent_t pair (as void*) recorded on `stream` immediately before and after the launch
+     * of the dominant evaluation kernel, so a caller can time that kernel alone (bench roofline). */
+    void *timing_event_begin;
+    void *timing_event_end;
 } wol_q3b_args;
 
 int wol_q3b_frames(const wol_q3b_args *args, void *stream);
@@ -167,9 +171,10 @@ int wol_q3b_frames(const wol_q3b_args *args, void *stream);
  * wol_workspace_bytes).  Synchronises `stream`.
  *   status_host[0]  number of centres that took the widened-search path (q with < 4 neighbours in 27 cells)
  *   status_host[1]  number of centres whose neighbour list overflowed the fast path
- *   status_host[2]  non-zero: a neighbour list overflowed even the large-capacity path -> results invalid
+ *   status_host[2]  non-zero: a neighbour list overflowed even the large-capacity path -> results invalid;
+ *                   this one is sticky across evaluations on the workspace and cleared by this call
  *   status_host[3]  reserved
- * Returns WOL_ERR_CAPACITY when status_host[2] != 0.
+ * Returns WOL_ERR_CAPACITY when status_host[2] != 0.  A fresh workspace must be zero-filled by the caller.
  */
 int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3],
                void *stream, int32_t status_host[4]);

@@ -251,6 +251,9 @@ int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n
     uint32_t c[kNumCounters];
     cudaError_t e = cudaMemcpyAsync(c, reinterpret_cast<const char *>(workspace) + lay.off_counters, sizeof(c),
                                     cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(const_cast<char *>(reinterpret_cast<const char *>(workspace)) + lay.off_counters + kCntFatal * 4, 0, 4,
+                            (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return set_cuda_error("wol_status", e);
     status_host[0] = (int32_t)c[kCntWidened];

@@ -561,6 +561,8 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
     Worker worker(P, gs[warp]);
     LaneStats st;
     const uint32_t n_items = P.counters[kCntFallback];
+    if (CAP == kBigCap && P.counters[kCntOverflow] == 0u) return;  // nothing overflowed: no list to redo
+    if (CAP != kBigCap && P.counters[kCntWidened] == 0u && P.counters[kCntOverflow] == 0u) return;
     const uint32_t warps_total = gridDim.x * (kBigThreads / 32);
     for (uint32_t it = blockIdx.x * (kBigThreads / 32) + warp; it < n_items; it += warps_total) {
         st.reset();
@@ -591,8 +593,9 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
     }
 }
 
+// the fatal counter is sticky (cleared by wol_status), the others describe the last evaluation
 __global__ void reset_counters_kernel(uint32_t *counters) {
-    if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0u;
+    if (threadIdx.x < kNumCounters && threadIdx.x != kCntFatal) counters[threadIdx.x] = 0u;
 }
 
 template <typename T, bool EXACT, int CAP>
@@ -614,6 +617,7 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
     typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> FastWorker;
     reset_counters_kernel<<<1, 32, 0, stream>>>(P.counters);
     add_launches(1);
+    if (P.ev_begin) cudaEventRecord((cudaEvent_t)P.ev_begin, stream);
     if (use_tpc) {
         int rc = q3b_tpc_launch(P, stream, EXACT);
         if (rc != WOL_OK) return rc;
@@ -634,6 +638,7 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
             add_launches(1);
         }
     }
+    if (P.ev_end) cudaEventRecord((cudaEvent_t)P.ev_end, stream);
     // queued centres: q-only ones in the light instantiation, list overflows in the large-capacity one
     int rc = WOL_OK;
     if (P.do_q) rc = launch_big<T, EXACT, kLightCap>(P, stream);
@@ -704,6 +709,8 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     // thread-per-centre fast path: fp64 mode, >= 4 cells per axis
     P.wrapped = (a.precision == WOL_PREC_FP64) ? reinterpret_cast<const float4 *>(ws + lay.off_wrapped) : nullptr;
     P.skip_q_only = 0;
+    P.ev_begin = a.timing_event_begin;
+    P.ev_end = a.timing_event_end;
     {
         double lmax = 0.0;  // upper bound of the box edges: every cell edge is < 2 * edge of the smallest frame ... use nc * edge bound
         // edge_min * nc underestimates L for the larger frames of an NPT batch; the caller-provided

@@ -44,6 +44,7 @@ struct Q3bParams {
     const float4 *wrapped;  // box-wrapped float coordinates in record order (nullptr: not built)
     float pre_thr2;         // prefilter acceptance threshold on the float squared distance
     int skip_q_only;        // large-capacity pass: 1 = leave q-only items to the light instantiation
+    void *ev_begin, *ev_end;  // optional cudaEvent_t around the dominant kernel
 };
 
 // ------------------------------------------------------------------------------------------------

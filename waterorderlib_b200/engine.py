@@ -102,7 +102,7 @@ class Workspace:
     def get(self, nbytes):
         if self.buf is None or self.buf.numel() < nbytes:
             self.buf = None
-            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            self.buf = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         off = (-self.buf.data_ptr()) % 256
         return self.buf.data_ptr() + off, self.buf.numel() - off
 
@@ -110,7 +110,7 @@ class Workspace:
 def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, high3=3.413, lowq=0.0, highq=10.0,
                nbins=500, bin_range=(0.0, 180.0), q_nbins=500, precision="fp64", hist_per_frame=False, r_cell=None,
                want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), out=None, workspace=None,
-               device=None, check_status=True):
+               device=None, check_status=True, timing_events=None):
     """Fused tetrahedral q + three-body angle histogram for a batch of frames.
 
     pos      (F,N,3) positions of all atoms that can be neighbours (reference: `Pos`)
@@ -187,6 +187,8 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
         a.angle_table = table.data_ptr() if table is not None else None
         for name, t in (("q", q), ("nn_idx", nn), ("n3", n3), ("ang_hist", ah), ("q_hist", qh), ("frame_stats", fs)):
             setattr(a, name, t.data_ptr() if t is not None else None)
+        if timing_events is not None:  # (begin, end) torch.cuda.Event pair, already recorded once
+            a.timing_event_begin, a.timing_event_end = timing_events[0].cuda_event, timing_events[1].cuda_event
         check(L.wol_q3b_frames(ctypes.byref(a), stream), "wol_q3b_frames")
         launches += L.wol_last_launch_count()
         res["launches"] = launches
@@ -211,3 +213,16 @@ def default_r_cell(do_q, do_3body, high3, highq):
     if do_q:
         r = max(r, min(float(highq), 3.5))
     return max(r, 1e-3)
+
+
+def workspace_status(ws, n_frames, n_pos, n_centres, r_cell, box):
+    """(widened, overflow) of the last evaluation on `ws`; raises WolError if a list overflowed the
+    large-capacity path at any point since the previous call.  Synchronises the current stream."""
+    box_h = as_host_boxes(box, n_frames)
+    nc, _edge, _bmax = plan_grid(box_h, r_cell)
+    need = lib().wol_workspace_bytes(n_frames, n_pos, n_centres, ctypes.byref(nc))
+    ws_ptr, _ = ws.get(need)
+    st = (ctypes.c_int32 * 4)()
+    check(lib().wol_status(ctypes.c_void_p(ws_ptr), n_frames, n_pos, n_centres, ctypes.byref(nc), _stream_ptr(),
+                           ctypes.byref(st)), "wol_status")
+    return int(st[0]), int(st[1])

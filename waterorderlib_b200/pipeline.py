@@ -1,0 +1,143 @@
+"""Host-fed trajectory pipeline: frames live in (pinned) host memory, as they do when a trajectory reader
+hands them over (structureLibs/orderParam_lib.py:1312-1316 reads one pytraj frame per iteration); the GPU
+sees them in batches.  Three streams overlap the host->device copy of batch i+1, the kernels of batch i and
+the device->host copy of batch i-1's per-water results.
+
+This is the call the frame drivers (waterorderlib_b200.orderParam_lib) and bench.py's end-to-end leg make.
+"""
+import numpy as np
+import torch
+
+from . import engine
+from ._capi import WOL_NSTATS
+
+
+class FramePipeline:
+    """Fused q + three-body analysis of host-resident frames.
+
+    n_atoms, frames_per_batch fix the device buffers; dtype is the storage type of the host frames
+    (float64 as pytraj gives them, or float32 as trajectory files store them).
+    """
+
+    def __init__(self, n_atoms, frames_per_batch, dtype=np.float64, device=None, *, do_q=True, do_3body=True,
+                 low3=0.0, high3=3.413, lowq=0.0, highq=10.0, nbins=500, bin_range=(0.0, 180.0), q_nbins=500,
+                 precision="fp64", hist_per_frame=False, r_cell=None, want_q=True, want_n3=True, want_nn=False):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_atoms, self.fpb = int(n_atoms), int(frames_per_batch)
+        self.tdtype = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.kw = dict(do_q=do_q, do_3body=do_3body, low3=low3, high3=high3, lowq=lowq, highq=highq, nbins=nbins,
+                       bin_range=bin_range, q_nbins=q_nbins, precision=precision, hist_per_frame=False, r_cell=r_cell)
+        self.hist_per_frame = hist_per_frame
+        self.do_q, self.do_3body = do_q, do_3body
+        self.nbins, self.q_nbins = nbins, q_nbins
+        self.qdtype = torch.float64 if precision == "fp64" else torch.float32
+        self.want_q, self.want_n3, self.want_nn = want_q and do_q, want_n3 and do_3body, want_nn and do_q
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_run, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+            B, N = self.fpb, self.n_atoms
+            self.slots = []
+            for _ in range(2):
+                slot = dict(pos=torch.empty((B, N, 3), dtype=self.tdtype, device=self.device),
+                            q=torch.empty((B, N), dtype=self.qdtype, device=self.device) if do_q else None,
+                            n3=torch.empty((B, N), dtype=torch.int32, device=self.device) if do_3body else None,
+                            nn=torch.empty((B, N, 4), dtype=torch.int32, device=self.device) if self.want_nn else None,
+                            loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event())
+                self.slots.append(slot)
+            self.ws = engine.Workspace(self.device)
+        self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, pos_host, box, out_q=None, out_n3=None, out_nn=None):
+        """pos_host (F,N,3) torch CPU tensor (pinned for overlap) or numpy array; box (3,) / (F,3).
+        Returns dict(ang_hist, q_hist, frame_stats [, q, n3, nn_idx]) of HOST tensors; per-water arrays
+        are written into out_q / out_n3 / out_nn (pinned CPU tensors) when given."""
+        pos_host = pos_host if isinstance(pos_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pos_host))
+        if pos_host.dtype != self.tdtype:
+            raise ValueError("pipeline was built for %s frames, got %s" % (self.tdtype, pos_host.dtype))
+        F, N = int(pos_host.shape[0]), int(pos_host.shape[1])
+        if N != self.n_atoms:
+            raise ValueError("pipeline was built for %d atoms per frame, got %d" % (self.n_atoms, N))
+        box_h = engine.as_host_boxes(box, F)
+        dev = self.device
+        pin = pos_host.is_pinned()
+        if self.want_q and out_q is None:
+            out_q = torch.empty((F, N), dtype=self.qdtype, pin_memory=True)
+        if self.want_n3 and out_n3 is None:
+            out_n3 = torch.empty((F, N), dtype=torch.int32, pin_memory=True)
+        if self.want_nn and out_nn is None:
+            out_nn = torch.empty((F, N, 4), dtype=torch.int32, pin_memory=True)
+        H = F if self.hist_per_frame else 1
+        self.launches = self.h2d_bytes = self.d2h_bytes = 0
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            acc = {"frame_stats": torch.zeros((F, WOL_NSTATS), dtype=torch.float64, device=dev)}
+            if self.do_3body:
+                acc["ang_hist"] = torch.zeros((H, self.nbins), dtype=torch.int64, device=dev)
+            if self.do_q:
+                acc["q_hist"] = torch.zeros((H, self.q_nbins), dtype=torch.int64, device=dev)
+            for s in (self.s_in, self.s_run, self.s_out):
+                s.wait_stream(main)
+            starts = list(range(0, F, self.fpb))
+
+            def load(i):
+                f0 = starts[i]
+                nb = min(self.fpb, F - f0)
+                slot = self.slots[i % 2]
+                with torch.cuda.stream(self.s_in):
+                    self.s_in.wait_event(slot["computed"])  # the kernels that read this buffer two batches ago
+                    slot["pos"][:nb].copy_(pos_host[f0:f0 + nb], non_blocking=pin)
+                    slot["loaded"].record(self.s_in)
+                self.h2d_bytes += nb * N * 3 * pos_host.element_size()
+
+            load(0)
+            for i, f0 in enumerate(starts):
+                nb = min(self.fpb, F - f0)
+                slot = self.slots[i % 2]
+                if i + 1 < len(starts):
+                    load(i + 1)
+                with torch.cuda.stream(self.s_run):
+                    self.s_run.wait_event(slot["loaded"])
+                    self.s_run.wait_event(slot["drained"])  # the D2H of this slot's previous results
+                    out = {"frame_stats": acc["frame_stats"][f0:f0 + nb]}
+                    if self.do_3body:
+                        out["ang_hist"] = acc["ang_hist"][f0:f0 + nb] if self.hist_per_frame else acc["ang_hist"]
+                        out["n3"] = slot["n3"][:nb]
+                    if self.do_q:
+                        out["q_hist"] = acc["q_hist"][f0:f0 + nb] if self.hist_per_frame else acc["q_hist"]
+                        out["q"] = slot["q"][:nb]
+                        if self.want_nn:
+                            out["nn_idx"] = slot["nn"][:nb]
+                    want = tuple(out.keys())
+                    kw = dict(self.kw)
+                    kw["hist_per_frame"] = self.hist_per_frame
+                    r = engine.q3b_frames(slot["pos"][:nb], box_h[f0:f0 + nb], out=out, want=want, workspace=self.ws,
+                                          device=dev, check_status=False, **kw)
+                    self.launches += r["launches"]
+                    slot["computed"].record(self.s_run)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(slot["computed"])
+                    if self.want_q:
+                        out_q[f0:f0 + nb].copy_(slot["q"][:nb], non_blocking=True)
+                        self.d2h_bytes += nb * N * out_q.element_size()
+                    if self.want_n3:
+                        out_n3[f0:f0 + nb].copy_(slot["n3"][:nb], non_blocking=True)
+                        self.d2h_bytes += nb * N * 4
+                    if self.want_nn:
+                        out_nn[f0:f0 + nb].copy_(slot["nn"][:nb], non_blocking=True)
+                        self.d2h_bytes += nb * N * 16
+                    slot["drained"].record(self.s_out)
+            res = {}
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_stream(self.s_run)
+                for k, t in acc.items():
+                    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    h.copy_(t, non_blocking=True)
+                    self.d2h_bytes += t.numel() * t.element_size()
+                    res[k] = h
+            main.wait_stream(self.s_out)
+            main.wait_stream(self.s_run)
+            main.wait_stream(self.s_in)
+        res["q"], res["n3"], res["nn_idx"] = out_q, out_n3, out_nn
+        res["_device"] = acc
+        return res

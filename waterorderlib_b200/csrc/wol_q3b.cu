@@ -560,13 +560,12 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
     const int warp = threadIdx.x >> 5;
     Worker worker(P, gs[warp]);
     LaneStats st;
-    const uint32_t n_items = P.counters[kCntFallback];
+    const uint32_t n_items = P.counters[P.list_counter];
     if (CAP == kBigCap && P.counters[kCntOverflow] == 0u) return;  // nothing overflowed: no list to redo
-    if (CAP != kBigCap && P.counters[kCntWidened] == 0u && P.counters[kCntOverflow] == 0u) return;
     const uint32_t warps_total = gridDim.x * (kBigThreads / 32);
     for (uint32_t it = blockIdx.x * (kBigThreads / 32) + warp; it < n_items; it += warps_total) {
         st.reset();
-        const uint32_t e = P.fb_list[it];
+        const uint32_t e = P.list[it];
         const uint32_t id = e & kFbIdMask;
         const bool do3 = (e & kFbNeed3b) != 0, doq = (e & kFbNeedQ) != 0;
         if (do3 != (CAP == kBigCap)) continue;
@@ -588,7 +587,7 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
         const int cy = cell_coord((double)ry, __ddiv_rn(1.0, bx[1]), P.nc1);
         const int cz = cell_coord((double)rz, __ddiv_rn(1.0, bx[2]), P.nc2);
         // a centre queued only for q already failed at half-width 1; an overflowed one starts over
-        worker.run(true, f, rx, ry, rz, cx, cy, cz, out_index, do3, doq, do3 ? 1 : 2, id, nullptr, P.table, st);
+        worker.run(true, f, rx, ry, rz, cx, cy, cz, out_index, do3, doq, do3 ? 1 : P.list_w_start, id, nullptr, P.table, st);
         flush_stats(P, f, st);
     }
 }
@@ -639,11 +638,27 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
         }
     }
     if (P.ev_end) cudaEventRecord((cudaEvent_t)P.ev_end, stream);
-    // queued centres: q-only ones in the light instantiation, list overflows in the large-capacity one
+    // queued centres.  List overflows: large-capacity group pass.  q-only: thread-per-centre widened pass
+    // at half-width 2 when available (what it cannot settle goes to the second-level queue), then the
+    // light group pass, which widens without bound.
     int rc = WOL_OK;
-    if (P.do_q) rc = launch_big<T, EXACT, kLightCap>(P, stream);
-    if (rc == WOL_OK) rc = launch_big<T, EXACT, kBigCap>(P, stream);
+    Q3bParams Q = P;
+    Q.list = P.fb_list;
+    Q.list_counter = kCntFallback;
+    Q.list_w_start = 2;
+    rc = launch_big<T, EXACT, kBigCap>(Q, stream);
     if (rc != WOL_OK) return rc;
+    if (P.do_q) {
+        if (use_tpc && q3b_tpc_widen_supported(P)) {
+            rc = q3b_tpc_widen_launch(Q, stream, EXACT);
+            if (rc != WOL_OK) return rc;
+            Q.list = P.list2;
+            Q.list_counter = kCntLevel2;
+            Q.list_w_start = 3;
+        }
+        rc = launch_big<T, EXACT, kLightCap>(Q, stream);
+        if (rc != WOL_OK) return rc;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("q3b launch", e);
     return WOL_OK;
@@ -722,7 +737,20 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
         const double margin = 16.0 * ldexp(1.0, -24) * lmax;
         const double thr2 = (rthr + margin) * (rthr + margin) * (1.0 + 1e-6);
         P.pre_thr2 = nextafterf((float)thr2, INFINITY);
+        // half-width-2 widened pass
+        const bool last2 = P.wq_max <= 2;
+        const double rsel2 = last2 ? a.highq : fmin(a.highq, 2.0 * P.rc1);
+        const double t2 = (rsel2 + margin) * (rsel2 + margin) * (1.0 + 1e-6);
+        P.pre_thr2_w2 = nextafterf((float)t2, INFINITY);
+        const double cst = (4.0 * margin * (rsel2 + margin) + 4.0 * margin * margin) * (1.0 + 1e-6) + 1e-6 * rsel2 * rsel2;
+        P.pre_cst_w2 = nextafterf((float)cst, INFINITY);
+        const double lo = (a.lowq + margin) * (a.lowq + margin) * (1.0 + 1e-6);
+        P.lowq_hi2 = nextafterf((float)lo, INFINITY);
     }
+    P.list = P.fb_list;
+    P.list2 = P.fb_list + lay.n_centres_total;
+    P.list_counter = kCntFallback;
+    P.list_w_start = 2;
     const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
     if (a.precision == WOL_PREC_FP64)
         return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);

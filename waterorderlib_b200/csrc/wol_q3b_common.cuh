@@ -45,6 +45,14 @@ struct Q3bParams {
     float pre_thr2;         // prefilter acceptance threshold on the float squared distance
     int skip_q_only;        // large-capacity pass: 1 = leave q-only items to the light instantiation
     void *ev_begin, *ev_end;  // optional cudaEvent_t around the dominant kernel
+    // which queue a large-capacity / widened launch walks
+    const uint32_t *list;     // entries
+    int list_counter;         // index into counters[] of its length
+    int list_w_start;         // half-width at which a q-only entry resumes its search
+    uint32_t *list2;          // second-level queue (appended to by the thread-per-centre widened pass)
+    float lowq_hi2;           // (lowq + margin)^2: float distances above this are certainly beyond lowCut
+    float pre_thr2_w2;        // prefilter threshold of the half-width-2 pass
+    float pre_cst_w2;         // slack added to the 4th-smallest float distance^2 of that pass
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +194,76 @@ __device__ __forceinline__ void load_centre(const Q3bParams &P, int f, int m, T 
 
 constexpr int kMaxSmemBins = 4096;
 
+// q of one centre from its (up to) four selected neighbours, given as record indices in selection
+// order; writes q / nn_idx / q histogram and accumulates the frame statistics.  fp64 reference
+// arithmetic: reimage (waterlib.f90:43-45), the second reimage tetraCosAng applies (:880-883),
+// CosAngle3's vectors and clamped cosine (:694-698), padding and sum of water_properties.py:379-388.
+template <bool EXACT>
+__device__ __forceinline__ void finish_q(const Q3bParams &P, int f, double rx, double ry, double rz, double Lx, double Ly,
+                                         double Lz, double iLx, double iLy, double iLz, const Top4<double> &top,
+                                         int n_found, size_t out_index, LaneStats &st) {
+    double vx[4], vy[4], vz[4], vn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        vx[k] = vy[k] = vz[k] = vn[k] = 0.0;
+        if (k < n_found) {
+            double px, py, pz;
+            int idx;
+            RecTraits<double>::load(P.recs, (size_t)top.p[k], px, py, pz, idx);
+            const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
+            const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
+            const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
+            const double ex = __dsub_rn(__dadd_rn(rx, dx), rx);
+            const double ey = __dsub_rn(__dadd_rn(ry, dy), ry);
+            const double ez = __dsub_rn(__dadd_rn(rz, dz), rz);
+            const double d2x = __dsub_rn(ex, __dmul_rn(Lx, anint_exact<double>(__dmul_rn(ex, iLx))));
+            const double d2y = __dsub_rn(ey, __dmul_rn(Ly, anint_exact<double>(__dmul_rn(ey, iLy))));
+            const double d2z = __dsub_rn(ez, __dmul_rn(Lz, anint_exact<double>(__dmul_rn(ez, iLz))));
+            vx[k] = __dsub_rn(__dadd_rn(rx, d2x), rx);
+            vy[k] = __dsub_rn(__dadd_rn(ry, d2y), ry);
+            vz[k] = __dsub_rn(__dadd_rn(rz, d2z), rz);
+            vn[k] = sumsq3<double>(vx[k], vy[k], vz[k]);
+        }
+    }
+    // real angles in triu order, then the 180-degree padding (cos = -1), summed left to right like np.sum
+    double acc = 0.0;
+    int n_real = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b)
+            if (b < n_found) {
+                double c;
+                if (vn[a] == 0.0 || vn[b] == 0.0) c = 1.0;
+                else c = clamped_cos<double>(dot3<double>(vx[a], vy[a], vz[a], vx[b], vy[b], vz[b]), vn[a], vn[b]);
+                const double u = c + (1.0 / 3.0);
+                acc += u * u;
+                ++n_real;
+            }
+    for (int k = n_real; k < 6; ++k) {
+        const double u = -1.0 + (1.0 / 3.0);
+        acc += u * u;
+    }
+    const double qv = (n_found == 0) ? 0.0 : 1.0 - (3.0 / 8.0) * acc;
+    if (P.q) reinterpret_cast<double *>(P.q)[out_index] = qv;
+    if (P.nn_idx) {
+        int4 o;
+        o.x = (n_found > 0) ? top.i[0] : -1;
+        o.y = (n_found > 1) ? top.i[1] : -1;
+        o.z = (n_found > 2) ? top.i[2] : -1;
+        o.w = (n_found > 3) ? top.i[3] : -1;
+        reinterpret_cast<int4 *>(P.nn_idx)[out_index] = o;
+    }
+    if (P.q_hist) {
+        const HistSpec hs = hist_spec(0.0, 1.0, P.q_nbins);
+        const int b = hist_bin(hs, qv);
+        if (b >= 0) atomicAdd(P.q_hist + (size_t)(P.hist_per_frame ? f : 0) * P.q_nbins + b, 1ull);
+    }
+    st.q_sum += qv;
+    st.q_sumsq += qv * qv;
+    st.n_centres += 1u;
+}
+
 // flush of a block's shared-memory angle histogram into the global int64 bins
 __device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist, int f, bool clear) {
     for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) {
@@ -196,6 +274,8 @@ __device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist,
 }
 
 int q3b_tpc_launch(const Q3bParams &P, cudaStream_t stream, bool exact);
+int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact);
+bool q3b_tpc_widen_supported(const Q3bParams &P);
 bool q3b_tpc_supported(const Q3bParams &P);
 
 }  // namespace wol

@@ -144,30 +144,58 @@ __global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_co
             } else if (cx == nc0 - 1) {
                 xb0 = 0; xb1 = 1; sxb = -Lxf;             // neighbours near x = 0 are images at x + L
             }
-#pragma unroll 1
+            // all 18 row bounds first (independent loads in flight together), then the rows
+            int rj0[9], rj1[9];
+            float rcy[9], rcz[9];
+#pragma unroll
             for (int row = 0; row < 9; ++row) {
-                const int dz = row / 3 - 1, dy = row - (row / 3) * 3 - 1;
+                const int dz = row / 3 - 1, dy = row % 3 - 1;
                 int y = cy + dy, z = cz + dz;
                 float cys = wy, czs = wz;
                 if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
                 if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
                 const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
-#pragma unroll 1
-                for (int piece = 0; piece < 2; ++piece) {
-                    int j0, j1;
-                    float cxs;
-                    if (piece == 0) {
-                        j0 = (int)__ldg(cs + xa0);
-                        j1 = (int)__ldg(cs + xa1);
-                        cxs = wx;
-                    } else {
-                        if (xb1 == 0) break;
-                        j0 = (int)__ldg(cs + xb0);
-                        j1 = (int)__ldg(cs + xb1);
-                        cxs = wx + sxb;
+                rj0[row] = (int)__ldg(cs + xa0);
+                rj1[row] = (int)__ldg(cs + xa1);
+                rcy[row] = cys;
+                rcz[row] = czs;
+            }
+            const float4 *wr = P.wrapped;
+#pragma unroll
+            for (int row = 0; row < 9; ++row) {
+                const float cys = rcy[row], czs = rcz[row];
+                const int j1 = rj1[row];
+                for (int j = rj0[row]; j < j1; j += 2) {
+                    const bool two = j + 1 < j1;
+                    const float4 w0 = __ldg(wr + j);
+                    const float4 w1 = __ldg(wr + (two ? j + 1 : j));
+                    const float ax = w0.x - wx, ay = w0.y - cys, az = w0.z - czs;
+                    const float bx = w1.x - wx, by = w1.y - cys, bz = w1.z - czs;
+                    const float ra = fmaf(az, az, fmaf(ay, ay, ax * ax));
+                    const float rb = fmaf(bz, bz, fmaf(by, by, bx * bx));
+                    if (ra <= pre_thr2 && j != self_j) {
+                        if (nl < kTpcListCap) S.lj[nl][tid] = j;
+                        ++nl;
                     }
-                    for (int j = j0; j < j1; ++j) {
-                        const float4 w = __ldg(P.wrapped + j);
+                    if (two && rb <= pre_thr2 && j + 1 != self_j) {
+                        if (nl < kTpcListCap) S.lj[nl][tid] = j + 1;
+                        ++nl;
+                    }
+                }
+            }
+            if (xb1 != 0) {  // the wrapped end of the x-run (first / last cell column only)
+                const float cxs = wx + sxb;
+#pragma unroll 1
+                for (int row = 0; row < 9; ++row) {
+                    const int dz = row / 3 - 1, dy = row % 3 - 1;
+                    int y = cy + dy, z = cz + dz;
+                    float cys = wy, czs = wz;
+                    if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
+                    if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
+                    const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
+                    const int j1 = (int)__ldg(cs + xb1);
+                    for (int j = (int)__ldg(cs + xb0); j < j1; ++j) {
+                        const float4 w = __ldg(wr + j);
                         const float dx = w.x - cxs, dyv = w.y - cys, dzv = w.z - czs;
                         const float r2 = fmaf(dzv, dzv, fmaf(dyv, dyv, dx * dx));
                         if (r2 <= pre_thr2 && j != self_j) {
@@ -185,11 +213,19 @@ __global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_co
         top.reset();
         int K3 = 0, nq = 0;
         if (valid && !overflow) {
+            double nx = 0, ny = 0, nz = 0;
+            int nidx = 0, nj = 0;
+            if (nl > 0) {
+                nj = S.lj[0][tid];
+                RecTraits<double>::load(P.recs, (size_t)nj, nx, ny, nz, nidx);
+            }
             for (int k = 0; k < nl; ++k) {
-                const int j = S.lj[k][tid];
-                double px, py, pz;
-                int idx;
-                RecTraits<double>::load(P.recs, (size_t)j, px, py, pz, idx);
+                const int j = nj, idx = nidx;
+                const double px = nx, py = ny, pz = nz;
+                if (k + 1 < nl) {  // next survivor's record is in flight while this one is evaluated
+                    nj = S.lj[k + 1][tid];
+                    RecTraits<double>::load(P.recs, (size_t)nj, nx, ny, nz, nidx);
+                }
                 const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
                 const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
                 const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
@@ -281,77 +317,221 @@ __global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_co
         }
 
         // ---------------- phase 3b: q from the four winners ---------------------------------------
-        if (q_go) {
-            const int n_found = min(nq, 4);
-            double vx[4], vy[4], vz[4], vn[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                vx[k] = vy[k] = vz[k] = vn[k] = 0.0;
-                if (k < n_found) {
-                    double px, py, pz;
-                    int idx;
-                    RecTraits<double>::load(P.recs, (size_t)top.p[k], px, py, pz, idx);
-                    const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
-                    const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
-                    const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
-                    const double ex = __dsub_rn(__dadd_rn(rx, dx), rx);
-                    const double ey = __dsub_rn(__dadd_rn(ry, dy), ry);
-                    const double ez = __dsub_rn(__dadd_rn(rz, dz), rz);
-                    // tetraCosAng reimages the already reimaged position again (waterlib.f90:880-883)
-                    const double d2x = __dsub_rn(ex, __dmul_rn(Lx, anint_exact<double>(__dmul_rn(ex, iLx))));
-                    const double d2y = __dsub_rn(ey, __dmul_rn(Ly, anint_exact<double>(__dmul_rn(ey, iLy))));
-                    const double d2z = __dsub_rn(ez, __dmul_rn(Lz, anint_exact<double>(__dmul_rn(ez, iLz))));
-                    vx[k] = __dsub_rn(__dadd_rn(rx, d2x), rx);
-                    vy[k] = __dsub_rn(__dadd_rn(ry, d2y), ry);
-                    vz[k] = __dsub_rn(__dadd_rn(rz, d2z), rz);
-                    vn[k] = sumsq3<double>(vx[k], vy[k], vz[k]);
-                }
-            }
-            // real angles in triu order, then the 180-degree padding (cos = -1) of
-            // water_properties.py:379-384, summed left to right like np.sum
-            double acc = 0.0;
-            int n_real = 0;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = a + 1; b < 4; ++b)
-                    if (b < n_found) {
-                        double c;
-                        if (vn[a] == 0.0 || vn[b] == 0.0) c = 1.0;
-                        else c = clamped_cos<double>(dot3<double>(vx[a], vy[a], vz[a], vx[b], vy[b], vz[b]), vn[a], vn[b]);
-                        const double u = c + (1.0 / 3.0);
-                        acc += u * u;
-                        ++n_real;
-                    }
-            for (int k = n_real; k < 6; ++k) {
-                const double u = -1.0 + (1.0 / 3.0);
-                acc += u * u;
-            }
-            const double qv = (n_found == 0) ? 0.0 : 1.0 - (3.0 / 8.0) * acc;
-            if (P.q) reinterpret_cast<double *>(P.q)[out_index] = qv;
-            if (P.nn_idx) {
-                int4 o;
-                o.x = (n_found > 0) ? top.i[0] : -1;
-                o.y = (n_found > 1) ? top.i[1] : -1;
-                o.z = (n_found > 2) ? top.i[2] : -1;
-                o.w = (n_found > 3) ? top.i[3] : -1;
-                reinterpret_cast<int4 *>(P.nn_idx)[out_index] = o;
-            }
-            if (P.q_hist) {
-                const HistSpec hs = hist_spec(0.0, 1.0, P.q_nbins);
-                const int b = hist_bin(hs, qv);
-                if (b >= 0) atomicAdd(P.q_hist + (size_t)(P.hist_per_frame ? f : 0) * P.q_nbins + b, 1ull);
-            }
-            st.q_sum += qv;
-            st.q_sumsq += qv * qv;
-            st.n_centres += 1u;
-        }
+        if (q_go) finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st);
     }
     if (cur_f >= 0) flush_stats(P, cur_f, st);
     if (smem_hist) {
         __syncthreads();
         if (cur_f >= 0) flush_hist(P, s_hist, cur_f, false);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Widened q search, one WARP per queued centre: half-width-2 stencil = 25 rows of a 5-cell x-run, one row
+// per lane, so the 25 dependent load chains of a centre run side by side.
+//   pass 1  every lane scans its row over the float coordinates and keeps its four smallest distances^2
+//           (only candidates certainly beyond lowCut count); four REDUX-min rounds give the warp's 4th
+//           smallest;
+//   pass 2  every lane rescans its row and appends whatever lies within that bound (+ rounding slack,
+//           capped at the radius the stencil guarantees) to a shared list -- a handful of candidates;
+//   exact   lane k evaluates survivor k in fp64 reference arithmetic; ranks by (distance, index) through
+//           shuffles pick the four winners; lanes 0-3 build their vectors, lanes 0-5 the pair terms.
+// A centre still short of four neighbours inside the guaranteed radius goes to the second-level queue
+// (group-per-centre pass, half-width 3 and up).
+constexpr int kWidenThreads = 128;
+constexpr int kWidenWarps = kWidenThreads / 32;
+
+__device__ __forceinline__ void widen_scan_row(const float4 *__restrict__ wr, int j0, int j1, float cxs, float cys, float czs,
+                                               int pass, float lowq_hi2, float thr, int self_j, float &a0, float &a1,
+                                               float &a2, float &a3, int *s_cnt, int *s_list) {
+    for (int j = j0; j < j1; ++j) {
+        const float4 w = __ldg(wr + j);
+        const float dx = w.x - cxs, dyv = w.y - cys, dzv = w.z - czs;
+        const float r2 = fmaf(dzv, dzv, fmaf(dyv, dyv, dx * dx));
+        if (pass == 0) {
+            if (r2 > lowq_hi2) {  // insert into the lane's sorted quadruple
+                float v = r2, m;
+                m = fminf(a0, v); v = fmaxf(a0, v); a0 = m;
+                m = fminf(a1, v); v = fmaxf(a1, v); a1 = m;
+                m = fminf(a2, v); v = fmaxf(a2, v); a2 = m;
+                a3 = fminf(a3, v);
+            }
+        } else if (r2 <= thr && j != self_j) {
+            const int at = atomicAdd(s_cnt, 1);
+            if (at < 32) s_list[at] = j;
+        }
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __grid_constant__ Q3bParams P) {
+    __shared__ int s_list[kWidenWarps][32];
+    __shared__ int s_cnt[kWidenWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_items = P.counters[P.list_counter];
+    if (P.counters[kCntWidened] == 0u) return;
+    const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
+    const double lowqsq = P.lowqsq, highqsq = P.highqsq;
+    const bool last2 = P.wq_max <= 2;
+    const double rsel = fmin(P.highq, 2.0 * P.rc1);
+    const double selsq2 = last2 ? highqsq : fmin(highqsq, rsel * rsel);
+    const float lowq_hi2 = P.lowq_hi2, thr_cap = P.pre_thr2_w2, cst = P.pre_cst_w2;
+    const float kInf = __int_as_float(0x7f800000);
+    const uint32_t warps_total = gridDim.x * kWidenWarps;
+    for (uint32_t it = blockIdx.x * kWidenWarps + warp; it < n_items; it += warps_total) {
+        const uint32_t e = P.list[it];
+        if ((e & kFbNeed3b) != 0u || (e & kFbNeedQ) == 0u) continue;  // list overflows belong to the large-capacity pass
+        const uint32_t id = e & kFbIdMask;
+        double rx, ry, rz;
+        float wx, wy, wz;
+        int cx, cy, cz, self_j = -1, f;
+        size_t out_index;
+        if (P.centres == nullptr) {
+            f = (int)(id / (uint32_t)P.n_pos);
+            const int4 *rp = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(P.recs) + id);
+            const int4 a = __ldg(rp), b = __ldg(rp + 1);
+            rx = __hiloint2double(a.y, a.x);
+            ry = __hiloint2double(a.w, a.z);
+            rz = __hiloint2double(b.y, b.x);
+            cx = b.w & 1023;
+            cy = (b.w >> 10) & 1023;
+            cz = (b.w >> 20) & 1023;
+            const float4 w = __ldg(P.wrapped + id);
+            wx = w.x; wy = w.y; wz = w.z;
+            self_j = (int)id;
+            out_index = (size_t)f * P.n_pos + b.z;
+        } else {
+            f = (int)(id / (uint32_t)P.n_centres);
+            load_centre<double>(P, f, (int)(id - (uint32_t)f * P.n_centres), rx, ry, rz);
+            out_index = id;
+        }
+        const double Lx = P.box[(size_t)f * 3 + 0], Ly = P.box[(size_t)f * 3 + 1], Lz = P.box[(size_t)f * 3 + 2];
+        const double iLx = __ddiv_rn(1.0, Lx), iLy = __ddiv_rn(1.0, Ly), iLz = __ddiv_rn(1.0, Lz);
+        if (P.centres != nullptr) {
+            cx = cell_coord(rx, iLx, nc0);
+            cy = cell_coord(ry, iLy, nc1);
+            cz = cell_coord(rz, iLz, nc2);
+            wx = wrapped_coord(rx, Lx, iLx);
+            wy = wrapped_coord(ry, Ly, iLy);
+            wz = wrapped_coord(rz, Lz, iLz);
+        }
+        const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
+        // this lane's row (lanes 25..31 have none) and the two pieces of its x-run [cx-2, cx+2]
+        int ja0 = 0, ja1 = 0, jb0 = 0, jb1 = 0;
+        float cys = wy, czs = wz, cxb = wx;
+        if (lane < 25) {
+            const int dz = lane / 5 - 2, dy = lane % 5 - 2;
+            int y = cy + dy, z = cz + dz;
+            if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
+            if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
+            const uint32_t *cs = P.cell_start + (size_t)f * nc0 * nc1 * nc2 + ((size_t)z * nc1 + y) * nc0;
+            ja0 = (int)__ldg(cs + max(cx - 2, 0));
+            ja1 = (int)__ldg(cs + min(cx + 2, nc0 - 1) + 1);
+            if (cx < 2) {
+                jb0 = (int)__ldg(cs + nc0 - (2 - cx));
+                jb1 = (int)__ldg(cs + nc0);
+                cxb = wx + Lxf;
+            } else if (cx > nc0 - 3) {
+                jb0 = (int)__ldg(cs);
+                jb1 = (int)__ldg(cs + cx + 3 - nc0);
+                cxb = wx - Lxf;
+            }
+        }
+        if (lane == 0) s_cnt[warp] = 0;
+        float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
+        widen_scan_row(P.wrapped, ja0, ja1, wx, cys, czs, 0, lowq_hi2, 0.f, self_j, a0, a1, a2, a3, nullptr, nullptr);
+        widen_scan_row(P.wrapped, jb0, jb1, cxb, cys, czs, 0, lowq_hi2, 0.f, self_j, a0, a1, a2, a3, nullptr, nullptr);
+        // 4th smallest over the warp: extract the minimum four times (non-negative floats order like uints)
+        float fourth = kInf;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned m = __reduce_min_sync(kFullMask, __float_as_uint(a0));
+            fourth = __uint_as_float(m);
+            const unsigned holders = __ballot_sync(kFullMask, __float_as_uint(a0) == m);
+            if (lane == __ffs(holders) - 1) {
+                a0 = a1; a1 = a2; a2 = a3; a3 = kInf;
+            }
+        }
+        const float thr = fminf(fourth + cst, thr_cap);
+        __syncwarp();
+        widen_scan_row(P.wrapped, ja0, ja1, wx, cys, czs, 1, lowq_hi2, thr, self_j, a0, a1, a2, a3, &s_cnt[warp], s_list[warp]);
+        widen_scan_row(P.wrapped, jb0, jb1, cxb, cys, czs, 1, lowq_hi2, thr, self_j, a0, a1, a2, a3, &s_cnt[warp], s_list[warp]);
+        __syncwarp();
+        const int n = s_cnt[warp];
+        // exact evaluation: lane k takes survivor k
+        bool elig = false;
+        double dist = 0.0;
+        int idx = INT_MAX, j = -1;
+        if (n <= 32 && lane < n) {
+            j = s_list[warp][lane];
+            double px, py, pz;
+            RecTraits<double>::load(P.recs, (size_t)j, px, py, pz, idx);
+            const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
+            const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
+            const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
+            const double s = sumsq3<double>(dx, dy, dz);
+            if ((s > lowqsq) && (s <= selsq2)) {
+                elig = true;
+                const double ex = __dsub_rn(__dadd_rn(rx, dx), rx);
+                const double ey = __dsub_rn(__dadd_rn(ry, dy), ry);
+                const double ez = __dsub_rn(__dadd_rn(rz, dz), rz);
+                dist = __dsqrt_rn(sumsq3<double>(ex, ey, ez));
+            }
+        }
+        const unsigned emask = __ballot_sync(kFullMask, elig);
+        const int nq = __popc(emask);
+        if (n > 32 || (nq < 4 && !last2)) {
+            if (lane == 0) {
+                const uint32_t at = atomicAdd(P.counters + kCntLevel2, 1u);
+                P.list2[at] = id | kFbNeedQ;
+            }
+            continue;
+        }
+        // rank among the eligible by (distance, atom index)
+        int rank = 0;
+        for (unsigned mm = emask; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const double od = __shfl_sync(kFullMask, dist, src);
+            const int oi = __shfl_sync(kFullMask, idx, src);
+            if (key_less(od, oi, dist, idx)) ++rank;
+        }
+        const int n_found = min(nq, 4);
+        Top4<double> top;
+        top.reset();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned who = __ballot_sync(kFullMask, elig && rank == r);
+            const int src = who ? __ffs(who) - 1 : 0;
+            const int wj = __shfl_sync(kFullMask, j, src), wi = __shfl_sync(kFullMask, idx, src);
+            if (r < n_found) {
+                top.p[r] = wj;
+                top.i[r] = wi;
+            }
+        }
+        if (lane == 0) {
+            LaneStats st;
+            st.reset();
+            finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, n_found, out_index, st);
+            if (P.stats) {
+                atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_Q_SUM, st.q_sum);
+                atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_Q_SUMSQ, st.q_sumsq);
+                atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_N_CENTRES, 1.0);
+            }
+        }
+    }
+}
+
+// adjacency image == minimum image needs 3 cell edges < L / 2
+bool q3b_tpc_widen_supported(const Q3bParams &P) {
+    return P.wrapped != nullptr && P.nc0 >= 7 && P.nc1 >= 7 && P.nc2 >= 7;
+}
+
+int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact) {
+    const int grid = sm_count() * 12;
+    if (exact) q3b_tpc_widen_kernel<true><<<grid, kWidenThreads, 0, stream>>>(P);
+    else q3b_tpc_widen_kernel<false><<<grid, kWidenThreads, 0, stream>>>(P);
+    add_launches(1);
+    return WOL_OK;
 }
 
 bool q3b_tpc_supported(const Q3bParams &P) {

@@ -32,6 +32,7 @@ enum {
     kCntWidened = 1,   // centres whose q search had to be widened
     kCntOverflow = 2,  // centres whose list overflowed the fast path
     kCntFatal = 3,     // centres whose list overflowed the large-capacity path
+    kCntLevel2 = 4,    // entries in the second-level list (widened search at half-width 2 was not enough)
     kNumCounters = 8
 };
 
@@ -48,7 +49,7 @@ struct WorkspaceLayout {
     size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
     size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates + atom index, same order as recs
     size_t off_counters;    // uint32[kNumCounters]
-    size_t off_fb_list;     // uint32[F*M]  centres the fast path handed to the large-capacity path
+    size_t off_fb_list;     // uint32[2*F*M]  centres the fast path handed on; second half = second level
     size_t total;
     int64_t n_cells_total;
     int64_t n_atoms_total;
@@ -82,7 +83,7 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     w.off_counters = o;
     o = align_up(o + kNumCounters * 4, 256);
     w.off_fb_list = o;
-    o = align_up(o + (size_t)w.n_centres_total * 4, 256);
+    o = align_up(o + (size_t)w.n_centres_total * 8, 256);
     w.total = o;
     return w;
 }

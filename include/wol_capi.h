@@ -179,6 +179,104 @@ int wol_q3b_frames(const wol_q3b_args *args, void *stream);
 int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3],
                void *stream, int32_t status_host[4]);
 
+/* ------------------------------------------------------------------------------------------------
+ * Value-returning routines of the same path: what the reference's Python API hands back as arrays.
+ * All fp64 in the reference's operation order.  They share the cell list of wol_cell_build.
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * Offsets of each centre's block inside the flat angle array getCosAngs returns
+ * (structureLibs/water_properties.py:247: np.hstack of the triu entries, centre by centre):
+ *   offsets[i] = sum_{k<i} n3[k] (n3[k] - 1) / 2,   i = 0..n   (offsets[n] = number of angles)
+ * n3 as written by wol_q3b_frames.  scratch: at least (n / 2048 + 2) uint32.
+ */
+int wol_angle_offsets(const int32_t *n3, int64_t n, uint32_t *offsets, uint32_t *scratch, void *stream);
+
+/*
+ * The angle VALUES (degrees) of getCosAngs in the reference's order: centres ascending, neighbours in
+ * ascending atom index, pairs in np.triu_indices(k=1) order (water_properties.py:241-247; CosAngle3
+ * fortran/waterlib.f90:683-703 incl. the -180 it returns for an exactly antiparallel pair).
+ * `centres` is required here (pass pos itself for the subPos == Pos branch).  Needs the cell list of
+ * wol_cell_build(FP64) over pos; at most 64 neighbours per centre (more -> wol_status reports it).
+ */
+int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos,
+                    int32_t n_centres, const int32_t nc[3], double edge_min, double low3, double high3, void *workspace,
+                    size_t workspace_bytes, const uint32_t *offsets, double *angles, void *stream);
+
+/*
+ * np.histogram(x, bins=nbins, range=[lo, hi]) counts (ACCUMULATED into hist) plus the sums
+ * tetrahedralMetrics takes over the window tet_lo <= x <= tet_hi (water_properties.py:328-335):
+ * tet_sums[0] += count, [1] += sum cos(x pi/180), [2] += sum cos^2.  tet_sums may be NULL.
+ */
+int wol_histogram(const double *x, int64_t n, double lo, double hi, int32_t nbins, int64_t *hist, double tet_lo,
+                  double tet_hi, double *tet_sums, void *stream);
+
+/*
+ * Dense neighbour matrix out[m][n] (int32 0/1) of nearNeighbors / allNearNeighbors
+ * (fortran/waterlib.f90:710-743, :830-862): lowcut^2 < r^2 <= highcut^2 under the minimum image.
+ * box[3] on the device; a negative edge disables wrapping on that axis as in the reference (:41).
+ * O(m n) by construction -- the drop-in for small systems; large ones use wol_q3b_frames.
+ */
+int wol_neighbor_matrix(const void *sub, int32_t sub_dtype, int32_t m, const void *pos, int32_t pos_dtype, int32_t n,
+                        const double *box, double lowcut, double highcut, int32_t *out, void *stream);
+
+/*
+ * mode 0: reimage (fortran/waterlib.f90:32-47): out[n][3] = ref + minimg(pos - ref)
+ * mode 1: lsiDists (fortran/waterlib.f90:900-918): out[n] = |minimg(pos - ref)|
+ */
+int wol_reimage(const double *pos, int32_t n, const double *ref, const double *box, double *out, int32_t mode,
+                void *stream);
+
+/* tetraCosAng (fortran/waterlib.f90:867-895): out[k][k] angles in degrees about `ref`; the diagonal,
+ * which the Fortran leaves unwritten, is set to 0. */
+int wol_tetracosang(const double *ref, const double *neigh, int32_t k, const double *box, double *out, void *stream);
+
+/*
+ * K3: hydrogen bonds, generalHbonds (fortran/waterlib.f90:1156-1210) + AngBetween (:954-965), reduced to
+ * the sums hbCalc takes (structureLibs/orderParam_lib.py:867-884) and, optionally, the dense matrix or
+ * the bonded pair list.  The cell list in `workspace` must have been built (FP64) over the DONOR heavy
+ * atoms: wol_cell_build(don, ..., n_pos = n_don, ...) with r_cell >= dist_cut.
+ *   bond(i, j)  <=>  1.0E-2f < r^2(acc_i, don_j) <= dist_cut^2  and  angle(acc_i - H_j, don_j - H_j) >= ang_cut
+ */
+typedef struct wol_hbond_args {
+    uint32_t struct_size;
+    int32_t n_frames;
+    int32_t n_acc;
+    int32_t n_don; /* donor heavy atoms == donor hydrogens (the reference stops otherwise, :1171-1174) */
+    int32_t acc_dtype;
+    int32_t donh_dtype;
+    const void *acc;  /* [n_frames][n_acc][3] */
+    const void *donh; /* [n_frames][n_don][3], hydrogen j belongs to donor heavy atom j */
+    const double *box;
+    void *workspace;
+    size_t workspace_bytes;
+    int32_t nc[3];
+    uint32_t pair_capacity;
+    double edge_min;
+    double dist_cut, ang_cut;
+    int32_t *acc_count;     /* [n_frames][n_acc] written                                   (may be NULL) */
+    int32_t *don_count;     /* [n_frames][n_don] ACCUMULATED with atomics                 (may be NULL) */
+    int32_t *dense;         /* [n_frames][n_acc][n_don], bonded entries set to 1          (may be NULL) */
+    int32_t *pairs;         /* [pair_capacity][2] (frame * n_acc + acceptor, donor)       (may be NULL) */
+    uint32_t *pair_counter; /* number of pairs found (may exceed pair_capacity: list truncated)          */
+} wol_hbond_args;
+
+int wol_hbond_counts(const wol_hbond_args *args, void *stream);
+
+/* H-bond locations of HBondsGeneral (structureLibs/water_properties.py:709-714): for each row of a pair
+ * list from wol_hbond_counts, out[p][3] = 0.5 * (reimage(H_donor, acceptor) + acceptor). */
+int wol_hbond_locations(const int32_t *pairs, int32_t n_pairs, const void *acc, int32_t acc_dtype, int32_t n_acc,
+                        const void *donh, int32_t donh_dtype, int32_t n_don, const double *box, double *out, void *stream);
+
+/*
+ * K4: hydration-shell selection (structureLibs/orderParam_lib.py:495-498 over nearNeighbors,
+ * fortran/waterlib.f90:710-743): mask[f][j] = 1 iff some solute atom lies within (lowcut, cutoff] of
+ * atom j of the cell list (built over the waters).  The caller zero-fills mask.
+ */
+int wol_shell_mask(const void *sol, int32_t sol_dtype, int32_t n_sol, const double *box, int32_t n_frames, int32_t n_pos,
+                   const int32_t nc[3], double edge_min, double lowcut, double cutoff, void *workspace,
+                   size_t workspace_bytes, int32_t *mask, void *stream);
+
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);
 

@@ -31,6 +31,21 @@ class Q3bArgs(ctypes.Structure):
     ]
 
 
+class HbondArgs(ctypes.Structure):
+    """struct wol_hbond_args (include/wol_capi.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("n_frames", c_i32), ("n_acc", c_i32), ("n_don", c_i32), ("acc_dtype", c_i32),
+        ("donh_dtype", c_i32), ("acc", c_vp), ("donh", c_vp), ("box", c_vp), ("workspace", c_vp),
+        ("workspace_bytes", ctypes.c_size_t), ("nc", c_i32 * 3), ("pair_capacity", ctypes.c_uint32),
+        ("edge_min", ctypes.c_double), ("dist_cut", ctypes.c_double), ("ang_cut", ctypes.c_double),
+        ("acc_count", c_vp), ("don_count", c_vp), ("dense", c_vp), ("pairs", c_vp), ("pair_counter", c_vp),
+    ]
+
+
+c_f64 = ctypes.c_double
+c_i64 = ctypes.c_int64
+_NC = ctypes.POINTER(c_i32 * 3)
+
 # name -> (restype, argtypes); every symbol include/wol_capi.h declares
 SIGNATURES = {
     "wol_version": (ctypes.c_char_p, []),
@@ -43,6 +58,17 @@ SIGNATURES = {
     "wol_cell_build": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_i32, c_vp, ctypes.c_size_t, c_vp]),
     "wol_angle_table": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, c_i32, ctypes.c_double, ctypes.c_double, c_vp]),
     "wol_q3b_frames": (ctypes.c_int, [ctypes.POINTER(Q3bArgs), c_vp]),
+    "wol_angle_offsets": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "wol_angles_fill": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp,
+                                       ctypes.c_size_t, c_vp, c_vp, c_vp]),
+    "wol_histogram": (ctypes.c_int, [c_vp, c_i64, c_f64, c_f64, c_i32, c_vp, c_f64, c_f64, c_vp, c_vp]),
+    "wol_neighbor_matrix": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_f64, c_f64, c_vp, c_vp]),
+    "wol_reimage": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    "wol_tetracosang": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "wol_hbond_counts": (ctypes.c_int, [ctypes.POINTER(HbondArgs), c_vp]),
+    "wol_hbond_locations": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "wol_shell_mask": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp,
+                                      ctypes.c_size_t, c_vp, c_vp]),
     "wol_status": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_vp, ctypes.POINTER(c_i32 * 4)]),
 }
 

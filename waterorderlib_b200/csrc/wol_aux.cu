@@ -1,0 +1,599 @@
+// The other routines of the per-frame path (sm_100a): the value-returning variants the reference's
+// Python API exposes (materialised angle lists, dense neighbour matrices, reimage / tetracosang /
+// lsidists), np.histogram on the device, hydrogen-bond counting and hydration-shell selection.
+// All fp64, reference operation order.  These are the drop-in paths for modest sizes; the throughput path
+// is the fused kernel of wol_q3b*.cu.
+//
+// Reference anchors (relative to /root/reference):
+//   getCosAngs            structureLibs/water_properties.py:210-250
+//   tetrahedralMetrics    structureLibs/water_properties.py:314-342
+//   nearNeighbors         fortran/waterlib.f90:710-743   allNearNeighbors :830-862
+//   reimage               fortran/waterlib.f90:32-47     tetraCosAng :867-895   lsiDists :900-918
+//   generalHbonds         fortran/waterlib.f90:1156-1210 AngBetween :954-965
+//   shell selection       structureLibs/orderParam_lib.py:495-498
+#include <math.h>
+
+#include "wol_q3b_common.cuh"
+
+namespace wol {
+
+struct CellGrid {
+    const uint32_t *cell_start;
+    const void *recs;
+    int nc0, nc1, nc2;
+};
+
+// Visits every record of the half-width-1 stencil around cell (cx, cy, cz) of frame f exactly once
+// (axes with <= 3 cells are enumerated completely).
+template <typename F>
+__device__ __forceinline__ void sweep_stencil1(const CellGrid &g, int f, int cx, int cy, int cz, F &&fn) {
+    const int cntx = min(3, g.nc0), cnty = min(3, g.nc1), cntz = min(3, g.nc2);
+    const int xs = (g.nc0 <= 3) ? 0 : (cx - 1 + g.nc0) % g.nc0;
+    const int ys = (g.nc1 <= 3) ? 0 : (cy - 1 + g.nc1) % g.nc1;
+    const int zs = (g.nc2 <= 3) ? 0 : (cz - 1 + g.nc2) % g.nc2;
+    const size_t base = (size_t)f * g.nc0 * g.nc1 * g.nc2;
+    for (int iz = 0; iz < cntz; ++iz) {
+        const int z = (zs + iz) % g.nc2;
+        for (int iy = 0; iy < cnty; ++iy) {
+            const int y = (ys + iy) % g.nc1;
+            for (int ix = 0; ix < cntx; ++ix) {
+                const int x = (xs + ix) % g.nc0;
+                const size_t c = base + ((size_t)z * g.nc1 + y) * g.nc0 + x;
+                const int j1 = (int)__ldg(g.cell_start + c + 1);
+                for (int j = (int)__ldg(g.cell_start + c); j < j1; ++j) fn(j);
+            }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load3(const void *p, int dtype, size_t i, T &x, T &y, T &z) {
+    if (dtype == WOL_F64) {
+        const double *d = reinterpret_cast<const double *>(p) + 3 * i;
+        x = (T)d[0]; y = (T)d[1]; z = (T)d[2];
+    } else {
+        const float *d = reinterpret_cast<const float *>(p) + 3 * i;
+        x = (T)d[0]; y = (T)d[1]; z = (T)d[2];
+    }
+}
+
+struct BoxD {
+    double Lx, Ly, Lz, iLx, iLy, iLz;
+};
+// iBoxL = merge(1/BoxL, 0, BoxL >= 0)  (waterlib.f90:41); the dense / small-array routines keep the
+// reference's "negative edge = not periodic" rule because they need no cell grid
+__device__ __forceinline__ BoxD load_box(const double *b) {
+    BoxD o;
+    o.Lx = b[0]; o.Ly = b[1]; o.Lz = b[2];
+    o.iLx = (o.Lx >= 0.0) ? __ddiv_rn(1.0, o.Lx) : 0.0;
+    o.iLy = (o.Ly >= 0.0) ? __ddiv_rn(1.0, o.Ly) : 0.0;
+    o.iLz = (o.Lz >= 0.0) ? __ddiv_rn(1.0, o.Lz) : 0.0;
+    return o;
+}
+
+// ---- exclusive scan of pair counts (n3 -> angle offsets) -----------------------------------------
+
+__global__ void pair_counts_kernel(const int32_t *__restrict__ n3, size_t n, uint32_t *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t k = (uint32_t)max(n3[i], 0);
+        out[i] = k * (k - (k ? 1u : 0u)) / 2u;
+    } else if (i == n) {
+        out[i] = 0u;
+    }
+}
+
+// ---- materialised three-body angles in the reference's order ---------------------------------------
+
+constexpr int kMatCap = 64;
+
+struct MatParams {
+    CellGrid grid;
+    const double *box;
+    const void *centres;
+    int centre_dtype;
+    int n_frames, n_pos, n_centres;
+    double lowsq, highsq;
+    const uint32_t *offsets;  // [n_frames * n_centres + 1]
+    double *angles;
+    uint32_t *counters;
+};
+
+__global__ void __launch_bounds__(128) angles_fill_kernel(const MatParams P) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)P.n_frames * P.n_centres;
+    if (g >= total) return;
+    const int f = (int)(g / P.n_centres);
+    const int m = (int)(g - (size_t)f * P.n_centres);
+    const BoxD b = load_box(P.box + (size_t)f * 3);
+    double rx, ry, rz;
+    if (P.centres) load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);
+    else load3<double>(P.centres, 0, 0, rx, ry, rz);  // unreachable: centres are always given (see launcher)
+    (void)m;
+    const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
+              cz = cell_coord(rz, b.iLz, P.grid.nc2);
+    int idx[kMatCap];
+    double ex[kMatCap], ey[kMatCap], ez[kMatCap], en[kMatCap];
+    int K = 0;
+    bool over = false;
+    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+        double px, py, pz;
+        int id;
+        RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+        const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
+        const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
+        const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+        const double s = sumsq3<double>(dx, dy, dz);
+        if (s > P.lowsq && s <= P.highsq) {
+            if (K >= kMatCap) {
+                over = true;
+                return;
+            }
+            // insertion by atom index: the reference gathers neighbours with a boolean mask, i.e. in
+            // ascending index order (water_properties.py:243)
+            int at = K;
+            while (at > 0 && idx[at - 1] > id) {
+                idx[at] = idx[at - 1]; ex[at] = ex[at - 1]; ey[at] = ey[at - 1]; ez[at] = ez[at - 1]; en[at] = en[at - 1];
+                --at;
+            }
+            idx[at] = id;
+            ex[at] = __dsub_rn(__dadd_rn(rx, dx), rx);
+            ey[at] = __dsub_rn(__dadd_rn(ry, dy), ry);
+            ez[at] = __dsub_rn(__dadd_rn(rz, dz), rz);
+            en[at] = sumsq3<double>(ex[at], ey[at], ez[at]);
+            ++K;
+        }
+    });
+    if (over) {
+        atomicAdd(P.counters + kCntFatal, 1u);
+        return;
+    }
+    size_t o = P.offsets[g];
+    if ((size_t)P.offsets[g + 1] - o != (size_t)K * (K - 1) / 2) {  // counts and fill disagree: never expected
+        atomicAdd(P.counters + kCntFatal, 1u);
+        return;
+    }
+    for (int a = 0; a < K; ++a)
+        for (int c = a + 1; c < K; ++c) {
+            double ang;
+            if (en[a] == 0.0 || en[c] == 0.0) ang = 0.0;
+            else ang = angle_deg_from_cos(clamped_cos<double>(dot3<double>(ex[a], ey[a], ez[a], ex[c], ey[c], ez[c]), en[a], en[c]));
+            P.angles[o++] = ang;
+        }
+}
+
+// ---- np.histogram + tetrahedral-window sums over an array of angles --------------------------------
+
+__global__ void __launch_bounds__(256) histogram_kernel(const double *__restrict__ x, size_t n, double lo, double hi, int nbins,
+                                                        unsigned long long *__restrict__ hist, double tet_lo, double tet_hi,
+                                                        double *__restrict__ tet) {
+    extern __shared__ unsigned s_hist[];
+    const bool use_smem = nbins <= kMaxSmemBins;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    const HistSpec hs = hist_spec(lo, hi, nbins);
+    double cnt = 0.0, sc = 0.0, sc2 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        const int b = hist_bin(hs, v);
+        if (b >= 0) {
+            if (use_smem) atomicAdd(s_hist + b, 1u);
+            else atomicAdd(hist + b, 1ull);
+        }
+        if (v >= tet_lo && v <= tet_hi) {
+            const double c = cos(__ddiv_rn(__dmul_rn(v, 3.141592653589793), 180.0));
+            cnt += 1.0;
+            sc += c;
+            sc2 += c * c;
+        }
+    }
+    cnt = warp_sum(cnt);
+    sc = warp_sum(sc);
+    sc2 = warp_sum(sc2);
+    if (tet && (threadIdx.x & 31) == 0 && cnt != 0.0) {
+        atomicAdd(tet + 0, cnt);
+        atomicAdd(tet + 1, sc);
+        atomicAdd(tet + 2, sc2);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+    }
+}
+
+// ---- dense neighbour matrix, reimage, tetracosang, lsidists (f2py-compatible small-array routines) ---
+
+__global__ void neighbor_matrix_kernel(const void *sub, int sub_dtype, int m, const void *pos, int pos_dtype, int n,
+                                       const double *box, double lowsq, double highsq, int32_t *out) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)m * n) return;
+    const int i = (int)(g / n), j = (int)(g - (size_t)i * n);
+    const BoxD b = load_box(box);
+    double rx, ry, rz, px, py, pz;
+    load3<double>(sub, sub_dtype, i, rx, ry, rz);
+    load3<double>(pos, pos_dtype, j, px, py, pz);
+    const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
+    const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
+    const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+    const double s = sumsq3<double>(dx, dy, dz);
+    out[g] = (s > lowsq && s <= highsq) ? 1 : 0;
+}
+
+// mode 0: reimaged positions (n,3); mode 1: lsiDists distances (n)
+__global__ void reimage_kernel(const double *pos, int n, const double *ref, const double *box, double *out, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BoxD b = load_box(box);
+    const double dx = min_image_1<double, true>(pos[3 * i + 0], ref[0], b.Lx, b.iLx);
+    const double dy = min_image_1<double, true>(pos[3 * i + 1], ref[1], b.Ly, b.iLy);
+    const double dz = min_image_1<double, true>(pos[3 * i + 2], ref[2], b.Lz, b.iLz);
+    if (mode == 0) {
+        out[3 * i + 0] = __dadd_rn(ref[0], dx);
+        out[3 * i + 1] = __dadd_rn(ref[1], dy);
+        out[3 * i + 2] = __dadd_rn(ref[2], dz);
+    } else {
+        out[i] = __dsqrt_rn(sumsq3<double>(dx, dy, dz));
+    }
+}
+
+__global__ void tetracosang_kernel(const double *ref, const double *neigh, int k, const double *box, double *out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= k * k) return;
+    const int a = g / k, c = g - a * k;
+    if (a == c) {
+        out[g] = 0.0;  // the Fortran leaves the diagonal unwritten; f2py users see zeros on fresh pages
+        return;
+    }
+    const BoxD b = load_box(box);
+    double v[2][3], nrm[2];
+    const int who[2] = {a, c};
+    for (int t = 0; t < 2; ++t) {
+        const double *p = neigh + 3 * who[t];
+        const double dx = min_image_1<double, true>(p[0], ref[0], b.Lx, b.iLx);
+        const double dy = min_image_1<double, true>(p[1], ref[1], b.Ly, b.iLy);
+        const double dz = min_image_1<double, true>(p[2], ref[2], b.Lz, b.iLz);
+        v[t][0] = __dsub_rn(__dadd_rn(ref[0], dx), ref[0]);
+        v[t][1] = __dsub_rn(__dadd_rn(ref[1], dy), ref[1]);
+        v[t][2] = __dsub_rn(__dadd_rn(ref[2], dz), ref[2]);
+        nrm[t] = sumsq3<double>(v[t][0], v[t][1], v[t][2]);
+    }
+    if (nrm[0] == 0.0 || nrm[1] == 0.0) {
+        out[g] = 0.0;
+        return;
+    }
+    out[g] = angle_deg_from_cos(clamped_cos<double>(dot3<double>(v[0][0], v[0][1], v[0][2], v[1][0], v[1][1], v[1][2]), nrm[0], nrm[1]));
+}
+
+// ---- hydrogen bonds (generalHbonds) -------------------------------------------------------------------
+
+struct HbParams {
+    CellGrid grid;  // cell list over the donor heavy atoms
+    const double *box;
+    const void *acc;
+    int acc_dtype;
+    const void *donh;
+    int donh_dtype;
+    int n_frames, n_acc, n_don;
+    double cutsq, tiny;
+    double cos_thr;        // bond <=> clamped cosine <= cos_thr (host bisection of AngBetween, wol_angle_threshold)
+    int minus_one_bonds;   // whether the -180 degrees AngBetween returns for cosine -1 passes angCut
+    int32_t *acc_count;    // [F][n_acc]
+    int32_t *don_count;    // [F][n_don]  (atomic)
+    int32_t *dense;        // optional [F][n_acc][n_don]
+    int2 *pairs;           // optional (acceptor, donor) list
+    uint32_t pair_capacity;
+    uint32_t *pair_counter;
+};
+
+__global__ void __launch_bounds__(128) hbond_kernel(const HbParams P) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)P.n_frames * P.n_acc) return;
+    const int f = (int)(g / P.n_acc);
+    const int i = (int)(g - (size_t)f * P.n_acc);
+    const BoxD b = load_box(P.box + (size_t)f * 3);
+    double ax, ay, az;
+    load3<double>(P.acc, P.acc_dtype, g, ax, ay, az);
+    const int cx = cell_coord(ax, b.iLx, P.grid.nc0), cy = cell_coord(ay, b.iLy, P.grid.nc1),
+              cz = cell_coord(az, b.iLz, P.grid.nc2);
+    int count = 0;
+    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+        double dxp, dyp, dzp;
+        int jd;
+        RecTraits<double>::load(P.grid.recs, (size_t)j, dxp, dyp, dzp, jd);
+        // distvec = donor - acceptor, reimaged; reject distSq > distCut^2 or distSq <= 1.0E-2 (:1184-1188)
+        const double ddx = min_image_1<double, true>(dxp, ax, b.Lx, b.iLx);
+        const double ddy = min_image_1<double, true>(dyp, ay, b.Ly, b.iLy);
+        const double ddz = min_image_1<double, true>(dzp, az, b.Lz, b.iLz);
+        const double s = sumsq3<double>(ddx, ddy, ddz);
+        if (!(s > P.tiny && s <= P.cutsq)) return;
+        double hx, hy, hz;
+        load3<double>(P.donh, P.donh_dtype, (size_t)f * P.n_don + jd, hx, hy, hz);
+        // unit vectors from the hydrogen to the acceptor and to the donor, each reimaged (:1190-1198)
+        double v1x = min_image_1<double, true>(ax, hx, b.Lx, b.iLx);
+        double v1y = min_image_1<double, true>(ay, hy, b.Ly, b.iLy);
+        double v1z = min_image_1<double, true>(az, hz, b.Lz, b.iLz);
+        const double n1 = __dsqrt_rn(sumsq3<double>(v1x, v1y, v1z));
+        v1x = __ddiv_rn(v1x, n1); v1y = __ddiv_rn(v1y, n1); v1z = __ddiv_rn(v1z, n1);
+        double v2x = min_image_1<double, true>(dxp, hx, b.Lx, b.iLx);
+        double v2y = min_image_1<double, true>(dyp, hy, b.Ly, b.iLy);
+        double v2z = min_image_1<double, true>(dzp, hz, b.Lz, b.iLz);
+        const double n2 = __dsqrt_rn(sumsq3<double>(v2x, v2y, v2z));
+        v2x = __ddiv_rn(v2x, n2); v2y = __ddiv_rn(v2y, n2); v2z = __ddiv_rn(v2z, n2);
+        const double c = fmin(1.0, fmax(-1.0, dot3<double>(v1x, v1y, v1z, v2x, v2y, v2z)));
+        const bool bond = (c == -1.0) ? (P.minus_one_bonds != 0) : (c <= P.cos_thr);
+        if (!bond) return;
+        ++count;
+        if (P.don_count) atomicAdd(P.don_count + (size_t)f * P.n_don + jd, 1);
+        if (P.dense) P.dense[((size_t)f * P.n_acc + i) * P.n_don + jd] = 1;
+        if (P.pairs) {
+            const uint32_t at = atomicAdd(P.pair_counter, 1u);
+            if (at < P.pair_capacity) P.pairs[at] = make_int2(f * P.n_acc + i, jd);
+        }
+    });
+    if (P.acc_count) P.acc_count[g] = count;
+}
+
+// H-bond locations of HBondsGeneral (structureLibs/water_properties.py:709-714): halfway between the
+// acceptor and the donor hydrogen imaged around it.
+__global__ void hbond_loc_kernel(const int2 *__restrict__ pairs, int n_pairs, const void *acc, int acc_dtype, int n_acc,
+                                 const void *donh, int donh_dtype, int n_don, const double *box, double *__restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_pairs) return;
+    const int2 pr = pairs[g];
+    const int f = pr.x / n_acc;
+    const BoxD b = load_box(box + (size_t)f * 3);
+    double ax, ay, az, hx, hy, hz;
+    load3<double>(acc, acc_dtype, (size_t)pr.x, ax, ay, az);
+    load3<double>(donh, donh_dtype, (size_t)f * n_don + pr.y, hx, hy, hz);
+    const double rx = __dadd_rn(ax, min_image_1<double, true>(hx, ax, b.Lx, b.iLx));
+    const double ry = __dadd_rn(ay, min_image_1<double, true>(hy, ay, b.Ly, b.iLy));
+    const double rz = __dadd_rn(az, min_image_1<double, true>(hz, az, b.Lz, b.iLz));
+    out[3 * (size_t)g + 0] = __dmul_rn(0.5, __dadd_rn(rx, ax));
+    out[3 * (size_t)g + 1] = __dmul_rn(0.5, __dadd_rn(ry, ay));
+    out[3 * (size_t)g + 2] = __dmul_rn(0.5, __dadd_rn(rz, az));
+}
+
+// ---- hydration shell: atoms of the cell list within (low, cutoff] of any solute atom --------------------
+
+struct ShellParams {
+    CellGrid grid;  // cell list over the waters
+    const double *box;
+    const void *sol;
+    int sol_dtype;
+    int n_frames, n_sol, n_pos;
+    double lowsq, highsq;
+    int32_t *mask;  // [F][n_pos], set to 1 (caller zero-fills)
+};
+
+__global__ void __launch_bounds__(128) shell_kernel(const ShellParams P) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)P.n_frames * P.n_sol) return;
+    const int f = (int)(g / P.n_sol);
+    const BoxD b = load_box(P.box + (size_t)f * 3);
+    double sx, sy, sz;
+    load3<double>(P.sol, P.sol_dtype, g, sx, sy, sz);
+    const int cx = cell_coord(sx, b.iLx, P.grid.nc0), cy = cell_coord(sy, b.iLy, P.grid.nc1),
+              cz = cell_coord(sz, b.iLz, P.grid.nc2);
+    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+        double px, py, pz;
+        int id;
+        RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+        const double dx = min_image_1<double, true>(px, sx, b.Lx, b.iLx);
+        const double dy = min_image_1<double, true>(py, sy, b.Ly, b.iLy);
+        const double dz = min_image_1<double, true>(pz, sz, b.Lz, b.iLz);
+        const double s = sumsq3<double>(dx, dy, dz);
+        if (s > P.lowsq && s <= P.highsq) P.mask[(size_t)f * P.n_pos + id] = 1;
+    });
+}
+
+static CellGrid make_grid(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
+    char *ws = reinterpret_cast<char *>(workspace);
+    CellGrid g;
+    g.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
+    g.recs = ws + lay.off_recs;
+    g.nc0 = nc[0];
+    g.nc1 = nc[1];
+    g.nc2 = nc[2];
+    return g;
+}
+
+}  // namespace wol
+
+using namespace wol;
+
+extern "C" {
+
+int wol_angle_offsets(const int32_t *n3, int64_t n, uint32_t *offsets, uint32_t *scratch, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || !offsets || !scratch || (!n3 && n > 0)) return set_error(WOL_ERR_INVALID, "wol_angle_offsets: null argument");
+    if (n >= (1LL << 26)) return set_error(WOL_ERR_RANGE, "wol_angle_offsets: more than 2^26 centres; materialise in batches");
+    const size_t cnt = (size_t)n + 1;
+    pair_counts_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(n3, (size_t)n, offsets);
+    add_launches(1);
+    exclusive_scan_u32(offsets, cnt, scratch, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_angle_offsets", e);
+    return WOL_OK;
+}
+
+int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos,
+                    int32_t n_centres, const int32_t nc[3], double edge_min, double low3, double high3, void *workspace,
+                    size_t workspace_bytes, const uint32_t *offsets, double *angles, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!centres || !box || !nc || !workspace || !offsets || (!angles)) return set_error(WOL_ERR_INVALID, "wol_angles_fill: null argument");
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && high3 * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "cutoff %.6g exceeds the planned cell edge %.6g", high3, edge_min);
+    const WorkspaceLayout lay = workspace_layout(n_frames, n_pos, n_centres, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    MatParams P;
+    P.grid = make_grid(workspace, lay, nc);
+    P.box = box;
+    P.centres = centres;
+    P.centre_dtype = centre_dtype;
+    P.n_frames = n_frames;
+    P.n_pos = n_pos;
+    P.n_centres = n_centres;
+    P.lowsq = low3 * low3;
+    P.highsq = high3 * high3;
+    P.offsets = offsets;
+    P.angles = angles;
+    P.counters = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + lay.off_counters);
+    const size_t total = (size_t)n_frames * n_centres;
+    if (total > 0) {
+        angles_fill_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_angles_fill", e);
+    return WOL_OK;
+}
+
+int wol_histogram(const double *x, int64_t n, double lo, double hi, int32_t nbins, int64_t *hist, double tet_lo,
+                  double tet_hi, double *tet_sums, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || nbins < 1 || !hist || !(hi > lo) || (!x && n > 0)) return set_error(WOL_ERR_INVALID, "wol_histogram: bad argument");
+    if (n == 0) return WOL_OK;
+    const size_t smem = nbins <= kMaxSmemBins ? sizeof(unsigned) * nbins : 0;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    histogram_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x, (size_t)n, lo, hi, nbins, reinterpret_cast<unsigned long long *>(hist),
+                                                              tet_lo, tet_hi, tet_sums);
+    add_launches(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_histogram", e);
+    return WOL_OK;
+}
+
+int wol_neighbor_matrix(const void *sub, int32_t sub_dtype, int32_t m, const void *pos, int32_t pos_dtype, int32_t n,
+                        const double *box, double lowcut, double highcut, int32_t *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 0 || n < 0 || !box || !out || !sub || !pos) return set_error(WOL_ERR_INVALID, "wol_neighbor_matrix: bad argument");
+    const size_t total = (size_t)m * n;
+    if (total >= (1ULL << 40)) return set_error(WOL_ERR_RANGE, "dense neighbour matrix too large");
+    if (total > 0) {
+        neighbor_matrix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(sub, sub_dtype, m, pos, pos_dtype, n, box,
+                                                                                  lowcut * lowcut, highcut * highcut, out);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_neighbor_matrix", e);
+    return WOL_OK;
+}
+
+int wol_reimage(const double *pos, int32_t n, const double *ref, const double *box, double *out, int32_t mode, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || !ref || !box || !out || (!pos && n > 0) || (mode != 0 && mode != 1)) return set_error(WOL_ERR_INVALID, "wol_reimage: bad argument");
+    if (n > 0) {
+        reimage_kernel<<<(n + 127) / 128, 128, 0, stream>>>(pos, n, ref, box, out, mode);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_reimage", e);
+    return WOL_OK;
+}
+
+int wol_tetracosang(const double *ref, const double *neigh, int32_t k, const double *box, double *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 0 || !ref || !box || !out || (!neigh && k > 0)) return set_error(WOL_ERR_INVALID, "wol_tetracosang: bad argument");
+    if (k > 0) {
+        tetracosang_kernel<<<(k * k + 127) / 128, 128, 0, stream>>>(ref, neigh, k, box, out);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_tetracosang", e);
+    return WOL_OK;
+}
+
+int wol_hbond_counts(const wol_hbond_args *a, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || a->struct_size != sizeof(wol_hbond_args)) return set_error(WOL_ERR_INVALID, "wol_hbond_counts: bad args struct");
+    if (!a->acc || !a->donh || !a->box || !a->workspace) return set_error(WOL_ERR_INVALID, "wol_hbond_counts: null argument");
+    if (a->n_frames < 1 || a->n_acc < 0 || a->n_don < 0) return set_error(WOL_ERR_INVALID, "wol_hbond_counts: negative size");
+    for (int k = 0; k < 3; ++k)
+        if (a->nc[k] > 3 && a->dist_cut * (1.0 + 1e-9) > a->edge_min)
+            return set_error(WOL_ERR_INVALID, "H-bond distance cutoff %.6g exceeds the planned cell edge %.6g", a->dist_cut, a->edge_min);
+    const WorkspaceLayout lay = workspace_layout(a->n_frames, a->n_don, a->n_don, a->nc);
+    if (a->workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", a->workspace_bytes, lay.total);
+    HbParams P;
+    P.grid = make_grid(a->workspace, lay, a->nc);
+    P.box = a->box;
+    P.acc = a->acc;
+    P.acc_dtype = a->acc_dtype;
+    P.donh = a->donh;
+    P.donh_dtype = a->donh_dtype;
+    P.n_frames = a->n_frames;
+    P.n_acc = a->n_acc;
+    P.n_don = a->n_don;
+    P.cutsq = a->dist_cut * a->dist_cut;
+    P.tiny = (double)1.0e-2f;  // the Fortran literal 1.0E-2 is single precision (waterlib.f90:1187)
+    int m1 = 0;
+    P.cos_thr = angle_cos_threshold(a->ang_cut, &m1);
+    P.minus_one_bonds = m1;
+    P.acc_count = a->acc_count;
+    P.don_count = a->don_count;
+    P.dense = a->dense;
+    P.pairs = reinterpret_cast<int2 *>(a->pairs);
+    P.pair_capacity = a->pair_capacity;
+    P.pair_counter = a->pair_counter;
+    const size_t total = (size_t)a->n_frames * a->n_acc;
+    if (total > 0 && a->n_don > 0) {
+        hbond_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_hbond_counts", e);
+    return WOL_OK;
+}
+
+int wol_hbond_locations(const int32_t *pairs, int32_t n_pairs, const void *acc, int32_t acc_dtype, int32_t n_acc,
+                        const void *donh, int32_t donh_dtype, int32_t n_don, const double *box, double *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs < 0 || n_acc < 1 || n_don < 1 || !acc || !donh || !box || !out || (!pairs && n_pairs > 0))
+        return set_error(WOL_ERR_INVALID, "wol_hbond_locations: bad argument");
+    if (n_pairs > 0) {
+        hbond_loc_kernel<<<(n_pairs + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const int2 *>(pairs), n_pairs, acc, acc_dtype,
+                                                                    n_acc, donh, donh_dtype, n_don, box, out);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_hbond_locations", e);
+    return WOL_OK;
+}
+
+int wol_shell_mask(const void *sol, int32_t sol_dtype, int32_t n_sol, const double *box, int32_t n_frames, int32_t n_pos,
+                   const int32_t nc[3], double edge_min, double lowcut, double cutoff, void *workspace, size_t workspace_bytes,
+                   int32_t *mask, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sol || !box || !nc || !workspace || !mask) return set_error(WOL_ERR_INVALID, "wol_shell_mask: null argument");
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && cutoff * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "shell cutoff %.6g exceeds the planned cell edge %.6g", cutoff, edge_min);
+    const WorkspaceLayout lay = workspace_layout(n_frames, n_pos, n_pos, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    ShellParams P;
+    P.grid = make_grid(workspace, lay, nc);
+    P.box = box;
+    P.sol = sol;
+    P.sol_dtype = sol_dtype;
+    P.n_frames = n_frames;
+    P.n_sol = n_sol;
+    P.n_pos = n_pos;
+    P.lowsq = lowcut * lowcut;
+    P.highsq = cutoff * cutoff;
+    P.mask = mask;
+    const size_t total = (size_t)n_frames * n_sol;
+    if (total > 0 && n_pos > 0) {
+        shell_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_shell_mask", e);
+    return WOL_OK;
+}
+
+}  // extern "C"

@@ -96,6 +96,11 @@ static double last_true(F pred) {
     return o2d(lo);
 }
 
+double angle_cos_threshold(double ang_deg, int *minus_one_passes) {
+    if (minus_one_passes) *minus_one_passes = ref_angle_deg(-1.0) >= ang_deg ? 1 : 0;
+    return last_true([&](double c) { return ref_angle_deg(c) >= ang_deg; });
+}
+
 }  // namespace wol
 
 using namespace wol;

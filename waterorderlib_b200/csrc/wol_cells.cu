@@ -222,6 +222,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__re
     }
 }
 
+int exclusive_scan_u32(uint32_t *data, size_t n, uint32_t *block_sums, cudaStream_t stream) {
+    const int blocks = (int)((n + kScanTile - 1) / kScanTile);
+    if (blocks < 1) return WOL_OK;
+    scan_reduce_kernel<<<blocks, kScanThreads, 0, stream>>>(data, n, block_sums);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, blocks);
+    scan_apply_kernel<<<blocks, kScanThreads, 0, stream>>>(data, n, block_sums);
+    add_launches(3);
+    return WOL_OK;
+}
+
 template <typename T, typename R>
 static void launch_passes(const BuildParams &p, unsigned blocks, bool scatter, cudaStream_t stream) {
     if (scatter)
@@ -269,10 +279,7 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
         launch_pass(p, (unsigned)blocks, false, pos_dtype, precision, stream);
         add_launches(1);
     }
-    scan_reduce_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, lay.scan_blocks);
-    scan_apply_kernel<<<lay.scan_blocks, kScanThreads, 0, stream>>>(p.cell_start, n_scan, block_sums);
-    add_launches(3);
+    exclusive_scan_u32(p.cell_start, n_scan, block_sums, stream);
     if (blocks > 0) {
         launch_pass(p, (unsigned)blocks, true, pos_dtype, precision, stream);
         add_launches(1);

@@ -19,4 +19,11 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
 
 int sm_count();
 
+// exclusive prefix sum over n uint32 values, in place (three launches); block_sums: n / kScanTile + 2 values
+int exclusive_scan_u32(uint32_t *data, size_t n, uint32_t *block_sums, cudaStream_t stream);
+
+// largest clamped cosine whose AngBetween angle (fortran/waterlib.f90:954-965) is >= ang_deg, found by
+// bisection with the host libm; *minus_one_passes = whether the -180 it returns for cosine -1 passes
+double angle_cos_threshold(double ang_deg, int *minus_one_passes);
+
 }  // namespace wol

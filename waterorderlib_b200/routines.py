@@ -1,0 +1,295 @@
+"""Host side of the value-returning routines of the per-frame path (include/wol_capi.h, second half):
+materialised three-body angles, np.histogram on the device, dense neighbour matrices, reimage /
+tetracosang / lsidists, hydrogen-bond counting and hydration-shell selection.
+
+Like engine.py this module only moves pointers: PyTorch owns device memory and streams, libwol.so's sm_100a
+kernels compute.  Inputs may be numpy arrays or torch tensors (CUDA tensors are used in place); outputs are
+torch CUDA tensors -- the numpy-in / numpy-out drop-in layer is waterorderlib_b200.structureLibs.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import engine
+from ._capi import WOL_F64, WOL_PREC_FP64, HbondArgs, check, lib
+
+_vp = ctypes.c_void_p
+
+
+def _device(device=None, *tensors):
+    if device is not None:
+        return torch.device(device)
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("waterorderlib_b200 needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f64(a, device, shape_tail=None):
+    """-> contiguous float64 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device, dtype=torch.float64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(device)
+    t = t.contiguous()
+    if shape_tail is not None and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise ValueError("expected trailing shape %s, got %s" % (shape_tail, tuple(t.shape)))
+    return t
+
+
+def _box3(box, device):
+    """BoxDims as (3,) or (1,3) -> float64 CUDA tensor of 3 values (the reference accepts both,
+    structureLibs/orderParam_lib.py:1315 vs :183)."""
+    t = _f64(box, device).reshape(-1)
+    if t.numel() != 3:
+        raise ValueError("box must hold 3 edge lengths, got %d values" % t.numel())
+    return t
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+class CellList:
+    """A built cell list over one batch of frames (FP64 records), reusable by several queries."""
+
+    def __init__(self, pos, box, r_cell, device=None, workspace=None, n_centres_max=0):
+        self.device = _device(device, pos)
+        self.pos = engine.as_device_positions(pos, self.device)
+        self.F, self.N = int(self.pos.shape[0]), int(self.pos.shape[1])
+        self.box_h = engine.as_host_boxes(box, self.F)
+        self.box_d = torch.from_numpy(self.box_h.copy()).to(self.device)
+        self.nc, self.edge_min, self.box_max = engine.plan_grid(self.box_h, r_cell)
+        self.n_centres_max = max(int(n_centres_max), self.N)
+        self.ws = workspace if workspace is not None else engine.Workspace(self.device)
+        need = lib().wol_workspace_bytes(self.F, self.N, self.n_centres_max, ctypes.byref(self.nc))
+        self.ws_ptr, self.ws_bytes = self.ws.get(need)
+        with torch.cuda.device(self.device):
+            check(lib().wol_cell_build(_vp(self.pos.data_ptr()), engine._dtype_code(self.pos), _vp(self.box_d.data_ptr()),
+                                       self.F, self.N, ctypes.byref(self.nc), WOL_PREC_FP64, _vp(self.ws_ptr), self.ws_bytes,
+                                       _stream()), "wol_cell_build")
+        self.launches = lib().wol_last_launch_count()
+
+    def status(self):
+        st = (ctypes.c_int32 * 4)()
+        with torch.cuda.device(self.device):
+            check(lib().wol_status(_vp(self.ws_ptr), self.F, self.N, self.n_centres_max, ctypes.byref(self.nc), _stream(),
+                                   ctypes.byref(st)), "wol_status")
+        return tuple(st)
+
+
+def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
+    """getCosAngs (structureLibs/water_properties.py:210-250) for one or several frames.
+    Returns (angles f64 (n_angles,), n3 int32 (F, M), offsets uint32-as-int64 (F*M+1,)): the flat angle
+    array in the reference's order, the per-centre neighbour counts and where each centre's block starts."""
+    device = _device(device, pos, sub)
+    pos_d = engine.as_device_positions(pos, device)
+    cen_d = pos_d if sub is None else engine.as_device_positions(sub, device)
+    if cen_d.shape[0] != pos_d.shape[0]:
+        raise ValueError("sub and pos must hold the same number of frames")
+    F, N, M = int(pos_d.shape[0]), int(pos_d.shape[1]), int(cen_d.shape[1])
+    if M == 0 or N == 0:
+        return (torch.zeros(0, dtype=torch.float64, device=device), torch.zeros((F, M), dtype=torch.int32, device=device),
+                torch.zeros(F * M + 1, dtype=torch.int64, device=device))
+    ws = engine.Workspace(device)
+    r = engine.q3b_frames(pos_d, box, cen_d, do_q=False, do_3body=True, low3=low, high3=high, want=("n3",),
+                          workspace=ws, device=device, r_cell=max(float(high), 1e-3))
+    n3 = r["n3"]
+    L = lib()
+    total = F * M
+    offsets = torch.empty(total + 1, dtype=torch.int32, device=device)
+    scratch = torch.empty(total // 2048 + 8, dtype=torch.int32, device=device)
+    box_h = engine.as_host_boxes(box, F)
+    box_d = torch.from_numpy(box_h.copy()).to(device)
+    nc, edge_min, _ = engine.plan_grid(box_h, max(float(high), 1e-3))
+    ws_ptr, ws_bytes = ws.get(L.wol_workspace_bytes(F, N, M, ctypes.byref(nc)))
+    with torch.cuda.device(device):
+        check(L.wol_angle_offsets(_vp(n3.data_ptr()), total, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()), _stream()),
+              "wol_angle_offsets")
+        n_angles = int(offsets[-1].item()) & 0xFFFFFFFF
+        angles = torch.empty(n_angles, dtype=torch.float64, device=device)
+        if n_angles > 0:
+            check(L.wol_angles_fill(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(box_d.data_ptr()), F, N, M,
+                                    ctypes.byref(nc), edge_min, float(low), float(high), _vp(ws_ptr), ws_bytes,
+                                    _vp(offsets.data_ptr()), _vp(angles.data_ptr()), _stream()), "wol_angles_fill")
+            st = (ctypes.c_int32 * 4)()
+            check(L.wol_status(_vp(ws_ptr), F, N, M, ctypes.byref(nc), _stream(), ctypes.byref(st)), "wol_status")
+    return angles, n3, offsets.to(torch.int64) & 0xFFFFFFFF
+
+
+def histogram(x, nbins=500, bin_range=(0.0, 180.0), tet_window=(100.0, 120.0), device=None):
+    """np.histogram(x, bins=nbins, range=bin_range) counts (int64 CUDA tensor) and the
+    (count, sum cos, sum cos^2) of tetrahedralMetrics' window (water_properties.py:328-335)."""
+    device = _device(device, x)
+    xd = _f64(x, device).reshape(-1)
+    hist = torch.zeros(nbins, dtype=torch.int64, device=device)
+    tet = torch.zeros(3, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_histogram(_vp(xd.data_ptr()), xd.numel(), float(bin_range[0]), float(bin_range[1]), int(nbins),
+                                  _vp(hist.data_ptr()), float(tet_window[0]), float(tet_window[1]), _vp(tet.data_ptr()),
+                                  _stream()), "wol_histogram")
+    return hist, tet
+
+
+def neighbor_matrix(sub, pos, box, low, high, device=None):
+    """nearNeighbors / allNearNeighbors (fortran/waterlib.f90:710-743, :830-862) -> (m, n) int32 CUDA tensor."""
+    device = _device(device, pos, sub)
+    pos_d = _f64(pos, device, (3,)).reshape(-1, 3)
+    sub_d = pos_d if sub is None else _f64(sub, device, (3,)).reshape(-1, 3)
+    box_d = _box3(box, device)
+    m, n = int(sub_d.shape[0]), int(pos_d.shape[0])
+    out = torch.empty((m, n), dtype=torch.int32, device=device)
+    if m and n:
+        with torch.cuda.device(device):
+            check(lib().wol_neighbor_matrix(_vp(sub_d.data_ptr()), WOL_F64, m, _vp(pos_d.data_ptr()), WOL_F64, n,
+                                            _vp(box_d.data_ptr()), float(low), float(high), _vp(out.data_ptr()), _stream()),
+                  "wol_neighbor_matrix")
+    return out
+
+
+def _reimage(pos, ref, box, mode, device):
+    device = _device(device, pos, ref)
+    pos_d = _f64(pos, device, (3,)).reshape(-1, 3)
+    ref_d = _f64(ref, device).reshape(-1)
+    if ref_d.numel() != 3:
+        raise ValueError("reference position must hold 3 values")
+    box_d = _box3(box, device)
+    n = int(pos_d.shape[0])
+    out = torch.empty((n, 3) if mode == 0 else (n,), dtype=torch.float64, device=device)
+    if n:
+        with torch.cuda.device(device):
+            check(lib().wol_reimage(_vp(pos_d.data_ptr()), n, _vp(ref_d.data_ptr()), _vp(box_d.data_ptr()),
+                                    _vp(out.data_ptr()), mode, _stream()), "wol_reimage")
+    return out
+
+
+def reimage(pos, ref, box, device=None):
+    """reimage (fortran/waterlib.f90:32-47): ref + minimum-image(pos - ref) -> (n,3)."""
+    return _reimage(pos, ref, box, 0, device)
+
+
+def lsidists(ref, neigh, box, device=None):
+    """lsiDists (fortran/waterlib.f90:900-918): minimum-image distances ref -> neigh, (n,)."""
+    return _reimage(neigh, ref, box, 1, device)
+
+
+def tetracosang(ref, neigh, box, device=None):
+    """tetraCosAng (fortran/waterlib.f90:867-895): (k,k) angles in degrees about ref, zero diagonal."""
+    device = _device(device, neigh, ref)
+    nd = _f64(neigh, device, (3,)).reshape(-1, 3)
+    rd = _f64(ref, device).reshape(-1)
+    box_d = _box3(box, device)
+    k = int(nd.shape[0])
+    out = torch.zeros((k, k), dtype=torch.float64, device=device)
+    if k:
+        with torch.cuda.device(device):
+            check(lib().wol_tetracosang(_vp(rd.data_ptr()), _vp(nd.data_ptr()), k, _vp(box_d.data_ptr()), _vp(out.data_ptr()),
+                                        _stream()), "wol_tetracosang")
+    return out
+
+
+def hbond_counts(acc, don, donh, box, dist_cut=3.5, ang_cut=150.0, dense=False, pairs=False, device=None,
+                 cells=None):
+    """generalHbonds (fortran/waterlib.f90:1156-1210) for one or several frames.
+    acc (F,Na,3) acceptors, don (F,Nd,3) donor heavy atoms (one entry per hydrogen), donh (F,Nd,3) hydrogens.
+    Returns dict(acc_count (F,Na) int32, don_count (F,Nd) int32 [, dense (F,Na,Nd) int32][, pairs (P,2) int32
+    rows (frame*Na + acceptor, donor)]).  `cells`: a CellList already built over `don` with r_cell >= dist_cut."""
+    device = _device(device, acc, don, donh)
+    acc_d = engine.as_device_positions(acc, device)
+    donh_d = engine.as_device_positions(donh, device)
+    F, Na = int(acc_d.shape[0]), int(acc_d.shape[1])
+    if cells is None:
+        don_d = engine.as_device_positions(don, device)
+        if don_d.shape != donh_d.shape:
+            raise ValueError("Number of donor hydrogens and heavy-atoms do not match.")  # waterlib.f90:1171-1174
+        Nd = int(don_d.shape[1])
+    else:
+        Nd = cells.N
+        if int(donh_d.shape[1]) != Nd:
+            raise ValueError("Number of donor hydrogens and heavy-atoms do not match.")
+    res = {"acc_count": torch.zeros((F, Na), dtype=torch.int32, device=device),
+           "don_count": torch.zeros((F, Nd), dtype=torch.int32, device=device)}
+    if dense:
+        res["dense"] = torch.zeros((F, Na, Nd), dtype=torch.int32, device=device)
+    if Na == 0 or Nd == 0:
+        if pairs:
+            res["pairs"] = torch.zeros((0, 2), dtype=torch.int32, device=device)
+        return res
+    if cells is None:
+        cells = CellList(don_d, box, max(float(dist_cut), 1e-3), device=device)
+    a = HbondArgs()
+    a.struct_size = ctypes.sizeof(HbondArgs)
+    a.n_frames, a.n_acc, a.n_don = F, Na, Nd
+    a.acc_dtype, a.donh_dtype = engine._dtype_code(acc_d), engine._dtype_code(donh_d)
+    a.acc, a.donh, a.box = acc_d.data_ptr(), donh_d.data_ptr(), cells.box_d.data_ptr()
+    a.workspace, a.workspace_bytes = cells.ws_ptr, cells.ws_bytes
+    a.nc = cells.nc
+    a.edge_min = cells.edge_min
+    a.dist_cut, a.ang_cut = float(dist_cut), float(ang_cut)
+    a.acc_count, a.don_count = res["acc_count"].data_ptr(), res["don_count"].data_ptr()
+    a.dense = res["dense"].data_ptr() if dense else None
+    counter = torch.zeros(1, dtype=torch.int32, device=device)
+    a.pair_counter = counter.data_ptr()
+    with torch.cuda.device(device):
+        if pairs:
+            # pass 1 counts (the per-acceptor sums are what bounds the list), pass 2 fills
+            check(lib().wol_hbond_counts(ctypes.byref(a), _stream()), "wol_hbond_counts")
+            n_pairs = int(res["acc_count"].sum().item())
+            plist = torch.empty((max(n_pairs, 1), 2), dtype=torch.int32, device=device)
+            res["don_count"].zero_()
+            a.pairs, a.pair_capacity = plist.data_ptr(), n_pairs
+            check(lib().wol_hbond_counts(ctypes.byref(a), _stream()), "wol_hbond_counts")
+            plist = plist[:n_pairs]
+            # the kernel appends in no particular order: sort rows by (acceptor, donor), the order the
+            # reference walks its matrix in (water_properties.py:705-713)
+            key = plist[:, 0].to(torch.int64) * (Nd + 1) + plist[:, 1].to(torch.int64)
+            res["pairs"] = plist[torch.argsort(key)]
+        else:
+            check(lib().wol_hbond_counts(ctypes.byref(a), _stream()), "wol_hbond_counts")
+    res["_keep"] = (acc_d, donh_d, cells)
+    return res
+
+
+def shell_mask(sol, wat, box, cutoff=4.0, low=0.0, device=None, cells=None):
+    """Hydration-shell selection (structureLibs/orderParam_lib.py:495-498): int32 mask (F, Nw), 1 where a
+    water lies within (low, cutoff] of any solute atom."""
+    device = _device(device, wat, sol)
+    sol_d = engine.as_device_positions(sol, device)
+    if cells is None:
+        wat_d = engine.as_device_positions(wat, device)
+        F, Nw = int(wat_d.shape[0]), int(wat_d.shape[1])
+    else:
+        F, Nw = cells.F, cells.N
+    mask = torch.zeros((F, Nw), dtype=torch.int32, device=device)
+    Ns = int(sol_d.shape[1])
+    if Ns == 0 or Nw == 0:
+        return mask
+    if cells is None:
+        cells = CellList(wat_d, box, max(float(cutoff), 1e-3), device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_shell_mask(_vp(sol_d.data_ptr()), engine._dtype_code(sol_d), Ns, _vp(cells.box_d.data_ptr()), F, Nw,
+                                   ctypes.byref(cells.nc), cells.edge_min, float(low), float(cutoff), _vp(cells.ws_ptr),
+                                   cells.ws_bytes, _vp(mask.data_ptr()), _stream()), "wol_shell_mask")
+    return mask
+
+
+def hbond_locations(pairs, acc, donh, box, device=None):
+    """HBloc of HBondsGeneral (structureLibs/water_properties.py:709-714) for a pair list from hbond_counts."""
+    device = _device(device, acc, donh)
+    acc_d = engine.as_device_positions(acc, device)
+    donh_d = engine.as_device_positions(donh, device)
+    F = int(acc_d.shape[0])
+    box_d = torch.from_numpy(engine.as_host_boxes(box, F).copy()).to(device)
+    pairs = pairs.to(device=device, dtype=torch.int32).contiguous()
+    n = int(pairs.shape[0])
+    out = torch.empty((n, 3), dtype=torch.float64, device=device)
+    if n:
+        with torch.cuda.device(device):
+            check(lib().wol_hbond_locations(_vp(pairs.data_ptr()), n, _vp(acc_d.data_ptr()), engine._dtype_code(acc_d),
+                                            int(acc_d.shape[1]), _vp(donh_d.data_ptr()), engine._dtype_code(donh_d),
+                                            int(donh_d.shape[1]), _vp(box_d.data_ptr()), _vp(out.data_ptr()), _stream()),
+                  "wol_hbond_locations")
+    return out

@@ -1,0 +1,116 @@
+"""Drop-in for the hot-path functions of the reference's ``structureLibs/water_properties.py``.
+
+Same names, positional order, keyword names, defaults and return values:
+
+    getOrderParamq(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0)                   reference :344-391
+    getCosAngs(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413)                      reference :210-250
+    tetrahedralMetrics(angVals, nBins=500, binRange=[0.0, 180.0])                    reference :314-342
+    HBondsGeneral(accPos, donPos, donHPos, boxL, accInds, donInds, donHInds,
+                  distCut=3.5, angCut=150.0)                                         reference :681-719
+
+numpy arrays in -> numpy arrays out; torch CUDA tensors in -> torch CUDA tensors out (zero copy).  The
+per-water Python loops and f2py calls of the reference are replaced by one pass of the cell-list kernels in
+libwol.so (include/wol_capi.h).  There is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from .. import engine, routines
+
+
+def _is_torch(*xs):
+    return any(isinstance(x, torch.Tensor) for x in xs)
+
+
+def _same(subPos, Pos):
+    """np.array_equal(subPos, Pos) of the reference (water_properties.py:235, :363)."""
+    if subPos is Pos:
+        return True
+    if _is_torch(subPos, Pos):
+        a, b = torch.as_tensor(subPos), torch.as_tensor(Pos)
+        return a.shape == b.shape and a.device == b.device and bool(torch.equal(a, b))
+    a, b = np.asarray(subPos), np.asarray(Pos)
+    return a.shape == b.shape and bool(np.array_equal(a, b))
+
+
+def _out(t, like_torch, dtype=None):
+    if like_torch:
+        return t if dtype is None else t.to(dtype)
+    a = t.detach().cpu().numpy()
+    return a if dtype is None else a.astype(dtype)
+
+
+def _pos2(a, name):
+    shape = tuple(a.shape)
+    if len(shape) != 2 or shape[1] != 3:
+        raise ValueError("%s must have shape (n,3), got %s" % (name, shape))
+    return a
+
+
+def getOrderParamq(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
+    """Tetrahedral order parameter q (Errington & Debenedetti 2001) of every position in subPos from its 4
+    nearest neighbours in Pos within (lowCut, highCut]; 1/2/3 neighbours are padded with 180-degree angles,
+    0 neighbours give q = 0 (reference water_properties.py:344-391)."""
+    tor = _is_torch(subPos, Pos)
+    subPos = subPos if tor else np.asarray(subPos)
+    Pos = Pos if tor else np.asarray(Pos)
+    _pos2(subPos, "subPos"); _pos2(Pos, "Pos")
+    if len(subPos) == 0:
+        return torch.zeros(0, dtype=torch.float64) if tor else np.zeros(0)
+    if len(Pos) == 0:
+        return _out(torch.zeros(len(subPos), dtype=torch.float64), tor)
+    r = engine.q3b_frames(Pos, BoxDims, None if _same(subPos, Pos) else subPos, do_q=True, do_3body=False,
+                          lowq=lowCut, highq=highCut, want=("q",))
+    return _out(r["q"][0], tor)
+
+
+def getCosAngs(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413):
+    """All three-body angles (degrees, despite the name) about each position of subPos among its neighbours in
+    Pos within (lowCut, highCut], in the reference's order, and the neighbour count per centre as float64
+    (reference water_properties.py:210-250)."""
+    tor = _is_torch(subPos, Pos)
+    subPos = subPos if tor else np.asarray(subPos)
+    Pos = Pos if tor else np.asarray(Pos)
+    _pos2(subPos, "subPos"); _pos2(Pos, "Pos")
+    ang, n3, _ = routines.three_body_angles(None if _same(subPos, Pos) else subPos, Pos, BoxDims, lowCut, highCut)
+    return _out(ang, tor), _out(n3[0], tor, torch.float64 if tor else np.float64)
+
+
+def tetrahedralMetrics(angVals, nBins=500, binRange=[0.0, 180.0]):  # noqa: B006 (the reference's default)
+    """(angDist, bins, fracTet, avgCos, varCos, entropy) of a set of three-body angles
+    (reference water_properties.py:314-342)."""
+    tor = _is_torch(angVals)
+    n = int(angVals.numel()) if tor else int(np.asarray(angVals).size)
+    hist, tet = routines.histogram(angVals, nBins, (binRange[0], binRange[1]))
+    angDist = hist.cpu().numpy()
+    cnt, s1, s2 = (float(v) for v in tet.cpu().numpy())
+    bins = np.linspace(binRange[0], binRange[1], nBins + 1)
+    fracTet = float(cnt) / float(n)  # ZeroDivisionError on empty input, like the reference (:333)
+    if cnt > 0:
+        avgCos = s1 / cnt
+        varCos = max(s2 / cnt - avgCos * avgCos, 0.0)
+    else:
+        avgCos = varCos = float("nan")  # np.mean / np.var of an empty array
+    angDens = angDist / float(np.sum(angDist))
+    angDens = angDens[np.where(angDens != 0)[0]]
+    entropy = -np.sum(angDens * np.log(angDens))
+    return angDist, bins, fracTet, avgCos, varCos, entropy
+
+
+def HBondsGeneral(accPos, donPos, donHPos, boxL, accInds, donInds, donHInds, distCut=3.5, angCut=150.0):
+    """Hydrogen bonds between acceptors and donor (heavy atom, hydrogen) pairs -> (NumHB, HBlist, HBloc)
+    (reference water_properties.py:681-719; criterion fortran/waterlib.f90:1184-1206)."""
+    tor = _is_torch(accPos, donPos, donHPos)
+    r = routines.hbond_counts(accPos, donPos, donHPos, boxL, distCut, angCut, pairs=True)
+    pairs = r["pairs"]
+    NumHB = int(pairs.shape[0])
+    loc = routines.hbond_locations(pairs, accPos, donHPos, boxL)
+    p = pairs.cpu().numpy()
+    HBlist = (-1) * np.ones((NumHB, 2))
+    if NumHB:
+        HBlist[:, 0] = np.asarray(accInds)[p[:, 0]]
+        HBlist[:, 1] = np.asarray(donInds)[p[:, 1]]
+    if tor:
+        return NumHB, torch.from_numpy(HBlist).to(loc.device), loc
+    return NumHB, HBlist, loc.cpu().numpy()
+

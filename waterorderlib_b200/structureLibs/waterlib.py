@@ -1,0 +1,64 @@
+"""f2py-compatible face of the hot-path routines of ``waterlib`` (built in the reference by
+fortran/buildWrappers.sh:3-5 and imported as ``wl`` at structureLibs/water_properties.py:42-43).
+
+Lower-case names and argument order as f2py generates them (signatures recovered from the reference's
+prebuilt module); logical outputs are int32 arrays, array outputs are Fortran-ordered like
+f2py's.  numpy in -> numpy out.  These are the small-array routines: O(m n) dense matrices by construction.
+Large systems go through water_properties / orderParam_lib, which call the fused cell-list kernels.
+"""
+import numpy as np
+import torch
+
+from .. import routines
+
+
+def _np(t, fortran=True):
+    a = t.detach().cpu().numpy()
+    return np.asfortranarray(a) if fortran and a.ndim > 1 else a
+
+
+def _check_pos(a, name):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("%s must have shape (n,3), got %s" % (name, a.shape))  # f2py raises waterlib.error here
+    return a
+
+
+def allnearneighbors(pos, boxl, lowcut, highcut):
+    """nneighbors = allnearneighbors(pos,boxl,lowcut,highcut)   (fortran/waterlib.f90:830-862)"""
+    pos = _check_pos(pos, "pos")
+    return _np(routines.neighbor_matrix(None, pos, boxl, lowcut, highcut))
+
+
+def nearneighbors(subpos, pos, boxl, lowcut, highcut):
+    """nneighbors = nearneighbors(subpos,pos,boxl,lowcut,highcut)   (fortran/waterlib.f90:710-743)"""
+    return _np(routines.neighbor_matrix(_check_pos(subpos, "subpos"), _check_pos(pos, "pos"), boxl, lowcut, highcut))
+
+
+def reimage(pos, refpos, boxl):
+    """reimagedpos = reimage(pos,refpos,boxl)   (fortran/waterlib.f90:32-47)"""
+    return _np(routines.reimage(_check_pos(pos, "pos"), refpos, boxl))
+
+
+def tetracosang(refpos, neighpos, boxl):
+    """allangs = tetracosang(refpos,neighpos,boxl)   (fortran/waterlib.f90:867-895); the diagonal, which the
+    Fortran never writes, is zero."""
+    return _np(routines.tetracosang(refpos, _check_pos(neighpos, "neighpos"), boxl))
+
+
+def lsidists(refpos, neighpos, boxl):
+    """dist1 = lsidists(refpos,neighpos,boxl)   (fortran/waterlib.f90:900-918)"""
+    return _np(routines.lsidists(refpos, _check_pos(neighpos, "neighpos"), boxl))
+
+
+def generalhbonds(acceptorpos, donorpos, donorhpos, boxl, distcut, angcut):
+    """bondbool = generalhbonds(acceptorpos,donorpos,donorhpos,boxl,distcut,angcut)
+    (fortran/waterlib.f90:1156-1210) -> (nacc, ndon) int32."""
+    acc, don, donh = _check_pos(acceptorpos, "acceptorpos"), _check_pos(donorpos, "donorpos"), _check_pos(donorhpos, "donorhpos")
+    if acc.shape[0] == 0 or don.shape[0] == 0:
+        if don.shape[0] != donh.shape[0]:
+            raise ValueError("Number of donor hydrogens and heavy-atoms do not match.")
+        return np.zeros((acc.shape[0], don.shape[0]), dtype=np.int32, order="F")
+    r = routines.hbond_counts(acc, don, donh, boxl, distcut, angcut, dense=True)
+    torch.cuda.current_stream().synchronize()
+    return _np(r["dense"][0])

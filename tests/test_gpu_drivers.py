@@ -1,0 +1,209 @@
+"""Parity of the frame drivers (waterorderlib_b200.structureLibs.orderParam_lib: tetOrderCalc, threeBodyCalc,
+hbCalc, getBoundWrap, getNeighborStats) against the reference's driver arithmetic restated here on top of
+the CPU oracle (oracle/port.py), frame by frame, the way structureLibs/orderParam_lib.py:1426-1503, :1269-1424,
+:729-917, :419-572 loop.  Small synthetic trajectories; the bootstrap CIs use numpy's global RNG exactly as
+the reference does, so seeding it makes them comparable too.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import port  # noqa: E402  (the checker)
+from waterorderlib_b200 import synth  # noqa: E402
+from waterorderlib_b200.structureLibs import orderParam_lib as opl  # noqa: E402
+from waterorderlib_b200.structureLibs.TrajObject import ArrayTrajectory, Topology, TrajObject  # noqa: E402
+
+SOL_NAMES = ["C1", "O1", "HO1", "N1", "HN1"]
+SOL_BONDS = [(0, 1), (1, 2), (0, 3), (3, 4)]
+
+
+def make_system(m, n_frames, n_sol=0, sigma=0.3, seed0=100):
+    """Waters (O,H1,H2 contiguous) preceded by n_sol five-atom cosolvent molecules (C, O-H, N-H)."""
+    n_w = 8 * m ** 3
+    names, resn, resid, bonds = [], [], [], []
+    for s in range(n_sol):
+        names += SOL_NAMES
+        resn += ["SOL"] * 5
+        resid += [s] * 5
+        bonds += [(5 * s + a, 5 * s + b) for a, b in SOL_BONDS]
+    o0 = 5 * n_sol
+    names += ["O", "H1", "H2"] * n_w
+    resn += ["WAT"] * (3 * n_w)
+    resid += list(np.repeat(np.arange(n_w) + n_sol, 3))
+    oi = o0 + 3 * np.arange(n_w)
+    bonds += [(int(o), int(o) + 1) for o in oi] + [(int(o), int(o) + 2) for o in oi]
+    top = Topology(names, resn, resid, bonds)
+    xyz = np.zeros((n_frames, len(names), 3))
+    boxes = np.zeros((n_frames, 3))
+    rng = np.random.default_rng(seed0)
+    for f in range(n_frames):
+        o, box = synth.water_box(m, sigma=sigma, seed=seed0 + f)
+        h = synth.add_hydrogens(o, seed=seed0 + f)
+        xyz[f, oi] = o
+        xyz[f, oi + 1] = h[0::2]
+        xyz[f, oi + 2] = h[1::2]
+        boxes[f] = box
+        for s in range(n_sol):
+            c = rng.random(3) * box
+            u = rng.normal(size=(2, 3))
+            u /= np.linalg.norm(u, axis=1, keepdims=True)
+            xyz[f, 5 * s + 0] = c
+            xyz[f, 5 * s + 1] = c + 1.43 * u[0]
+            xyz[f, 5 * s + 2] = c + 1.43 * u[0] + 0.96 * u[1]
+            xyz[f, 5 * s + 3] = c - 1.47 * u[0]
+            xyz[f, 5 * s + 4] = c - 1.47 * u[0] - 1.01 * u[1]
+    xyz = xyz.astype(np.float32).astype(np.float64)
+    return top, ArrayTrajectory(xyz, boxes, top=top)
+
+
+@pytest.fixture()
+def in_tmp(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    return tmp_path
+
+
+def test_tetOrderCalc_matches_reference_loop(in_tmp):
+    T = 40
+    top, traj = make_system(3, T)
+    obj = TrajObject(top, traj)
+    watInds, _, lenWat = obj.getWatInds()
+    assert lenWat == 3 and len(watInds) == 216
+    rng = np.random.default_rng(3)
+    subInds = [[np.sort(rng.choice(watInds, 30, replace=False)), watInds[rng.random(216) < 0.1]] for _ in range(T)]
+    # reference loop (orderParam_lib.py:1458-1480) on the oracle
+    avg = np.zeros((3, T)); var = np.zeros((3, T)); qall = [[], [], []]
+    for t in range(T):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        watPos = pos[watInds]
+        for j, sub in enumerate([watPos, pos[subInds[t][0]], pos[subInds[t][1]]]):
+            q = port.getOrderParamq(sub, watPos, box)
+            qall[j].append(q)
+            avg[j, t], var[j, t] = np.mean(q), np.var(q)
+    np.random.seed(7)
+    ref_ci = [opl.blockAverage(avg[j]) for j in range(3)]
+    np.random.seed(7)
+    avgQ, varQ = opl.tetOrderCalc(top, traj, subInds=subInds, nPops=2)
+    assert np.allclose(avgQ[0], avg.mean(axis=1), rtol=1e-9) and np.allclose(varQ[0], var.mean(axis=1), rtol=1e-7)
+    assert avgQ[1].shape == (3,) and abs(avgQ[1][0] - ref_ci[0]) < 1e-9  # first CI drawn from the same RNG state
+    for j in range(3):
+        got = np.loadtxt("qDistribution_%d.txt" % j)
+        want, edges = np.histogram(np.concatenate(qall[j]), bins=500, range=[0.0, 1.0])
+        assert got.shape == (500, 2) and np.array_equal(got[:, 1], np.array([float("%.3e" % v) for v in want]))
+        assert np.allclose(got[:, 0], 0.5 * (edges[:-1] + edges[1:]), rtol=2e-3)
+
+
+def test_threeBodyCalc_matches_reference_loop(in_tmp):
+    T = 24
+    top, traj = make_system(3, T, sigma=0.35, seed0=300)
+    obj = TrajObject(top, traj)
+    watInds, _, _ = obj.getWatInds()
+    rng = np.random.default_rng(5)
+    subInds = [[np.sort(rng.choice(watInds, 40, replace=False))] for _ in range(T)]
+    series = np.zeros((2, 4, T)); pooled = [[], []]
+    for t in range(T):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        watPos = pos[watInds]
+        for j, sub in enumerate([watPos, pos[subInds[t][0]]]):
+            ang, _ = port.getCosAngs(sub, watPos, box)
+            pooled[j].append(ang)
+            _, _, a, b, c, d = port.tetrahedralMetrics(ang)
+            series[j, :, t] = (a, b, c, d)
+    pTet, avgCos, varCos, entropy, nWats = opl.threeBodyCalc(top, traj, subInds=subInds, nPops=1)
+    for j in range(2):
+        assert abs(pTet[0][j] - series[j, 0].mean()) < 1e-12
+        assert abs(avgCos[0][j] - series[j, 1].mean()) < 1e-12
+        assert abs(varCos[0][j] - series[j, 2].mean()) < 1e-12
+        assert abs(entropy[0][j] - series[j, 3].mean()) < 1e-12
+        got = np.loadtxt("3bDistribution_%d.txt" % j)
+        want = port.histogram(np.concatenate(pooled[j]), 500, 0.0, 180.0)
+        assert np.array_equal(got[:, 1], np.array([float("%.3e" % v) for v in want]))
+    assert nWats[0][0] == 216 and nWats[0][1] == 40
+    with pytest.raises(NotImplementedError):
+        opl.threeBodyCalc(top, traj, output2D=True)
+
+
+def ref_hbcalc(top, traj, obj):
+    """hbCalc's arithmetic (orderParam_lib.py:742-884) with oracle matrices."""
+    watInds, watHInds, _ = obj.getWatInds()
+    solInds, solHInds, _c, solNInds, solOInds, _s = obj.getSolInds()
+    (sAccO, sDonO, sDonHO), (sAccN, sDonN, sDonHN) = opl.getHBInds(top, traj[0], solInds, solHInds, solNInds, solOInds)
+    (wAcc, wDon, wDonH), _ = opl.getHBInds(top, traj[0], watInds, watHInds, [], watInds)
+    nSol = top.n_residues('(!:WAT)')
+    nAccO, nAccN, nDonO, nDonN = (int(len(x) / nSol) for x in (sAccO, sAccN, sDonO, sDonN))
+    numWat, numSol = [], []
+    for t in range(len(traj)):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        hb = lambda a, d, h: port.hbonds(pos[a], pos[d], pos[h], box, 3.5, 120.0, dense=True)[2]  # noqa: E731
+        ww, wsO, swO = hb(wAcc, wDon, wDonH), hb(wAcc, sDonO, sDonHO), hb(sAccO, wDon, wDonH)
+        wsN, swN = hb(wAcc, sDonN, sDonHN), hb(sAccN, wDon, wDonH)
+        OO, ON, NO, NN = hb(sAccO, sDonO, sDonHO), hb(sAccO, sDonN, sDonHN), hb(sAccN, sDonO, sDonHO), hb(sAccN, sDonN, sDonHN)
+        solOAcc = swO.sum(1) + OO.sum(1) + ON.sum(1)
+        solODon = wsO.sum(0) + OO.sum(0) + NO.sum(0)
+        solOAcc = sum(solOAcc[i::nAccO] for i in range(nAccO))
+        solODon = sum(solODon[i::nDonO] for i in range(nDonO))
+        solNAcc = swN.sum(1) + NN.sum(1) + NO.sum(1)
+        solNDon = wsN.sum(0) + NN.sum(0) + ON.sum(0)
+        solNAcc = sum(solNAcc[i::nAccN] for i in range(nAccN))
+        solNDon = sum(solNDon[i::nDonN] for i in range(nDonN))
+        numSol.append(solNAcc + solNDon + solOAcc + solODon)
+        d = ww.sum(0); dO = swO.sum(0); dN = swN.sum(0)
+        numWat.append(ww.sum(1) + d[::2] + d[1::2] + wsO.sum(1) + dO[::2] + dO[1::2] + wsN.sum(1) + dN[::2] + dN[1::2])
+    return np.concatenate(numWat), np.concatenate(numSol)
+
+
+def test_hbCalc_matches_reference_loop(in_tmp):
+    top, traj = make_system(3, 6, n_sol=5, seed0=500)
+    obj = TrajObject(top, traj)
+    numWat, numSol = ref_hbcalc(top, traj, obj)
+    avgW, avgS = opl.hbCalc(top, traj)
+    assert avgW == np.mean(numWat) and avgS == np.mean(numSol)
+    assert numSol.sum() > 0  # the cosolvent really bonds in this system
+    got = np.loadtxt("hbDistribution_water.txt")
+    assert np.array_equal(got[:, 1], np.histogram(numWat, bins=np.arange(11))[0].astype(float))
+    got = np.loadtxt("hbDistribution_cosolv.txt")
+    assert np.array_equal(got[:, 1], np.histogram(numSol, bins=np.arange(11))[0].astype(float))
+
+
+def test_getBoundWrap_matches_reference(in_tmp):
+    top, traj = make_system(4, 1, n_sol=6, seed0=700)
+    obj = TrajObject(top, traj)
+    watInds, watHInds, _ = obj.getWatInds()
+    solInds, solHInds, solCInds, solNInds, solOInds, solSInds = obj.getSolInds()
+    frame = traj[0]
+    bound, wrap, shell, non = opl.getBoundWrap(top, frame, watInds, watHInds, solInds, solHInds, solCInds, solOInds,
+                                               solNInds, solSInds)
+    # reference arithmetic (orderParam_lib.py:495-570) with oracle matrices
+    pos, box = traj.xyz[0], traj.boxes[0]
+    nb = port.neighbor_matrix(pos[solInds], pos[watInds], box, 0.0, 4.0)
+    mask = np.unique(np.where(nb == 1)[1])
+    shell_ref = watInds[mask]
+    (sAccO, sDonO, sDonHO), _ = opl.getHBInds(top, frame, solInds, solHInds, solNInds, solOInds)
+    (wAcc, wDon, wDonH), _ = opl.getHBInds(top, frame, shell_ref, watHInds, solNInds, shell_ref)
+    hb = lambda a, d, h: port.hbonds(pos[a], pos[d], pos[h], box, 3.0, 150.0, dense=True)[2]  # noqa: E731
+    watSol, solWat = hb(wAcc, sDonO, sDonHO), hb(sAccO, wDon, wDonH)
+    b_wat = np.unique(np.where(watSol == 1)[0])
+    dummy = np.zeros(len(wDon)); dummy[np.unique(np.where(solWat == 1)[1])] = 1
+    b_sol = np.where(np.ceil(0.5 * (dummy[0::2] + dummy[1::2])))[0]
+    bmask = np.sort(np.unique(np.concatenate([b_wat, b_sol]))).astype(int)
+    keep = np.ones(len(shell_ref), dtype=bool); keep[bmask] = False
+    assert np.array_equal(shell, shell_ref) and np.array_equal(non, np.delete(watInds, mask))
+    assert np.array_equal(bound, shell_ref[bmask]) and np.array_equal(wrap, shell_ref[keep])
+    assert len(shell) > 0 and len(bound) > 0 and len(wrap) > 0
+
+
+def test_getNeighborStats(in_tmp):
+    top, traj = make_system(3, 3, n_sol=4, seed0=900)
+    obj = TrajObject(top, traj)
+    watInds, _, _ = obj.getWatInds()
+    solInds = obj.getSolInds()[0]
+    got = opl.getNeighborStats(top, traj, solInds, watInds, 3, 1, distCut=4.0)
+    vals = []
+    for t in range(3):
+        nb = port.neighbor_matrix(traj.xyz[t][solInds], traj.xyz[t][watInds], traj.boxes[t], 0.0, 4.0)
+        for n in range(len(solInds) // 3):
+            vals.append(len(np.unique(np.where(nb[3 * n:3 * n + 3] == 1)[1])))
+    assert got == np.mean(vals) and os.path.exists("coordDistribution.txt")

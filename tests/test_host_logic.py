@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic around the kernels: Amber-mask selection and TrajObject, the H-bond index
+bookkeeping, the bootstrap statistics, and the multi-rank frame sharding / reduction (world_size 2, gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from waterorderlib_b200 import distributed as wdist
+from waterorderlib_b200.structureLibs.TrajObject import ArrayTrajectory, Topology, TrajObject
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def small_top():
+    names = ["C1", "O1", "HO1", "N1", "HN1", "S1"] + ["O", "H1", "H2", "EPW"] * 3
+    resn = ["GLY"] * 6 + ["WAT"] * 12
+    resid = [0] * 6 + [1] * 4 + [2] * 4 + [3] * 4
+    bonds = [(1, 2), (3, 4), (0, 1), (0, 3)] + [(6 + 4 * k, 7 + 4 * k) for k in range(3)] + [(6 + 4 * k, 8 + 4 * k) for k in range(3)]
+    return Topology(names, resn, resid, bonds)
+
+
+def test_amber_masks():
+    top = small_top()
+    assert list(top.select("(:WAT)")) == list(range(6, 18))
+    assert list(top.select("(!:WAT)")) == list(range(6))
+    assert list(top.select("(:WAT)&(!@H=)&(!@EP=)")) == [6, 10, 14]
+    assert list(top.select("(:WAT)&(@H=)")) == [7, 8, 11, 12, 15, 16]
+    assert list(top.select("(@C=)|(@S=)")) == [0, 5]
+    assert list(top.select("(!:WAT)&(!@H=)")) == [0, 1, 3, 5]
+    assert list(top.select(":GLY & @O1,N1")) == [1, 3]
+    with pytest.raises(ValueError):
+        top.select("(:WAT")
+    assert top.n_residues() == 4 and top.n_residues("(!:WAT)") == 1
+
+
+def test_trajobject_indices_and_frames(tmp_path):
+    top = small_top()
+    xyz = np.arange(5 * 18 * 3, dtype=np.float64).reshape(5, 18, 3)
+    traj = ArrayTrajectory(xyz, np.array([10.0, 11.0, 12.0]))
+    obj = TrajObject(top, traj, stride=2)
+    assert len(obj.traj) == 3 and np.array_equal(obj.traj[1].xyz, xyz[2])
+    assert np.array_equal(obj.traj[0].box.values, [10.0, 11.0, 12.0, 90.0, 90.0, 90.0])
+    watInds, watHInds, lenWat = obj.getWatInds()
+    assert list(watInds) == [6, 10, 14] and lenWat == 4 and len(watHInds) == 6
+    sol = obj.getSolInds()
+    assert [list(s) for s in sol] == [[0, 1, 3, 5], [2, 4], [0], [3], [1], [5]]
+    assert list(obj.getHeavyInds()) == [0, 1, 3, 5, 6, 10, 14]
+    # .npz round trip
+    top.save(tmp_path / "top.npz")
+    traj.save(tmp_path / "traj.npz")
+    obj2 = TrajObject(str(tmp_path / "top.npz"), str(tmp_path / "traj.npz"))
+    assert len(obj2.traj) == 5 and list(obj2.getWatInds()[0]) == [6, 10, 14]
+    assert [f.xyz[0, 0] for f in obj2.traj] == [0.0, 54.0, 108.0, 162.0, 216.0]
+
+
+def test_getHBInds():
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    top = small_top()
+    hbO, hbN = opl.getHBInds(top, None, [0, 1, 3, 5], [2, 4], [3], [1])
+    assert [list(x) for x in hbO] == [[1], [1], [2]] and [list(x) for x in hbN] == [[3], [3], [4]]
+    wat = [6, 10, 14]
+    hbW, _ = opl.getHBInds(top, None, wat, [7, 8, 11, 12, 15, 16], [], wat)
+    assert list(hbW[0]) == wat and list(hbW[1]) == [6, 6, 10, 10, 14, 14] and list(hbW[2]) == [7, 8, 11, 12, 15, 16]
+
+
+def test_blockAverage_matches_reference_loop():
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    vals = np.random.default_rng(0).normal(size=173)
+
+    def reference(vals, nBlocks=20):  # structureLibs/orderParam_lib.py:394-417, literally
+        obsBlocks = np.zeros(nBlocks)
+        lenBlock = len(vals) / nBlocks
+        for i in range(nBlocks):
+            obsBlocks[i] = np.mean(vals[int(i * lenBlock):int((i + 1) * lenBlock)])
+        obsMeans = np.zeros(10000)
+        for n in range(10000):
+            obsMeans[n] = np.mean(np.random.choice(obsBlocks, nBlocks))
+        return opl.getCI(np.sort(obsMeans))
+
+    np.random.seed(11)
+    want = reference(vals)
+    np.random.seed(11)
+    assert opl.blockAverage(vals) == want
+
+
+def test_shard_frames_partition():
+    for n in (0, 1, 7, 8, 1000):
+        for ws in (1, 2, 3, 8):
+            blocks = [wdist.shard_frames(n, r, ws) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sizes == wdist.shard_sizes(n, ws)
+
+
+def _rank_main(rank, ws, port, n_frames, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        b, e = wdist.shard_frames(n_frames)
+        # every frame contributes a known histogram and a known stats row
+        g = torch.Generator().manual_seed(1)
+        all_hist = torch.randint(0, 1000, (n_frames, 50), generator=g, dtype=torch.int64)
+        all_rows = torch.rand((n_frames, 8), generator=g, dtype=torch.float64)
+        h1 = all_hist[b:e].sum(dim=0)
+        h2 = (all_hist[b:e] * 3).sum(dim=0).reshape(5, 10)
+        wdist.reduce_histograms(h1, h2)
+        rows = wdist.gather_frame_rows(all_rows[b:e].clone(), n_frames)
+        mx = wdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+        ok = (torch.equal(h1, all_hist.sum(dim=0)) and torch.equal(h2.reshape(-1), all_hist.sum(dim=0) * 3)
+              and torch.equal(rows, all_rows) and mx == float(ws))
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [7, 8])
+def test_two_rank_reduce_and_gather_gloo(tmp_path, n_frames):
+    port = 29500 + (os.getpid() % 2000) + n_frames
+    mp.spawn(_rank_main, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / ("ok%d" % r)).read() for r in range(2)] == ["1", "1"]
+
+
+def test_reduce_rejects_non_integer_histograms_single_rank():
+    h = torch.zeros(4, dtype=torch.int64)
+    assert wdist.reduce_histograms(h)[0] is h  # identity without a process group
+    assert wdist.world() == (0, 1)
+    rows = torch.ones((3, 2))
+    assert wdist.gather_frame_rows(rows, 3) is rows

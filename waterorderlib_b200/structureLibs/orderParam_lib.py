@@ -1,0 +1,386 @@
+"""Drop-in for the hot-path frame drivers of the reference's ``structureLibs/orderParam_lib.py``.
+
+Same names, positional order, keyword names, defaults, return values and output files:
+
+    tetOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, watResName, stride=1)       reference :1426-1503
+    threeBodyCalc(topFile, trajFile, subInds=None, nPops=0, solResName, watResName, nBins=500,
+                  stride=1, output2D=False)                                                          reference :1269-1424
+    hbCalc(topFile, trajFile, solResName, watResName, stride=1)                                     reference :729-917
+    getBoundWrap(topFile, frame, watInds, watHInds, solInds, solHInds, solCInds, solOInds, solNInds,
+                 solSInds, cutoff=4.0, hbDist=3.0, hbAng=150.0)                                      reference :419-572
+    getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1, distCut=3.4,
+                     switch=False)                                                                   reference :313-384
+    getHBInds(top, frame, solInds, solHInds, solNInds, solOInds)                                     reference :46-120
+    blockAverage(vals, nBlocks=20), getCI(means)                                                     reference :386-417
+
+``topFile`` / ``trajFile`` are whatever ``TrajObject`` accepts (in-memory objects, .npz, or AMBER files when
+parmed/pytraj are installed).  Where the reference loops over frames calling f2py routines per water, these
+drivers push BATCHES of frames through the fused cell-list kernels of libwol.so and keep histograms and
+per-frame sums on the device; under ``torch.distributed`` (one process per GPU) frames are sharded across
+ranks and combined with one all-reduce + one all-gather (waterorderlib_b200.distributed).
+"""
+import numpy as np
+import torch
+
+from .. import distributed as wdist
+from .. import engine, routines
+from .._capi import STAT_NAMES
+from . import waterlib as wl
+from .TrajObject import TrajObject
+
+_S = {n: i for i, n in enumerate(STAT_NAMES)}
+_MAX_ATOMS_PER_BATCH = 8_000_000
+
+
+# ---- statistics helpers (host side, O(frames)) ------------------------------------------------------
+
+def getCI(means):
+    """reference orderParam_lib.py:386-391"""
+    meanCI = means[int(0.5 * len(means))]
+    upperCI = means[int(0.975 * len(means))] - meanCI
+    lowerCI = meanCI - means[int(0.025 * len(means))]
+    return max(upperCI, lowerCI)
+
+
+def blockAverage(vals, nBlocks=20):
+    """Bootstrap confidence interval over block means (reference orderParam_lib.py:394-417): 20 blocks,
+    10 000 resamples with np.random.choice (unseeded there and here; seed numpy's global RNG to reproduce)."""
+    vals = np.asarray(vals)
+    obsBlocks = np.zeros(nBlocks)
+    lenBlock = len(vals) / nBlocks
+    for i in range(nBlocks):
+        obsBlocks[i] = np.mean(vals[int(i * lenBlock):int((i + 1) * lenBlock)])
+    nSamp = nBlocks
+    nResamp = 10000
+    obsMeans = np.mean(np.random.choice(obsBlocks, (nResamp, nSamp)), axis=1)
+    obsMeans = np.sort(obsMeans)
+    return getCI(obsMeans)
+
+
+def _mean_ci(series):
+    with np.errstate(all="ignore"):
+        return np.mean(series), blockAverage(series)
+
+
+def getHBInds(top, frame, solInds, solHInds, solNInds, solOInds):
+    """Acceptor / donor / donor-hydrogen index lists from the bonded topology (reference :46-120):
+    every O (N) in solOInds (solNInds) is an acceptor and appears once per bonded hydrogen as a donor."""
+    solO, solN = set(int(i) for i in solOInds), set(int(i) for i in solNInds)
+    acc = {"O": [], "N": []}
+    don = {"O": [], "N": []}
+    donH = {"O": [], "N": []}
+    for i, atom in enumerate(top.atoms):
+        kind = "O" if i in solO else ("N" if i in solN else None)
+        if kind is None:
+            continue
+        count = 0
+        for jatom in atom.bond_partners:
+            if 'H' in jatom.name:
+                donH[kind].append(jatom.idx)
+                count += 1
+        acc[kind].append(i)
+        don[kind].extend([i] * count)
+    hbOInds = [np.array(acc["O"], dtype=int), np.array(don["O"], dtype=int), np.array(donH["O"], dtype=int)]
+    hbNInds = [np.array(acc["N"], dtype=int), np.array(don["N"], dtype=int), np.array(donH["N"], dtype=int)]
+    return hbOInds, hbNInds
+
+
+# ---- frame batching ----------------------------------------------------------------------------------
+
+def _frame_arrays(traj, begin, end):
+    """(xyz (f, natom, 3), box (f, 3)) of frames [begin, end) of an ArrayTrajectory or any pytraj-like iterable."""
+    if hasattr(traj, "boxes") and hasattr(traj, "xyz") and getattr(traj.xyz, "ndim", 0) == 3:
+        return traj.xyz[begin:end], traj.boxes[begin:end, :3]
+    xyz, box = [], []
+    for t in range(begin, end):
+        frame = traj[t]
+        xyz.append(np.array(frame.xyz))
+        box.append(np.array(frame.box.values[:3]))
+    return np.stack(xyz), np.stack(box)
+
+
+def _batches(begin, end, n_atoms):
+    per = max(1, _MAX_ATOMS_PER_BATCH // max(n_atoms, 1))
+    for b in range(begin, end, per):
+        yield b, min(end, b + per)
+
+
+def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
+    """Shared core of tetOrderCalc / threeBodyCalc: every frame of this rank's shard through the fused kernel,
+    population 0 (all waters) a whole batch of frames per call, sub-populations frame by frame (their
+    centres change every frame, structureLibs/orderParam_lib.py:1343-1346, :1475-1478).
+    Returns numpy arrays holding ALL frames on every rank: stats (T, P, NSTATS) f64, per-frame angle
+    histograms (T, P, nBins) i64 or None, pooled q histograms (P, 500) i64 or None, members (T, P)."""
+    traj = obj.traj
+    watInds, _watHInds, _lenWat = obj.getWatInds()
+    T, P, NS = len(traj), nPops + 1, len(STAT_NAMES)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    begin, end = wdist.shard_frames(T)
+    Tl = end - begin
+    stats = torch.zeros((P, Tl, NS), dtype=torch.float64, device=dev)
+    ang_hist = torch.zeros((P, Tl, nBins), dtype=torch.int64, device=dev) if do_3body else None
+    q_hist = torch.zeros((P, 1, 500), dtype=torch.int64, device=dev) if do_q else None
+    members = torch.zeros((Tl, P), dtype=torch.float64, device=dev)
+    ws, sub_ws = engine.Workspace(dev), engine.Workspace(dev)
+    # angle histograms are kept per frame (the drivers report per-frame entropies), q histograms are pooled;
+    # the two never run together here
+    kw = dict(do_q=do_q, do_3body=do_3body, nbins=nBins, device=dev, hist_per_frame=do_3body)
+
+    def outputs(j, l0, l1):
+        o = {"frame_stats": stats[j, l0:l1]}
+        if do_3body:
+            o["ang_hist"] = ang_hist[j, l0:l1]
+        if do_q:
+            o["q_hist"] = q_hist[j]
+        return o
+
+    for b0, b1 in _batches(begin, end, len(watInds)):
+        xyz, box = _frame_arrays(traj, b0, b1)
+        xyz = np.asarray(xyz)
+        watPos = torch.from_numpy(np.ascontiguousarray(xyz[:, watInds])).to(dev)
+        l0, l1 = b0 - begin, b1 - begin
+        o = outputs(0, l0, l1)
+        engine.q3b_frames(watPos, box, None, out=o, want=tuple(o.keys()), workspace=ws, **kw)
+        members[l0:l1, 0] = float(len(watInds))
+        for t in range(b0, b1):
+            for j in range(1, P):
+                inds = np.asarray(subInds[t][j - 1], dtype=np.int64)
+                members[t - begin, j] = float(len(inds))
+                if len(inds) == 0:
+                    continue
+                cen = torch.from_numpy(np.ascontiguousarray(xyz[t - b0][inds])).to(dev)
+                o = outputs(j, t - begin, t - begin + 1)
+                engine.q3b_frames(watPos[t - b0], box[t - b0], cen, out=o, want=tuple(o.keys()), workspace=sub_ws,
+                                  **kw)
+    # ---- combine ranks: one all-reduce of the integer histograms, one all-gather of the per-frame rows ----
+    rows = [stats.permute(1, 0, 2).reshape(Tl, P * NS), members]
+    if do_3body:
+        rows.append(ang_hist.permute(1, 0, 2).reshape(Tl, P * nBins).to(torch.float64))  # counts < 2^53: exact
+    rows = wdist.gather_frame_rows(torch.cat(rows, dim=1).contiguous(), T)
+    if do_q:
+        wdist.reduce_histograms(q_hist)
+    rows = rows.cpu().numpy()
+    stats_np = rows[:, :P * NS].reshape(T, P, NS)
+    members_np = rows[:, P * NS:P * NS + P]
+    hist_np = np.rint(rows[:, P * NS + P:]).astype(np.int64).reshape(T, P, nBins) if do_3body else None
+    return stats_np, hist_np, (q_hist[:, 0].cpu().numpy() if do_q else None), members_np
+
+
+# ---- drivers -----------------------------------------------------------------------------------------
+
+def tetOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)', watResName='(:WAT)', stride=1):
+    """Tetrahedral order parameter statistics and distribution for all waters and nPops sub-populations
+    (reference orderParam_lib.py:1426-1503).  Returns (avgQ, varQ), each [means, CIs] over populations, and
+    writes qDistribution_<j>.txt (two columns, "%.3e")."""
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    if subInds is None:
+        nPops = 0
+    stats, _, q_hist, _ = _run_populations(obj, subInds, nPops, True, False, 500)
+    P = nPops + 1
+    with np.errstate(all="ignore"):
+        n = stats[:, :, _S["n_centres"]]
+        mean_t = stats[:, :, _S["q_sum"]] / n
+        var_t = np.maximum(stats[:, :, _S["q_sumsq"]] / n - mean_t * mean_t, 0.0)
+    avgQ_mean, avgQ_CI, varQ_mean, varQ_CI = (np.zeros(P) for _ in range(4))
+    for j in range(P):
+        avgQ_mean[j], avgQ_CI[j] = _mean_ci(mean_t[:, j])
+        varQ_mean[j], varQ_CI[j] = _mean_ci(var_t[:, j])
+    if wdist.world()[0] == 0:
+        bins = np.linspace(0.0, 1.0, 501)
+        for j in range(P):
+            np.savetxt('qDistribution_' + str(j) + '.txt', np.stack([0.5 * (bins[:-1] + bins[1:]), q_hist[j]], axis=1),
+                       header='qVal    frequency', fmt="%.3e")
+    return [avgQ_mean, avgQ_CI], [varQ_mean, varQ_CI]
+
+
+def _entropy(counts):
+    tot = float(np.sum(counts))
+    if tot == 0.0:
+        return 0.0
+    dens = counts / tot
+    dens = dens[dens != 0]
+    return float(-np.sum(dens * np.log(dens)))
+
+
+def threeBodyCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)', watResName='(:WAT)', nBins=500, stride=1,
+                  output2D=False):
+    """Three-body angle distribution statistics for all waters and nPops sub-populations (reference
+    orderParam_lib.py:1269-1424).  Returns (pTet, avgCos, varCos, entropy, nWats), each [means, CIs], and writes
+    3bDistribution_<j>.txt.  output2D (a matplotlib figure in the reference) is not part of the hot path."""
+    if output2D:
+        raise NotImplementedError("output2D draws a matplotlib figure in the reference (orderParam_lib.py:1384-1422); "
+                                  "it is outside the hot path this backend replaces")
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    if subInds is None:
+        nPops = 0
+    stats, hist, _, members = _run_populations(obj, subInds, nPops, False, True, nBins)
+    T, P = stats.shape[0], nPops + 1
+    n_ang = stats[:, :, _S["n_angles"]]
+    cnt = stats[:, :, _S["tet_count"]]
+    pTet_t, avgCos_t, varCos_t, ent_t = (np.zeros((T, P)) for _ in range(4))
+    with np.errstate(all="ignore"):
+        has = n_ang > 0
+        pTet_t[has] = cnt[has] / n_ang[has]
+        mean = stats[:, :, _S["tet_cos"]] / cnt
+        var = np.maximum(stats[:, :, _S["tet_cossq"]] / cnt - mean * mean, 0.0)
+        avgCos_t[has] = mean[has]
+        varCos_t[has] = var[has]
+    for t in range(T):
+        for j in range(P):
+            ent_t[t, j] = _entropy(hist[t, j]) if has[t, j] else 0.0
+    out = []
+    for series in (pTet_t, avgCos_t, varCos_t, ent_t, members):
+        m, ci = np.zeros(P), np.zeros(P)
+        for j in range(P):
+            m[j], ci[j] = _mean_ci(series[:, j])
+        out.append([m, ci])
+    if wdist.world()[0] == 0:
+        bins = np.linspace(0.0, 180.0, nBins + 1)
+        for j in range(P):
+            if n_ang[:, j].sum() != 0:
+                np.savetxt('3bDistribution_' + str(j) + '.txt',
+                           np.stack([0.5 * (bins[:-1] + bins[1:]), hist[:, j].sum(axis=0)], axis=1),
+                           header='3-body angle (deg)    frequency', fmt="%.3e")
+    pTet, avgCos, varCos, entropy, nWats = out
+    return pTet, avgCos, varCos, entropy, nWats
+
+
+def _hb_sums(acc, don, donh, box, dist, ang):
+    """(row sums, column sums) of generalhbonds(acc, don, donh) for a batch of frames, as int64 numpy (F, n)."""
+    F = acc.shape[0]
+    if acc.shape[1] == 0 or don.shape[1] == 0:
+        return np.zeros((F, acc.shape[1]), dtype=np.int64), np.zeros((F, don.shape[1]), dtype=np.int64)
+    r = routines.hbond_counts(acc, don, donh, box, dist, ang)
+    return r["acc_count"].cpu().numpy().astype(np.int64), r["don_count"].cpu().numpy().astype(np.int64)
+
+
+def hbCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', stride=1):
+    """Average hydrogen bonds per water and per cosolvent molecule, 3.5 A / 120 deg (reference
+    orderParam_lib.py:729-917).  Returns (avgWatHBs, avgSolHBs) and writes hbDistribution_water.txt /
+    hbDistribution_cosolv.txt."""
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    top, traj = obj.top, obj.traj
+    watInds, watHInds, _lenWat = obj.getWatInds()
+    solInds, solHInds, _solC, solNInds, solOInds, _solS = obj.getSolInds()
+    hbO, hbN = getHBInds(top, traj[0], solInds, solHInds, solNInds, solOInds)
+    sAccO, sDonO, sDonHO = hbO
+    sAccN, sDonN, sDonHN = hbN
+    hbW, _ = getHBInds(top, traj[0], watInds, watHInds, [], watInds)
+    wAcc, wDon, wDonH = hbW
+    nSol = top.n_residues(solResName) if hasattr(top, "n_residues") else traj[:1, solResName].topology.n_residues
+    T = len(traj)
+    begin, end = wdist.shard_frames(T)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    wat_rows, sol_rows = [], []
+    for b0, b1 in _batches(begin, end, 3 * len(watInds) + len(solInds)):
+        xyz, box = _frame_arrays(traj, b0, b1)
+        xyz = np.asarray(xyz)
+        g = lambda idx: np.ascontiguousarray(xyz[:, idx])  # noqa: E731
+        D, A = 3.5, 120.0
+        ww_a, ww_d = _hb_sums(g(wAcc), g(wDon), g(wDonH), box, D, A)
+        wsO_a, wsO_d = _hb_sums(g(wAcc), g(sDonO), g(sDonHO), box, D, A)
+        swO_a, swO_d = _hb_sums(g(sAccO), g(wDon), g(wDonH), box, D, A)
+        wsN_a, wsN_d = _hb_sums(g(wAcc), g(sDonN), g(sDonHN), box, D, A)
+        swN_a, swN_d = _hb_sums(g(sAccN), g(wDon), g(wDonH), box, D, A)
+        OO_a, OO_d = _hb_sums(g(sAccO), g(sDonO), g(sDonHO), box, D, A)
+        ON_a, ON_d = _hb_sums(g(sAccO), g(sDonN), g(sDonHN), box, D, A)
+        NO_a, NO_d = _hb_sums(g(sAccN), g(sDonO), g(sDonHO), box, D, A)
+        NN_a, NN_d = _hb_sums(g(sAccN), g(sDonN), g(sDonHN), box, D, A)
+        # per water molecule (reference :867-884); donors are listed once per hydrogen, two per water
+        fold = lambda d: d[:, ::2] + d[:, 1::2]  # noqa: E731
+        wat_rows.append(ww_a + fold(ww_d) + wsO_a + fold(swO_d) + wsN_a + fold(swN_d))
+        if nSol > 0:
+            def per_mol(v, n_per):  # sum( [ v[i::n] for i in range(n) ] )  (reference :850-851)
+                return sum(v[:, i::n_per] for i in range(n_per)) if n_per > 0 else np.zeros((v.shape[0], nSol), dtype=np.int64)
+            nAccO, nAccN = int(len(sAccO) / nSol), int(len(sAccN) / nSol)
+            nDonO, nDonN = int(len(sDonO) / nSol), int(len(sDonN) / nSol)
+            solOAcc = per_mol(swO_a + OO_a + ON_a, nAccO)
+            solODon = per_mol(wsO_d + OO_d + NO_d, nDonO)
+            solNAcc = per_mol(swN_a + NN_a + NO_a, nAccN)
+            solNDon = per_mol(wsN_d + NN_d + ON_d, nDonN)
+            sol_rows.append(solNAcc + solNDon + solOAcc + solODon)
+    numWat = np.concatenate(wat_rows) if wat_rows else np.zeros((0, len(wAcc)), dtype=np.int64)
+    numSol = np.concatenate(sol_rows) if sol_rows else np.zeros((end - begin, 0), dtype=np.int64)
+    # combine ranks: per-frame rows gathered in frame order
+    numWat = wdist.gather_frame_rows(torch.from_numpy(numWat).to(dev), T).cpu().numpy()
+    if nSol > 0:
+        numSol = wdist.gather_frame_rows(torch.from_numpy(numSol).to(dev), T).cpu().numpy()
+    numWatHBs, numSolHBs = numWat.reshape(-1), numSol.reshape(-1)
+    with np.errstate(all="ignore"):
+        avgWatHBs = np.mean(numWatHBs)
+        avgSolHBs = np.mean(numSolHBs) if numSolHBs.size else float("nan")
+    if wdist.world()[0] == 0:
+        edges = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+        for vals, name in ((numWatHBs, 'hbDistribution_water.txt'), (numSolHBs, 'hbDistribution_cosolv.txt')):
+            hbDist, bins = np.histogram(vals, bins=edges, density=False)
+            np.savetxt(name, np.stack([0.5 * (bins[:-1] + bins[1:]), hbDist], axis=1), header='# hbs    frequency', fmt="%.3e")
+    return avgWatHBs, avgSolHBs
+
+
+def getBoundWrap(topFile, frame, watInds, watHInds, solInds, solHInds, solCInds, solOInds, solNInds, solSInds,
+                 cutoff=4.0, hbDist=3.0, hbAng=150.0):
+    """Hydration-shell waters of a solute split into "bound" (hydrogen-bonded to it) and "wrap" (the rest)
+    (reference orderParam_lib.py:419-572).  Returns (boundInds, wrapInds, shellInds, nonShellInds)."""
+    obj = TrajObject(topFile, trajFile=None, stride=1, solResName=None, watResName=None)
+    top = obj.top
+    hbOInds, _hbNInds = getHBInds(top, frame, solInds, solHInds, solNInds, solOInds)
+    sAccO, sDonO, sDonHO = hbOInds
+    pos = np.array(frame.xyz)
+    thisbox = np.array(frame.box.values[:3])
+    watInds = np.asarray(watInds)
+    watPos, solPos = pos[watInds], pos[np.asarray(solInds, dtype=int)]
+    # waters within `cutoff` of any solute heavy atom (reference :495-498)
+    mask = routines.shell_mask(solPos, watPos, thisbox, cutoff).cpu().numpy()[0].astype(bool)
+    shellInds = watInds[mask]
+    nonShellInds = watInds[~mask]
+    hbW, _ = getHBInds(top, frame, shellInds, watHInds, solNInds, shellInds)
+    wAcc, wDon, wDonH = hbW
+
+    def counts(acc, don, donh):
+        if len(acc) == 0 or len(don) == 0:
+            return np.zeros(len(acc), dtype=np.int32), np.zeros(len(don), dtype=np.int32)
+        r = routines.hbond_counts(pos[acc], pos[don], pos[donh], thisbox, hbDist, hbAng)
+        return r["acc_count"].cpu().numpy()[0], r["don_count"].cpu().numpy()[0]
+
+    # water accepts from the solute (rows = shell waters), solute accepts from water (columns = water donors)
+    watSol_a, _ = counts(wAcc, sDonO, sDonHO)
+    boundMask_wat = np.nonzero(watSol_a > 0)[0]
+    _, solWat_d = counts(sAccO, wDon, wDonH)
+    dummy = (solWat_d > 0).astype(np.float64)
+    boundMask_sol = np.where(np.ceil(0.5 * (dummy[0::2] + dummy[1::2])))[0]
+    boundMask = np.sort(np.unique(np.concatenate([boundMask_wat, boundMask_sol]))).astype(int)
+    keep = np.ones(len(shellInds), dtype=bool)
+    keep[boundMask] = False
+    return shellInds[boundMask], shellInds[keep], shellInds, nonShellInds
+
+
+def getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1, distCut=3.4, switch=False):
+    """Mean number of distinct neighbouring atoms per molecule of type 1 (reference orderParam_lib.py:313-384);
+    writes coordDistribution.txt."""
+    obj = TrajObject(topFile, trajFile=trajFile, stride=stride, solResName=None, watResName=None)
+    numberCoord = []
+    Inds1, Inds2 = np.asarray(Inds1, dtype=int), np.asarray(Inds2, dtype=int)
+    for frame in obj.traj:
+        thisbox = np.reshape(np.array(frame.box.values[:3]), (1, 3))
+        thispos = np.array(frame.xyz)
+        subPos1, subPos2 = thispos[Inds1], thispos[Inds2]
+        nRes = int(len(Inds1) / nAtoms1)
+        resNumbers = np.zeros(nRes, dtype=int)
+        if switch:
+            neighbors = wl.allnearneighbors(subPos1, thisbox, 0.0, distCut)
+        else:
+            neighbors = wl.nearneighbors(subPos1, subPos2, thisbox, 0.0, distCut)
+        for n in range(nRes):
+            nNeighbors = neighbors[int(n * nAtoms1):int((n + 1) * nAtoms1), :]
+            if switch:
+                # the reference's own-molecule exclusion indexes a slice of the slice (:349-350); for molecules
+                # after the first it is empty, so only molecule 0 has its own atoms removed.  Reproduced.
+                nNeighbors[int(n * nAtoms1):int((n + 1) * nAtoms1), int(n * nAtoms1):int((n + 1) * nAtoms1)] = 0
+            resNumbers[n] = len(np.unique(np.where(nNeighbors == 1)[1]))
+        numberCoord.append(resNumbers)
+    numberCoord = np.concatenate(numberCoord)
+    meanCoord = np.mean(numberCoord)
+    coordDist, bins = np.histogram(numberCoord, bins=[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10], density=False)
+    np.savetxt('coordDistribution.txt', np.stack([0.5 * (bins[:-1] + bins[1:]), coordDist], axis=1),
+               header='# coords    frequency', fmt="%.3e")
+    return meanCoord

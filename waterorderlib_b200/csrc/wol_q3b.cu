@@ -746,6 +746,7 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
         P.pre_cst_w2 = nextafterf((float)cst, INFINITY);
         const double lo = (a.lowq + margin) * (a.lowq + margin) * (1.0 + 1e-6);
         P.lowq_hi2 = nextafterf((float)lo, INFINITY);
+        P.cell_eps = (float)(4.0 * margin);
     }
     P.list = P.fb_list;
     P.list2 = P.fb_list + lay.n_centres_total;

@@ -39,6 +39,7 @@ struct Q3bParams {
     uint32_t *counters;
     uint32_t *fb_list;
     int tiles_per_frame;
+    int chunk_tiles;          // thread-per-centre path: tiles per round-robin chunk
     long long total_tiles;
     // thread-per-centre fast path
     const float4 *wrapped;  // box-wrapped float coordinates in record order (nullptr: not built)
@@ -53,6 +54,7 @@ struct Q3bParams {
     float lowq_hi2;           // (lowq + margin)^2: float distances above this are certainly beyond lowCut
     float pre_thr2_w2;        // prefilter threshold of the half-width-2 pass
     float pre_cst_w2;         // slack added to the 4th-smallest float distance^2 of that pass
+    float cell_eps;           // how far a wrapped float coordinate can sit outside its cell's nominal box
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -201,7 +203,7 @@ constexpr int kMaxSmemBins = 4096;
 template <bool EXACT>
 __device__ __forceinline__ void finish_q(const Q3bParams &P, int f, double rx, double ry, double rz, double Lx, double Ly,
                                          double Lz, double iLx, double iLy, double iLz, const Top4<double> &top,
-                                         int n_found, size_t out_index, LaneStats &st) {
+                                         int n_found, size_t out_index, LaneStats &st, unsigned *s_qhist) {
     double vx[4], vy[4], vz[4], vn[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -257,20 +259,28 @@ __device__ __forceinline__ void finish_q(const Q3bParams &P, int f, double rx, d
     if (P.q_hist) {
         const HistSpec hs = hist_spec(0.0, 1.0, P.q_nbins);
         const int b = hist_bin(hs, qv);
-        if (b >= 0) atomicAdd(P.q_hist + (size_t)(P.hist_per_frame ? f : 0) * P.q_nbins + b, 1ull);
+        if (b >= 0) {
+            if (s_qhist) atomicAdd(s_qhist + b, 1u);
+            else atomicAdd(P.q_hist + (size_t)(P.hist_per_frame ? f : 0) * P.q_nbins + b, 1ull);
+        }
     }
     st.q_sum += qv;
     st.q_sumsq += qv * qv;
     st.n_centres += 1u;
 }
 
-// flush of a block's shared-memory angle histogram into the global int64 bins
-__device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist, int f, bool clear) {
-    for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) {
-        const unsigned v = s_hist[i];
-        if (v) atomicAdd(P.ang_hist + (size_t)(P.hist_per_frame ? f : 0) * P.nbins + i, (unsigned long long)v);
-        if (clear) s_hist[i] = 0u;
+// flush of a block's shared-memory histograms into the global int64 bins
+__device__ __forceinline__ void flush_bins(unsigned *s_bins, unsigned long long *g_bins, int nbins, bool clear) {
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        const unsigned v = s_bins[i];
+        if (v) atomicAdd(g_bins + i, (unsigned long long)v);
+        if (clear) s_bins[i] = 0u;
     }
+}
+__device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist, unsigned *s_qhist, int f, bool clear) {
+    const size_t row = (size_t)(P.hist_per_frame ? f : 0);
+    if (s_hist) flush_bins(s_hist, P.ang_hist + row * P.nbins, P.nbins, clear);
+    if (s_qhist) flush_bins(s_qhist, P.q_hist + row * P.q_nbins, P.q_nbins, clear);
 }
 
 int q3b_tpc_launch(const Q3bParams &P, cudaStream_t stream, bool exact);

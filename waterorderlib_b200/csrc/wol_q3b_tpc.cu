@@ -21,11 +21,13 @@
 // below 2 L; the acceptance threshold is widened by 16 * 2^-24 * Lmax (see q3b_tpc_launch), several
 // times the worst case.  For >= 4 cells per axis the image implied by cell adjacency IS the minimum
 // image for every candidate closer than two cell edges.
+#include <stdlib.h>
+
 #include "wol_q3b_common.cuh"
 
 namespace wol {
 
-constexpr int kTpcThreads = 128;
+constexpr int kTpcThreads = 256;  // two blocks per SM: the bin table and block histograms are shared by 8 warps
 constexpr int kTpcListCap = 16;  // prefilter survivors per centre
 constexpr int kTpcEntCap = 10;   // three-body neighbours per centre
 constexpr int kTpcMaxPairs = kTpcEntCap * (kTpcEntCap - 1) / 2;
@@ -38,20 +40,24 @@ struct TpcSmem {
 };
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_constant__ Q3bParams P) {
+__global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_constant__ Q3bParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TpcSmem &S = *reinterpret_cast<TpcSmem *>(smem_raw);
     unsigned char *after = smem_raw + sizeof(TpcSmem);
     const bool smem_hist = P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins;
+    const bool smem_qhist = P.do_q && P.q_hist && P.q_nbins <= kMaxSmemBins;
     const bool smem_tab = P.nbins <= kMaxSmemBins;
     const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
     double *s_tab = reinterpret_cast<double *>(after);
     unsigned *s_hist = reinterpret_cast<unsigned *>(after + (smem_tab ? sizeof(double) * tab_len : 0));
+    unsigned *s_qhist = s_hist + (smem_hist ? P.nbins : 0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (smem_tab)
         for (int i = tid; i < tab_len; i += kTpcThreads) s_tab[i] = P.table[i];
     if (smem_hist)
         for (int i = tid; i < P.nbins; i += kTpcThreads) s_hist[i] = 0u;
+    if (smem_qhist)
+        for (int i = tid; i < P.q_nbins; i += kTpcThreads) s_qhist[i] = 0u;
     if (tid < kTpcMaxPairs) {
         // p = b (b - 1) / 2 + a, a < b
         int b = 1;
@@ -70,20 +76,23 @@ __global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_co
 
     LaneStats st;
     st.reset();
-    const long long chunk = (P.total_tiles + gridDim.x - 1) / gridDim.x;
-    const long long t_begin = chunk * blockIdx.x;
-    const long long t_end = min(P.total_tiles, t_begin + chunk);
+    // Tiles are dealt to the blocks in round-robin chunks of P.chunk_tiles: at any moment the whole grid works
+    // on one neighbourhood of one frame, so the stencil rows a block reads are (or soon will be) in L2 on
+    // behalf of its neighbours and the DRAM traffic stays near one read of the frame.  Within a chunk the
+    // tiles are consecutive, which keeps the rows shared by consecutive tiles in L1.
+    const long long n_chunks = (P.total_tiles + P.chunk_tiles - 1) / P.chunk_tiles;
     int cur_f = -1;
     double Lx = 1, Ly = 1, Lz = 1, iLx = 1, iLy = 1, iLz = 1;
-    for (long long tile = t_begin; tile < t_end; ++tile) {
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+    for (long long tile = chunk * P.chunk_tiles, t_end = min(P.total_tiles, tile + P.chunk_tiles); tile < t_end; ++tile) {
         const int f = (int)(tile / P.tiles_per_frame);
         const int m = (int)(tile - (long long)f * P.tiles_per_frame) * kTpcThreads + tid;
         if (f != cur_f) {
             if (cur_f >= 0) {
                 flush_stats(P, cur_f, st);
-                if (smem_hist && P.hist_per_frame) {
+                if ((smem_hist || smem_qhist) && P.hist_per_frame) {
                     __syncthreads();
-                    flush_hist(P, s_hist, cur_f, true);
+                    flush_hist(P, smem_hist ? s_hist : nullptr, smem_qhist ? s_qhist : nullptr, cur_f, true);
                     __syncthreads();
                 }
             }
@@ -317,39 +326,50 @@ __global__ void __launch_bounds__(kTpcThreads, 4) q3b_tpc_kernel(const __grid_co
         }
 
         // ---------------- phase 3b: q from the four winners ---------------------------------------
-        if (q_go) finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st);
+        if (q_go)
+            finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st, smem_qhist ? s_qhist : nullptr);
     }
     if (cur_f >= 0) flush_stats(P, cur_f, st);
-    if (smem_hist) {
+    if (smem_hist || smem_qhist) {
         __syncthreads();
-        if (cur_f >= 0) flush_hist(P, s_hist, cur_f, false);
+        if (cur_f >= 0) flush_hist(P, smem_hist ? s_hist : nullptr, smem_qhist ? s_qhist : nullptr, cur_f, false);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Widened q search, one WARP per queued centre: half-width-2 stencil = 25 rows of a 5-cell x-run, one row
-// per lane, so the 25 dependent load chains of a centre run side by side.
-//   pass 1  every lane scans its row over the float coordinates and keeps its four smallest distances^2
-//           (only candidates certainly beyond lowCut count); four REDUX-min rounds give the warp's 4th
-//           smallest;
-//   pass 2  every lane rescans its row and appends whatever lies within that bound (+ rounding slack,
-//           capped at the radius the stencil guarantees) to a shared list -- a handful of candidates;
-//   exact   lane k evaluates survivor k in fp64 reference arithmetic; ranks by (distance, index) through
-//           shuffles pick the four winners; lanes 0-3 build their vectors, lanes 0-5 the pair terms.
-// A centre still short of four neighbours inside the guaranteed radius goes to the second-level queue
-// (group-per-centre pass, half-width 3 and up).
+// Widened q search, one THREAD per queued centre (a centre with fewer than four neighbours inside the radius
+// the 27-cell stencil guarantees).  The four nearest are almost always just outside that radius, so the search
+// is driven by a BOUND instead of by the stencil size:
+//   bound   the thread scans its 27-cell stencil over the float coordinates and keeps the four smallest
+//           distances^2 (only candidates certainly beyond lowCut count).  Whatever else there is can only
+//           matter if it is closer than the 4th of them (+ rounding slack, capped at the radius a
+//           half-width-2 stencil guarantees).
+//   collect the 25 rows of the half-width-2 stencil, each clipped to the cells the bound can reach: a row is
+//           skipped when the (y, z) distance from the centre to the row's box already exceeds the bound, and
+//           its x-run shrinks to the cells within sqrt(bound^2 - that distance^2).  In practice a few
+//           cells behind the faces the sphere pokes through.  Survivors go to a per-thread shared list.
+//   exact   survivors re-evaluated in fp64 reference arithmetic, register top-4 by (distance, atom index), q.
+// A centre still short of four neighbours inside the guaranteed radius (or with more survivors than the list
+// holds) goes to the second-level queue (group-per-centre pass, half-width 3 and up).
 constexpr int kWidenThreads = 128;
-constexpr int kWidenWarps = kWidenThreads / 32;
+constexpr int kWidenListCap = 16;
 
-__device__ __forceinline__ void widen_scan_row(const float4 *__restrict__ wr, int j0, int j1, float cxs, float cys, float czs,
-                                               int pass, float lowq_hi2, float thr, int self_j, float &a0, float &a1,
-                                               float &a2, float &a3, int *s_cnt, int *s_list) {
+// distance from a point at offset u inside its own cell (edge e) to the cell d cells away, along one axis
+__device__ __forceinline__ float cell_gap(int d, float u, float e) {
+    return d > 0 ? (float)d * e - u : (d < 0 ? u + (float)(-d - 1) * e : 0.f);
+}
+
+// One contiguous run of records [j0, j1) seen from a (shifted) centre.  MODE 0: keep the four smallest
+// distances^2 beyond `lo2`.  MODE 1: append everything within `thr` to the thread's list.
+template <int MODE>
+__device__ __forceinline__ void widen_scan(const float4 *__restrict__ wr, int j0, int j1, float sx, float sy, float sz, float lo2,
+                                           float thr, int self_j, float &a0, float &a1, float &a2, float &a3, int *list, int &nl) {
     for (int j = j0; j < j1; ++j) {
         const float4 w = __ldg(wr + j);
-        const float dx = w.x - cxs, dyv = w.y - cys, dzv = w.z - czs;
-        const float r2 = fmaf(dzv, dzv, fmaf(dyv, dyv, dx * dx));
-        if (pass == 0) {
-            if (r2 > lowq_hi2) {  // insert into the lane's sorted quadruple
+        const float dx = w.x - sx, dy = w.y - sy, dz = w.z - sz;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (MODE == 0) {
+            if (r2 > lo2) {
                 float v = r2, m;
                 m = fminf(a0, v); v = fmaxf(a0, v); a0 = m;
                 m = fminf(a1, v); v = fmaxf(a1, v); a1 = m;
@@ -357,34 +377,62 @@ __device__ __forceinline__ void widen_scan_row(const float4 *__restrict__ wr, in
                 a3 = fminf(a3, v);
             }
         } else if (r2 <= thr && j != self_j) {
-            const int at = atomicAdd(s_cnt, 1);
-            if (at < 32) s_list[at] = j;
+            if (nl < kWidenListCap) list[nl * kWidenThreads] = j;
+            ++nl;
         }
     }
 }
 
+// The x-run of cells [cx + lo, cx + hi] of row `cs` (lo, hi within [-2, 2]), split where it wraps around the box.
+template <int MODE>
+__device__ __forceinline__ void widen_row(const float4 *__restrict__ wr, const uint32_t *__restrict__ cs, int nc0, int cx, int lo,
+                                          int hi, float wx, float sy, float sz, float Lxf, float lo2, float thr, int self_j,
+                                          float &a0, float &a1, float &a2, float &a3, int *list, int &nl) {
+    const int x0 = cx + lo, x1 = cx + hi;  // inclusive, may leave [0, nc0)
+    const int m0 = max(x0, 0), m1 = min(x1, nc0 - 1);
+    widen_scan<MODE>(wr, (int)__ldg(cs + m0), (int)__ldg(cs + m1 + 1), wx, sy, sz, lo2, thr, self_j, a0, a1, a2, a3, list, nl);
+    if (x0 < 0)  // cells x0 + nc0 .. nc0 - 1 hold the images at x - L
+        widen_scan<MODE>(wr, (int)__ldg(cs + x0 + nc0), (int)__ldg(cs + nc0), wx + Lxf, sy, sz, lo2, thr, self_j, a0, a1, a2, a3, list, nl);
+    if (x1 >= nc0)  // cells 0 .. x1 - nc0 hold the images at x + L
+        widen_scan<MODE>(wr, (int)__ldg(cs), (int)__ldg(cs + x1 - nc0 + 1), wx - Lxf, sy, sz, lo2, thr, self_j, a0, a1, a2, a3, list, nl);
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __grid_constant__ Q3bParams P) {
-    __shared__ int s_list[kWidenWarps][32];
-    __shared__ int s_cnt[kWidenWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_list[kWidenListCap * kWidenThreads];
+    extern __shared__ unsigned s_qhist_dyn[];
     const uint32_t n_items = P.counters[P.list_counter];
     if (P.counters[kCntWidened] == 0u) return;
+    // one shared row only: the queue mixes frames, so per-frame histograms go straight to global memory
+    unsigned *s_qhist = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? s_qhist_dyn : nullptr;
+    if (s_qhist) {
+        for (int i = threadIdx.x; i < P.q_nbins; i += kWidenThreads) s_qhist[i] = 0u;
+        __syncthreads();
+    }
     const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
     const double lowqsq = P.lowqsq, highqsq = P.highqsq;
     const bool last2 = P.wq_max <= 2;
     const double rsel = fmin(P.highq, 2.0 * P.rc1);
     const double selsq2 = last2 ? highqsq : fmin(highqsq, rsel * rsel);
-    const float lowq_hi2 = P.lowq_hi2, thr_cap = P.pre_thr2_w2, cst = P.pre_cst_w2;
+    const float lowq_hi2 = P.lowq_hi2, thr_cap = P.pre_thr2_w2, cst = P.pre_cst_w2, eps = P.cell_eps;
     const float kInf = __int_as_float(0x7f800000);
-    const uint32_t warps_total = gridDim.x * kWidenWarps;
-    for (uint32_t it = blockIdx.x * kWidenWarps + warp; it < n_items; it += warps_total) {
-        const uint32_t e = P.list[it];
-        if ((e & kFbNeed3b) != 0u || (e & kFbNeedQ) == 0u) continue;  // list overflows belong to the large-capacity pass
+    const float4 *__restrict__ wr = P.wrapped;
+    int *list = s_list + threadIdx.x;
+    // warp-uniform trip count: the statistics of a warp's centres are combined with shuffles
+    for (uint32_t it0 = blockIdx.x * kWidenThreads + (threadIdx.x & ~31u); it0 < n_items; it0 += gridDim.x * kWidenThreads) {
+        const uint32_t it = it0 + (threadIdx.x & 31u);
+        const uint32_t e = it < n_items ? P.list[it] : 0u;
+        // list overflows (three-body redo) belong to the large-capacity pass
+        const bool valid = it < n_items && (e & kFbNeed3b) == 0u && (e & kFbNeedQ) != 0u;
+        bool done = false;
+        int f = 0;
+        LaneStats st;
+        st.reset();
+        if (valid) {
         const uint32_t id = e & kFbIdMask;
         double rx, ry, rz;
         float wx, wy, wz;
-        int cx, cy, cz, self_j = -1, f;
+        int cx, cy, cz, self_j = -1;
         size_t out_index;
         if (P.centres == nullptr) {
             f = (int)(id / (uint32_t)P.n_pos);
@@ -396,7 +444,7 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
             cx = b.w & 1023;
             cy = (b.w >> 10) & 1023;
             cz = (b.w >> 20) & 1023;
-            const float4 w = __ldg(P.wrapped + id);
+            const float4 w = __ldg(wr + id);
             wx = w.x; wy = w.y; wz = w.z;
             self_j = (int)id;
             out_index = (size_t)f * P.n_pos + b.z;
@@ -416,108 +464,96 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
             wz = wrapped_coord(rz, Lz, iLz);
         }
         const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
-        // this lane's row (lanes 25..31 have none) and the two pieces of its x-run [cx-2, cx+2]
-        int ja0 = 0, ja1 = 0, jb0 = 0, jb1 = 0;
-        float cys = wy, czs = wz, cxb = wx;
-        if (lane < 25) {
-            const int dz = lane / 5 - 2, dy = lane % 5 - 2;
-            int y = cy + dy, z = cz + dz;
-            if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
-            if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
-            const uint32_t *cs = P.cell_start + (size_t)f * nc0 * nc1 * nc2 + ((size_t)z * nc1 + y) * nc0;
-            ja0 = (int)__ldg(cs + max(cx - 2, 0));
-            ja1 = (int)__ldg(cs + min(cx + 2, nc0 - 1) + 1);
-            if (cx < 2) {
-                jb0 = (int)__ldg(cs + nc0 - (2 - cx));
-                jb1 = (int)__ldg(cs + nc0);
-                cxb = wx + Lxf;
-            } else if (cx > nc0 - 3) {
-                jb0 = (int)__ldg(cs);
-                jb1 = (int)__ldg(cs + cx + 3 - nc0);
-                cxb = wx - Lxf;
-            }
-        }
-        if (lane == 0) s_cnt[warp] = 0;
+        const uint32_t *cs_frame = P.cell_start + (size_t)f * nc0 * nc1 * nc2;
+
+        // ---- bound: four smallest float distances^2 inside the 27-cell stencil ---------------------
         float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
-        widen_scan_row(P.wrapped, ja0, ja1, wx, cys, czs, 0, lowq_hi2, 0.f, self_j, a0, a1, a2, a3, nullptr, nullptr);
-        widen_scan_row(P.wrapped, jb0, jb1, cxb, cys, czs, 0, lowq_hi2, 0.f, self_j, a0, a1, a2, a3, nullptr, nullptr);
-        // 4th smallest over the warp: extract the minimum four times (non-negative floats order like uints)
-        float fourth = kInf;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned m = __reduce_min_sync(kFullMask, __float_as_uint(a0));
-            fourth = __uint_as_float(m);
-            const unsigned holders = __ballot_sync(kFullMask, __float_as_uint(a0) == m);
-            if (lane == __ffs(holders) - 1) {
-                a0 = a1; a1 = a2; a2 = a3; a3 = kInf;
+        int nl = 0;
+#pragma unroll 1
+        for (int row = 0; row < 9; ++row) {
+            int y = cy + row % 3 - 1, z = cz + row / 3 - 1;
+            float sy = wy, sz = wz;
+            if (y < 0) { y += nc1; sy += Lyf; } else if (y >= nc1) { y -= nc1; sy -= Lyf; }
+            if (z < 0) { z += nc2; sz += Lzf; } else if (z >= nc2) { z -= nc2; sz -= Lzf; }
+            widen_row<0>(wr, cs_frame + ((size_t)z * nc1 + y) * nc0, nc0, cx, -1, 1, wx, sy, sz, Lxf, lowq_hi2, 0.f, self_j, a0, a1,
+                         a2, a3, list, nl);
+        }
+        const float thr = fminf(a3 + cst, thr_cap);
+
+        // ---- collect: the rows and cells of the half-width-2 stencil the bound can reach -----------
+        {
+            const float ex = Lxf / (float)nc0, ey = Lyf / (float)nc1, ez = Lzf / (float)nc2, iex = 1.0f / ex;
+            const float ux = wx - (float)cx * ex, uy = wy - (float)cy * ey, uz = wz - (float)cz * ez;
+#pragma unroll 1
+            for (int row = 0; row < 25; ++row) {
+                const int oy = row % 5 - 2, oz = row / 5 - 2;
+                const float gy = fmaxf(cell_gap(oy, uy, ey) - eps, 0.f), gz = fmaxf(cell_gap(oz, uz, ez) - eps, 0.f);
+                const float left = thr - fmaf(gz, gz, gy * gy);
+                if (left < 0.f) continue;
+                const float reach = sqrtf(left) + eps;
+                const int lo = max(-2, (int)floorf((ux - reach) * iex)), hi = min(2, (int)floorf((ux + reach) * iex));
+                int y = cy + oy, z = cz + oz;
+                float sy = wy, sz = wz;
+                if (y < 0) { y += nc1; sy += Lyf; } else if (y >= nc1) { y -= nc1; sy -= Lyf; }
+                if (z < 0) { z += nc2; sz += Lzf; } else if (z >= nc2) { z -= nc2; sz -= Lzf; }
+                widen_row<1>(wr, cs_frame + ((size_t)z * nc1 + y) * nc0, nc0, cx, lo, hi, wx, sy, sz, Lxf, 0.f, thr, self_j, a0, a1,
+                             a2, a3, list, nl);
             }
         }
-        const float thr = fminf(fourth + cst, thr_cap);
-        __syncwarp();
-        widen_scan_row(P.wrapped, ja0, ja1, wx, cys, czs, 1, lowq_hi2, thr, self_j, a0, a1, a2, a3, &s_cnt[warp], s_list[warp]);
-        widen_scan_row(P.wrapped, jb0, jb1, cxb, cys, czs, 1, lowq_hi2, thr, self_j, a0, a1, a2, a3, &s_cnt[warp], s_list[warp]);
-        __syncwarp();
-        const int n = s_cnt[warp];
-        // exact evaluation: lane k takes survivor k
-        bool elig = false;
-        double dist = 0.0;
-        int idx = INT_MAX, j = -1;
-        if (n <= 32 && lane < n) {
-            j = s_list[warp][lane];
-            double px, py, pz;
-            RecTraits<double>::load(P.recs, (size_t)j, px, py, pz, idx);
-            const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
-            const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
-            const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
-            const double s = sumsq3<double>(dx, dy, dz);
-            if ((s > lowqsq) && (s <= selsq2)) {
-                elig = true;
-                const double ex = __dsub_rn(__dadd_rn(rx, dx), rx);
-                const double ey = __dsub_rn(__dadd_rn(ry, dy), ry);
-                const double ez = __dsub_rn(__dadd_rn(rz, dz), rz);
-                dist = __dsqrt_rn(sumsq3<double>(ex, ey, ez));
-            }
-        }
-        const unsigned emask = __ballot_sync(kFullMask, elig);
-        const int nq = __popc(emask);
-        if (n > 32 || (nq < 4 && !last2)) {
-            if (lane == 0) {
-                const uint32_t at = atomicAdd(P.counters + kCntLevel2, 1u);
-                P.list2[at] = id | kFbNeedQ;
-            }
-            continue;
-        }
-        // rank among the eligible by (distance, atom index)
-        int rank = 0;
-        for (unsigned mm = emask; mm; mm &= mm - 1) {
-            const int src = __ffs(mm) - 1;
-            const double od = __shfl_sync(kFullMask, dist, src);
-            const int oi = __shfl_sync(kFullMask, idx, src);
-            if (key_less(od, oi, dist, idx)) ++rank;
-        }
-        const int n_found = min(nq, 4);
+
+        // ---- exact evaluation of the survivors ------------------------------------------------------
         Top4<double> top;
         top.reset();
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned who = __ballot_sync(kFullMask, elig && rank == r);
-            const int src = who ? __ffs(who) - 1 : 0;
-            const int wj = __shfl_sync(kFullMask, j, src), wi = __shfl_sync(kFullMask, idx, src);
-            if (r < n_found) {
-                top.p[r] = wj;
-                top.i[r] = wi;
+        int nq = 0;
+        if (nl <= kWidenListCap) {
+            for (int k = 0; k < nl; ++k) {
+                const int j = list[k * kWidenThreads];
+                double px, py, pz;
+                int idx;
+                RecTraits<double>::load(P.recs, (size_t)j, px, py, pz, idx);
+                const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
+                const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
+                const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
+                const double s = sumsq3<double>(dx, dy, dz);
+                if ((s > lowqsq) && (s <= selsq2)) {
+                    ++nq;
+                    const double vx = __dsub_rn(__dadd_rn(rx, dx), rx);
+                    const double vy = __dsub_rn(__dadd_rn(ry, dy), ry);
+                    const double vz = __dsub_rn(__dadd_rn(rz, dz), rz);
+                    top.insert(__dsqrt_rn(sumsq3<double>(vx, vy, vz)), idx, j);
+                }
             }
         }
-        if (lane == 0) {
-            LaneStats st;
-            st.reset();
-            finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, n_found, out_index, st);
-            if (P.stats) {
+        if (nl > kWidenListCap || (nq < 4 && !last2)) {
+            const uint32_t at = atomicAdd(P.counters + kCntLevel2, 1u);
+            P.list2[at] = id | kFbNeedQ;
+        } else {
+            finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st, s_qhist);
+            done = true;
+        }
+        }  // valid
+        // frame statistics: one set of atomics per warp when its centres share a frame (the queue is nearly
+        // frame-ordered), per thread otherwise
+        const unsigned fin = __ballot_sync(kFullMask, done);
+        if (fin != 0u && P.stats) {
+            const int f0 = __shfl_sync(kFullMask, f, __ffs(fin) - 1);
+            if (__all_sync(kFullMask, !done || f == f0)) {
+                const double s1 = warp_sum(st.q_sum), s2 = warp_sum(st.q_sumsq);
+                if ((threadIdx.x & 31) == 0) {
+                    atomicAdd(P.stats + (size_t)f0 * WOL_NSTATS + WOL_STAT_Q_SUM, s1);
+                    atomicAdd(P.stats + (size_t)f0 * WOL_NSTATS + WOL_STAT_Q_SUMSQ, s2);
+                    atomicAdd(P.stats + (size_t)f0 * WOL_NSTATS + WOL_STAT_N_CENTRES, (double)__popc(fin));
+                }
+            } else if (done) {
                 atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_Q_SUM, st.q_sum);
                 atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_Q_SUMSQ, st.q_sumsq);
                 atomicAdd(P.stats + (size_t)f * WOL_NSTATS + WOL_STAT_N_CENTRES, 1.0);
             }
         }
+    }
+    if (s_qhist) {
+        __syncthreads();
+        flush_bins(s_qhist, P.q_hist, P.q_nbins, false);
     }
 }
 
@@ -527,9 +563,10 @@ bool q3b_tpc_widen_supported(const Q3bParams &P) {
 }
 
 int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact) {
-    const int grid = sm_count() * 12;
-    if (exact) q3b_tpc_widen_kernel<true><<<grid, kWidenThreads, 0, stream>>>(P);
-    else q3b_tpc_widen_kernel<false><<<grid, kWidenThreads, 0, stream>>>(P);
+    const int grid = sm_count() * 8;
+    const size_t smem = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? sizeof(unsigned) * P.q_nbins : 0;
+    if (exact) q3b_tpc_widen_kernel<true><<<grid, kWidenThreads, smem, stream>>>(P);
+    else q3b_tpc_widen_kernel<false><<<grid, kWidenThreads, smem, stream>>>(P);
     add_launches(1);
     return WOL_OK;
 }
@@ -547,6 +584,7 @@ static int launch_tpc(const Q3bParams &P0, cudaStream_t stream) {
     size_t smem = sizeof(TpcSmem);
     if (P.nbins <= kMaxSmemBins) smem += sizeof(double) * tab_len;
     if (P.do_3b && P.ang_hist && P.nbins <= kMaxSmemBins) smem += sizeof(unsigned) * P.nbins;
+    if (P.do_q && P.q_hist && P.q_nbins <= kMaxSmemBins) smem += sizeof(unsigned) * P.q_nbins;
     cudaError_t e = cudaFuncSetAttribute(q3b_tpc_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(tpc)", e);
     int per_sm = 0;
@@ -554,6 +592,12 @@ static int launch_tpc(const Q3bParams &P0, cudaStream_t stream) {
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > P.total_tiles) grid = P.total_tiles;
+    {
+        const char *env = getenv("WOL_TPC_CHUNK");
+        const int c = env ? atoi(env) : 1;
+        P.chunk_tiles = c > 0 ? c : (int)((P.total_tiles + grid - 1) / (grid > 0 ? grid : 1));
+        if (P.chunk_tiles < 1) P.chunk_tiles = 1;
+    }
     if (grid > 0) {
         q3b_tpc_kernel<EXACT><<<(unsigned)grid, kTpcThreads, smem, stream>>>(P);
         add_launches(1);

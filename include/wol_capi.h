@@ -277,6 +277,61 @@ int wol_shell_mask(const void *sol, int32_t sol_dtype, int32_t n_sol, const doub
                    const int32_t nc[3], double edge_min, double lowcut, double cutoff, void *workspace,
                    size_t workspace_bytes, int32_t *mask, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Slab / interface routines (BASELINE config 4) and the all-Fortran triplet histogram.  One frame per call.
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * K5: Willard-Chandler density, WillardDensityField / WillardDensityPoints (fortran/waterlib.f90:1286-1341,
+ * :1351-1398; called at structureLibs/surface_library.py:197): at every point the sum over waters of a
+ * Gaussian of width smoothlen truncated and shifted to zero at 3 smoothlen, and the normalised gradient.
+ *   points == NULL : the nx * ny * nz grid points (gridx[i], gridy[j], gridz[k]); outputs [nx][ny][nz] and
+ *                    [nx][ny][nz][3] row-major.  Otherwise n_points explicit points [n_points][3].
+ *   workspace      : cell list of wol_cell_build(FP64) over the n_pos water oxygens with r_cell >= 3 smoothlen.
+ * densnorms may be NULL.  A point farther than 3 smoothlen from every water gets a NaN normal (0/0), as in
+ * the reference.  The terms are summed in cell order rather than atom order (differences ~1e-16 relative).
+ */
+int wol_willard_density(const double *points, int64_t n_points, const double *gridx, const double *gridy, const double *gridz,
+                        int32_t nx, int32_t ny, int32_t nz, const double *box, int32_t n_pos, const int32_t nc[3], double edge_min,
+                        double smoothlen, void *workspace, size_t workspace_bytes, double *densvals, double *densnorms,
+                        void *stream);
+
+/*
+ * InterfaceWater (fortran/waterlib.f90:1414-1469): for every water the nearest interface point (0-based,
+ * first index on ties, -1 if none within distance^2 < 1000 -- the Fortran leaves that entry unwritten) and
+ * its signed depth allwatdists = (water - point) . normal; for every interface point the nearest water;
+ * numwater (ACCUMULATED, caller zero-fills) = waters with depth <= cutoff.  surfclose / numwater may be NULL.
+ * Waters without an interface point in range get depth 0 and are not counted.
+ */
+int wol_interface_water(const double *pos, int32_t n_pos, const double *gridpos, const double *gridnorm, int32_t n_grid,
+                        double cutoff, const double *box, int32_t *watclose, int32_t *surfclose, int32_t *numwater,
+                        double *allwatdists, void *stream);
+
+/*
+ * Depth-binned profile of a per-water observable (config 4: q against the interface depth).  The reference
+ * has the ingredients but no such function; bin = floor((coord - lo) / width), values
+ * outside [0, nbins) are skipped.  count / sum / sumsq are ACCUMULATED.
+ */
+int wol_profile_bins(const double *value, const double *coord, int64_t n, double lo, double width, int32_t nbins, int64_t *count,
+                     double *sum, double *sumsq, void *stream);
+
+/*
+ * Angle-bin table for the Fortran ceiling rule bin = ceiling(angle / ang_width) (fortran/waterlib.f90:1584),
+ * same layout and construction as wol_angle_table (nbins + 1 + WOL_TABLE_EXTRA doubles, host-only).
+ */
+int wol_angle_table_ceil(double ang_width, int32_t nbins, double *table_host);
+
+/*
+ * histrr3b (fortran/waterlib.f90:1550-1593): histogram over triplets (i; j < k) of (distance i-j, distance
+ * i-k, angle j-i-k) with ceiling binning; hist[d_num][d_num][a_num] int64, ACCUMULATED.  workspace: cell
+ * list over the n_pos atoms with r_cell >= d_num * dist_width; angle_table: device copy of
+ * wol_angle_table_ceil.  Triplets that index bin 0 in the Fortran (coincident atoms, 0 or -180 degree
+ * angles; an out-of-bounds write there) are skipped.  At most 192 neighbours per atom inside the range.
+ */
+int wol_histrr3b(const double *box, int32_t n_pos, const int32_t nc[3], double edge_min, double dist_width, int32_t d_num,
+                 double ang_width, int32_t a_num, const double *angle_table, void *workspace, size_t workspace_bytes, int64_t *hist,
+                 void *stream);
+
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);
 

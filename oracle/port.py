@@ -183,3 +183,46 @@ def angles_from_cos(c):
     out = np.zeros_like(c)
     _lib().wol_oracle_angles_from_cos(_ptr(c, _dp), ctypes.c_int64(c.size), _ptr(out, _dp))
     return out
+
+
+def willard_density_points(pos, denspts, BoxL, smoothlen):
+    """WillardDensityPoints (fortran/waterlib.f90:1351-1398) -> (densvals (npts,), densnorms (npts,3))."""
+    pos, pts, box = _pos(pos), _pos(denspts), _box(BoxL)
+    dens = np.zeros(pts.shape[0], dtype=np.float64)
+    norms = np.zeros((pts.shape[0], 3), dtype=np.float64)
+    _lib().wol_oracle_willard_points(_ptr(pos, _dp), pos.shape[0], _ptr(pts, _dp), ctypes.c_int64(pts.shape[0]),
+                                     _ptr(box, _dp), ctypes.c_double(smoothlen), _ptr(dens, _dp), _ptr(norms, _dp))
+    return dens, norms
+
+
+def willard_density_field(pos, gridx, gridy, gridz, BoxL, smoothlen):
+    """WillardDensityField (fortran/waterlib.f90:1286-1341) -> (densvals (nx,ny,nz), densnorms (nx,ny,nz,3))."""
+    gx, gy, gz = (np.asarray(g, dtype=np.float64) for g in (gridx, gridy, gridz))
+    X, Y, Z = np.meshgrid(gx, gy, gz, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    dens, norms = willard_density_points(pos, pts, BoxL, smoothlen)
+    return dens.reshape(gx.size, gy.size, gz.size), norms.reshape(gx.size, gy.size, gz.size, 3)
+
+
+def interface_water(pos, gridpos, gridnorm, cutoff, BoxL):
+    """InterfaceWater (fortran/waterlib.f90:1414-1469) with 0-based indices, -1 = none within r^2 < 1000.
+    -> (watclose int32 (n,), surfclose int32 (ng,), numwater, allwatdists f64 (n,))."""
+    pos, gp, gn, box = _pos(pos), _pos(gridpos), _pos(gridnorm), _box(BoxL)
+    n, ng = pos.shape[0], gp.shape[0]
+    watclose = np.zeros(n, dtype=np.int32)
+    surfclose = np.zeros(ng, dtype=np.int32)
+    numwater = ctypes.c_int32(0)
+    dists = np.zeros(n, dtype=np.float64)
+    _lib().wol_oracle_interface_water(_ptr(pos, _dp), n, _ptr(gp, _dp), _ptr(gn, _dp), ng, ctypes.c_double(cutoff),
+                                      _ptr(box, _dp), _ptr(watclose, _ip), _ptr(surfclose, _ip), ctypes.byref(numwater),
+                                      _ptr(dists, _dp))
+    return watclose, surfclose, int(numwater.value), dists
+
+
+def histrr3b(Pos, BoxL, distWidth, dNum, angWidth, aNum):
+    """histrr3b (fortran/waterlib.f90:1550-1593) -> int64 counts (dNum, dNum, aNum)."""
+    pos, box = _pos(Pos), _box(BoxL)
+    hist = np.zeros((dNum, dNum, aNum), dtype=np.int64)
+    _lib().wol_oracle_histrr3b(_ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(distWidth), int(dNum),
+                               ctypes.c_double(angWidth), int(aNum), _ptr(hist, _lp))
+    return hist

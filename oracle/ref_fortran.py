@@ -172,6 +172,30 @@ class RefWaterlib:
             ctypes.byref(ctypes.c_int32(anum)), _dp(out), ctypes.byref(ctypes.c_int32(n)))
         return out
 
+    # fortran/waterlib.f90:1286-1341 -> (densvals (nx,ny,nz), densnorms (nx,ny,nz,3)), C-ordered copies
+    def willarddensityfield(self, pos, gridx, gridy, gridz, boxl, smoothlen):
+        pos = _f64(pos)
+        gx, gy, gz = (np.ascontiguousarray(np.asarray(g, dtype=np.float64)) for g in (gridx, gridy, gridz))
+        nx, ny, nz = gx.size, gy.size, gz.size
+        dens = np.zeros((nx, ny, nz), dtype=np.float64, order="F")
+        norms = np.zeros((nx, ny, nz, 3), dtype=np.float64, order="F")
+        self._lib.willarddensityfield_(
+            _dp(pos), _dp(gx), _dp(gy), _dp(gz), _dp(_box(boxl)), ctypes.byref(ctypes.c_double(smoothlen)),
+            _dp(dens), _dp(norms), ctypes.byref(ctypes.c_int32(pos.shape[0])), ctypes.byref(ctypes.c_int32(nx)),
+            ctypes.byref(ctypes.c_int32(ny)), ctypes.byref(ctypes.c_int32(nz)))
+        return np.ascontiguousarray(dens), np.ascontiguousarray(norms)
+
+    # fortran/waterlib.f90:1351-1398
+    def willarddensitypoints(self, pos, denspts, boxl, smoothlen):
+        pos, pts = _f64(pos), _f64(denspts)
+        npts = pts.shape[0]
+        dens = np.zeros(npts, dtype=np.float64)
+        norms = np.zeros((npts, 3), dtype=np.float64, order="F")
+        self._lib.willarddensitypoints_(
+            _dp(pos), _dp(pts), _dp(_box(boxl)), ctypes.byref(ctypes.c_double(smoothlen)), _dp(dens), _dp(norms),
+            ctypes.byref(ctypes.c_int32(pos.shape[0])), ctypes.byref(ctypes.c_int32(npts)))
+        return dens, np.ascontiguousarray(norms)
+
     # fortran/waterlib.f90:683-703
     def cosangle3(self, p1, p2, p3):
         a = [np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(3)) for p in (p1, p2, p3)]
@@ -188,7 +212,7 @@ class RefWaterlib:
         pos, gp, gn = _f64(pos), _f64(gridpos), _f64(gridnorm)
         n, g = pos.shape[0], gp.shape[0]
         watclose = np.zeros(n, dtype=np.int32)
-        surfclose = np.zeros(n, dtype=np.int32)
+        surfclose = np.zeros(g, dtype=np.int32)
         numwater = ctypes.c_int32(0)
         allwatdists = np.zeros(n, dtype=np.float64)
         self._lib.interfacewater_(

@@ -476,3 +476,115 @@ int wol_oracle_angles_from_cos(const double *c, int64_t n, double *ang) {
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Slab / interface routines and the all-Fortran triplet histogram.                            */
+
+/* WillardDensityField / WillardDensityPoints (waterlib.f90:1286-1341, :1351-1398): truncated, shifted
+ * Gaussian density and its normalised gradient at `npts` points.  Sum over waters in index order, exactly
+ * as the reference loops (every water is tested; the cut-off only zeroes its term). */
+int wol_oracle_willard_points(const double *pos, int n, const double *pts, int64_t npts, const double *boxl,
+                              double smoothlen, double *densvals, double *densnorms) {
+    box_t b;
+    box_init(&b, boxl);
+    const double s2 = smoothlen * smoothlen;
+    const double pref = pow(2.0 * kPi * s2, 1.5);
+    const double shiftterm = exp(-9.0 / 2.0) / pref;
+    const double cut = 9.0 * (smoothlen * smoothlen);
+#pragma omp parallel for schedule(static) if (npts > 256)
+    for (int64_t g = 0; g < npts; ++g) {
+        const double *a = pts + 3 * (size_t)g;
+        double dens = 0.0, nv[3] = {0.0, 0.0, 0.0};
+        for (int l = 0; l < n; ++l) {
+            double v[3];
+            min_image(&b, a, pos + 3 * (size_t)l, v); /* thisvec = apos - watpos */
+            double r2 = sumsq(v);
+            if (r2 >= cut) continue; /* adds 0.0: no effect on the sums */
+            double expterm = -r2 / (2.0 * s2);
+            double densfunc = exp(expterm) / pref - shiftterm;
+            for (int c = 0; c < 3; ++c) nv[c] = nv[c] + (-v[c] * (densfunc + shiftterm) / s2);
+            dens = dens + densfunc;
+        }
+        densvals[g] = dens;
+        double nn = sqrt(sumsq(nv));
+        for (int c = 0; c < 3; ++c) densnorms[3 * (size_t)g + c] = nv[c] / nn;
+    }
+    return 0;
+}
+
+/* InterfaceWater (waterlib.f90:1414-1469).  Indices are 0-based here, -1 = no interface point (water) inside
+ * distance^2 < 1000; such waters get allwatdists = 0 (the Fortran reads an uninitialised index there). */
+int wol_oracle_interface_water(const double *pos, int n, const double *gridpos, const double *gridnorm, int ng,
+                               double cutoff, const double *boxl, int32_t *watclose, int32_t *surfclose,
+                               int32_t *numwater, double *allwatdists) {
+    box_t b;
+    box_init(&b, boxl);
+    double *griddists = (double *)malloc((size_t)(ng > 0 ? ng : 1) * sizeof(double));
+    for (int j = 0; j < ng; ++j) {
+        griddists[j] = 1000.0;
+        surfclose[j] = -1;
+    }
+    int count = 0;
+    for (int i = 0; i < n; ++i) {
+        const double *w = pos + 3 * (size_t)i;
+        double watdist = 1000.0, d[3];
+        int close = -1;
+        for (int j = 0; j < ng; ++j) {
+            min_image(&b, w, gridpos + 3 * (size_t)j, d);
+            double s = sumsq(d);
+            if (s < watdist) {
+                close = j;
+                watdist = s;
+            }
+            if (s < griddists[j]) {
+                surfclose[j] = i;
+                griddists[j] = s;
+            }
+        }
+        watclose[i] = close;
+        double proj = 0.0;
+        if (close >= 0) {
+            const double *cn = gridnorm + 3 * (size_t)close;
+            min_image(&b, w, gridpos + 3 * (size_t)close, d);
+            proj = (d[0] * cn[0] + d[1] * cn[1]) + d[2] * cn[2];
+            if (proj <= cutoff) ++count;
+        }
+        allwatdists[i] = proj;
+    }
+    *numwater = count;
+    free(griddists);
+    return 0;
+}
+
+/* histrr3b (waterlib.f90:1550-1593): triplet histogram with ceiling binning.  hist[d1][d2][a] (0-based, C
+ * order) counts; triplets whose bin index would be 0 or negative in the Fortran (coincident atoms, the 0 and
+ * -180 degree returns of CosAngle3) write out of bounds there and are skipped here. */
+int wol_oracle_histrr3b(const double *pos, int n, const double *boxl, double dwidth, int dnum, double awidth, int anum,
+                        int64_t *hist) {
+    box_t b;
+    box_init(&b, boxl);
+    const double zero[3] = {0.0, 0.0, 0.0};
+    double *vec = (double *)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(double));
+    int *bin = (int *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+    for (int i = 0; i < n; ++i) {
+        const double *r = pos + 3 * (size_t)i;
+        for (int j = 0; j < n; ++j) {
+            min_image(&b, pos + 3 * (size_t)j, r, vec + 3 * (size_t)j);
+            bin[j] = (int)ceil(sqrt(sumsq(vec + 3 * (size_t)j)) / dwidth);
+        }
+        for (int j = 0; j < n; ++j) {
+            if (j == i || bin[j] > dnum) continue;
+            for (int k = j + 1; k < n; ++k) {
+                if (k == i || bin[k] > dnum) continue;
+                double ang = cos_angle3(vec + 3 * (size_t)j, zero, vec + 3 * (size_t)k);
+                int ab = (int)ceil(ang / awidth);
+                if (ab > anum) continue;
+                if (bin[j] < 1 || bin[k] < 1 || ab < 1) continue;
+                hist[((size_t)(bin[j] - 1) * dnum + (bin[k] - 1)) * anum + (ab - 1)]++;
+            }
+        }
+    }
+    free(vec);
+    free(bin);
+    return 0;
+}

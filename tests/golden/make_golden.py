@@ -113,6 +113,29 @@ def main():
                         tetra=wl.cosangle3([1, 1, 1], [0, 0, 0], [1, -1, -1]))
     print("routines ok")
 
+    # slab (cfg4 building blocks): Willard-Chandler density on a grid and at points, InterfaceWater against the
+    # analytic faces, all from the reference's compiled Fortran (waterlib.f90:1286-1469)
+    pos, box, z_lo, z_hi = synth.slab_box(4, 4, 2, sigma=0.3, seed=31)
+    gx = np.linspace(0.0, box[0], 9, endpoint=False)
+    gy = np.linspace(0.0, box[1], 8, endpoint=False)
+    gz = np.linspace(0.0, box[2], 25, endpoint=False)
+    dens, norms = wl.willarddensityfield(pos, gx, gy, gz, box, 2.4)
+    pts = (rng.random((64, 3)) * box).astype(np.float32).astype(np.float64)
+    pdens, pnorms = wl.willarddensitypoints(pos, pts, box, 2.4)
+    gp, gn = synth.plane_interface(box, z_lo, z_hi, spacing=2.0)
+    watclose, surfclose, numwater, dists = wl.interfacewater(pos, gp, gn, 3.0, box)
+    np.savez_compressed(os.path.join(OUT, "slab_n256.npz"), pos=pos, box=box, z_lo=z_lo, z_hi=z_hi, gx=gx, gy=gy, gz=gz,
+                        smoothlen=2.4, dens=dens, norms=norms, pts=pts, pdens=pdens, pnorms=pnorms, gridpos=gp, gridnorm=gn,
+                        cutoff=3.0, watclose=watclose, surfclose=surfclose, numwater=np.int64(numwater), allwatdists=dists)
+    print("slab", pos.shape[0], "waters", gp.shape[0], "interface points", numwater, "within cutoff")
+
+    # histrr3b (waterlib.f90:1550-1593): triplet histogram, ceiling bins
+    pos, box = synth.water_box(3, sigma=0.35, seed=8)
+    h = wl.histrr3b(pos, box, 0.5, 8, 5.0, 36)
+    np.savez_compressed(os.path.join(OUT, "histrr3b_n216.npz"), pos=pos, box=box, dwidth=0.5, dnum=8, awidth=5.0, anum=36,
+                        hist=np.ascontiguousarray(h).astype(np.int64))
+    print("histrr3b", int(h.sum()))
+
 
 if __name__ == "__main__":
     main()

@@ -80,3 +80,23 @@ def test_fixtures_match_generator(golden_dir):
     pos, box = synth.water_box(4, sigma=0.25, seed=1234)
     assert np.array_equal(pos, g["pos"]) and np.array_equal(box, g["box"])
     assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 10
+
+
+def test_slab_routines_against_golden(golden_dir):
+    """Willard-Chandler density, InterfaceWater (fortran/waterlib.f90:1286-1469)."""
+    g = np.load(os.path.join(golden_dir, "slab_n256.npz"))
+    d, n = port.willard_density_field(g["pos"], g["gx"], g["gy"], g["gz"], g["box"], float(g["smoothlen"]))
+    fin = np.isfinite(g["norms"])
+    assert np.allclose(d, g["dens"], rtol=1e-13, atol=1e-18) and np.array_equal(np.isfinite(n), fin)
+    assert np.allclose(n[fin], g["norms"][fin], rtol=0, atol=1e-12)
+    d, n = port.willard_density_points(g["pos"], g["pts"], g["box"], float(g["smoothlen"]))
+    assert np.allclose(d, g["pdens"], rtol=1e-13, atol=1e-18)
+    wc, sc, nw, dist = port.interface_water(g["pos"], g["gridpos"], g["gridnorm"], float(g["cutoff"]), g["box"])
+    assert np.array_equal(wc + 1, g["watclose"]) and np.array_equal(sc + 1, g["surfclose"])
+    assert nw == int(g["numwater"]) and np.array_equal(dist, g["allwatdists"])
+
+
+def test_histrr3b_against_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "histrr3b_n216.npz"))
+    h = port.histrr3b(g["pos"], g["box"], float(g["dwidth"]), int(g["dnum"]), float(g["awidth"]), int(g["anum"]))
+    assert np.array_equal(h, g["hist"])

@@ -69,6 +69,12 @@ SIGNATURES = {
     "wol_hbond_locations": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "wol_shell_mask": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp,
                                       ctypes.c_size_t, c_vp, c_vp]),
+    "wol_willard_density": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, _NC, c_f64, c_f64, c_vp,
+                                           ctypes.c_size_t, c_vp, c_vp, c_vp]),
+    "wol_interface_water": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "wol_profile_bins": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "wol_angle_table_ceil": (ctypes.c_int, [c_f64, c_i32, c_vp]),
+    "wol_histrr3b": (ctypes.c_int, [c_vp, c_i32, _NC, c_f64, c_f64, c_i32, c_f64, c_i32, c_vp, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "wol_status": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_vp, ctypes.POINTER(c_i32 * 4)]),
 }
 

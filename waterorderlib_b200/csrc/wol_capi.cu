@@ -212,6 +212,31 @@ int wol_angle_table(double hist_lo, double hist_hi, int32_t nbins, double tet_lo
     return WOL_OK;
 }
 
+int wol_angle_table_ceil(double ang_width, int32_t nbins, double *table_host) {
+    if (!table_host || nbins < 1 || !(ang_width > 0.0))
+        return set_error(WOL_ERR_INVALID, "wol_angle_table_ceil: need nbins >= 1, a positive width and an output array");
+    // 0-based bin of the Fortran rule bin = ceiling(x / width) (waterlib.f90:1584): -1 for x <= 0, nbins beyond
+    auto position = [&](double c) {
+        volatile double q = ref_angle_deg(c) / ang_width;
+        const double t = ceil(q);
+        if (!(t >= 1.0)) return -1;
+        if (t > (double)nbins) return (int)nbins;
+        return (int)t - 1;
+    };
+    for (int k = 0; k <= nbins; ++k) table_host[k] = last_true([&](double c) { return position(c) >= k; });
+    double *extra = table_host + nbins + 1;
+    extra[0] = (double)position(-1.0);  // the -180 CosAngle3 returns for an antiparallel pair: no bin
+    extra[1] = -1.0;                    // 0 degrees (coincident positions): bin 0 of the Fortran, out of bounds
+    extra[2] = extra[3] = 0.0;
+    int ok = 1;
+    for (int k = 1; k <= nbins && ok; ++k)
+        if (table_host[k] > table_host[k - 1]) ok = 0;
+    extra[4] = (double)ok;
+    extra[5] = extra[6] = extra[7] = 0.0;
+    if (!ok) return set_error(WOL_ERR_UNSUPPORTED, "wol_angle_table_ceil: host acos is not monotone near a bin edge");
+    return WOL_OK;
+}
+
 int wol_q3b_frames(const wol_q3b_args *a, void *stream) {
     g_launches = 0;
     if (!a) return set_error(WOL_ERR_INVALID, "wol_q3b_frames: null args");

@@ -1,0 +1,472 @@
+// Slab / interface routines (BASELINE config 4) and the all-Fortran triplet histogram, sm_100a, fp64 in the
+// reference's operation order:
+//   willard_kernel        WillardDensityField / WillardDensityPoints   fortran/waterlib.f90:1286-1341, :1351-1398
+//   iface_water_kernel    InterfaceWater, per-water part                 fortran/waterlib.f90:1431-1468
+//   iface_surf_kernel     InterfaceWater, per-surface-point part         fortran/waterlib.f90:1447-1450
+//   profile_kernel        depth-binned profile of a per-water observable (the cfg-4 composition; the reference
+//                         has the ingredients, structureLibs/surface_library.py:170-210, but no such function)
+//   histrr3b_kernel       histrr3b                                        fortran/waterlib.f90:1550-1593
+#include <math.h>
+
+#include "wol_q3b_common.cuh"
+
+namespace wol {
+
+struct CellGridS {
+    const uint32_t *cell_start;
+    const void *recs;
+    int nc0, nc1, nc2;
+};
+
+struct Box3 {
+    double L[3], iL[3];
+};
+// iBoxL = merge(1/BoxL, 0, BoxL >= 0)  (waterlib.f90:41)
+__device__ __forceinline__ Box3 load_box3(const double *b) {
+    Box3 o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.L[k] = b[k];
+        o.iL[k] = (b[k] >= 0.0) ? __ddiv_rn(1.0, b[k]) : 0.0;
+    }
+    return o;
+}
+
+// ---- Willard-Chandler density ------------------------------------------------------------------------
+
+struct WillardParams {
+    CellGridS grid;  // cell list over the waters, cell edge >= 3 smoothlen
+    const double *box;
+    const double *pts;                 // explicit points [n][3], or nullptr: the grid below
+    const double *gx, *gy, *gz;        // grid axes
+    int nx, ny, nz;
+    long long n_points;
+    double s2, pref, shiftterm, cut;   // smoothlen^2, (2 pi s2)^1.5, exp(-4.5)/pref, 9 smoothlen^2
+    double *dens;                      // [n_points]
+    double *norms;                     // [n_points][3]
+};
+
+__global__ void __launch_bounds__(128) willard_kernel(const WillardParams P) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.n_points) return;
+    double ax, ay, az;
+    if (P.pts) {
+        ax = P.pts[3 * g + 0]; ay = P.pts[3 * g + 1]; az = P.pts[3 * g + 2];
+    } else {
+        const int k = (int)(g % P.nz), j = (int)((g / P.nz) % P.ny), i = (int)(g / ((long long)P.nz * P.ny));
+        ax = P.gx[i]; ay = P.gy[j]; az = P.gz[k];
+    }
+    const Box3 b = load_box3(P.box);
+    const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+    const int cx = cell_coord(ax, b.iL[0], nc0), cy = cell_coord(ay, b.iL[1], nc1), cz = cell_coord(az, b.iL[2], nc2);
+    const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+    const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+              zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+    double dens = 0.0, nvx = 0.0, nvy = 0.0, nvz = 0.0;
+    for (int iz = 0; iz < cntz; ++iz) {
+        const int z = (zs + iz) % nc2;
+        for (int iy = 0; iy < cnty; ++iy) {
+            const int y = (ys + iy) % nc1;
+            for (int ix = 0; ix < cntx; ++ix) {
+                const int x = (xs + ix) % nc0;
+                const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
+                const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
+                for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
+                    double px, py, pz;
+                    int id;
+                    RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+                    // thisvec = apos - watpos, minimum image (waterlib.f90:1313-1314)
+                    const double vx = min_image_1<double, true>(ax, px, b.L[0], b.iL[0]);
+                    const double vy = min_image_1<double, true>(ay, py, b.L[1], b.iL[1]);
+                    const double vz = min_image_1<double, true>(az, pz, b.L[2], b.iL[2]);
+                    const double r2 = sumsq3<double>(vx, vy, vz);
+                    if (r2 >= P.cut) continue;
+                    const double expterm = __ddiv_rn(-r2, __dmul_rn(2.0, P.s2));
+                    const double densfunc = __dsub_rn(__ddiv_rn(exp(expterm), P.pref), P.shiftterm);
+                    const double w = __dadd_rn(densfunc, P.shiftterm);
+                    nvx = __dadd_rn(nvx, __ddiv_rn(__dmul_rn(-vx, w), P.s2));
+                    nvy = __dadd_rn(nvy, __ddiv_rn(__dmul_rn(-vy, w), P.s2));
+                    nvz = __dadd_rn(nvz, __ddiv_rn(__dmul_rn(-vz, w), P.s2));
+                    dens = __dadd_rn(dens, densfunc);
+                }
+            }
+        }
+    }
+    P.dens[g] = dens;
+    if (P.norms) {
+        const double nn = __dsqrt_rn(sumsq3<double>(nvx, nvy, nvz));  // 0/0 = NaN far from every water, as in the reference
+        P.norms[3 * g + 0] = __ddiv_rn(nvx, nn);
+        P.norms[3 * g + 1] = __ddiv_rn(nvy, nn);
+        P.norms[3 * g + 2] = __ddiv_rn(nvz, nn);
+    }
+}
+
+// ---- InterfaceWater -----------------------------------------------------------------------------------
+// Both kernels are tiled brute force (the search radius, sqrt(1000) A, is most of a box): every thread owns
+// one row entity and walks all column entities through shared-memory tiles in ascending index order with the
+// reference's strict '<', so ties resolve to the same index as the Fortran loops.
+
+constexpr int kIfaceThreads = 128;
+constexpr int kIfaceTile = 256;
+
+__global__ void __launch_bounds__(kIfaceThreads) iface_water_kernel(const double *__restrict__ pos, int n_pos,
+                                                                    const double *__restrict__ gridpos,
+                                                                    const double *__restrict__ gridnorm, int n_grid,
+                                                                    const double *__restrict__ box, double cutoff,
+                                                                    int32_t *__restrict__ watclose, double *__restrict__ dists,
+                                                                    int32_t *__restrict__ numwater) {
+    __shared__ double s_g[kIfaceTile * 3];
+    const int i = blockIdx.x * kIfaceThreads + threadIdx.x;
+    const bool valid = i < n_pos;
+    const Box3 b = load_box3(box);
+    double wx = 0, wy = 0, wz = 0;
+    if (valid) {
+        wx = pos[3 * (size_t)i + 0]; wy = pos[3 * (size_t)i + 1]; wz = pos[3 * (size_t)i + 2];
+    }
+    double best = 1000.0;
+    int close = -1;
+    for (int t0 = 0; t0 < n_grid; t0 += kIfaceTile) {
+        const int nt = min(kIfaceTile, n_grid - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_g[k] = gridpos[3 * (size_t)t0 + k];
+        __syncthreads();
+        if (valid) {
+#pragma unroll 4
+            for (int t = 0; t < nt; ++t) {
+                const double dx = min_image_1<double, true>(wx, s_g[3 * t + 0], b.L[0], b.iL[0]);
+                const double dy = min_image_1<double, true>(wy, s_g[3 * t + 1], b.L[1], b.iL[1]);
+                const double dz = min_image_1<double, true>(wz, s_g[3 * t + 2], b.L[2], b.iL[2]);
+                const double s = sumsq3<double>(dx, dy, dz);
+                if (s < best) {
+                    best = s;
+                    close = t0 + t;
+                }
+            }
+        }
+    }
+    bool counted = false;
+    if (valid) {
+        double proj = 0.0;
+        if (close >= 0) {
+            const double *g = gridpos + 3 * (size_t)close, *cn = gridnorm + 3 * (size_t)close;
+            const double dx = min_image_1<double, true>(wx, g[0], b.L[0], b.iL[0]);
+            const double dy = min_image_1<double, true>(wy, g[1], b.L[1], b.iL[1]);
+            const double dz = min_image_1<double, true>(wz, g[2], b.L[2], b.iL[2]);
+            proj = dot3<double>(dx, dy, dz, cn[0], cn[1], cn[2]);  // sum(normvec * closenorm)  (:1464)
+            counted = proj <= cutoff;
+        }
+        watclose[i] = close;
+        dists[i] = proj;
+    }
+    const unsigned m = __ballot_sync(kFullMask, counted);
+    if ((threadIdx.x & 31) == 0 && m != 0u && numwater) atomicAdd(numwater, __popc(m));
+}
+
+__global__ void __launch_bounds__(kIfaceThreads) iface_surf_kernel(const double *__restrict__ pos, int n_pos,
+                                                                   const double *__restrict__ gridpos, int n_grid,
+                                                                   const double *__restrict__ box, int32_t *__restrict__ surfclose) {
+    __shared__ double s_w[kIfaceTile * 3];
+    const int j = blockIdx.x * kIfaceThreads + threadIdx.x;
+    const bool valid = j < n_grid;
+    const Box3 b = load_box3(box);
+    double gx = 0, gy = 0, gz = 0;
+    if (valid) {
+        gx = gridpos[3 * (size_t)j + 0]; gy = gridpos[3 * (size_t)j + 1]; gz = gridpos[3 * (size_t)j + 2];
+    }
+    double best = 1000.0;
+    int close = -1;
+    for (int t0 = 0; t0 < n_pos; t0 += kIfaceTile) {
+        const int nt = min(kIfaceTile, n_pos - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_w[k] = pos[3 * (size_t)t0 + k];
+        __syncthreads();
+        if (valid) {
+#pragma unroll 4
+            for (int t = 0; t < nt; ++t) {
+                // distvec = watpos - gpos (:1440)
+                const double dx = min_image_1<double, true>(s_w[3 * t + 0], gx, b.L[0], b.iL[0]);
+                const double dy = min_image_1<double, true>(s_w[3 * t + 1], gy, b.L[1], b.iL[1]);
+                const double dz = min_image_1<double, true>(s_w[3 * t + 2], gz, b.L[2], b.iL[2]);
+                const double s = sumsq3<double>(dx, dy, dz);
+                if (s < best) {
+                    best = s;
+                    close = t0 + t;
+                }
+            }
+        }
+    }
+    if (valid) surfclose[j] = close;
+}
+
+// ---- depth-binned profile -------------------------------------------------------------------------------
+
+constexpr int kProfileMaxBins = 2048;
+
+__global__ void __launch_bounds__(256) profile_kernel(const double *__restrict__ value, const double *__restrict__ coord, long long n,
+                                                      double lo, double width, int nbins, unsigned long long *__restrict__ count,
+                                                      double *__restrict__ sum, double *__restrict__ sumsq) {
+    extern __shared__ double s_acc[];  // [3][nbins] when it fits
+    const bool smem = nbins <= kProfileMaxBins;
+    if (smem) {
+        for (int i = threadIdx.x; i < 3 * nbins; i += blockDim.x) s_acc[i] = 0.0;
+        __syncthreads();
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d = coord[i], v = value[i];
+        const double t = floor(__ddiv_rn(__dsub_rn(d, lo), width));
+        if (!(t >= 0.0) || !(t < (double)nbins)) continue;
+        const int bin = (int)t;
+        if (smem) {
+            atomicAdd(s_acc + bin, 1.0);
+            atomicAdd(s_acc + nbins + bin, v);
+            atomicAdd(s_acc + 2 * nbins + bin, v * v);
+        } else {
+            atomicAdd(count + bin, 1ull);
+            atomicAdd(sum + bin, v);
+            atomicAdd(sumsq + bin, v * v);
+        }
+    }
+    if (smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+            const double c = s_acc[i];
+            if (c != 0.0) {
+                atomicAdd(count + i, (unsigned long long)c);
+                atomicAdd(sum + i, s_acc[nbins + i]);
+                atomicAdd(sumsq + i, s_acc[2 * nbins + i]);
+            }
+        }
+    }
+}
+
+// ---- histrr3b ---------------------------------------------------------------------------------------------
+// One warp per centre.  The lanes walk the candidates of the 27-cell stencil (cell edge >= dNum * distWidth),
+// keep those whose distance bin is inside the histogram in a shared list, then spread the list's pairs over
+// the lanes: the pair's lower ATOM INDEX supplies the first distance bin (the reference's j < k loops), the
+// angle bin comes from the clamped cosine through the ceiling-rule threshold table.
+
+constexpr int kRR3Threads = 128;
+constexpr int kRR3Cap = 192;  // neighbours per centre inside the histogram's distance range
+
+struct RR3Params {
+    CellGridS grid;
+    const double *box;
+    int n_pos;
+    double dwidth, awidth;
+    int dnum, anum;
+    const double *table;  // ceiling-rule angle table (wol_angle_table_ceil)
+    unsigned long long *hist;  // [dnum][dnum][anum]
+    uint32_t *counters;
+};
+
+struct RR3Smem {
+    Vec4<double> v[kRR3Cap];
+    int bin[kRR3Cap];
+    int idx[kRR3Cap];
+    int n;
+};
+
+__global__ void __launch_bounds__(kRR3Threads) histrr3b_kernel(const RR3Params P) {
+    __shared__ RR3Smem S[kRR3Threads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RR3Smem &W = S[warp];
+    const Box3 b = load_box3(P.box);
+    const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+    const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+    const int ncell27 = cntx * cnty * cntz;
+    const double inv_aw = 1.0 / P.awidth;
+    for (int i = blockIdx.x * (kRR3Threads / 32) + warp; i < P.n_pos; i += gridDim.x * (kRR3Threads / 32)) {
+        // centre i = record i (cell order); the histogram does not depend on the order of the centres
+        double rx, ry, rz;
+        int self_idx;
+        RecTraits<double>::load(P.grid.recs, (size_t)i, rx, ry, rz, self_idx);
+        const int cx = cell_coord(rx, b.iL[0], nc0), cy = cell_coord(ry, b.iL[1], nc1), cz = cell_coord(rz, b.iL[2], nc2);
+        const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+                  zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+        __syncwarp();
+        if (lane == 0) W.n = 0;
+        __syncwarp();
+        for (int c27 = lane; c27 < ncell27; c27 += 32) {
+            const int ix = c27 % cntx, iy = (c27 / cntx) % cnty, iz = c27 / (cntx * cnty);
+            const size_t c = ((size_t)((zs + iz) % nc2) * nc1 + (ys + iy) % nc1) * nc0 + (xs + ix) % nc0;
+            const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
+            for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
+                if (j == i) continue;
+                double px, py, pz;
+                int id;
+                RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+                Vec4<double> v;
+                v.x = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
+                v.y = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
+                v.z = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
+                v.w = sumsq3<double>(v.x, v.y, v.z);
+                const double t = ceil(__ddiv_rn(__dsqrt_rn(v.w), P.dwidth));  // dbin = ceiling(dist / distWidth)
+                if (!(t <= (double)P.dnum) || t < 1.0) continue;                // bin 0 (coincident atoms) is out of bounds in the Fortran
+                const int at = atomicAdd(&W.n, 1);
+                if (at < kRR3Cap) {
+                    W.v[at] = v;
+                    W.bin[at] = (int)t - 1;
+                    W.idx[at] = id;
+                }
+            }
+        }
+        __syncwarp();
+        const int n = W.n;
+        if (n > kRR3Cap) {
+            if (lane == 0) atomicAdd(P.counters + kCntFatal, 1u);
+            continue;
+        }
+        const int npairs = n * (n - 1) / 2;
+        for (int p = lane; p < npairs; p += 32) {
+            int hi = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (hi * (hi - 1) / 2 > p) --hi;
+            while ((hi + 1) * hi / 2 <= p) ++hi;
+            const int lo = p - hi * (hi - 1) / 2;
+            const Vec4<double> va = W.v[lo], vb = W.v[hi];
+            const bool lo_first = W.idx[lo] < W.idx[hi];
+            const int d1 = lo_first ? W.bin[lo] : W.bin[hi], d2 = lo_first ? W.bin[hi] : W.bin[lo];
+            // CosAngle3(distvec1, 0, distvec2) (:1583): Vec21 = distvec1 - 0, Vec23 = distvec2 - 0
+            const double c = clamped_cos<double>(dot3<double>(va.x, va.y, va.z, vb.x, vb.y, vb.z), va.w, vb.w);
+            const int pos = angle_position(c, P.table, P.anum, 0.0, inv_aw);
+            if (pos >= 0 && pos < P.anum) atomicAdd(P.hist + ((size_t)d1 * P.dnum + d2) * P.anum + pos, 1ull);
+        }
+    }
+}
+
+static CellGridS make_grid_s(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
+    char *ws = reinterpret_cast<char *>(workspace);
+    CellGridS g;
+    g.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
+    g.recs = ws + lay.off_recs;
+    g.nc0 = nc[0];
+    g.nc1 = nc[1];
+    g.nc2 = nc[2];
+    return g;
+}
+
+}  // namespace wol
+
+using namespace wol;
+
+extern "C" {
+
+int wol_willard_density(const double *points, int64_t n_points, const double *gridx, const double *gridy, const double *gridz,
+                        int32_t nx, int32_t ny, int32_t nz, const double *box, int32_t n_pos, const int32_t nc[3], double edge_min,
+                        double smoothlen, void *workspace, size_t workspace_bytes, double *densvals, double *densnorms,
+                        void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!box || !nc || !workspace || !densvals) return set_error(WOL_ERR_INVALID, "wol_willard_density: null argument");
+    if (!(smoothlen > 0.0)) return set_error(WOL_ERR_INVALID, "wol_willard_density: smoothlen must be positive");
+    long long n = n_points;
+    if (!points) {
+        if (!gridx || !gridy || !gridz || nx < 0 || ny < 0 || nz < 0) return set_error(WOL_ERR_INVALID, "wol_willard_density: bad grid");
+        n = (long long)nx * ny * nz;
+    }
+    if (n < 0) return set_error(WOL_ERR_INVALID, "wol_willard_density: negative size");
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && 3.0 * smoothlen * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "Gaussian cut-off %.6g exceeds the planned cell edge %.6g", 3.0 * smoothlen, edge_min);
+    const WorkspaceLayout lay = workspace_layout(1, n_pos, n_pos, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    WillardParams P;
+    P.grid = make_grid_s(workspace, lay, nc);
+    P.box = box;
+    P.pts = points;
+    P.gx = gridx; P.gy = gridy; P.gz = gridz;
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.n_points = n;
+    const double pi = 3.1415926535897931;
+    P.s2 = smoothlen * smoothlen;
+    P.pref = pow(2.0 * pi * (smoothlen * smoothlen), 1.5);   // host libm, like the reference's Fortran runtime
+    P.shiftterm = exp(-9.0 / 2.0) / P.pref;
+    P.cut = 9.0 * (smoothlen * smoothlen);
+    P.dens = densvals;
+    P.norms = densnorms;
+    if (n > 0) {
+        willard_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_willard_density", e);
+    return WOL_OK;
+}
+
+int wol_interface_water(const double *pos, int32_t n_pos, const double *gridpos, const double *gridnorm, int32_t n_grid,
+                        double cutoff, const double *box, int32_t *watclose, int32_t *surfclose, int32_t *numwater,
+                        double *allwatdists, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pos < 0 || n_grid < 0 || !box || (!pos && n_pos > 0) || ((!gridpos || !gridnorm) && n_grid > 0) || !watclose || !allwatdists)
+        return set_error(WOL_ERR_INVALID, "wol_interface_water: bad argument");
+    if (n_pos > 0) {
+        iface_water_kernel<<<(n_pos + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
+            pos, n_pos, gridpos, gridnorm, n_grid, box, cutoff, watclose, allwatdists, numwater);
+        add_launches(1);
+    }
+    if (surfclose && n_grid > 0) {
+        iface_surf_kernel<<<(n_grid + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(pos, n_pos, gridpos, n_grid, box,
+                                                                                                     surfclose);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_interface_water", e);
+    return WOL_OK;
+}
+
+int wol_profile_bins(const double *value, const double *coord, int64_t n, double lo, double width, int32_t nbins, int64_t *count,
+                     double *sum, double *sumsq, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || nbins < 1 || !(width > 0.0) || !count || !sum || !sumsq || ((!value || !coord) && n > 0))
+        return set_error(WOL_ERR_INVALID, "wol_profile_bins: bad argument");
+    if (n == 0) return WOL_OK;
+    const size_t smem = nbins <= kProfileMaxBins ? sizeof(double) * 3 * nbins : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(profile)", e);
+    }
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    profile_kernel<<<(unsigned)blocks, 256, smem, stream>>>(value, coord, n, lo, width, nbins, reinterpret_cast<unsigned long long *>(count),
+                                                            sum, sumsq);
+    add_launches(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_profile_bins", e);
+    return WOL_OK;
+}
+
+int wol_histrr3b(const double *box, int32_t n_pos, const int32_t nc[3], double edge_min, double dist_width, int32_t d_num,
+                 double ang_width, int32_t a_num, const double *angle_table, void *workspace, size_t workspace_bytes, int64_t *hist,
+                 void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!box || !nc || !workspace || !hist || !angle_table) return set_error(WOL_ERR_INVALID, "wol_histrr3b: null argument");
+    if (d_num < 1 || a_num < 1 || !(dist_width > 0.0) || !(ang_width > 0.0)) return set_error(WOL_ERR_INVALID, "wol_histrr3b: bad bin spec");
+    const double reach = dist_width * d_num;
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && reach * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "histogram range %.6g exceeds the planned cell edge %.6g", reach, edge_min);
+    const WorkspaceLayout lay = workspace_layout(1, n_pos, n_pos, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    RR3Params P;
+    P.grid = make_grid_s(workspace, lay, nc);
+    P.box = box;
+    P.n_pos = n_pos;
+    P.dwidth = dist_width;
+    P.awidth = ang_width;
+    P.dnum = d_num;
+    P.anum = a_num;
+    P.table = angle_table;
+    P.hist = reinterpret_cast<unsigned long long *>(hist);
+    P.counters = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + lay.off_counters);
+    if (n_pos > 0) {
+        long long blocks = ((long long)n_pos + 3) / 4;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        histrr3b_kernel<<<(unsigned)blocks, kRR3Threads, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_histrr3b", e);
+    return WOL_OK;
+}
+
+}  // extern "C"

@@ -293,3 +293,107 @@ def hbond_locations(pairs, acc, donh, box, device=None):
                                             int(donh_d.shape[1]), _vp(box_d.data_ptr()), _vp(out.data_ptr()), _stream()),
                   "wol_hbond_locations")
     return out
+
+
+# ---- slab / interface routines (BASELINE config 4) and histrr3b ----------------------------------------
+
+def willard_density(pos, box, smoothlen=2.4, grid=None, points=None, want_normals=True, device=None):
+    """WillardDensityField (grid=(gridx, gridy, gridz)) or WillardDensityPoints (points=(n,3)),
+    fortran/waterlib.f90:1286-1398.  Returns (densvals, densnorms) CUDA tensors shaped (nx,ny,nz) /
+    (nx,ny,nz,3) or (n,) / (n,3)."""
+    if (grid is None) == (points is None):
+        raise ValueError("give exactly one of grid=(gridx, gridy, gridz) or points=")
+    device = _device(device, pos)
+    cells = CellList(pos, box, 3.0 * float(smoothlen) * (1.0 + 1e-9), device=device)
+    if cells.F != 1:
+        raise ValueError("the density field is evaluated one frame at a time")
+    if grid is not None:
+        gx, gy, gz = (_f64(np.asarray(g, dtype=np.float64).reshape(-1) if not isinstance(g, torch.Tensor) else g.reshape(-1), device)
+                      for g in grid)
+        nx, ny, nz = int(gx.numel()), int(gy.numel()), int(gz.numel())
+        n = nx * ny * nz
+        shape = (nx, ny, nz)
+        pts_ptr, g_ptrs = None, (_vp(gx.data_ptr()), _vp(gy.data_ptr()), _vp(gz.data_ptr()))
+    else:
+        pts = _f64(points, device, (3,)).reshape(-1, 3)
+        n = int(pts.shape[0])
+        nx = ny = nz = 0
+        shape = (n,)
+        pts_ptr, g_ptrs = _vp(pts.data_ptr()), (None, None, None)
+    dens = torch.empty(shape, dtype=torch.float64, device=device)
+    norms = torch.empty(shape + (3,), dtype=torch.float64, device=device) if want_normals else None
+    with torch.cuda.device(device):
+        check(lib().wol_willard_density(pts_ptr, n, g_ptrs[0], g_ptrs[1], g_ptrs[2], nx, ny, nz, _vp(cells.box_d.data_ptr()), cells.N,
+                                        ctypes.byref(cells.nc), cells.edge_min, float(smoothlen), _vp(cells.ws_ptr), cells.ws_bytes,
+                                        _vp(dens.data_ptr()), _vp(norms.data_ptr()) if norms is not None else None, _stream()),
+              "wol_willard_density")
+        torch.cuda.current_stream().synchronize()  # the cell list (cells) dies with this frame
+    return dens, norms
+
+
+def interface_water(pos, gridpos, gridnorm, cutoff, box, want_surfclose=True, device=None):
+    """InterfaceWater (fortran/waterlib.f90:1414-1469) -> dict(watclose int32 (n,) 0-based / -1, surfclose int32
+    (ng,), numwater int, allwatdists f64 (n,))."""
+    device = _device(device, pos, gridpos)
+    pos_d = _f64(pos, device, (3,)).reshape(-1, 3)
+    gp = _f64(gridpos, device, (3,)).reshape(-1, 3)
+    gn = _f64(gridnorm, device, (3,)).reshape(-1, 3)
+    if gp.shape != gn.shape:
+        raise ValueError("gridpos and gridnorm differ in shape")
+    box_d = _box3(box, device)
+    n, ng = int(pos_d.shape[0]), int(gp.shape[0])
+    watclose = torch.full((n,), -1, dtype=torch.int32, device=device)
+    surfclose = torch.full((ng,), -1, dtype=torch.int32, device=device) if want_surfclose else None
+    numwater = torch.zeros(1, dtype=torch.int32, device=device)
+    dists = torch.zeros(n, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_interface_water(_vp(pos_d.data_ptr()), n, _vp(gp.data_ptr()), _vp(gn.data_ptr()), ng, float(cutoff),
+                                        _vp(box_d.data_ptr()), _vp(watclose.data_ptr()),
+                                        _vp(surfclose.data_ptr()) if surfclose is not None else None, _vp(numwater.data_ptr()),
+                                        _vp(dists.data_ptr()), _stream()), "wol_interface_water")
+    return {"watclose": watclose, "surfclose": surfclose, "numwater": numwater, "allwatdists": dists, "_keep": (pos_d, gp, gn, box_d)}
+
+
+def profile_bins(value, coord, lo, width, nbins, out=None, device=None):
+    """Depth-binned profile: (count int64, sum f64, sumsq f64) per bin of floor((coord - lo) / width), accumulated
+    into `out` when given (a tuple of three tensors)."""
+    device = _device(device, value, coord)
+    v = _f64(value, device).reshape(-1)
+    c = _f64(coord, device).reshape(-1)
+    if v.numel() != c.numel():
+        raise ValueError("value and coord differ in length")
+    if out is None:
+        out = (torch.zeros(nbins, dtype=torch.int64, device=device), torch.zeros(nbins, dtype=torch.float64, device=device),
+               torch.zeros(nbins, dtype=torch.float64, device=device))
+    with torch.cuda.device(device):
+        check(lib().wol_profile_bins(_vp(v.data_ptr()), _vp(c.data_ptr()), v.numel(), float(lo), float(width), int(nbins),
+                                     _vp(out[0].data_ptr()), _vp(out[1].data_ptr()), _vp(out[2].data_ptr()), _stream()),
+              "wol_profile_bins")
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
+_CEIL_TABLES = {}
+
+
+def histrr3b(pos, box, dist_width, d_num, ang_width, a_num, device=None):
+    """histrr3b (fortran/waterlib.f90:1550-1593) -> int64 counts (d_num, d_num, a_num) CUDA tensor."""
+    device = _device(device, pos)
+    key = (float(ang_width), int(a_num), str(device))
+    table = _CEIL_TABLES.get(key)
+    if table is None:
+        from ._capi import WOL_TABLE_EXTRA
+        host = np.zeros(a_num + 1 + WOL_TABLE_EXTRA, dtype=np.float64)
+        check(lib().wol_angle_table_ceil(float(ang_width), int(a_num), host.ctypes.data_as(_vp)), "wol_angle_table_ceil")
+        table = torch.from_numpy(host).to(device)
+        _CEIL_TABLES[key] = table
+    cells = CellList(pos, box, float(dist_width) * int(d_num) * (1.0 + 1e-9), device=device)
+    if cells.F != 1:
+        raise ValueError("histrr3b takes one frame")
+    hist = torch.zeros((d_num, d_num, a_num), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_histrr3b(_vp(cells.box_d.data_ptr()), cells.N, ctypes.byref(cells.nc), cells.edge_min, float(dist_width),
+                                 int(d_num), float(ang_width), int(a_num), _vp(table.data_ptr()), _vp(cells.ws_ptr), cells.ws_bytes,
+                                 _vp(hist.data_ptr()), _stream()), "wol_histrr3b")
+        cells.status()  # raises if a neighbour list overflowed; also synchronises
+    return hist

@@ -62,3 +62,32 @@ def generalhbonds(acceptorpos, donorpos, donorhpos, boxl, distcut, angcut):
     r = routines.hbond_counts(acc, don, donh, boxl, distcut, angcut, dense=True)
     torch.cuda.current_stream().synchronize()
     return _np(r["dense"][0])
+
+
+def willarddensityfield(pos, gridx, gridy, gridz, boxl, smoothlen):
+    """densvals,densnorms = willarddensityfield(pos,gridx,gridy,gridz,boxl,smoothlen)
+    (fortran/waterlib.f90:1286-1341) -> (nx,ny,nz) and (nx,ny,nz,3), Fortran-ordered like f2py's."""
+    dens, norms = routines.willard_density(_check_pos(pos, "pos"), boxl, smoothlen, grid=(gridx, gridy, gridz))
+    return _np(dens), _np(norms)
+
+
+def willarddensitypoints(pos, denspts, boxl, smoothlen):
+    """densvals,densnorms = willarddensitypoints(pos,denspts,boxl,smoothlen)   (fortran/waterlib.f90:1351-1398)"""
+    dens, norms = routines.willard_density(_check_pos(pos, "pos"), boxl, smoothlen, points=_check_pos(denspts, "denspts"))
+    return _np(dens), _np(norms)
+
+
+def interfacewater(pos, gridpos, gridnorm, cutoff, boxl):
+    """watclose,surfclose,numwater,allwatdists = interfacewater(pos,gridpos,gridnorm,cutoff,boxl)
+    (fortran/waterlib.f90:1414-1469).  Indices are 1-BASED, as the Fortran returns them through f2py;
+    0 marks an entry the Fortran would have left unwritten (nothing within distance^2 < 1000)."""
+    r = routines.interface_water(_check_pos(pos, "pos"), _check_pos(gridpos, "gridpos"), _check_pos(gridnorm, "gridnorm"),
+                                 cutoff, boxl)
+    return (_np(r["watclose"]) + 1, _np(r["surfclose"]) + 1, int(r["numwater"].item()), _np(r["allwatdists"]))
+
+
+def histrr3b(pos, boxl, distwidth, dnum, angwidth, anum):
+    """histout = histrr3b(pos,boxl,distwidth,dnum,angwidth,anum)   (fortran/waterlib.f90:1550-1593) -> float64
+    (dnum,dnum,anum), Fortran-ordered."""
+    h = routines.histrr3b(_check_pos(pos, "pos"), boxl, distwidth, dnum, angwidth, anum)
+    return np.asfortranarray(h.cpu().numpy().astype(np.float64))

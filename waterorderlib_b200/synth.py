@@ -94,3 +94,18 @@ def trajectory(m, n_frames, sigma=0.25, seed0=1234, dims=None):
         frames.append(p)
         boxes.append(b)
     return np.stack(frames), np.stack(boxes)
+
+
+def plane_interface(box, z_lo, z_hi, spacing=2.0):
+    """cfg4 parity interface: the two ideal faces of a slab sampled on a square grid, with outward unit
+    normals (-z at z_lo, +z at z_hi).  Stands in for the marching-cubes surface of the reference
+    (structureLibs/surface_library.py:202), which needs skimage.  Returns (gridpos (G,3), gridnorm (G,3))."""
+    nx, ny = max(1, int(round(box[0] / spacing))), max(1, int(round(box[1] / spacing)))
+    x = (np.arange(nx) + 0.5) * (box[0] / nx)
+    y = (np.arange(ny) + 0.5) * (box[1] / ny)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    pts, nrm = [], []
+    for z, s in ((z_lo, -1.0), (z_hi, 1.0)):
+        pts.append(np.stack([X.ravel(), Y.ravel(), np.full(X.size, z)], axis=1))
+        nrm.append(np.tile(np.array([0.0, 0.0, s]), (X.size, 1)))
+    return (np.concatenate(pts).astype(np.float32).astype(np.float64), np.concatenate(nrm))

@@ -174,7 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=N_CELLS_1M, help="diamond-cubic cells per edge (50 -> 1M waters)")
-    ap.add_argument("--frames-per-step", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--frames-per-step", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=1, help="frames per pipeline batch of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cells", type=int, default=8, help="reference sample box: 8 -> 4096 waters")
     args = ap.parse_args()
@@ -291,7 +292,7 @@ def main():
     n_angles = int(out["ang_hist"].sum().item())
 
     # ---- end-to-end timed region (host buffers in, host results out) -------------------------------
-    pipe = FramePipeline(n_waters, max(1, B // 2), dtype=np.float64, device=dev)
+    pipe = FramePipeline(n_waters, max(1, min(B, args.e2e_batch)), dtype=np.float64, device=dev)
     q_h = torch.empty((B, n_waters), dtype=torch.float64, pin_memory=True)
     n3_h = torch.empty((B, n_waters), dtype=torch.int32, pin_memory=True)
     for _ in range(2):

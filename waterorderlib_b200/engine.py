@@ -110,13 +110,14 @@ class Workspace:
 def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, high3=3.413, lowq=0.0, highq=10.0,
                nbins=500, bin_range=(0.0, 180.0), q_nbins=500, precision="fp64", hist_per_frame=False, r_cell=None,
                want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), out=None, workspace=None,
-               device=None, check_status=True, timing_events=None):
+               device=None, check_status=True, timing_events=None, box_device=None):
     """Fused tetrahedral q + three-body angle histogram for a batch of frames.
 
     pos      (F,N,3) positions of all atoms that can be neighbours (reference: `Pos`)
     box      (3,), (1,3) or (F,3) orthorhombic box edges (reference: `BoxDims`)
     centres  None = every atom of pos is a centre (reference: subPos is Pos); else (F,M,3) (`subPos`)
     out      optional dict of preallocated output tensors to accumulate into / overwrite
+    box_device  optional (F,3) float64 CUDA tensor holding the same boxes (skips the upload)
     Returns a Q3bResult of device tensors; histograms and frame_stats ACCUMULATE into `out` if given.
     """
     if device is None:
@@ -125,7 +126,9 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     pos_d = as_device_positions(pos, device)
     F, N = int(pos_d.shape[0]), int(pos_d.shape[1])
     box_h = as_host_boxes(box, F)
-    box_d = torch.from_numpy(box_h.copy()).to(device)
+    # a pageable host->device copy blocks the host behind everything queued on the stream: callers that pipeline
+    # batches upload all boxes once and pass the slice (box_device)
+    box_d = box_device if box_device is not None else torch.from_numpy(box_h.copy()).to(device)
     cen_d = None
     M = N
     if centres is not None:

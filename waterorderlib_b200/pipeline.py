@@ -1,7 +1,7 @@
 """Host-fed trajectory pipeline: frames live in (pinned) host memory, as they do when a trajectory reader
 hands them over (structureLibs/orderParam_lib.py:1312-1316 reads one pytraj frame per iteration); the GPU
-sees them in batches.  Three streams overlap the host->device copy of batch i+1, the kernels of batch i and
-the device->host copy of batch i-1's per-water results.
+sees them in batches.  Three streams overlap the host->device copies of the next batches (n_slots - 1 of them in flight), the kernels
+of batch i and the device->host copy of batch i-1's per-water results.
 
 This is the call the frame drivers (waterorderlib_b200.orderParam_lib) and bench.py's end-to-end leg make.
 """
@@ -21,7 +21,7 @@ class FramePipeline:
 
     def __init__(self, n_atoms, frames_per_batch, dtype=np.float64, device=None, *, do_q=True, do_3body=True,
                  low3=0.0, high3=3.413, lowq=0.0, highq=10.0, nbins=500, bin_range=(0.0, 180.0), q_nbins=500,
-                 precision="fp64", hist_per_frame=False, r_cell=None, want_q=True, want_n3=True, want_nn=False):
+                 precision="fp64", hist_per_frame=False, r_cell=None, want_q=True, want_n3=True, want_nn=False, n_slots=4):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_atoms, self.fpb = int(n_atoms), int(frames_per_batch)
         self.tdtype = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
@@ -36,7 +36,8 @@ class FramePipeline:
             self.s_in, self.s_run, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
             B, N = self.fpb, self.n_atoms
             self.slots = []
-            for _ in range(2):
+            self.n_slots = max(2, int(n_slots))
+            for _ in range(self.n_slots):
                 slot = dict(pos=torch.empty((B, N, 3), dtype=self.tdtype, device=self.device),
                             q=torch.empty((B, N), dtype=self.qdtype, device=self.device) if do_q else None,
                             n3=torch.empty((B, N), dtype=torch.int32, device=self.device) if do_3body else None,
@@ -76,6 +77,7 @@ class FramePipeline:
                 acc["ang_hist"] = torch.zeros((H, self.nbins), dtype=torch.int64, device=dev)
             if self.do_q:
                 acc["q_hist"] = torch.zeros((H, self.q_nbins), dtype=torch.int64, device=dev)
+            box_d = torch.from_numpy(box_h.copy()).to(dev)  # all boxes once: nothing in the loop blocks the host
             for s in (self.s_in, self.s_run, self.s_out):
                 s.wait_stream(main)
             starts = list(range(0, F, self.fpb))
@@ -83,19 +85,21 @@ class FramePipeline:
             def load(i):
                 f0 = starts[i]
                 nb = min(self.fpb, F - f0)
-                slot = self.slots[i % 2]
+                slot = self.slots[i % self.n_slots]
                 with torch.cuda.stream(self.s_in):
-                    self.s_in.wait_event(slot["computed"])  # the kernels that read this buffer two batches ago
+                    self.s_in.wait_event(slot["computed"])  # the kernels that last read this buffer
                     slot["pos"][:nb].copy_(pos_host[f0:f0 + nb], non_blocking=pin)
                     slot["loaded"].record(self.s_in)
                 self.h2d_bytes += nb * N * 3 * pos_host.element_size()
 
-            load(0)
+            ahead = self.n_slots - 1  # copies in flight ahead of the kernels
+            for i in range(min(ahead, len(starts))):
+                load(i)
             for i, f0 in enumerate(starts):
                 nb = min(self.fpb, F - f0)
-                slot = self.slots[i % 2]
-                if i + 1 < len(starts):
-                    load(i + 1)
+                slot = self.slots[i % self.n_slots]
+                if i + ahead < len(starts):
+                    load(i + ahead)
                 with torch.cuda.stream(self.s_run):
                     self.s_run.wait_event(slot["loaded"])
                     self.s_run.wait_event(slot["drained"])  # the D2H of this slot's previous results
@@ -112,7 +116,7 @@ class FramePipeline:
                     kw = dict(self.kw)
                     kw["hist_per_frame"] = self.hist_per_frame
                     r = engine.q3b_frames(slot["pos"][:nb], box_h[f0:f0 + nb], out=out, want=want, workspace=self.ws,
-                                          device=dev, check_status=False, **kw)
+                                          device=dev, check_status=False, box_device=box_d[f0:f0 + nb], **kw)
                     self.launches += r["launches"]
                     slot["computed"].record(self.s_run)
                 with torch.cuda.stream(self.s_out):

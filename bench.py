@@ -291,6 +291,33 @@ def main():
     st = engine.workspace_status(ws, B, n_waters, n_waters, engine.default_r_cell(True, True, 3.413, 10.0), box)
     n_angles = int(out["ang_hist"].sum().item())
 
+    # ---- FP32 arithmetic mode, same frames, device-resident (north_star: both modes reported) ---------
+    out32 = {"q": torch.zeros((B, n_waters), dtype=torch.float32, device=dev),
+             "n3": torch.zeros((B, n_waters), dtype=torch.int32, device=dev),
+             "ang_hist": torch.zeros((1, 500), dtype=torch.int64, device=dev),
+             "q_hist": torch.zeros((1, 500), dtype=torch.int64, device=dev),
+             "frame_stats": torch.zeros((B, 8), dtype=torch.float64, device=dev)}
+    ws32 = engine.Workspace(dev)
+
+    def step32():
+        return engine.q3b_frames(pos_d, box, out=out32, want=want, workspace=ws32, device=dev, check_status=False,
+                                 precision="fp32")
+
+    for _ in range(3):
+        step32()
+    out32["ang_hist"].zero_()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        step32()
+    g1.record()
+    barrier()
+    ms32 = g0.elapsed_time(g1)
+    q_err32 = float((out32["q"].double() - out["q"]).abs().max().item())
+    hist_l1 = float((out32["ang_hist"] - out["ang_hist"]).abs().sum().item()) / max(1.0, float(out["ang_hist"].sum().item()))
+    del out32, ws32
+
     # ---- end-to-end timed region (host buffers in, host results out) -------------------------------
     pipe = FramePipeline(n_waters, max(1, min(B, args.e2e_batch)), dtype=np.float64, device=dev)
     q_h = torch.empty((B, n_waters), dtype=torch.float64, pin_memory=True)
@@ -320,6 +347,7 @@ def main():
         return float(t.item())
 
     ms_total = max_over_ranks(ms_total)
+    ms32 = max_over_ranks(ms32)
     e2e_ms_total = max_over_ranks(e2e_ms_total)
     kernel_ms = max_over_ranks(kernel_ms)
     wf_per_step = float(world) * B * n_waters
@@ -342,6 +370,9 @@ def main():
                          "kernel_ms": kernel_ms, "bytes_per_water_frame": BYTES_PER_WF_FP64, "peak_source": peak_src,
                          "note": "the sweep is issue/FP64-bound by construction (about 1.2 kFLOP per water-frame, SURVEY 8d)"},
             "clocks": sampler.summary(),
+            "fp32_mode": {"value": float(world) * B * n_waters * args.steps / (ms32 * 1e-3), "unit": UNIT,
+                          "ms_per_step": ms32 / args.steps, "max_abs_q_error_vs_fp64": q_err32,
+                          "angle_hist_L1_distance_vs_fp64": hist_l1, "tolerance": 1e-4},
             "checks": {"angles_binned": n_angles, "widened": st[0], "overflow": st[1]}}
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline

@@ -1,0 +1,60 @@
+"""FP32 arithmetic mode of the fused path (precision="fp32"): the north_star tolerance is 1e-4 on per-molecule q and
+cosines; neighbour selection and histogram bins can legitimately differ from the fp64 reference where two
+distances (or an angle and a bin edge) agree to ~1e-7 relative, so those are compared statistically."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import port  # noqa: E402  (the checker)
+from waterorderlib_b200 import engine, synth  # noqa: E402
+
+Q_ATOL = 1e-4  # north_star tolerance for fp32 mode (q is O(1))
+
+
+def compare(r, f, pos, box, sub=None, **cut):
+    q, nn4, _ = port.order_param_q(pos if sub is None else sub, pos, box, cut.get("lowq", 0.0), cut.get("highq", 10.0))
+    tb = port.three_body(pos if sub is None else sub, pos, box, cut.get("low3", 0.0), cut.get("high3", 3.413), materialize=False)
+    m = q.shape[0]
+    same_nn = np.all(r.nn_idx.cpu().numpy()[f] == nn4, axis=1)
+    assert same_nn.mean() > 0.995, same_nn.mean()
+    qd = np.abs(r.q.cpu().numpy()[f].astype(np.float64) - q)
+    assert qd[same_nn].max() < Q_ATOL, qd[same_nn].max()
+    assert (r.n3.cpu().numpy()[f] == tb["numAngs"]).mean() > 0.998
+    h = r.ang_hist.cpu().numpy()[f if r.ang_hist.shape[0] > 1 else 0]
+    assert abs(int(h.sum()) - int(tb["hist"].sum())) <= 0.002 * tb["hist"].sum() + 5
+    assert np.abs(h - tb["hist"]).sum() <= 0.01 * tb["hist"].sum() + 10  # L1 distance: bin-edge flips only
+    return m
+
+
+@pytest.mark.parametrize("name", ["cfg1_n512_ice", "cfg1_n512_liq", "cfg2_n4096_frame0"])
+def test_fp32_mode_against_golden_inputs(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    r = engine.q3b_frames(g["pos"].astype(np.float32), g["box"], precision="fp32")
+    torch.cuda.synchronize()
+    assert r.q.dtype == torch.float32
+    compare(r, 0, g["pos"], g["box"])
+
+
+def test_fp32_mode_batched_large_box():
+    """1M-water box edge (310 A): ulp(310 A) in float32 is 3e-5 A -- the mode must stay inside 1e-4 on q."""
+    pos, box = synth.water_box(24, sigma=0.3, seed=3)  # 110,592 waters, L = 149 A
+    shift = np.floor(np.array([150.0, 0.0, 75.0]) / box) * box  # unwrapped coordinates far from the origin
+    r = engine.q3b_frames(np.stack([pos, pos + shift]).astype(np.float32), box, precision="fp32", hist_per_frame=True)
+    torch.cuda.synchronize()
+    compare(r, 0, pos, box)
+    compare(r, 1, pos, box)
+
+
+def test_fp32_mode_subpopulation_and_widening():
+    rng = np.random.default_rng(4)
+    box = np.array([40.0, 36.0, 44.0])
+    pos = (rng.random((3000, 3)) * box).astype(np.float32).astype(np.float64)  # dilute: most centres need the widened search
+    sub = (rng.random((500, 3)) * box).astype(np.float32).astype(np.float64)
+    r = engine.q3b_frames(pos.astype(np.float32), box, sub.astype(np.float32), precision="fp32", highq=9.0)
+    torch.cuda.synchronize()
+    compare(r, 0, pos, box, sub=sub, highq=9.0)
+    assert r.n_widened > 0

@@ -46,6 +46,7 @@ struct BuildParams {
     uint32_t *slot;
     void *recs;
     float4 *wrapped;
+    uint32_t *cellpack;  // FP32 records only: packed cell coordinates per sorted atom (RecD carries them itself)
 };
 
 // T = storage type of the input positions, R = record type (RecD keeps doubles, RecF floats).
@@ -117,6 +118,17 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
             r.z = (float)z;
             r.idx = a0 + t;
             *reinterpret_cast<int4 *>(reinterpret_cast<RecF *>(p.recs) + dst) = *reinterpret_cast<const int4 *>(&r);
+            if (p.wrapped) {
+                // the FP32 sweep works on box-wrapped coordinates throughout (same binning input as the count pass)
+                float4 w;
+                w.x = wrapped_coord((double)r.x, s_L[0], s_iL[0]);
+                w.y = wrapped_coord((double)r.y, s_L[1], s_iL[1]);
+                w.z = wrapped_coord((double)r.z, s_L[2], s_iL[2]);
+                w.w = __int_as_float(a0 + t);
+                p.wrapped[dst] = w;
+                const int cxy = (int)(c % (uint32_t)(p.nc0 * p.nc1));
+                p.cellpack[dst] = (uint32_t)((cxy % p.nc0) | ((cxy / p.nc0) << 10) | ((int)(c / (uint32_t)(p.nc0 * p.nc1)) << 20));
+            }
         }
     }
 }
@@ -267,7 +279,9 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     p.cell_id = reinterpret_cast<uint32_t *>(ws + lay.off_cell_id);
     p.slot = reinterpret_cast<uint32_t *>(ws + lay.off_slot);
     p.recs = ws + lay.off_recs;
-    p.wrapped = (precision == WOL_PREC_FP64) ? reinterpret_cast<float4 *>(ws + lay.off_wrapped) : nullptr;
+    p.wrapped = reinterpret_cast<float4 *>(ws + lay.off_wrapped);
+    // FP32 records fill only the first half of the record region; the packed cells of the sorted atoms follow
+    p.cellpack = reinterpret_cast<uint32_t *>(ws + lay.off_recs + (size_t)lay.n_atoms_total * sizeof(RecF));
     uint32_t *block_sums = reinterpret_cast<uint32_t *>(ws + lay.off_block_sums);
     const size_t n_scan = (size_t)lay.n_cells_total + 1;
 

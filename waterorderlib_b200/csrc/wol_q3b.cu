@@ -618,7 +618,7 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
     add_launches(1);
     if (P.ev_begin) cudaEventRecord((cudaEvent_t)P.ev_begin, stream);
     if (use_tpc) {
-        int rc = q3b_tpc_launch(P, stream, EXACT);
+        int rc = (sizeof(T) == 8) ? q3b_tpc_launch(P, stream, EXACT) : q3b_tpc32_launch(P, stream);
         if (rc != WOL_OK) return rc;
     } else {
         const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;
@@ -650,7 +650,7 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
     if (rc != WOL_OK) return rc;
     if (P.do_q) {
         if (use_tpc && q3b_tpc_widen_supported(P)) {
-            rc = q3b_tpc_widen_launch(Q, stream, EXACT);
+            rc = q3b_tpc_widen_launch(Q, stream, EXACT, sizeof(T) == 4);
             if (rc != WOL_OK) return rc;
             Q.list = P.list2;
             Q.list_counter = kCntLevel2;
@@ -722,7 +722,8 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     const bool exact = reach > 0.49 * a.edge_min * (double)(P.nc0 < P.nc1 ? (P.nc0 < P.nc2 ? P.nc0 : P.nc2)
                                                                           : (P.nc1 < P.nc2 ? P.nc1 : P.nc2));
     // thread-per-centre fast path: fp64 mode, >= 4 cells per axis
-    P.wrapped = (a.precision == WOL_PREC_FP64) ? reinterpret_cast<const float4 *>(ws + lay.off_wrapped) : nullptr;
+    P.wrapped = reinterpret_cast<const float4 *>(ws + lay.off_wrapped);
+    P.cellpack = reinterpret_cast<const uint32_t *>(ws + lay.off_recs + (size_t)lay.n_atoms_total * sizeof(RecF));
     P.skip_q_only = 0;
     P.ev_begin = a.timing_event_begin;
     P.ev_end = a.timing_event_end;
@@ -755,7 +756,8 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
     if (a.precision == WOL_PREC_FP64)
         return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);
-    return exact ? launch_typed<float, true>(P, stream, false) : launch_typed<float, false>(P, stream, false);
+    const bool use_tpc32 = use_tpc && getenv("WOL_NO_TPC32") == nullptr;
+    return exact ? launch_typed<float, true>(P, stream, false) : launch_typed<float, false>(P, stream, use_tpc32);
 }
 
 }  // namespace wol

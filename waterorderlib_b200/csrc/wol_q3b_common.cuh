@@ -43,6 +43,7 @@ struct Q3bParams {
     long long total_tiles;
     // thread-per-centre fast path
     const float4 *wrapped;  // box-wrapped float coordinates in record order (nullptr: not built)
+    const uint32_t *cellpack;  // FP32 mode: packed cell coordinates in record order
     float pre_thr2;         // prefilter acceptance threshold on the float squared distance
     int skip_q_only;        // large-capacity pass: 1 = leave q-only items to the light instantiation
     void *ev_begin, *ev_end;  // optional cudaEvent_t around the dominant kernel
@@ -284,7 +285,8 @@ __device__ __forceinline__ void flush_hist(const Q3bParams &P, unsigned *s_hist,
 }
 
 int q3b_tpc_launch(const Q3bParams &P, cudaStream_t stream, bool exact);
-int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact);
+int q3b_tpc32_launch(const Q3bParams &P, cudaStream_t stream);
+int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact, bool f32);
 bool q3b_tpc_widen_supported(const Q3bParams &P);
 bool q3b_tpc_supported(const Q3bParams &P);
 

@@ -23,7 +23,7 @@
 // image for every candidate closer than two cell edges.
 #include <stdlib.h>
 
-#include "wol_q3b_common.cuh"
+#include "wol_q3b_f32.cuh"
 
 namespace wol {
 
@@ -397,7 +397,7 @@ __device__ __forceinline__ void widen_row(const float4 *__restrict__ wr, const u
         widen_scan<MODE>(wr, (int)__ldg(cs), (int)__ldg(cs + x1 - nc0 + 1), wx - Lxf, sy, sz, lo2, thr, self_j, a0, a1, a2, a3, list, nl);
 }
 
-template <bool EXACT>
+template <bool EXACT, bool F32>
 __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __grid_constant__ Q3bParams P) {
     __shared__ int s_list[kWidenListCap * kWidenThreads];
     extern __shared__ unsigned s_qhist_dyn[];
@@ -430,11 +430,19 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
         st.reset();
         if (valid) {
         const uint32_t id = e & kFbIdMask;
-        double rx, ry, rz;
+        double rx = 0, ry = 0, rz = 0;
         float wx, wy, wz;
         int cx, cy, cz, self_j = -1;
         size_t out_index;
-        if (P.centres == nullptr) {
+        if (P.centres == nullptr && F32) {  // FP32 records: everything the search needs is in the wrapped array
+            f = (int)(id / (uint32_t)P.n_pos);
+            const float4 w = __ldg(wr + id);
+            const uint32_t cp = __ldg(P.cellpack + id);
+            wx = w.x; wy = w.y; wz = w.z;
+            cx = cp & 1023; cy = (cp >> 10) & 1023; cz = (cp >> 20) & 1023;
+            self_j = (int)id;
+            out_index = (size_t)f * P.n_pos + __float_as_int(w.w);
+        } else if (P.centres == nullptr) {
             f = (int)(id / (uint32_t)P.n_pos);
             const int4 *rp = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(P.recs) + id);
             const int4 a = __ldg(rp), b = __ldg(rp + 1);
@@ -501,6 +509,35 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
             }
         }
 
+        if (F32) {
+            // ---- FP32 mode: the float minimum-image distance IS the distance --------------------------------
+            const float lowqsq_f = (float)lowqsq, selsq2_f = (float)selsq2;
+            const float iLxf = 1.0f / Lxf, iLyf = 1.0f / Lyf, iLzf = 1.0f / Lzf;
+            Top4F top;
+            top.reset();
+            int nq = 0;
+            if (nl <= kWidenListCap) {
+                for (int k = 0; k < nl; ++k) {
+                    const float4 w = __ldg(wr + list[k * kWidenThreads]);
+                    float dx = w.x - wx, dy = w.y - wy, dz = w.z - wz;
+                    dx -= Lxf * rintf(dx * iLxf);
+                    dy -= Lyf * rintf(dy * iLyf);
+                    dz -= Lzf * rintf(dz * iLzf);
+                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (r2 > lowqsq_f && r2 <= selsq2_f) {
+                        ++nq;
+                        top.insert(r2, __float_as_int(w.w), dx, dy, dz);
+                    }
+                }
+            }
+            if (nl > kWidenListCap || (nq < 4 && !last2)) {
+                const uint32_t at = atomicAdd(P.counters + kCntLevel2, 1u);
+                P.list2[at] = id | kFbNeedQ;
+            } else {
+                finish_q32(P, f, top, min(nq, 4), out_index, st, s_qhist, hist_spec(0.0, 1.0, P.q_nbins));
+                done = true;
+            }
+        } else {
         // ---- exact evaluation of the survivors ------------------------------------------------------
         Top4<double> top;
         top.reset();
@@ -531,6 +568,7 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
             finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st, s_qhist);
             done = true;
         }
+        }  // fp64 evaluation
         }  // valid
         // frame statistics: one set of atomics per warp when its centres share a frame (the queue is nearly
         // frame-ordered), per thread otherwise
@@ -562,11 +600,12 @@ bool q3b_tpc_widen_supported(const Q3bParams &P) {
     return P.wrapped != nullptr && P.nc0 >= 7 && P.nc1 >= 7 && P.nc2 >= 7;
 }
 
-int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact) {
+int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact, bool f32) {
     const int grid = sm_count() * 8;
     const size_t smem = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? sizeof(unsigned) * P.q_nbins : 0;
-    if (exact) q3b_tpc_widen_kernel<true><<<grid, kWidenThreads, smem, stream>>>(P);
-    else q3b_tpc_widen_kernel<false><<<grid, kWidenThreads, smem, stream>>>(P);
+    if (f32) q3b_tpc_widen_kernel<false, true><<<grid, kWidenThreads, smem, stream>>>(P);
+    else if (exact) q3b_tpc_widen_kernel<true, false><<<grid, kWidenThreads, smem, stream>>>(P);
+    else q3b_tpc_widen_kernel<false, false><<<grid, kWidenThreads, smem, stream>>>(P);
     add_launches(1);
     return WOL_OK;
 }

@@ -1,0 +1,124 @@
+"""Edge cases of the fused path and the drop-in API, against the CPU oracle: empty and tiny inputs, boxes smaller
+than the cell grid the fast path needs (cutoffs beyond L/2, where the exact round-half-away anint matters), atoms
+exactly on cell boundaries and box faces, coincident atoms with and without a lower cutoff, per-frame boxes
+(NPT), ragged sub-populations, and the error paths."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import port  # noqa: E402  (the checker)
+from waterorderlib_b200 import engine, routines, synth  # noqa: E402
+from waterorderlib_b200._capi import WolError  # noqa: E402
+from waterorderlib_b200.structureLibs import water_properties as wp  # noqa: E402
+
+
+def check(pos, box, sub=None, **cut):
+    r = engine.q3b_frames(pos, box, sub, low3=cut.get("low3", 0.0), high3=cut.get("high3", 3.413), lowq=cut.get("lowq", 0.0),
+                          highq=cut.get("highq", 10.0))
+    torch.cuda.synchronize()
+    c = pos if sub is None else sub
+    q, nn4, _ = port.order_param_q(c, pos, box, cut.get("lowq", 0.0), cut.get("highq", 10.0))
+    tb = port.three_body(c, pos, box, cut.get("low3", 0.0), cut.get("high3", 3.413), materialize=False)
+    assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)
+    assert np.array_equal(r.n3.cpu().numpy()[0], tb["numAngs"])
+    assert np.array_equal(r.ang_hist.cpu().numpy()[0], tb["hist"])
+    assert np.allclose(r.q.cpu().numpy()[0], q, rtol=1e-6, atol=1e-9)
+    return r
+
+
+def test_empty_and_tiny_inputs():
+    box = np.array([20.0, 20.0, 20.0])
+    assert wp.getOrderParamq(np.zeros((0, 3)), np.zeros((0, 3)), box).shape == (0,)
+    one = np.array([[1.0, 2.0, 3.0]])
+    assert wp.getOrderParamq(one, one, box)[0] == 0.0  # no neighbours: q = 0 (water_properties.py:358)
+    ang, num = wp.getCosAngs(one, one, box)
+    assert ang.shape == (0,) and num[0] == 0.0
+    sub = np.array([[5.0, 5.0, 5.0], [15.0, 15.0, 15.0]])
+    assert np.array_equal(wp.getOrderParamq(sub, np.zeros((0, 3)), box), np.zeros(2))
+    two = np.array([[1.0, 1.0, 1.0], [3.5, 1.0, 1.0]])
+    check(two, box)
+    r = engine.q3b_frames(np.zeros((2, 0, 3)), box)  # frames without atoms
+    assert r.ang_hist.sum().item() == 0
+
+
+@pytest.mark.parametrize("L,n,highq", [(9.0, 30, 10.0), (7.5, 12, 10.0), (12.0, 60, 6.0), (10.5, 25, 5.25)])
+def test_small_boxes_cutoff_beyond_half_box(L, n, highq):
+    """nc < 4 cells per axis: generic path; highCut > L/2 keeps only the nearest image of every atom, like the
+    reference's min-image loops; pairs exactly L/2 apart exercise anint's round-half-away."""
+    rng = np.random.default_rng(int(L * 10) + n)
+    box = np.array([L, L * 1.1, L * 0.9])
+    pos = (rng.random((n, 3)) * box).astype(np.float32).astype(np.float64)
+    pos[1] = pos[0] + np.array([L / 2, 0.0, 0.0])  # exactly half a box apart along x
+    check(pos, box, highq=highq, high3=min(3.413, 0.45 * L))
+
+
+def test_atoms_on_cell_boundaries_and_faces():
+    box = np.array([28.0, 28.0, 28.0])  # r_cell 3.5 -> exactly 8 cells of 3.5 A
+    g = np.arange(8) * 3.5
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)  # every atom on a cell corner
+    rng = np.random.default_rng(2)
+    extra = rng.random((300, 3)) * box
+    extra[:50, 0] = 28.0   # exactly on the upper face
+    extra[50:100, 1] = 0.0
+    extra[100:120] = -extra[100:120]  # outside the box, negative
+    pos = np.concatenate([pos, extra]).astype(np.float32).astype(np.float64)
+    check(pos, box, high3=3.5, highq=7.0)
+
+
+def test_coincident_atoms_and_lower_cutoffs():
+    rng = np.random.default_rng(8)
+    box = np.array([22.0, 25.0, 21.0])
+    pos = (rng.random((700, 3)) * box).astype(np.float32).astype(np.float64)
+    pos[10] = pos[3]; pos[11] = pos[3]  # triple coincidence: excluded at lowCut = 0, never a neighbour of itself
+    pos[20] = pos[4] + box               # the same point one box over: distance 0 under the minimum image
+    check(pos, box)
+    check(pos, box, low3=2.0, high3=3.6, lowq=2.5, highq=8.0)
+
+
+def test_per_frame_boxes_npt():
+    frames, boxes = [], []
+    for f, scale in enumerate((0.98, 1.0, 1.03)):
+        p, b = synth.water_box(6, sigma=0.4, seed=60 + f)
+        frames.append((p * scale).astype(np.float32).astype(np.float64))
+        boxes.append(b * scale)
+    pos, box = np.stack(frames), np.stack(boxes)
+    r = engine.q3b_frames(pos, box, hist_per_frame=True)
+    torch.cuda.synchronize()
+    for f in range(3):
+        q, nn4, _ = port.order_param_q(pos[f], pos[f], box[f])
+        tb = port.three_body(pos[f], pos[f], box[f], materialize=False)
+        assert np.array_equal(r.nn_idx.cpu().numpy()[f], nn4) and np.array_equal(r.n3.cpu().numpy()[f], tb["numAngs"])
+        assert np.array_equal(r.ang_hist.cpu().numpy()[f], tb["hist"])
+        assert np.allclose(r.q.cpu().numpy()[f], q, rtol=1e-6, atol=1e-9)
+        assert np.array_equal(r.q_hist.cpu().numpy()[f], np.histogram(q, bins=500, range=[0.0, 1.0])[0])
+
+
+def test_ragged_subpopulations_same_workspace():
+    pos, box = synth.water_box(5, sigma=0.5, seed=3)
+    rng = np.random.default_rng(3)
+    ws = engine.Workspace(torch.device("cuda"))
+    for m in (1, 7, 130, 999, 2):
+        sub = np.concatenate([pos[rng.choice(len(pos), m // 2, replace=False)], rng.random((m - m // 2, 3)) * box])
+        r = engine.q3b_frames(pos, box, sub, workspace=ws, highq=7.0)
+        q, nn4, _ = port.order_param_q(sub, pos, box, 0.0, 7.0)
+        assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4) and np.allclose(r.q.cpu().numpy()[0], q, rtol=1e-6, atol=1e-9)
+
+
+def test_error_paths():
+    pos, box = synth.water_box(3, sigma=0.3, seed=1)
+    with pytest.raises(ValueError):
+        engine.q3b_frames(pos, np.array([18.0, -1.0, 18.0]))     # non-periodic axis: not supported by the cell list
+    with pytest.raises(ValueError):
+        engine.q3b_frames(pos, box, r_cell=2.0)                  # three-body cutoff beyond the planned cell edge
+    with pytest.raises(ValueError):
+        engine.q3b_frames(pos[:, :2], box)
+    with pytest.raises(ValueError):
+        wp.getOrderParamq(pos, pos, np.array([1.0, 2.0]))
+    with pytest.raises(ValueError):
+        routines.hbond_counts(pos, pos, pos[:-1], box)           # donors and hydrogens differ in number (waterlib.f90:1171)
+    # more neighbours than the large-capacity path holds -> WOL_ERR_CAPACITY, not a silent truncation
+    blob = np.random.default_rng(0).random((1500, 3)) * 2.0 + 9.0
+    with pytest.raises(WolError):
+        engine.q3b_frames(np.concatenate([blob, pos]), box, high3=3.4)

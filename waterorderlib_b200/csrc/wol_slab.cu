@@ -1,8 +1,8 @@
 // Slab / interface routines (BASELINE config 4) and the all-Fortran triplet histogram, sm_100a, fp64 in the
 // reference's operation order:
 //   willard_kernel        WillardDensityField / WillardDensityPoints   fortran/waterlib.f90:1286-1341, :1351-1398
-//   iface_water_kernel    InterfaceWater, per-water part                 fortran/waterlib.f90:1431-1468
-//   iface_surf_kernel     InterfaceWater, per-surface-point part         fortran/waterlib.f90:1447-1450
+//   iface_nearest_kernel  InterfaceWater: nearest surface point per water (+ signed depth) and nearest water per
+//                         surface point                                 fortran/waterlib.f90:1431-1468
 //   profile_kernel        depth-binned profile of a per-water observable (the cfg-4 composition; the reference
 //                         has the ingredients, structureLibs/surface_library.py:170-210, but no such function)
 //   histrr3b_kernel       histrr3b                                        fortran/waterlib.f90:1550-1593
@@ -102,100 +102,112 @@ __global__ void __launch_bounds__(128) willard_kernel(const WillardParams P) {
 }
 
 // ---- InterfaceWater -----------------------------------------------------------------------------------
-// Both kernels are tiled brute force (the search radius, sqrt(1000) A, is most of a box): every thread owns
-// one row entity and walks all column entities through shared-memory tiles in ascending index order with the
-// reference's strict '<', so ties resolve to the same index as the Fortran loops.
+// Tiled brute force (the search radius, sqrt(1000) A, is most of a box): every thread owns one row entity and
+// walks all column entities through shared-memory tiles in ascending index order.
 
 constexpr int kIfaceThreads = 128;
-constexpr int kIfaceTile = 256;
+constexpr int kIfaceTile = 512;
 
-__global__ void __launch_bounds__(kIfaceThreads) iface_water_kernel(const double *__restrict__ pos, int n_pos,
-                                                                    const double *__restrict__ gridpos,
-                                                                    const double *__restrict__ gridnorm, int n_grid,
-                                                                    const double *__restrict__ box, double cutoff,
-                                                                    int32_t *__restrict__ watclose, double *__restrict__ dists,
-                                                                    int32_t *__restrict__ numwater) {
-    __shared__ double s_g[kIfaceTile * 3];
-    const int i = blockIdx.x * kIfaceThreads + threadIdx.x;
-    const bool valid = i < n_pos;
-    const Box3 b = load_box3(box);
-    double wx = 0, wy = 0, wz = 0;
-    if (valid) {
-        wx = pos[3 * (size_t)i + 0]; wy = pos[3 * (size_t)i + 1]; wz = pos[3 * (size_t)i + 2];
+// Nearest column entity of one row entity.  A float pass over the shared-memory tile rejects almost every
+// candidate (float minimum image, ~10 instructions); only a candidate whose float distance^2 is inside the
+// current best (+ a margin that covers float rounding of coordinates up to ~2000 A) is re-evaluated with the
+// reference's fp64 arithmetic, and only the fp64 value decides, with the strict '<' and ascending order of the
+// Fortran loops -- so index ties resolve identically.
+struct NearestScan {
+    double best;     // exact distance^2 of the best candidate so far (1000 = none, waterlib.f90:1427,1435)
+    float bound;     // float distance^2 above which a candidate certainly does not beat `best`
+    int close;
+    __device__ __forceinline__ void reset() {
+        best = 1000.0;
+        bound = 1000.0f * (1.0f + 1e-3f) + 5e-2f;
+        close = -1;
     }
-    double best = 1000.0;
-    int close = -1;
-    for (int t0 = 0; t0 < n_grid; t0 += kIfaceTile) {
-        const int nt = min(kIfaceTile, n_grid - t0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_g[k] = gridpos[3 * (size_t)t0 + k];
-        __syncthreads();
-        if (valid) {
+};
+
+// row = the entity that owns the search (rx, ry, rz fp64 + float copy); columns come from `col` (fp64, global)
+// through the float tile.  ROW_IS_WATER selects the operand order of distvec = watpos - gpos (:1440).
+template <bool ROW_IS_WATER>
+__device__ __forceinline__ void nearest_tile(NearestScan &S, const float *__restrict__ s_t, int nt, int t0,
+                                             const double *__restrict__ col, double rx, double ry, double rz, float fx, float fy,
+                                             float fz, const Box3 &b, float Lxf, float Lyf, float Lzf, float iLxf, float iLyf,
+                                             float iLzf) {
 #pragma unroll 4
-            for (int t = 0; t < nt; ++t) {
-                const double dx = min_image_1<double, true>(wx, s_g[3 * t + 0], b.L[0], b.iL[0]);
-                const double dy = min_image_1<double, true>(wy, s_g[3 * t + 1], b.L[1], b.iL[1]);
-                const double dz = min_image_1<double, true>(wz, s_g[3 * t + 2], b.L[2], b.iL[2]);
-                const double s = sumsq3<double>(dx, dy, dz);
-                if (s < best) {
-                    best = s;
-                    close = t0 + t;
-                }
+    for (int t = 0; t < nt; ++t) {
+        float dx = s_t[3 * t + 0] - fx, dy = s_t[3 * t + 1] - fy, dz = s_t[3 * t + 2] - fz;
+        dx -= Lxf * rintf(dx * iLxf);
+        dy -= Lyf * rintf(dy * iLyf);
+        dz -= Lzf * rintf(dz * iLzf);
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (r2 <= S.bound) {
+            const double *c = col + 3 * (size_t)(t0 + t);
+            double ex, ey, ez;
+            if (ROW_IS_WATER) {  // distvec = watpos - gpos
+                ex = min_image_1<double, true>(rx, c[0], b.L[0], b.iL[0]);
+                ey = min_image_1<double, true>(ry, c[1], b.L[1], b.iL[1]);
+                ez = min_image_1<double, true>(rz, c[2], b.L[2], b.iL[2]);
+            } else {
+                ex = min_image_1<double, true>(c[0], rx, b.L[0], b.iL[0]);
+                ey = min_image_1<double, true>(c[1], ry, b.L[1], b.iL[1]);
+                ez = min_image_1<double, true>(c[2], rz, b.L[2], b.iL[2]);
+            }
+            const double s = sumsq3<double>(ex, ey, ez);
+            if (s < S.best) {
+                S.best = s;
+                S.close = t0 + t;
+                S.bound = (float)s * (1.0f + 1e-3f) + 5e-2f;
             }
         }
+    }
+}
+
+template <bool ROW_IS_WATER>
+__global__ void __launch_bounds__(kIfaceThreads) iface_nearest_kernel(const double *__restrict__ row, int n_row,
+                                                                      const double *__restrict__ col, int n_col,
+                                                                      const double *__restrict__ gridnorm,
+                                                                      const double *__restrict__ box, double cutoff,
+                                                                      int32_t *__restrict__ closest, double *__restrict__ dists,
+                                                                      int32_t *__restrict__ numwater) {
+    __shared__ float s_t[kIfaceTile * 3];
+    const int i = blockIdx.x * kIfaceThreads + threadIdx.x;
+    const bool valid = i < n_row;
+    const Box3 b = load_box3(box);
+    // a non-periodic axis (negative edge, iBoxL = 0) simply never wraps in the float pass either
+    const float Lxf = (float)b.L[0], Lyf = (float)b.L[1], Lzf = (float)b.L[2];
+    const float iLxf = (float)b.iL[0], iLyf = (float)b.iL[1], iLzf = (float)b.iL[2];
+    double rx = 0, ry = 0, rz = 0;
+    if (valid) {
+        rx = row[3 * (size_t)i + 0]; ry = row[3 * (size_t)i + 1]; rz = row[3 * (size_t)i + 2];
+    }
+    const float fx = (float)rx, fy = (float)ry, fz = (float)rz;
+    NearestScan S;
+    S.reset();
+    for (int t0 = 0; t0 < n_col; t0 += kIfaceTile) {
+        const int nt = min(kIfaceTile, n_col - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_t[k] = (float)col[3 * (size_t)t0 + k];
+        __syncthreads();
+        if (valid) nearest_tile<ROW_IS_WATER>(S, s_t, nt, t0, col, rx, ry, rz, fx, fy, fz, b, Lxf, Lyf, Lzf, iLxf, iLyf, iLzf);
+    }
+    if (!ROW_IS_WATER) {
+        if (valid) closest[i] = S.close;
+        return;
     }
     bool counted = false;
     if (valid) {
         double proj = 0.0;
-        if (close >= 0) {
-            const double *g = gridpos + 3 * (size_t)close, *cn = gridnorm + 3 * (size_t)close;
-            const double dx = min_image_1<double, true>(wx, g[0], b.L[0], b.iL[0]);
-            const double dy = min_image_1<double, true>(wy, g[1], b.L[1], b.iL[1]);
-            const double dz = min_image_1<double, true>(wz, g[2], b.L[2], b.iL[2]);
+        if (S.close >= 0) {
+            const double *g = col + 3 * (size_t)S.close, *cn = gridnorm + 3 * (size_t)S.close;
+            const double dx = min_image_1<double, true>(rx, g[0], b.L[0], b.iL[0]);
+            const double dy = min_image_1<double, true>(ry, g[1], b.L[1], b.iL[1]);
+            const double dz = min_image_1<double, true>(rz, g[2], b.L[2], b.iL[2]);
             proj = dot3<double>(dx, dy, dz, cn[0], cn[1], cn[2]);  // sum(normvec * closenorm)  (:1464)
             counted = proj <= cutoff;
         }
-        watclose[i] = close;
+        closest[i] = S.close;
         dists[i] = proj;
     }
     const unsigned m = __ballot_sync(kFullMask, counted);
     if ((threadIdx.x & 31) == 0 && m != 0u && numwater) atomicAdd(numwater, __popc(m));
-}
-
-__global__ void __launch_bounds__(kIfaceThreads) iface_surf_kernel(const double *__restrict__ pos, int n_pos,
-                                                                   const double *__restrict__ gridpos, int n_grid,
-                                                                   const double *__restrict__ box, int32_t *__restrict__ surfclose) {
-    __shared__ double s_w[kIfaceTile * 3];
-    const int j = blockIdx.x * kIfaceThreads + threadIdx.x;
-    const bool valid = j < n_grid;
-    const Box3 b = load_box3(box);
-    double gx = 0, gy = 0, gz = 0;
-    if (valid) {
-        gx = gridpos[3 * (size_t)j + 0]; gy = gridpos[3 * (size_t)j + 1]; gz = gridpos[3 * (size_t)j + 2];
-    }
-    double best = 1000.0;
-    int close = -1;
-    for (int t0 = 0; t0 < n_pos; t0 += kIfaceTile) {
-        const int nt = min(kIfaceTile, n_pos - t0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_w[k] = pos[3 * (size_t)t0 + k];
-        __syncthreads();
-        if (valid) {
-#pragma unroll 4
-            for (int t = 0; t < nt; ++t) {
-                // distvec = watpos - gpos (:1440)
-                const double dx = min_image_1<double, true>(s_w[3 * t + 0], gx, b.L[0], b.iL[0]);
-                const double dy = min_image_1<double, true>(s_w[3 * t + 1], gy, b.L[1], b.iL[1]);
-                const double dz = min_image_1<double, true>(s_w[3 * t + 2], gz, b.L[2], b.iL[2]);
-                const double s = sumsq3<double>(dx, dy, dz);
-                if (s < best) {
-                    best = s;
-                    close = t0 + t;
-                }
-            }
-        }
-    }
-    if (valid) surfclose[j] = close;
 }
 
 // ---- depth-binned profile -------------------------------------------------------------------------------
@@ -398,13 +410,13 @@ int wol_interface_water(const double *pos, int32_t n_pos, const double *gridpos,
     if (n_pos < 0 || n_grid < 0 || !box || (!pos && n_pos > 0) || ((!gridpos || !gridnorm) && n_grid > 0) || !watclose || !allwatdists)
         return set_error(WOL_ERR_INVALID, "wol_interface_water: bad argument");
     if (n_pos > 0) {
-        iface_water_kernel<<<(n_pos + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
-            pos, n_pos, gridpos, gridnorm, n_grid, box, cutoff, watclose, allwatdists, numwater);
+        iface_nearest_kernel<true><<<(n_pos + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
+            pos, n_pos, gridpos, n_grid, gridnorm, box, cutoff, watclose, allwatdists, numwater);
         add_launches(1);
     }
     if (surfclose && n_grid > 0) {
-        iface_surf_kernel<<<(n_grid + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(pos, n_pos, gridpos, n_grid, box,
-                                                                                                     surfclose);
+        iface_nearest_kernel<false><<<(n_grid + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
+            gridpos, n_grid, pos, n_pos, nullptr, box, cutoff, surfclose, nullptr, nullptr);
         add_launches(1);
     }
     cudaError_t e = cudaGetLastError();

@@ -164,7 +164,8 @@ struct LaneStats {
     }
 };
 
-__device__ __forceinline__ void flush_stats(const Q3bParams &P, int f, LaneStats &st) {
+// (cold: once per frame a block touches -- kept out of line so the hot loop stays compact in the instruction cache)
+static __device__ __noinline__ void flush_stats(const Q3bParams &P, int f, LaneStats &st) {
     double v[8];
     v[WOL_STAT_Q_SUM] = st.q_sum;
     v[WOL_STAT_Q_SUMSQ] = st.q_sumsq;

@@ -153,42 +153,61 @@ __global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_co
             } else if (cx == nc0 - 1) {
                 xb0 = 0; xb1 = 1; sxb = -Lxf;             // neighbours near x = 0 are images at x + L
             }
-            // all 18 row bounds first (independent loads in flight together), then the rows
-            int rj0[9], rj1[9];
-            float rcy[9], rcz[9];
-#pragma unroll
-            for (int row = 0; row < 9; ++row) {
-                const int dz = row / 3 - 1, dy = row % 3 - 1;
-                int y = cy + dy, z = cz + dz;
-                float cys = wy, czs = wz;
-                if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
-                if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
-                const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
-                rj0[row] = (int)__ldg(cs + xa0);
-                rj1[row] = (int)__ldg(cs + xa1);
-                rcy[row] = cys;
-                rcz[row] = czs;
-            }
             const float4 *wr = P.wrapped;
+            const int j_last = P.n_frames * P.n_pos - 1;
+            // One z-plane of the stencil at a time (keeps the loop body small enough for the instruction cache);
+            // inside a plane: the 6 row bounds first (independent loads in flight together), then the 3 rows.
+#pragma unroll 1
+            for (int pz = -1; pz <= 1; ++pz) {
+                int z = cz + pz;
+                float czs = wz;
+                if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
+                int rj0[3], rj1[3];
+                float rcy[3];
 #pragma unroll
-            for (int row = 0; row < 9; ++row) {
-                const float cys = rcy[row], czs = rcz[row];
-                const int j1 = rj1[row];
-                for (int j = rj0[row]; j < j1; j += 2) {
-                    const bool two = j + 1 < j1;
-                    const float4 w0 = __ldg(wr + j);
-                    const float4 w1 = __ldg(wr + (two ? j + 1 : j));
-                    const float ax = w0.x - wx, ay = w0.y - cys, az = w0.z - czs;
-                    const float bx = w1.x - wx, by = w1.y - cys, bz = w1.z - czs;
-                    const float ra = fmaf(az, az, fmaf(ay, ay, ax * ax));
-                    const float rb = fmaf(bz, bz, fmaf(by, by, bx * bx));
-                    if (ra <= pre_thr2 && j != self_j) {
-                        if (nl < kTpcListCap) S.lj[nl][tid] = j;
-                        ++nl;
+                for (int row = 0; row < 3; ++row) {
+                    int y = cy + row - 1;
+                    float cys = wy;
+                    if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
+                    const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
+                    rj0[row] = (int)__ldg(cs + xa0);
+                    rj1[row] = (int)__ldg(cs + xa1);
+                    rcy[row] = cys;
+                }
+                // Software pipeline: the first pair of the NEXT row and the next pair of THIS row are in flight while
+                // a pair is evaluated (rows hold ~4 candidates).  Prefetch indices are clamped into the array; a
+                // prefetched element beyond its row is never used.
+                float4 p0 = __ldg(wr + min(rj0[0], j_last)), p1 = __ldg(wr + min(rj0[0] + 1, j_last));
+#pragma unroll
+                for (int row = 0; row < 3; ++row) {
+                    const float cys = rcy[row];
+                    const int j1 = rj1[row];
+                    int j = rj0[row];
+                    float4 w0 = p0, w1 = p1;
+                    if (row < 2) {
+                        p0 = __ldg(wr + min(rj0[row < 2 ? row + 1 : 2], j_last));
+                        p1 = __ldg(wr + min(rj0[row < 2 ? row + 1 : 2] + 1, j_last));
                     }
-                    if (two && rb <= pre_thr2 && j + 1 != self_j) {
-                        if (nl < kTpcListCap) S.lj[nl][tid] = j + 1;
-                        ++nl;
+                    while (j < j1) {
+                        const int jn = j + 2;
+                        float4 n0 = w0, n1 = w1;
+                        if (jn < j1) {
+                            n0 = __ldg(wr + jn);
+                            n1 = __ldg(wr + min(jn + 1, j_last));
+                        }
+                        const float ax = w0.x - wx, ay = w0.y - cys, az = w0.z - czs;
+                        const float bx = w1.x - wx, by = w1.y - cys, bz = w1.z - czs;
+                        const float ra = fmaf(az, az, fmaf(ay, ay, ax * ax));
+                        const float rb = fmaf(bz, bz, fmaf(by, by, bx * bx));
+                        if (ra <= pre_thr2 && j != self_j) {
+                            if (nl < kTpcListCap) S.lj[nl][tid] = j;
+                            ++nl;
+                        }
+                        if (j + 1 < j1 && rb <= pre_thr2 && j + 1 != self_j) {
+                            if (nl < kTpcListCap) S.lj[nl][tid] = j + 1;
+                            ++nl;
+                        }
+                        w0 = n0; w1 = n1; j = jn;
                     }
                 }
             }

@@ -132,29 +132,35 @@ __global__ void __launch_bounds__(kT32Threads, 3) q3b_tpc32_kernel(const __grid_
             } else if (cx == nc0 - 1) {
                 xb0 = 0; xb1 = 1; sxb = -Lxf;
             }
-            // all 18 row bounds first (independent loads in flight together), then the rows
-            int rj0[9], rj1[9];
+            // One z-plane of the stencil at a time (keeps the loop body small enough for the instruction cache);
+            // inside a plane: the 6 row bounds first (independent loads in flight together), then the 3 rows.
+#pragma unroll 1
+            for (int pz = -1; pz <= 1; ++pz) {
+                int z = cz + pz;
+                float czs = wz;
+                if (z < 0) { z += nc2; czs += Lzf; } else if (z >= nc2) { z -= nc2; czs -= Lzf; }
+                int rj0[3], rj1[3];
+                float rcy[3];
 #pragma unroll
-            for (int row = 0; row < 9; ++row) {
-                int y = cy + row % 3 - 1, z = cz + row / 3 - 1;
-                if (y < 0) y += nc1; else if (y >= nc1) y -= nc1;
-                if (z < 0) z += nc2; else if (z >= nc2) z -= nc2;
-                const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
-                rj0[row] = (int)__ldg(cs + xa0);
-                rj1[row] = (int)__ldg(cs + xa1);
-            }
+                for (int row = 0; row < 3; ++row) {
+                    int y = cy + row - 1;
+                    float cys = wy;
+                    if (y < 0) { y += nc1; cys += Lyf; } else if (y >= nc1) { y -= nc1; cys -= Lyf; }
+                    const uint32_t *cs = P.cell_start + cell_base + ((size_t)z * nc1 + y) * nc0;
+                    rj0[row] = (int)__ldg(cs + xa0);
+                    rj1[row] = (int)__ldg(cs + xa1);
+                    rcy[row] = cys;
+                }
 #pragma unroll
-            for (int row = 0; row < 9; ++row) {
-                const int y = cy + row % 3 - 1, z = cz + row / 3 - 1;
-                const float cys = wy + (y < 0 ? Lyf : (y >= nc1 ? -Lyf : 0.f));
-                const float czs = wz + (z < 0 ? Lzf : (z >= nc2 ? -Lzf : 0.f));
-                const int j1 = rj1[row];
-                for (int j = rj0[row]; j < j1; j += 2) {
-                    const bool two = j + 1 < j1;
-                    const float4 w0 = __ldg(wr + j);
-                    const float4 w1 = __ldg(wr + (two ? j + 1 : j));
-                    visit(j, w0, wx, cys, czs);
-                    if (two) visit(j + 1, w1, wx, cys, czs);
+                for (int row = 0; row < 3; ++row) {
+                    const int j1 = rj1[row];
+                    for (int j = rj0[row]; j < j1; j += 2) {
+                        const bool two = j + 1 < j1;
+                        const float4 w0 = __ldg(wr + j);
+                        const float4 w1 = __ldg(wr + (two ? j + 1 : j));
+                        visit(j, w0, wx, rcy[row], czs);
+                        if (two) visit(j + 1, w1, wx, rcy[row], czs);
+                    }
                 }
             }
             if (xb1 != 0) {  // the wrapped end of the x-run (first / last cell column only)

@@ -232,6 +232,19 @@ int wol_reimage(const double *pos, int32_t n, const double *ref, const double *b
 int wol_tetracosang(const double *ref, const double *neigh, int32_t k, const double *box, double *out, void *stream);
 
 /*
+ * Local structure index, getLSI (structureLibs/water_properties.py:252-311; distances: lsiDists,
+ * fortran/waterlib.f90:900-918).  For each centre with more than one neighbour inside (lowcut, highcut] and at
+ * least one in the next shell (highcut, highcut + 3.7]: the population variance of the gaps between the sorted
+ * minimum-image distances of those neighbours plus the next-shell atom with the smallest NON-periodic distance
+ * (the reference's choice, :289).  num[f][i] = number of gaps (0: the centre has no value, lsi = 0).
+ * workspace: cell list over pos with r_cell >= highcut + 3.7.  `centres` is required.  At most 47 neighbours
+ * inside highcut (more -> wol_status reports it).
+ */
+int wol_lsi(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos, int32_t n_centres,
+            const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes,
+            double *lsi, int32_t *num, void *stream);
+
+/*
  * K3: hydrogen bonds, generalHbonds (fortran/waterlib.f90:1156-1210) + AngBetween (:954-965), reduced to
  * the sums hbCalc takes (structureLibs/orderParam_lib.py:867-884) and, optionally, the dense matrix or
  * the bonded pair list.  The cell list in `workspace` must have been built (FP64) over the DONOR heavy

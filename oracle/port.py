@@ -226,3 +226,15 @@ def histrr3b(Pos, BoxL, distWidth, dNum, angWidth, aNum):
     _lib().wol_oracle_histrr3b(_ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(distWidth), int(dNum),
                                ctypes.c_double(angWidth), int(aNum), _ptr(hist, _lp))
     return hist
+
+
+def getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7):
+    """structureLibs/water_properties.py:252-311 -> (lsiVals of the centres that have one, numLSI f64 (m,))."""
+    sub, pos, box = _pos(subPos), _pos(Pos), _box(BoxDims)
+    m = sub.shape[0]
+    lsi = np.zeros(m, dtype=np.float64)
+    num = np.zeros(m, dtype=np.int32)
+    has = np.zeros(m, dtype=np.int32)
+    _lib().wol_oracle_lsi(_ptr(sub, _dp), m, _ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(lowCut),
+                          ctypes.c_double(highCut), _ptr(lsi, _dp), _ptr(num, _ip), _ptr(has, _ip))
+    return lsi[has.astype(bool)], num.astype(np.float64)

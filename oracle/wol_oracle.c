@@ -588,3 +588,66 @@ int wol_oracle_histrr3b(const double *pos, int n, const double *boxl, double dwi
     free(bin);
     return 0;
 }
+
+/* getLSI (structureLibs/water_properties.py:252-311): local structure index per centre.
+ *   near  = atoms with lowcut^2 < r2 <= highcut^2 (minimum image), next = highcut^2 < r2 <= (highcut+3.7)^2
+ *   a centre gets a value only if it has > 1 near and >= 1 next neighbours; the next neighbour taken is the one
+ *   with the smallest NON-periodic distance sqrt(sum((Pos - apos)**2)) (:289, first index on ties); the sorted
+ *   minimum-image distances (lsiDists, waterlib.f90:900-918) of near + that one give deltas whose population
+ *   variance is the LSI.  lsi[i] is written only where has[i] = 1; num[i] = number of deltas (= near count). */
+static int cmp_double(const void *a, const void *b) {
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+int wol_oracle_lsi(const double *sub, int m, const double *pos, int n, const double *boxl, double lowcut, double highcut,
+                   double *lsi, int32_t *num, int32_t *has) {
+    box_t b;
+    box_init(&b, boxl);
+    const double lowsq = lowcut * lowcut, highsq = highcut * highcut;
+    const double nextsq = (highcut + 3.7) * (highcut + 3.7);
+    double *dist = (double *)malloc((size_t)(n + 1) * sizeof(double));
+    for (int i = 0; i < m; ++i) {
+        const double *r = sub + 3 * (size_t)i;
+        int k = 0, next = -1, n_next = 0;
+        double next_raw = 0.0, d[3];
+        for (int j = 0; j < n; ++j) {
+            const double *p = pos + 3 * (size_t)j;
+            min_image(&b, p, r, d);
+            double s = sumsq(d);
+            if (s > lowsq && s <= highsq) {
+                dist[k++] = sqrt(s);
+            } else if (s > highsq && s <= nextsq) {
+                double e0 = p[0] - r[0], e1 = p[1] - r[1], e2 = p[2] - r[2];
+                double raw = sqrt((e0 * e0 + e1 * e1) + e2 * e2);
+                if (n_next == 0 || raw < next_raw) {
+                    next_raw = raw;
+                    next = j;
+                }
+                ++n_next;
+            }
+        }
+        num[i] = 0;
+        has[i] = 0;
+        lsi[i] = 0.0;
+        if (k > 1 && n_next > 0) {
+            min_image(&b, pos + 3 * (size_t)next, r, d);
+            dist[k++] = sqrt(sumsq(d));
+            qsort(dist, (size_t)k, sizeof(double), cmp_double);
+            int nd = k - 1;
+            double mean = 0.0;
+            for (int t = 0; t < nd; ++t) mean += dist[t + 1] - dist[t];
+            mean /= (double)nd;
+            double var = 0.0;
+            for (int t = 0; t < nd; ++t) {
+                double x = (dist[t + 1] - dist[t]) - mean;
+                var += x * x;
+            }
+            lsi[i] = var / (double)nd;
+            num[i] = nd;
+            has[i] = 1;
+        }
+    }
+    free(dist);
+    return 0;
+}

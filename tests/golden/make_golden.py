@@ -129,6 +129,16 @@ def main():
                         cutoff=3.0, watclose=watclose, surfclose=surfclose, numwater=np.int64(numwater), allwatdists=dists)
     print("slab", pos.shape[0], "waters", gp.shape[0], "interface points", numwater, "within cutoff")
 
+    # getLSI (water_properties.py:252-311), whole system and a sub-population with non-default cutoffs
+    pos, box = synth.water_box(4, sigma=0.6, seed=1234)
+    fn_lsi = ref_fortran.load_reference_functions(names=("getLSI",), wl=wl)["getLSI"]
+    v, n = fn_lsi(pos, pos, box)
+    sub = np.concatenate([pos[::9], (rng.random((30, 3)) * box).astype(np.float32).astype(np.float64)])
+    v2, n2 = fn_lsi(sub, pos, box, 0.5, 3.5)
+    np.savez_compressed(os.path.join(OUT, "lsi_n512.npz"), pos=pos, box=box, lsi=v, num=n, sub=sub, lsi_sub=v2, num_sub=n2,
+                        low_sub=0.5, high_sub=3.5)
+    print("lsi", v.size, "of", pos.shape[0], "values, mean %.5f" % v.mean())
+
     # histrr3b (waterlib.f90:1550-1593): triplet histogram, ceiling bins
     pos, box = synth.water_box(3, sigma=0.35, seed=8)
     h = wl.histrr3b(pos, box, 0.5, 8, 5.0, 36)

@@ -180,3 +180,29 @@ def test_shell_mask_golden(golden_dir):
     assert np.array_equal(np.nonzero(mask.cpu().numpy()[0])[0].astype(np.int32), g["shell"])
     nb = wl.nearneighbors(g["sol"], g["pos"], g["box"], 0.0, float(g["cutoff"]))
     assert np.array_equal(np.unique(np.where(nb == 1)[1]).astype(np.int32), g["shell"])  # orderParam_lib.py:495-496
+
+
+def test_getLSI_golden(golden_dir):
+    g = load(golden_dir, "lsi_n512")
+    v, n = wp.getLSI(g["pos"], g["pos"], g["box"])
+    assert np.array_equal(n, g["num"]) and v.shape == g["lsi"].shape
+    assert np.allclose(v, g["lsi"], rtol=1e-10, atol=1e-16)
+    v, n = wp.getLSI(g["sub"], g["pos"], g["box"], float(g["low_sub"]), float(g["high_sub"]))
+    assert np.array_equal(n, g["num_sub"]) and np.allclose(v, g["lsi_sub"], rtol=1e-10, atol=1e-16)
+
+
+def test_getLSI_vs_oracle_unwrapped_coordinates():
+    """The next-shell neighbour is chosen by NON-periodic distance (water_properties.py:289): unwrapped inputs."""
+    pos, box = synth.water_box(5, sigma=0.5, seed=12)
+    rng = np.random.default_rng(12)
+    pos = pos + box * rng.integers(-1, 2, size=pos.shape)
+    v, n = wp.getLSI(pos, pos, box)
+    v_ref, n_ref = port.getLSI(pos, pos, box)
+    assert np.array_equal(n, n_ref) and np.allclose(v, v_ref, rtol=1e-10, atol=1e-16)
+    # dilute gas: centres with fewer than two neighbours (or an empty next shell) have no value -- skipped in
+    # lsiVals, 0 in numLSI
+    gas = rng.random((400, 3)) * np.array([40.0, 42.0, 38.0])
+    v, n = wp.getLSI(gas, gas, np.array([40.0, 42.0, 38.0]))
+    v_ref, n_ref = port.getLSI(gas, gas, np.array([40.0, 42.0, 38.0]))
+    assert (n_ref == 0).any() and (n_ref > 0).any() and v.shape == v_ref.shape
+    assert np.array_equal(n, n_ref) and np.allclose(v, v_ref, rtol=1e-10, atol=1e-16)

@@ -52,7 +52,7 @@ def test_fp32_mode_batched_large_box():
 def test_fp32_mode_subpopulation_and_widening():
     rng = np.random.default_rng(4)
     box = np.array([40.0, 36.0, 44.0])
-    pos = (rng.random((3000, 3)) * box).astype(np.float32).astype(np.float64)  # dilute: most centres need the widened search
+    pos = (rng.random((900, 3)) * box).astype(np.float32).astype(np.float64)  # dilute gas (0.014 per A^3): many centres need the widened search
     sub = (rng.random((500, 3)) * box).astype(np.float32).astype(np.float64)
     r = engine.q3b_frames(pos.astype(np.float32), box, sub.astype(np.float32), precision="fp32", highq=9.0)
     torch.cuda.synchronize()

@@ -100,3 +100,12 @@ def test_histrr3b_against_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "histrr3b_n216.npz"))
     h = port.histrr3b(g["pos"], g["box"], float(g["dwidth"]), int(g["dnum"]), float(g["awidth"]), int(g["anum"]))
     assert np.array_equal(h, g["hist"])
+
+
+def test_lsi_against_golden(golden_dir):
+    """getLSI (structureLibs/water_properties.py:252-311), values from the reference's own function body."""
+    g = np.load(os.path.join(golden_dir, "lsi_n512.npz"))
+    v, n = port.getLSI(g["pos"], g["pos"], g["box"])
+    assert np.array_equal(n, g["num"]) and np.allclose(v, g["lsi"], rtol=1e-12, atol=1e-18)
+    v, n = port.getLSI(g["sub"], g["pos"], g["box"], float(g["low_sub"]), float(g["high_sub"]))
+    assert np.array_equal(n, g["num_sub"]) and np.allclose(v, g["lsi_sub"], rtol=1e-12, atol=1e-18)

@@ -132,3 +132,17 @@ def test_histrr3b_matches_live(ref):
     h_ref = wl.histrr3b(pos, box, 0.5, 8, 5.0, 36)
     h = port.histrr3b(pos, box, 0.5, 8, 5.0, 36)
     assert h.sum() > 1000 and np.array_equal(h.astype(np.float64), np.ascontiguousarray(h_ref))
+
+
+def test_lsi_matches_live(ref):
+    """getLSI incl. its non-periodic choice of the next neighbour (water_properties.py:289)."""
+    wl, fn = ref
+    for m, sigma, seed in ((3, 0.4, 5), (4, 0.6, 6)):
+        pos, box = synth.water_box(m, sigma=sigma, seed=seed)
+        v_ref, n_ref = fn["getLSI"](pos, pos, box)
+        v, n = port.getLSI(pos, pos, box)
+        assert np.array_equal(n, n_ref) and v.shape == v_ref.shape and np.allclose(v, v_ref, rtol=1e-12, atol=1e-18)
+    sub = pos[::7] + 0.3
+    v_ref, n_ref = fn["getLSI"](sub, pos, box, 0.5, 3.5)
+    v, n = port.getLSI(sub, pos, box, 0.5, 3.5)
+    assert np.array_equal(n, n_ref) and np.allclose(v, v_ref, rtol=1e-12, atol=1e-18)

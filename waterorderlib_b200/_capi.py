@@ -65,6 +65,7 @@ SIGNATURES = {
     "wol_neighbor_matrix": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_f64, c_f64, c_vp, c_vp]),
     "wol_reimage": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "wol_tetracosang": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "wol_lsi": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp, ctypes.c_size_t, c_vp, c_vp, c_vp]),
     "wol_hbond_counts": (ctypes.c_int, [ctypes.POINTER(HbondArgs), c_vp]),
     "wol_hbond_locations": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "wol_shell_mask": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp,

@@ -389,6 +389,101 @@ __global__ void __launch_bounds__(128) shell_kernel(const ShellParams P) {
     });
 }
 
+// ---- local structure index (getLSI, structureLibs/water_properties.py:252-311) -------------------------------
+// One thread per centre over a cell list of edge >= highCut + 3.7: the minimum-image distances of the neighbours
+// inside (lowCut, highCut] go to a small sorted list; of the atoms in the next shell (highCut, highCut + 3.7] the one
+// with the smallest NON-periodic distance to the centre (the reference compares raw coordinate differences there,
+// :289; first atom index on ties) contributes its minimum-image distance too; the LSI is the population variance
+// of the gaps between consecutive sorted distances.
+
+constexpr int kLsiCap = 48;
+
+struct LsiParams {
+    CellGrid grid;
+    const double *box;
+    const void *centres;
+    int centre_dtype;
+    int n_frames, n_pos, n_centres;
+    double lowsq, highsq, nextsq;
+    double *lsi;       // [F][M], written where has == 1 (0 elsewhere)
+    int32_t *num;      // [F][M] number of gaps (= neighbours inside highCut), 0 when the centre has no value
+    uint32_t *counters;
+};
+
+__global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)P.n_frames * P.n_centres) return;
+    const int f = (int)(g / P.n_centres);
+    const BoxD b = load_box(P.box + (size_t)f * 3);
+    double rx, ry, rz;
+    load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);
+    const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
+              cz = cell_coord(rz, b.iLz, P.grid.nc2);
+    double dist[kLsiCap];
+    int k = 0, n_next = 0, next_idx = 0;
+    double next_raw = 0.0, next_min = 0.0;
+    bool over = false;
+    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+        double px, py, pz;
+        int id;
+        RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+        const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
+        const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
+        const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+        const double s = sumsq3<double>(dx, dy, dz);
+        if (s > P.lowsq && s <= P.highsq) {
+            if (k >= kLsiCap - 1) {
+                over = true;
+                return;
+            }
+            // insertion into the ascending list (np.sort of lsidists, :300)
+            const double d = __dsqrt_rn(s);
+            int at = k;
+            while (at > 0 && dist[at - 1] > d) {
+                dist[at] = dist[at - 1];
+                --at;
+            }
+            dist[at] = d;
+            ++k;
+        } else if (s > P.highsq && s <= P.nextsq) {
+            // np.sqrt(np.sum((Pos[next] - apos)**2.0, axis=1)): raw differences, no minimum image (:287-289)
+            const double raw = __dsqrt_rn(sumsq3<double>(__dsub_rn(px, rx), __dsub_rn(py, ry), __dsub_rn(pz, rz)));
+            if (n_next == 0 || raw < next_raw || (raw == next_raw && id < next_idx)) {  // np.argmin: first index on ties
+                next_raw = raw;
+                next_idx = id;
+                next_min = __dsqrt_rn(s);
+            }
+            ++n_next;
+        }
+    });
+    if (over) {
+        atomicAdd(P.counters + kCntFatal, 1u);
+        return;
+    }
+    double val = 0.0;
+    int nd = 0;
+    if (k > 1 && n_next > 0) {
+        int at = k;
+        while (at > 0 && dist[at - 1] > next_min) {
+            dist[at] = dist[at - 1];
+            --at;
+        }
+        dist[at] = next_min;
+        ++k;
+        nd = k - 1;
+        double mean = 0.0;
+        for (int t = 0; t < nd; ++t) mean += dist[t + 1] - dist[t];
+        mean /= (double)nd;
+        for (int t = 0; t < nd; ++t) {
+            const double x = (dist[t + 1] - dist[t]) - mean;
+            val += x * x;
+        }
+        val /= (double)nd;
+    }
+    P.lsi[g] = val;
+    P.num[g] = nd;
+}
+
 static CellGrid make_grid(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
     char *ws = reinterpret_cast<char *>(workspace);
     CellGrid g;
@@ -506,6 +601,41 @@ int wol_tetracosang(const double *ref, const double *neigh, int32_t k, const dou
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_tetracosang", e);
+    return WOL_OK;
+}
+
+int wol_lsi(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos, int32_t n_centres,
+            const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes,
+            double *lsi, int32_t *num, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!centres || !box || !nc || !workspace || !lsi || !num) return set_error(WOL_ERR_INVALID, "wol_lsi: null argument");
+    const double reach = highcut + 3.7;  // width of the next-neighbour shell, hard-coded in the reference (:269, :274)
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && reach * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "LSI search radius %.6g exceeds the planned cell edge %.6g", reach, edge_min);
+    const WorkspaceLayout lay = workspace_layout(n_frames, n_pos, n_centres, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    LsiParams P;
+    P.grid = make_grid(workspace, lay, nc);
+    P.box = box;
+    P.centres = centres;
+    P.centre_dtype = centre_dtype;
+    P.n_frames = n_frames;
+    P.n_pos = n_pos;
+    P.n_centres = n_centres;
+    P.lowsq = lowcut * lowcut;
+    P.highsq = highcut * highcut;
+    P.nextsq = reach * reach;
+    P.lsi = lsi;
+    P.num = num;
+    P.counters = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + lay.off_counters);
+    const size_t total = (size_t)n_frames * n_centres;
+    if (total > 0 && n_pos > 0) {
+        lsi_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_lsi", e);
     return WOL_OK;
 }
 

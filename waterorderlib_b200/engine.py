@@ -207,14 +207,15 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
 
 
 def default_r_cell(do_q, do_3body, high3, highq):
-    """Cell edge request: at least the three-body cutoff (the 27-cell sweep must contain it).  For q the
-    4 nearest oxygens of liquid water sit inside ~3.5 A, so a cell of that size makes the widened search
-    rare without inflating the candidate count."""
+    """Cell edge request: at least the three-body cutoff (the 27-cell sweep must contain it).  For q the 4th
+    nearest oxygen of liquid water sits inside ~3.8 A for all but a few per cent of the molecules; measured on
+    1M-water boxes (B200): 3.5 A sends 4 % (jittered ice) / 20 % (liquid-like) of the centres to the widened
+    search, 3.8 A 0.2 % / 1.5 %, for ~25 % more candidates per sweep -- a net gain of 2 % / 30 %."""
     r = 0.0
     if do_3body:
         r = max(r, float(high3))
     if do_q:
-        r = max(r, min(float(highq), 3.5))
+        r = max(r, min(float(highq), 3.8))
     return max(r, 1e-3)
 
 

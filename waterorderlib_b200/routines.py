@@ -397,3 +397,25 @@ def histrr3b(pos, box, dist_width, d_num, ang_width, a_num, device=None):
                                  _vp(hist.data_ptr()), _stream()), "wol_histrr3b")
         cells.status()  # raises if a neighbour list overflowed; also synchronises
     return hist
+
+
+def lsi(sub, pos, box, low=0.0, high=3.7, device=None):
+    """getLSI (structureLibs/water_properties.py:252-311) for one or several frames -> (lsi f64 (F, M), num int32
+    (F, M)); num == 0 marks centres without a value (fewer than two neighbours or an empty next shell)."""
+    device = _device(device, pos, sub)
+    pos_d = engine.as_device_positions(pos, device)
+    cen_d = pos_d if sub is None else engine.as_device_positions(sub, device)
+    if cen_d.shape[0] != pos_d.shape[0]:
+        raise ValueError("sub and pos must hold the same number of frames")
+    F, N, M = int(pos_d.shape[0]), int(pos_d.shape[1]), int(cen_d.shape[1])
+    out = torch.zeros((F, M), dtype=torch.float64, device=device)
+    num = torch.zeros((F, M), dtype=torch.int32, device=device)
+    if M == 0 or N == 0:
+        return out, num
+    cells = CellList(pos_d, box, (float(high) + 3.7) * (1.0 + 1e-9), device=device, n_centres_max=M)
+    with torch.cuda.device(device):
+        check(lib().wol_lsi(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
+                            ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr), cells.ws_bytes,
+                            _vp(out.data_ptr()), _vp(num.data_ptr()), _stream()), "wol_lsi")
+        cells.status()
+    return out, num

@@ -7,6 +7,7 @@ Same names, positional order, keyword names, defaults and return values:
     tetrahedralMetrics(angVals, nBins=500, binRange=[0.0, 180.0])                    reference :314-342
     HBondsGeneral(accPos, donPos, donHPos, boxL, accInds, donInds, donHInds,
                   distCut=3.5, angCut=150.0)                                         reference :681-719
+    getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7)                            reference :252-311
 
 numpy arrays in -> numpy arrays out; torch CUDA tensors in -> torch CUDA tensors out (zero copy).  The
 per-water Python loops and f2py calls of the reference are replaced by one pass of the cell-list kernels in
@@ -114,3 +115,18 @@ def HBondsGeneral(accPos, donPos, donHPos, boxL, accInds, donInds, donHInds, dis
         return NumHB, torch.from_numpy(HBlist).to(loc.device), loc
     return NumHB, HBlist, loc.cpu().numpy()
 
+
+
+def getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7):
+    """Local structure index (Shiratani & Sasai 1996) -> (lsiVals, numLSI) (reference water_properties.py:252-311):
+    lsiVals holds one value per centre that has more than one neighbour inside highCut and a next-shell neighbour,
+    in centre order; numLSI[i] is the number of distance gaps of centre i (0 where it has no value).  Includes the
+    reference's choice of the next neighbour by NON-periodic distance (:289)."""
+    tor = _is_torch(subPos, Pos)
+    subPos = subPos if tor else np.asarray(subPos)
+    Pos = Pos if tor else np.asarray(Pos)
+    _pos2(subPos, "subPos"); _pos2(Pos, "Pos")
+    vals, num = routines.lsi(None if _same(subPos, Pos) else subPos, Pos, BoxDims, lowCut, highCut)
+    vals, num = vals[0], num[0]
+    lsiVals = vals[num > 0]
+    return _out(lsiVals, tor), _out(num, tor, torch.float64 if tor else np.float64)

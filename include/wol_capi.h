@@ -345,6 +345,35 @@ int wol_histrr3b(const double *box, int32_t n_pos, const int32_t nc[3], double e
                  double ang_width, int32_t a_num, const double *angle_table, void *workspace, size_t workspace_bytes, int64_t *hist,
                  void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Same-sweep observables.
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * Pair-distance histograms with the Fortran binning nbin = ceiling(dist / binwidth):
+ *   mode 0  RadialDist            (fortran/waterlib.f90:193-231)  outer = Pos2, cell list over Pos1, every pair
+ *   mode 1  RadialDistSame        (fortran/waterlib.f90:316-353)  outer = Pos (input order), cell list over the same Pos,
+ *                                                                 each pair once (inner index > outer index)
+ *   mode 2  PairDistanceHistogram (fortran/waterlib.f90:358-389)  outer = Pos1, cell list over Pos2, 3-D
+ * counts[totbins] int64, ACCUMULATED (the g(r) normalisation of the first two, O(totbins), is left to the caller:
+ * counts(k) / (N * BulkDens * (4./3.) * pi * binwidth**3 * (k**3 - (k-1)**3)) with the Fortran's single-precision
+ * 4./3. and truncated pi).  Pairs at distance exactly 0 index bin 0 in the Fortran (out of bounds) and are skipped.
+ * workspace: cell list (FP64) over the n_inner atoms with r_cell >= totbins * binwidth.
+ */
+int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t n_outer, const double *box, int32_t n_inner,
+                  const int32_t nc[3], double edge_min, double binwidth, int32_t totbins, void *workspace, size_t workspace_bytes,
+                  int64_t *counts, void *stream);
+
+/*
+ * getOrderParamPsi (structureLibs/water_properties.py:393-433): per centre, | mean over pairs of neighbours inside
+ * (lowcut, highcut] of cos(6 theta) | -- the reference stores its complex mean of exp(6 i theta) into a real array,
+ * which keeps only the real part, and that behaviour is reproduced; 0 with fewer than two neighbours.
+ * workspace: cell list over pos with r_cell >= highcut.  At most 320 neighbours per centre.
+ */
+int wol_psi(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos, int32_t n_centres,
+            const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes, double *psi,
+            void *stream);
+
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);
 

@@ -238,3 +238,48 @@ def getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7):
     _lib().wol_oracle_lsi(_ptr(sub, _dp), m, _ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(lowCut),
                           ctypes.c_double(highCut), _ptr(lsi, _dp), _ptr(num, _ip), _ptr(has, _ip))
     return lsi[has.astype(bool)], num.astype(np.float64)
+
+
+def _pair_hist(mode, pos1, pos2, box, binwidth, totbins):
+    p1, b = _pos(pos1), _box(box)
+    p2 = _pos(pos2) if pos2 is not None else p1
+    counts = np.zeros(totbins, dtype=np.int64)
+    _lib().wol_oracle_pair_hist(mode, _ptr(p1, _dp), p1.shape[0], _ptr(p2, _dp), p2.shape[0], _ptr(b, _dp),
+                                ctypes.c_double(binwidth), int(totbins), _ptr(counts, _lp))
+    return counts
+
+
+_FOUR_THIRDS = float(np.float32(4.0) / np.float32(3.0))  # the Fortran literal (4./3.) is single precision
+_PI_RDF = 3.141592653589                                 # and its pi is truncated (waterlib.f90:204,327)
+
+
+def rdf_normalise(counts, n_norm, binwidth, bulkdens):
+    """counts(k) / (N * BulkDens * (4./3.) * pi * binwidth**3 * (k**3 - (k-1)**3)), in the Fortran's order."""
+    k = np.arange(1, len(counts) + 1, dtype=np.int64)
+    shell = (k ** 3 - (k - 1) ** 3).astype(np.float64)
+    denom = ((((float(n_norm) * bulkdens) * _FOUR_THIRDS) * _PI_RDF) * ((binwidth * binwidth) * binwidth)) * shell
+    return counts.astype(np.float64) / denom
+
+
+def radialdist(pos1, pos2, binwidth, totbins, bulkdens, boxl):
+    """RadialDist (fortran/waterlib.f90:193-231)."""
+    return rdf_normalise(_pair_hist(0, pos1, pos2, boxl, binwidth, totbins), _pos(pos1).shape[0], binwidth, bulkdens)
+
+
+def radialdistsame(pos, binwidth, totbins, bulkdens, boxl):
+    """RadialDistSame (fortran/waterlib.f90:316-353)."""
+    return rdf_normalise(_pair_hist(1, pos, None, boxl, binwidth, totbins), _pos(pos).shape[0], binwidth, bulkdens)
+
+
+def pairdistancehistogram(pos1, pos2, binwidth, totbins, boxl):
+    """PairDistanceHistogram (fortran/waterlib.f90:358-389), 3-D."""
+    return _pair_hist(2, pos1, pos2, boxl, binwidth, totbins).astype(np.float64)
+
+
+def getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
+    """structureLibs/water_properties.py:393-433."""
+    sub, pos, box = _pos(subPos), _pos(Pos), _box(BoxDims)
+    psi = np.zeros(sub.shape[0], dtype=np.float64)
+    _lib().wol_oracle_psi(_ptr(sub, _dp), sub.shape[0], _ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(lowCut),
+                          ctypes.c_double(highCut), _ptr(psi, _dp))
+    return psi

@@ -196,6 +196,34 @@ class RefWaterlib:
             ctypes.byref(ctypes.c_int32(pos.shape[0])), ctypes.byref(ctypes.c_int32(npts)))
         return dens, np.ascontiguousarray(norms)
 
+    # fortran/waterlib.f90:193-231
+    def radialdist(self, pos1, pos2, binwidth, totbins, bulkdens, boxl):
+        p1, p2 = _f64(pos1), _f64(pos2)
+        rdf = np.zeros(totbins, dtype=np.float64)
+        self._lib.radialdist_(_dp(p1), _dp(p2), ctypes.byref(ctypes.c_double(binwidth)), ctypes.byref(ctypes.c_int32(totbins)),
+                              ctypes.byref(ctypes.c_double(bulkdens)), _dp(_box(boxl)), _dp(rdf),
+                              ctypes.byref(ctypes.c_int32(p1.shape[0])), ctypes.byref(ctypes.c_int32(p2.shape[0])))
+        return rdf
+
+    # fortran/waterlib.f90:316-353
+    def radialdistsame(self, pos, binwidth, totbins, bulkdens, boxl):
+        p = _f64(pos)
+        rdf = np.zeros(totbins, dtype=np.float64)
+        self._lib.radialdistsame_(_dp(p), ctypes.byref(ctypes.c_double(binwidth)), ctypes.byref(ctypes.c_int32(totbins)),
+                                  ctypes.byref(ctypes.c_double(bulkdens)), _dp(_box(boxl)), _dp(rdf),
+                                  ctypes.byref(ctypes.c_int32(p.shape[0])))
+        return rdf
+
+    # fortran/waterlib.f90:358-389
+    def pairdistancehistogram(self, pos1, pos2, binwidth, totbins, boxl):
+        p1, p2 = _f64(pos1), _f64(pos2)
+        hist = np.zeros(totbins, dtype=np.float64)
+        self._lib.pairdistancehistogram_(_dp(p1), _dp(p2), ctypes.byref(ctypes.c_double(binwidth)),
+                                         ctypes.byref(ctypes.c_int32(totbins)), _dp(_box(boxl)), _dp(hist),
+                                         ctypes.byref(ctypes.c_int32(p1.shape[0])), ctypes.byref(ctypes.c_int32(p2.shape[0])),
+                                         ctypes.byref(ctypes.c_int32(3)))
+        return hist
+
     # fortran/waterlib.f90:683-703
     def cosangle3(self, p1, p2, p3):
         a = [np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(3)) for p in (p1, p2, p3)]
@@ -222,7 +250,7 @@ class RefWaterlib:
         return watclose, surfclose, int(numwater.value), allwatdists
 
 
-_WP_FUNCS = ("getCosAngs", "getOrderParamq", "tetrahedralMetrics", "getLSI", "HBondsGeneral")
+_WP_FUNCS = ("getCosAngs", "getOrderParamq", "tetrahedralMetrics", "getLSI", "HBondsGeneral", "getOrderParamPsi")
 
 
 def load_reference_functions(names=_WP_FUNCS, wl=None):

@@ -651,3 +651,73 @@ int wol_oracle_lsi(const double *sub, int m, const double *pos, int n, const dou
     free(dist);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Pair-distance histograms: RadialDist / RadialDistSame / PairDistanceHistogram (waterlib.f90:193-231, :316-353,
+ * :358-389).  counts[k], k = 0-based bin of nbin = ceiling(dist / binwidth); distances that index bin 0 in the
+ * Fortran (dist == 0, an out-of-bounds write there) are skipped.
+ *   mode 0  RadialDist:            every (i in pos2, j in pos1) pair
+ *   mode 1  RadialDistSame:        pairs i < j of pos1 (pos2 ignored)
+ *   mode 2  PairDistanceHistogram: every (i in pos1, j in pos2) pair, dist == 0 skipped */
+int wol_oracle_pair_hist(int mode, const double *pos1, int n1, const double *pos2, int n2, const double *boxl,
+                         double binwidth, int totbins, int64_t *counts) {
+    box_t b;
+    box_init(&b, boxl);
+    const double *outer = (mode == 0) ? pos2 : pos1, *inner = (mode == 2) ? pos2 : pos1;
+    const int no = (mode == 0) ? n2 : n1, ni = (mode == 2) ? n2 : n1;
+    double d[3];
+    for (int i = 0; i < no; ++i)
+        for (int j = (mode == 1) ? i + 1 : 0; j < ni; ++j) {
+            min_image(&b, inner + 3 * (size_t)j, outer + 3 * (size_t)i, d); /* distVec = jPos - iPos */
+            double dist = sqrt(sumsq(d));
+            double nb = ceil(dist / binwidth);
+            if (nb >= 1.0 && nb <= (double)totbins) counts[(int)nb - 1]++;
+        }
+    return 0;
+}
+
+/* getOrderParamPsi (structureLibs/water_properties.py:393-433).  Intended: psi_i = | mean over neighbour pairs of
+ * exp(6 i theta) |.  ACTUAL: the complex mean is stored into a float64 array (:428), which discards its imaginary
+ * part (numpy ComplexWarning), so what the reference returns is | mean cos(6 theta) |.  That is what is restated.
+ * theta from tetraCosAng/CosAngle3 (degrees, then * pi / 180), neighbours inside (lowcut, highcut]; 0 when the
+ * centre has fewer than two neighbours.  The reference sorts the neighbours by distance first; the mean does not
+ * depend on the order beyond rounding, ascending index is used here. */
+int wol_oracle_psi(const double *sub, int m, const double *pos, int n, const double *boxl, double lowcut, double highcut,
+                   double *psi) {
+    box_t b;
+    box_init(&b, boxl);
+    const double lowsq = lowcut * lowcut, highsq = highcut * highcut;
+    double *img = (double *)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(double));
+    for (int i = 0; i < m; ++i) {
+        const double *r = sub + 3 * (size_t)i;
+        int k = 0;
+        double d[3];
+        for (int j = 0; j < n; ++j) {
+            min_image(&b, pos + 3 * (size_t)j, r, d);
+            double s = sumsq(d);
+            if (s > lowsq && s <= highsq) {
+                /* reimage (ref + d), then tetraCosAng reimages again: ref + minimg((ref + d) - ref) */
+                double p[3], d2[3];
+                for (int c = 0; c < 3; ++c) p[c] = r[c] + d[c];
+                min_image(&b, p, r, d2);
+                for (int c = 0; c < 3; ++c) img[3 * k + c] = r[c] + d2[c];
+                ++k;
+            }
+        }
+        psi[i] = 0.0;
+        if (k > 1) {
+            double re = 0.0;
+            long np_ = 0;
+            for (int a = 0; a < k; ++a)
+                for (int c2 = a + 1; c2 < k; ++c2) {
+                    double ang = cos_angle3(img + 3 * a, r, img + 3 * c2) * kPi / 180.0;
+                    re += cos(6.0 * ang);
+                    ++np_;
+                }
+            re /= (double)np_;
+            psi[i] = sqrt(re * re);
+        }
+    }
+    free(img);
+    return 0;
+}

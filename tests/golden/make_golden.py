@@ -139,6 +139,20 @@ def main():
                         low_sub=0.5, high_sub=3.5)
     print("lsi", v.size, "of", pos.shape[0], "values, mean %.5f" % v.mean())
 
+    # pair-distance histograms (waterlib.f90:193-231, :316-353, :358-389) and psi (water_properties.py:393-433)
+    pos, box = synth.water_box(4, sigma=0.5, seed=77)
+    sol = (rng.random((40, 3)) * box).astype(np.float32).astype(np.float64)
+    fn_psi = ref_fortran.load_reference_functions(names=("getOrderParamPsi",), wl=wl)["getOrderParamPsi"]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # the reference's complex -> real assignment (:428)
+        psi_all = fn_psi(pos, pos, box, 0.0, 4.5)
+        psi_sub = fn_psi(sol, pos, box, 1.0, 6.0)
+    np.savez_compressed(os.path.join(OUT, "pairs_n512.npz"), pos=pos, sol=sol, box=box,
+                        rdf_same=wl.radialdistsame(pos, 0.1, 120, 1.0, box), rdf_cross=wl.radialdist(sol, pos, 0.1, 120, 0.0334, box),
+                        pdh=wl.pairdistancehistogram(sol, pos, 0.25, 40, box), psi_all=psi_all, psi_sub=psi_sub)
+    print("pairs: rdf peak %.3f, <psi> %.4f" % (wl.radialdistsame(pos, 0.1, 120, 1.0, box).max(), psi_all.mean()))
+
     # histrr3b (waterlib.f90:1550-1593): triplet histogram, ceiling bins
     pos, box = synth.water_box(3, sigma=0.35, seed=8)
     h = wl.histrr3b(pos, box, 0.5, 8, 5.0, 36)

@@ -206,3 +206,30 @@ def test_getLSI_vs_oracle_unwrapped_coordinates():
     v_ref, n_ref = port.getLSI(gas, gas, np.array([40.0, 42.0, 38.0]))
     assert (n_ref == 0).any() and (n_ref > 0).any() and v.shape == v_ref.shape
     assert np.array_equal(n, n_ref) and np.allclose(v, v_ref, rtol=1e-10, atol=1e-16)
+
+
+def test_pair_histograms_golden(golden_dir):
+    """radialdistsame / radialdist / pairdistancehistogram: bit-exact g(r) incl. the Fortran's normalisation."""
+    g = load(golden_dir, "pairs_n512")
+    assert np.array_equal(wl.radialdistsame(g["pos"], 0.1, 120, 1.0, g["box"]), g["rdf_same"])
+    assert np.array_equal(wl.radialdist(g["sol"], g["pos"], 0.1, 120, 0.0334, g["box"]), g["rdf_cross"])
+    assert np.array_equal(wl.pairdistancehistogram(g["sol"], g["pos"], 0.25, 40, g["box"]), g["pdh"])
+    # a range the cell grid cannot hold (> L / 3): every cell is enumerated, still each pair once
+    big = wl.radialdistsame(g["pos"], 0.5, 40, 1.0, g["box"].reshape(1, 3))
+    assert np.array_equal(big, port.radialdistsame(g["pos"], 0.5, 40, 1.0, g["box"]))
+    # coincident atoms (distance 0) are not counted; 4096 waters through the real cell list
+    pos, box = synth.water_box(8, sigma=0.4, seed=6)
+    pos[5] = pos[4]
+    assert np.array_equal(wl.radialdistsame(pos, 0.1, 100, 1.0, box), port.radialdistsame(pos, 0.1, 100, 1.0, box))
+    assert np.array_equal(wl.pairdistancehistogram(pos[:300], pos, 0.2, 50, box), port.pairdistancehistogram(pos[:300], pos, 0.2, 50, box))
+
+
+def test_getOrderParamPsi_golden(golden_dir):
+    g = load(golden_dir, "pairs_n512")
+    assert np.allclose(wp.getOrderParamPsi(g["pos"], g["pos"], g["box"], 0.0, 4.5), g["psi_all"], rtol=1e-9, atol=1e-13)
+    assert np.allclose(wp.getOrderParamPsi(g["sol"], g["pos"], g["box"], 1.0, 6.0), g["psi_sub"], rtol=1e-9, atol=1e-13)
+    # default cutoff 10 A (~140 neighbours, ~10^4 pairs per centre) and the fewer-than-two-neighbours rule
+    pos, box = synth.water_box(4, sigma=0.3, seed=3)
+    assert np.allclose(wp.getOrderParamPsi(pos[:40], pos, box), port.getOrderParamPsi(pos[:40], pos, box), rtol=1e-9, atol=1e-13)
+    lone = np.array([[1.0, 1.0, 1.0], [3.0, 1.0, 1.0], [20.0, 20.0, 20.0]])
+    assert np.array_equal(wp.getOrderParamPsi(lone, lone, np.array([40.0, 40.0, 40.0]), 0.0, 5.0), np.zeros(3))

@@ -109,3 +109,13 @@ def test_lsi_against_golden(golden_dir):
     assert np.array_equal(n, g["num"]) and np.allclose(v, g["lsi"], rtol=1e-12, atol=1e-18)
     v, n = port.getLSI(g["sub"], g["pos"], g["box"], float(g["low_sub"]), float(g["high_sub"]))
     assert np.array_equal(n, g["num_sub"]) and np.allclose(v, g["lsi_sub"], rtol=1e-12, atol=1e-18)
+
+
+def test_pairs_against_golden(golden_dir):
+    """RadialDistSame / RadialDist / PairDistanceHistogram (waterlib.f90:193-389), getOrderParamPsi (:393-433)."""
+    g = np.load(os.path.join(golden_dir, "pairs_n512.npz"))
+    assert np.array_equal(port.radialdistsame(g["pos"], 0.1, 120, 1.0, g["box"]), g["rdf_same"])
+    assert np.array_equal(port.radialdist(g["sol"], g["pos"], 0.1, 120, 0.0334, g["box"]), g["rdf_cross"])
+    assert np.array_equal(port.pairdistancehistogram(g["sol"], g["pos"], 0.25, 40, g["box"]), g["pdh"])
+    assert np.allclose(port.getOrderParamPsi(g["pos"], g["pos"], g["box"], 0.0, 4.5), g["psi_all"], rtol=1e-10, atol=1e-14)
+    assert np.allclose(port.getOrderParamPsi(g["sol"], g["pos"], g["box"], 1.0, 6.0), g["psi_sub"], rtol=1e-10, atol=1e-14)

@@ -146,3 +146,25 @@ def test_lsi_matches_live(ref):
     v_ref, n_ref = fn["getLSI"](sub, pos, box, 0.5, 3.5)
     v, n = port.getLSI(sub, pos, box, 0.5, 3.5)
     assert np.array_equal(n, n_ref) and np.allclose(v, v_ref, rtol=1e-12, atol=1e-18)
+
+
+def test_pair_histograms_match_live(ref):
+    """RadialDist / RadialDistSame / PairDistanceHistogram incl. the single-precision (4./3.) and truncated pi."""
+    wl, _ = ref
+    pos, box = synth.water_box(3, sigma=0.4, seed=2)
+    rng = np.random.default_rng(2)
+    sol = rng.random((23, 3)) * box
+    assert np.array_equal(port.radialdistsame(pos, 0.1, 90, 1.0, box), wl.radialdistsame(pos, 0.1, 90, 1.0, box))
+    assert np.array_equal(port.radialdist(sol, pos, 0.1, 90, 0.0334, box), wl.radialdist(sol, pos, 0.1, 90, 0.0334, box))
+    assert np.array_equal(port.radialdistsame(pos, 0.25, 400, 1.0, box.reshape(1, 3)), wl.radialdistsame(pos, 0.25, 400, 1.0, box))
+    assert np.array_equal(port.pairdistancehistogram(sol, pos, 0.2, 60, box), wl.pairdistancehistogram(sol, pos, 0.2, 60, box))
+    assert np.array_equal(port.pairdistancehistogram(pos, pos, 0.2, 60, box), wl.pairdistancehistogram(pos, pos, 0.2, 60, box))
+
+
+def test_psi_matches_live(ref):
+    wl, fn = ref
+    pos, box = synth.water_box(3, sigma=0.3, seed=4)
+    for sub, lo, hi in ((pos, 0.0, 4.5), (pos[::5] + 0.2, 1.0, 6.0)):
+        want = fn["getOrderParamPsi"](sub, pos, box, lo, hi)
+        got = port.getOrderParamPsi(sub, pos, box, lo, hi)
+        assert np.allclose(got, want, rtol=1e-10, atol=1e-14) and want.max() > 0.05

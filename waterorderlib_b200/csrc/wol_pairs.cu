@@ -1,0 +1,300 @@
+// Same-sweep observables over the cell list, sm_100a, fp64 in the reference's
+// operation order:
+//   pair_hist_kernel   RadialDist / RadialDistSame / PairDistanceHistogram   fortran/waterlib.f90:193-231, :316-353, :358-389
+//   psi_kernel         getOrderParamPsi                                         structureLibs/water_properties.py:393-433
+#include <math.h>
+
+#include "wol_q3b_common.cuh"
+
+namespace wol {
+
+struct PGrid {
+    const uint32_t *cell_start;
+    const void *recs;
+    int nc0, nc1, nc2;
+};
+
+struct PBox {
+    double L[3], iL[3];
+};
+__device__ __forceinline__ PBox load_pbox(const double *b) {
+    PBox o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.L[k] = b[k];
+        o.iL[k] = (b[k] >= 0.0) ? __ddiv_rn(1.0, b[k]) : 0.0;
+    }
+    return o;
+}
+
+template <typename T>
+__device__ __forceinline__ void pload3(const void *p, int dtype, size_t i, T &x, T &y, T &z) {
+    if (dtype == WOL_F64) {
+        const double *d = reinterpret_cast<const double *>(p) + 3 * i;
+        x = (T)d[0]; y = (T)d[1]; z = (T)d[2];
+    } else {
+        const float *d = reinterpret_cast<const float *>(p) + 3 * i;
+        x = (T)d[0]; y = (T)d[1]; z = (T)d[2];
+    }
+}
+
+// ---- pair-distance histograms --------------------------------------------------------------------------
+// One thread per OUTER atom; it sweeps the 27-cell stencil (cell edge >= totbins * binwidth; every cell when an
+// axis has <= 3) of the cell list built over the INNER set, bins nbin = ceiling(dist / binwidth) exactly as the
+// Fortran does, and counts into a block-shared histogram flushed once.
+//   mode 0 RadialDist            outer = Pos2, inner = Pos1, every pair
+//   mode 1 RadialDistSame        outer = inner = Pos, pairs with inner index > outer index (the i < j loops)
+//   mode 2 PairDistanceHistogram outer = Pos1, inner = Pos2, dist == 0 skipped
+
+struct PairHistParams {
+    PGrid grid;
+    const double *box;
+    const void *outer;
+    int outer_dtype;
+    int n_outer;
+    int mode;
+    double binwidth;
+    int totbins;
+    unsigned long long *counts;
+};
+
+__global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) {
+    extern __shared__ unsigned s_cnt[];
+    const bool smem = P.totbins <= kMaxSmemBins;
+    if (smem) {
+        for (int i = threadIdx.x; i < P.totbins; i += blockDim.x) s_cnt[i] = 0u;
+        __syncthreads();
+    }
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < P.n_outer) {
+        const PBox b = load_pbox(P.box);
+        double rx, ry, rz;
+        pload3<double>(P.outer, P.outer_dtype, (size_t)g, rx, ry, rz);
+        const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+        const int cx = cell_coord(rx, b.iL[0], nc0), cy = cell_coord(ry, b.iL[1], nc1), cz = cell_coord(rz, b.iL[2], nc2);
+        const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+        const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+                  zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+        for (int iz = 0; iz < cntz; ++iz) {
+            const int z = (zs + iz) % nc2;
+            for (int iy = 0; iy < cnty; ++iy) {
+                const int y = (ys + iy) % nc1;
+                // the x cells of a row are contiguous in memory: one run, or two when the row wraps
+                for (int ix = 0; ix < cntx; ++ix) {
+                    const int x = (xs + ix) % nc0;
+                    const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
+                    const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
+                    for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
+                        double px, py, pz;
+                        int id;
+                        RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+                        if (P.mode == 1 && id <= g) continue;  // do j = i + 1, NPos
+                        // distVec = jPos - iPos, minimum image (:213-214)
+                        const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
+                        const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
+                        const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
+                        const double dist = __dsqrt_rn(sumsq3<double>(dx, dy, dz));
+                        const double nb = ceil(__ddiv_rn(dist, P.binwidth));
+                        if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) continue;  // bin 0 (dist == 0) is out of bounds in the Fortran
+                        if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
+                        else atomicAdd(P.counts + (int)nb - 1, 1ull);
+                    }
+                }
+            }
+        }
+    }
+    if (smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.totbins; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(P.counts + i, (unsigned long long)s_cnt[i]);
+    }
+}
+
+// ---- psi (hexagonal order parameter) -------------------------------------------------------------------------
+// One warp per centre: the lanes gather the neighbours inside (lowCut, highCut] (vectors as tetraCosAng sees them:
+// reimaged twice, waterlib.f90:43-45 and :880-883) into a shared list, then share its K (K - 1) / 2 pairs.
+// cos(6 theta) is the Chebyshev polynomial T6 of the clamped cosine, so no acos is needed; an exactly antiparallel
+// pair (the -180 degrees of CosAngle3) gives T6(-1) = 1 = cos(-6 pi) and coincident positions (0 degrees) T6(1) = 1.
+// The reference stores the complex mean of exp(6 i theta) into a real array (water_properties.py:428), which keeps
+// only the real part: what it returns, and what is computed here, is | mean cos(6 theta) |.
+
+constexpr int kPsiThreads = 128;
+constexpr int kPsiCap = 320;  // neighbours per centre
+
+struct PsiParams {
+    PGrid grid;
+    const double *box;
+    const void *centres;
+    int centre_dtype;
+    int n_frames, n_pos, n_centres;
+    double lowsq, highsq;
+    double *psi;
+    uint32_t *counters;
+};
+
+struct PsiSmem {
+    Vec4<double> v[kPsiCap];
+    int n;
+};
+
+__global__ void __launch_bounds__(kPsiThreads) psi_kernel(const PsiParams P) {
+    extern __shared__ __align__(16) unsigned char psi_raw[];
+    PsiSmem *S = reinterpret_cast<PsiSmem *>(psi_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PsiSmem &W = S[warp];
+    const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+    const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+    const int ncell27 = cntx * cnty * cntz;
+    const long long total = (long long)P.n_frames * P.n_centres;
+    for (long long g = (long long)blockIdx.x * (kPsiThreads / 32) + warp; g < total; g += (long long)gridDim.x * (kPsiThreads / 32)) {
+        const int f = (int)(g / P.n_centres);
+        const PBox b = load_pbox(P.box + (size_t)f * 3);
+        double rx, ry, rz;
+        pload3<double>(P.centres, P.centre_dtype, (size_t)g, rx, ry, rz);
+        const int cx = cell_coord(rx, b.iL[0], nc0), cy = cell_coord(ry, b.iL[1], nc1), cz = cell_coord(rz, b.iL[2], nc2);
+        const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+                  zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+        const size_t cell_base = (size_t)f * nc0 * nc1 * nc2;
+        __syncwarp();
+        if (lane == 0) W.n = 0;
+        __syncwarp();
+        for (int c27 = lane; c27 < ncell27; c27 += 32) {
+            const int ix = c27 % cntx, iy = (c27 / cntx) % cnty, iz = c27 / (cntx * cnty);
+            const size_t c = cell_base + ((size_t)((zs + iz) % nc2) * nc1 + (ys + iy) % nc1) * nc0 + (xs + ix) % nc0;
+            const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
+            for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
+                double px, py, pz;
+                int id;
+                RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+                const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
+                const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
+                const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
+                const double s = sumsq3<double>(dx, dy, dz);
+                if (!(s > P.lowsq && s <= P.highsq)) continue;
+                // reimage: ref + d; tetraCosAng: ref + minimg((ref + d) - ref); CosAngle3: that - ref
+                const double ex = __dsub_rn(__dadd_rn(rx, dx), rx), ey = __dsub_rn(__dadd_rn(ry, dy), ry),
+                             ez = __dsub_rn(__dadd_rn(rz, dz), rz);
+                const double d2x = __dsub_rn(ex, __dmul_rn(b.L[0], anint_exact<double>(__dmul_rn(ex, b.iL[0]))));
+                const double d2y = __dsub_rn(ey, __dmul_rn(b.L[1], anint_exact<double>(__dmul_rn(ey, b.iL[1]))));
+                const double d2z = __dsub_rn(ez, __dmul_rn(b.L[2], anint_exact<double>(__dmul_rn(ez, b.iL[2]))));
+                Vec4<double> v;
+                v.x = __dsub_rn(__dadd_rn(rx, d2x), rx);
+                v.y = __dsub_rn(__dadd_rn(ry, d2y), ry);
+                v.z = __dsub_rn(__dadd_rn(rz, d2z), rz);
+                v.w = sumsq3<double>(v.x, v.y, v.z);
+                const int at = atomicAdd(&W.n, 1);
+                if (at < kPsiCap) W.v[at] = v;
+            }
+        }
+        __syncwarp();
+        const int n = W.n;
+        if (n > kPsiCap) {
+            if (lane == 0) atomicAdd(P.counters + kCntFatal, 1u);
+            continue;
+        }
+        double acc = 0.0;
+        const int npairs = n * (n - 1) / 2;
+        for (int p = lane; p < npairs; p += 32) {
+            int hi = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (hi * (hi - 1) / 2 > p) --hi;
+            while ((hi + 1) * hi / 2 <= p) ++hi;
+            const int lo = p - hi * (hi - 1) / 2;
+            const Vec4<double> va = W.v[lo], vb = W.v[hi];
+            double c = 1.0;  // coincident positions: CosAngle3 returns 0 degrees (:690-693)
+            if (va.w != 0.0 && vb.w != 0.0) c = clamped_cos<double>(dot3<double>(va.x, va.y, va.z, vb.x, vb.y, vb.z), va.w, vb.w);
+            const double c2 = c * c;
+            acc += ((32.0 * c2 - 48.0) * c2 + 18.0) * c2 - 1.0;  // T6(c) = cos(6 theta)
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) P.psi[g] = (n > 1) ? fabs(acc / (double)npairs) : 0.0;
+    }
+}
+
+static PGrid make_pgrid(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
+    char *ws = reinterpret_cast<char *>(workspace);
+    PGrid g;
+    g.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
+    g.recs = ws + lay.off_recs;
+    g.nc0 = nc[0];
+    g.nc1 = nc[1];
+    g.nc2 = nc[2];
+    return g;
+}
+
+}  // namespace wol
+
+using namespace wol;
+
+extern "C" {
+
+int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t n_outer, const double *box, int32_t n_inner,
+                  const int32_t nc[3], double edge_min, double binwidth, int32_t totbins, void *workspace, size_t workspace_bytes,
+                  int64_t *counts, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (mode < 0 || mode > 2 || !outer || !box || !nc || !workspace || !counts) return set_error(WOL_ERR_INVALID, "wol_pair_hist: bad argument");
+    if (totbins < 1 || !(binwidth > 0.0) || n_outer < 0 || n_inner < 0) return set_error(WOL_ERR_INVALID, "wol_pair_hist: bad bin spec or size");
+    const double reach = binwidth * totbins;
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && reach * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "histogram range %.6g exceeds the planned cell edge %.6g", reach, edge_min);
+    const WorkspaceLayout lay = workspace_layout(1, n_inner, n_inner, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    PairHistParams P;
+    P.grid = make_pgrid(workspace, lay, nc);
+    P.box = box;
+    P.outer = outer;
+    P.outer_dtype = outer_dtype;
+    P.n_outer = n_outer;
+    P.mode = mode;
+    P.binwidth = binwidth;
+    P.totbins = totbins;
+    P.counts = reinterpret_cast<unsigned long long *>(counts);
+    if (n_outer > 0 && n_inner > 0) {
+        const size_t smem = totbins <= kMaxSmemBins ? sizeof(unsigned) * totbins : 0;
+        pair_hist_kernel<<<(n_outer + 127) / 128, 128, smem, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_pair_hist", e);
+    return WOL_OK;
+}
+
+int wol_psi(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos, int32_t n_centres,
+            const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes, double *psi,
+            void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!centres || !box || !nc || !workspace || !psi) return set_error(WOL_ERR_INVALID, "wol_psi: null argument");
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && highcut * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "cutoff %.6g exceeds the planned cell edge %.6g", highcut, edge_min);
+    const WorkspaceLayout lay = workspace_layout(n_frames, n_pos, n_centres, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    PsiParams P;
+    P.grid = make_pgrid(workspace, lay, nc);
+    P.box = box;
+    P.centres = centres;
+    P.centre_dtype = centre_dtype;
+    P.n_frames = n_frames;
+    P.n_pos = n_pos;
+    P.n_centres = n_centres;
+    P.lowsq = lowcut * lowcut;
+    P.highsq = highcut * highcut;
+    P.psi = psi;
+    P.counters = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + lay.off_counters);
+    const long long total = (long long)n_frames * n_centres;
+    if (total > 0) {
+        const size_t smem = sizeof(PsiSmem) * (kPsiThreads / 32);
+        cudaError_t e = cudaFuncSetAttribute(psi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(psi)", e);
+        long long blocks = (total + 3) / 4;
+        const long long cap = (long long)sm_count() * 4;
+        if (blocks > cap) blocks = cap;
+        psi_kernel<<<(unsigned)blocks, kPsiThreads, smem, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_psi", e);
+    return WOL_OK;
+}
+
+}  // extern "C"

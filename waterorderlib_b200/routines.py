@@ -419,3 +419,58 @@ def lsi(sub, pos, box, low=0.0, high=3.7, device=None):
                             _vp(out.data_ptr()), _vp(num.data_ptr()), _stream()), "wol_lsi")
         cells.status()
     return out, num
+
+
+# ---- same-sweep observables: pair-distance histograms, psi ------------------------------------------------------
+
+_FOUR_THIRDS = float(np.float32(4.0) / np.float32(3.0))  # the Fortran literal (4./3.) is single precision (waterlib.f90:228)
+_PI_RDF = 3.141592653589                                 # and its pi is truncated (waterlib.f90:204)
+
+
+def pair_hist(mode, pos1, pos2, box, binwidth, totbins, device=None):
+    """Counts of RadialDist (mode 0: pos1 = Pos1, pos2 = Pos2), RadialDistSame (mode 1: pos1 only) or
+    PairDistanceHistogram (mode 2) -> int64 CUDA tensor (totbins,)."""
+    device = _device(device, pos1, pos2)
+    p1 = _f64(pos1, device, (3,)).reshape(-1, 3)
+    p2 = p1 if pos2 is None else _f64(pos2, device, (3,)).reshape(-1, 3)
+    outer, inner = (p2, p1) if mode == 0 else ((p1, p1) if mode == 1 else (p1, p2))
+    counts = torch.zeros(int(totbins), dtype=torch.int64, device=device)
+    if outer.shape[0] == 0 or inner.shape[0] == 0:
+        return counts
+    cells = CellList(inner, box, float(binwidth) * int(totbins) * (1.0 + 1e-9), device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_pair_hist(int(mode), _vp(outer.data_ptr()), WOL_F64, int(outer.shape[0]), _vp(cells.box_d.data_ptr()), cells.N,
+                                  ctypes.byref(cells.nc), cells.edge_min, float(binwidth), int(totbins), _vp(cells.ws_ptr),
+                                  cells.ws_bytes, _vp(counts.data_ptr()), _stream()), "wol_pair_hist")
+        torch.cuda.current_stream().synchronize()
+    return counts
+
+
+def rdf_normalise(counts, n_norm, binwidth, bulkdens):
+    """counts(k) / (N * BulkDens * (4./3.) * pi * binwidth**3 * (k**3 - (k-1)**3)) in the Fortran's order of
+    operations (waterlib.f90:227-229); O(totbins) on the host."""
+    c = counts.cpu().numpy().astype(np.float64)
+    k = np.arange(1, c.size + 1, dtype=np.int64)
+    shell = (k ** 3 - (k - 1) ** 3).astype(np.float64)
+    denom = ((((float(n_norm) * float(bulkdens)) * _FOUR_THIRDS) * _PI_RDF) * ((binwidth * binwidth) * binwidth)) * shell
+    return c / denom
+
+
+def psi(sub, pos, box, low=0.0, high=10.0, device=None):
+    """getOrderParamPsi (structureLibs/water_properties.py:393-433) for one or several frames -> f64 (F, M)."""
+    device = _device(device, pos, sub)
+    pos_d = engine.as_device_positions(pos, device)
+    cen_d = pos_d if sub is None else engine.as_device_positions(sub, device)
+    if cen_d.shape[0] != pos_d.shape[0]:
+        raise ValueError("sub and pos must hold the same number of frames")
+    F, N, M = int(pos_d.shape[0]), int(pos_d.shape[1]), int(cen_d.shape[1])
+    out = torch.zeros((F, M), dtype=torch.float64, device=device)
+    if M == 0 or N == 0:
+        return out
+    cells = CellList(pos_d, box, max(float(high), 1e-3) * (1.0 + 1e-9), device=device, n_centres_max=M)
+    with torch.cuda.device(device):
+        check(lib().wol_psi(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
+                            ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr), cells.ws_bytes,
+                            _vp(out.data_ptr()), _stream()), "wol_psi")
+        cells.status()
+    return out

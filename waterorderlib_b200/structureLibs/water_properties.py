@@ -8,6 +8,7 @@ Same names, positional order, keyword names, defaults and return values:
     HBondsGeneral(accPos, donPos, donHPos, boxL, accInds, donInds, donHInds,
                   distCut=3.5, angCut=150.0)                                         reference :681-719
     getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7)                            reference :252-311
+    getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0)                 reference :393-433
 
 numpy arrays in -> numpy arrays out; torch CUDA tensors in -> torch CUDA tensors out (zero copy).  The
 per-water Python loops and f2py calls of the reference are replaced by one pass of the cell-list kernels in
@@ -130,3 +131,16 @@ def getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7):
     vals, num = vals[0], num[0]
     lsiVals = vals[num > 0]
     return _out(lsiVals, tor), _out(num, tor, torch.float64 if tor else np.float64)
+
+
+def getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
+    """Hexagonal order parameter of Dallin & van Lehn (2019) as the reference computes it (water_properties.py:393-433).
+    NOTE: the reference assigns the complex mean of exp(6 i theta) into a float array (:428), which drops the imaginary
+    part, so its result -- reproduced here for drop-in parity -- is |mean cos(6 theta)| over the pairs of neighbours inside
+    (lowCut, highCut], not |mean exp(6 i theta)|.  0 for centres with fewer than two neighbours."""
+    tor = _is_torch(subPos, Pos)
+    subPos = subPos if tor else np.asarray(subPos)
+    Pos = Pos if tor else np.asarray(Pos)
+    _pos2(subPos, "subPos"); _pos2(Pos, "Pos")
+    r = routines.psi(None if _same(subPos, Pos) else subPos, Pos, BoxDims, lowCut, highCut)
+    return _out(r[0], tor)

@@ -91,3 +91,22 @@ def histrr3b(pos, boxl, distwidth, dnum, angwidth, anum):
     (dnum,dnum,anum), Fortran-ordered."""
     h = routines.histrr3b(_check_pos(pos, "pos"), boxl, distwidth, dnum, angwidth, anum)
     return np.asfortranarray(h.cpu().numpy().astype(np.float64))
+
+
+def radialdist(pos1, pos2, binwidth, totbins, bulkdens, boxl):
+    """rdf = radialdist(pos1,pos2,binwidth,totbins,bulkdens,boxl)   (fortran/waterlib.f90:193-231)"""
+    p1 = _check_pos(pos1, "pos1")
+    counts = routines.pair_hist(0, p1, _check_pos(pos2, "pos2"), boxl, binwidth, totbins)
+    return routines.rdf_normalise(counts, p1.shape[0], binwidth, bulkdens)
+
+
+def radialdistsame(pos, binwidth, totbins, bulkdens, boxl):
+    """rdf = radialdistsame(pos,binwidth,totbins,bulkdens,boxl)   (fortran/waterlib.f90:316-353)"""
+    p = _check_pos(pos, "pos")
+    return routines.rdf_normalise(routines.pair_hist(1, p, None, boxl, binwidth, totbins), p.shape[0], binwidth, bulkdens)
+
+
+def pairdistancehistogram(pos1, pos2, binwidth, totbins, boxl):
+    """hist = pairdistancehistogram(pos1,pos2,binwidth,totbins,boxl)   (fortran/waterlib.f90:358-389), 3-D positions"""
+    counts = routines.pair_hist(2, _check_pos(pos1, "pos1"), _check_pos(pos2, "pos2"), boxl, binwidth, totbins)
+    return counts.cpu().numpy().astype(np.float64)

@@ -365,6 +365,15 @@ def main():
     achieved = BYTES_PER_WF_FP64 * B * n_waters / (kernel_ms * 1e-3) / 1e9
     q_ok = bool(torch.equal(q_h.to(dev), out["q"]))
 
+    # FP roofline of the dominant kernel: 17 flop per candidate pair evaluation + 37 per angle, candidates
+    # = 27 cells * cell volume * number density, angles = three-body angles (measured) + 6 for q
+    nc_used = step()["nc"]
+    cand = 27.0 * n_waters / float(nc_used[0] * nc_used[1] * nc_used[2])
+    ang_per_wf = n_angles / (float(B) * n_waters * args.steps) + 6.0
+    flop_per_wf = 17.0 * cand + 37.0 * ang_per_wf
+    fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal FP64 FMA peak of a B200 at 1965 MHz, TFLOP/s
+    fp_achieved = flop_per_wf * B * n_waters / (kernel_ms * 1e-3) / 1e12
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
@@ -376,7 +385,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": kernel_traffic(n_waters, B), "kernel": "wol::q3b_tpc_kernel",
                          "kernel_ms": kernel_ms, "bytes_per_water_frame": BYTES_PER_WF_FP64, "peak_source": peak_src,
-                         "note": "the sweep is issue/FP64-bound by construction (about 1.2 kFLOP per water-frame, SURVEY 8d)"},
+                         "note": "the sweep is issue/FP64-bound by construction (about 1.3 kFLOP per water-frame, SURVEY 8d); see roofline_fp"},
+            "roofline_fp": {"bound": "fp64 pipe (nominal, 148 SM x 64 FMA lanes x 2 x 1.965 GHz)", "flop_per_water_frame": flop_per_wf,
+                            "candidates_per_water": cand, "angles_per_water": ang_per_wf, "achieved": fp_achieved,
+                            "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp_achieved / fp64_peak},
             "clocks": sampler.summary(),
             "fp32_mode": {"value": float(world) * B * n_waters * args.steps / (ms32 * 1e-3), "unit": UNIT,
                           "ms_per_step": ms32 / args.steps, "max_abs_q_error_vs_fp64_same_neighbours": q_err32,

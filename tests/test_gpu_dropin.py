@@ -233,3 +233,19 @@ def test_getOrderParamPsi_golden(golden_dir):
     assert np.allclose(wp.getOrderParamPsi(pos[:40], pos, box), port.getOrderParamPsi(pos[:40], pos, box), rtol=1e-9, atol=1e-13)
     lone = np.array([[1.0, 1.0, 1.0], [3.0, 1.0, 1.0], [20.0, 20.0, 20.0]])
     assert np.array_equal(wp.getOrderParamPsi(lone, lone, np.array([40.0, 40.0, 40.0]), 0.0, 5.0), np.zeros(3))
+
+
+def test_integration_md_ctypes_stub_runs(golden_dir):
+    """The ctypes binding printed in INTEGRATION.md section 3 is real code: extract it, point it at the built library and
+    check its output against the golden fixture."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "def q_and_three_body" in b)
+    stub = stub.replace("/path/to/waterorderlib_b200/libwol.so", os.path.join(root, "waterorderlib_b200", "libwol.so"))
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    g = load(golden_dir, "cfg1_n512_liq")
+    q, n3, hist = ns["q_and_three_body"](g["pos"], g["box"])
+    assert np.allclose(q, g["q"], rtol=Q_RTOL, atol=1e-9) and np.array_equal(n3, g["n3"]) and np.array_equal(hist, g["hist"])

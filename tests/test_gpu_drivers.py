@@ -207,3 +207,40 @@ def test_getNeighborStats(in_tmp):
         for n in range(len(solInds) // 3):
             vals.append(len(np.unique(np.where(nb[3 * n:3 * n + 3] == 1)[1])))
     assert got == np.mean(vals) and os.path.exists("coordDistribution.txt")
+
+
+def test_lsiCalc_and_hexOrderCalc_match_reference_loops(in_tmp):
+    T = 20
+    top, traj = make_system(3, T, sigma=0.45, seed0=1100)
+    obj = TrajObject(top, traj)
+    watInds, _, _ = obj.getWatInds()
+    rng = np.random.default_rng(9)
+    subInds = [[np.sort(rng.choice(watInds, 50, replace=False))] for _ in range(T)]
+    # lsiCalc (orderParam_lib.py:1617-1661)
+    avg = np.zeros((2, T)); var = np.zeros((2, T)); pooled = [[], []]
+    for t in range(T):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        for j, sub in enumerate([pos[watInds], pos[subInds[t][0]]]):
+            v, _ = port.getLSI(sub, pos[watInds], box)
+            pooled[j].append(v); avg[j, t], var[j, t] = np.mean(v), np.var(v)
+    avgL, varL = opl.lsiCalc(top, traj, subInds=subInds, nPops=1)
+    assert np.allclose(avgL[0], avg.mean(axis=1), rtol=1e-10) and np.allclose(varL[0], var.mean(axis=1), rtol=1e-9)
+    for j in range(2):
+        got = np.loadtxt("lsiDistribution_%d.txt" % j)
+        want = np.histogram(np.concatenate(pooled[j]), bins=500, range=[0.0, 0.3])[0]
+        assert np.array_equal(got[:, 1], np.array([float("%.3e" % v) for v in want]))
+    # hexOrderCalc (orderParam_lib.py:1537-1582): every second end atom, 0 / 7.0 for the whole set, 0 / 10 for sub-populations
+    ends = watInds[1::2]
+    subE = [[np.sort(rng.choice(ends, 20, replace=False))] for _ in range(T)]
+    avg = np.zeros((2, T)); pooled = [[], []]
+    for t in range(T):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        a = port.getOrderParamPsi(pos[ends], pos[ends], box, 0.0, 7.0)
+        b = port.getOrderParamPsi(pos[subE[t][0]], pos[ends], box, 0.0, 10.0)
+        avg[0, t], avg[1, t] = a.mean(), b.mean()
+        pooled[0].append(a); pooled[1].append(b)
+    avgP, varP = opl.hexOrderCalc(top, traj, subInds=subE, nPops=1)
+    assert np.allclose(avgP[0], avg.mean(axis=1), rtol=1e-8)
+    got = np.loadtxt("psiDistribution_0.txt")
+    want = np.histogram(np.concatenate(pooled[0]), bins=500, range=[0.0, 1.0])[0]
+    assert abs(got[:, 1] - want).sum() <= 2  # psi values agree to ~1e-12: a value on a bin edge may move one bin

@@ -1,6 +1,6 @@
 """BASELINE.json configs 1-4 on one B200, each checked against the CPU oracle on the same inputs and timed next to
 the CPU path (the reference's compiled Fortran + Python loops where its dense matrices fit, else the C restatement).
-Writes profiles/configs_<tag>.json.   usage: python scripts/config_times.py <tag>"""
+Writes profiles/configs_<tag>.json.   usage: python tests/tools/config_times.py <tag>   (lives under tests/ because it runs the CPU oracle as the checker)"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import port, ref_driver, ref_fortran  # noqa: E402  (checker / CPU baseline only)
 from waterorderlib_b200 import engine, routines, synth  # noqa: E402

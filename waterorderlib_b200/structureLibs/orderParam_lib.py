@@ -11,6 +11,9 @@ Same names, positional order, keyword names, defaults, return values and output 
     getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1, distCut=3.4,
                      switch=False)                                                                   reference :313-384
     getHBInds(top, frame, solInds, solHInds, solNInds, solOInds)                                     reference :46-120
+    lsiCalc(topFile, trajFile, subInds=None, nPops=0, solResName, watResName, stride=1)            reference :1586-1663
+    hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, endResName, stride=1,
+                 lowCut=0.0, highCut=7.0)                                                            reference :1505-1584
     blockAverage(vals, nBlocks=20), getCI(means)                                                     reference :386-417
 
 ``topFile`` / ``trajFile`` are whatever ``TrajObject`` accepts (in-memory objects, .npz, or AMBER files when
@@ -384,3 +387,74 @@ def getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1
     np.savetxt('coordDistribution.txt', np.stack([0.5 * (bins[:-1] + bins[1:]), coordDist], axis=1),
                header='# coords    frequency', fmt="%.3e")
     return meanCoord
+
+
+def _value_driver(obj, centreInds, subInds, nPops, per_frame, hist_range, fname, header):
+    """Shared frame loop of lsiCalc / hexOrderCalc (reference orderParam_lib.py:1617-1661, :1537-1582): a per-centre
+    observable for all centres and for nPops sub-populations, per-frame mean / variance, bootstrap CIs, pooled 500-bin
+    histograms written as two-column text.  per_frame(j, sub, pos, box) -> 1-D numpy array of values (j = population)."""
+    traj = obj.traj
+    T, P = len(traj), nPops + 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    begin, end = wdist.shard_frames(T)
+    rows = np.zeros((end - begin, 2 * P))
+    hists = torch.zeros((P, 500), dtype=torch.int64, device=dev)
+    for t in range(begin, end):
+        frame = traj[t]
+        pos = np.array(frame.xyz)
+        thisbox = np.array(frame.box.values[:3])
+        cenPos = pos[centreInds]
+        for j in range(P):
+            sub = cenPos if j == 0 else pos[np.asarray(subInds[t][j - 1], dtype=np.int64)]
+            vals = per_frame(j, sub, cenPos, thisbox)
+            with np.errstate(all="ignore"):
+                rows[t - begin, 2 * j], rows[t - begin, 2 * j + 1] = np.mean(vals), np.var(vals)
+            if vals.size:
+                h, _ = routines.histogram(vals, 500, hist_range)
+                hists[j] += h
+    rows = wdist.gather_frame_rows(torch.from_numpy(rows).to(dev), T).cpu().numpy()
+    wdist.reduce_histograms(hists)
+    avg_mean, avg_ci, var_mean, var_ci = (np.zeros(P) for _ in range(4))
+    for j in range(P):
+        avg_mean[j], avg_ci[j] = _mean_ci(rows[:, 2 * j])
+        var_mean[j], var_ci[j] = _mean_ci(rows[:, 2 * j + 1])
+    if wdist.world()[0] == 0:
+        bins = np.linspace(hist_range[0], hist_range[1], 501)
+        counts = hists.cpu().numpy()
+        for j in range(P):
+            np.savetxt(fname % j, np.stack([0.5 * (bins[:-1] + bins[1:]), counts[j]], axis=1), header=header, fmt="%.3e")
+    return [avg_mean, avg_ci], [var_mean, var_ci]
+
+
+def lsiCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)', watResName='(:WAT)', stride=1):
+    """Local structure index statistics and distribution for all waters and nPops sub-populations (reference
+    orderParam_lib.py:1586-1663).  Returns (avgLSI, varLSI), each [means, CIs]; writes lsiDistribution_<j>.txt
+    (500 bins on [0, 0.3] A^2)."""
+    from . import water_properties as wp
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    watInds, _watHInds, _lenWat = obj.getWatInds()
+    if subInds is None:
+        nPops = 0
+    return _value_driver(obj, watInds, subInds, nPops, lambda j, sub, pos, box: wp.getLSI(sub, pos, box, lowCut=0.0, highCut=3.7)[0],
+                         (0.0, 0.3), 'lsiDistribution_%d.txt', 'lsiVal [A^2]    frequency')
+
+
+def hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)', endResName='(:WAT)', stride=1, lowCut=0.0,
+                 highCut=7.0):
+    """Hexagonal order parameter statistics and distribution for chain-end atoms (reference orderParam_lib.py:1505-1584).
+    As in the reference: every second selected end atom is used (:1526), the all-ends population is evaluated with
+    the hard-coded cutoffs 0 / 7.0 (:1549) and the sub-populations with getOrderParamPsi's defaults 0 / 10 (:1556);
+    the lowCut / highCut arguments are accepted and, like there, unused.  Writes psiDistribution_<j>.txt."""
+    from . import water_properties as wp
+    obj = TrajObject(topFile, trajFile, stride, solResName, endResName)
+    endInds, _endHInds, _lenEnd = obj.getWatInds()
+    endInds = endInds[1::2]
+    if subInds is None:
+        nPops = 0
+
+    def per_frame(j, sub, pos, box):
+        if j == 0:
+            return wp.getOrderParamPsi(sub, pos, box, lowCut=0.0, highCut=7.0)
+        return wp.getOrderParamPsi(sub, pos, box)
+
+    return _value_driver(obj, endInds, subInds, nPops, per_frame, (0.0, 1.0), 'psiDistribution_%d.txt', 'psiVal    frequency')

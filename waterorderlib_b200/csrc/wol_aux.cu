@@ -20,6 +20,7 @@ namespace wol {
 struct CellGrid {
     const uint32_t *cell_start;
     const void *recs;
+    const float4 *wrapped;  // box-wrapped float coordinates in record order (float prefilter)
     int nc0, nc1, nc2;
 };
 
@@ -44,6 +45,50 @@ __device__ __forceinline__ void sweep_stencil1(const CellGrid &g, int f, int cx,
             }
         }
     }
+}
+
+// The same sweep behind a float prefilter: fn(j) runs only for records whose float minimum-image distance^2 from the
+// (box-wrapped) point (wx, wy, wz) is within thr2 -- a bound the caller widens by float_margin() so that no record
+// inside the exact cutoff can be rejected; everything that decides a result is then recomputed exactly by fn.
+struct FloatBox {
+    float Lx, Ly, Lz, iLx, iLy, iLz;
+};
+__device__ __forceinline__ FloatBox float_box(double Lx, double Ly, double Lz) {
+    FloatBox b;
+    b.Lx = (float)Lx; b.Ly = (float)Ly; b.Lz = (float)Lz;
+    b.iLx = 1.0f / b.Lx; b.iLy = 1.0f / b.Ly; b.iLz = 1.0f / b.Lz;
+    return b;
+}
+// squared float acceptance threshold for an exact cutoff `cut` in a box whose largest edge is lmax: wrapped
+// coordinates carry an absolute error below 2^-24 lmax each, the float arithmetic a few more roundings of that size
+__device__ __forceinline__ float float_margin_thr2(double cut, double lmax) {
+    const double m = cut + 16.0 * 5.9604644775390625e-8 * lmax;
+    return __double2float_ru(m * m * (1.0 + 1e-6));
+}
+// Two steps, because the exact work is heavy and only a few records per thread pass: the sweep appends the survivors
+// to the thread's column of a shared list (a few instructions inside the divergent loop), fn runs over the list in a
+// dense loop -- when the list fills up and once more at the end, so there is no capacity limit.
+constexpr int kPrefThreads = 128;
+constexpr int kPrefCap = 16;
+template <typename F>
+__device__ __forceinline__ void sweep_stencil1_pref(const CellGrid &g, int f, int cx, int cy, int cz, float wx, float wy, float wz,
+                                                    const FloatBox &fb, float thr2, int *list, F &&fn) {
+    int nl = 0;
+    sweep_stencil1(g, f, cx, cy, cz, [&](int j) {
+        const float4 w = __ldg(g.wrapped + j);
+        float dx = w.x - wx, dy = w.y - wy, dz = w.z - wz;
+        dx -= fb.Lx * rintf(dx * fb.iLx);
+        dy -= fb.Ly * rintf(dy * fb.iLy);
+        dz -= fb.Lz * rintf(dz * fb.iLz);
+        if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr2) {
+            list[nl * kPrefThreads] = j;
+            if (++nl == kPrefCap) {
+                for (int k = 0; k < kPrefCap; ++k) fn(list[k * kPrefThreads]);
+                nl = 0;
+            }
+        }
+    });
+    for (int k = 0; k < nl; ++k) fn(list[k * kPrefThreads]);
 }
 
 template <typename T>
@@ -99,7 +144,8 @@ struct MatParams {
     uint32_t *counters;
 };
 
-__global__ void __launch_bounds__(128) angles_fill_kernel(const MatParams P) {
+__global__ void __launch_bounds__(kPrefThreads) angles_fill_kernel(const MatParams P) {
+    __shared__ int s_list[kPrefCap * kPrefThreads];
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)P.n_frames * P.n_centres;
     if (g >= total) return;
@@ -116,7 +162,10 @@ __global__ void __launch_bounds__(128) angles_fill_kernel(const MatParams P) {
     double ex[kMatCap], ey[kMatCap], ez[kMatCap], en[kMatCap];
     int K = 0;
     bool over = false;
-    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+    const FloatBox fb = float_box(b.Lx, b.Ly, b.Lz);
+    const float thr2 = float_margin_thr2(sqrt(P.highsq), fmax(b.Lx, fmax(b.Ly, b.Lz)));
+    sweep_stencil1_pref(P.grid, f, cx, cy, cz, wrapped_coord(rx, b.Lx, b.iLx), wrapped_coord(ry, b.Ly, b.iLy),
+                        wrapped_coord(rz, b.Lz, b.iLz), fb, thr2, s_list + threadIdx.x, [&](int j) {
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
@@ -288,7 +337,8 @@ struct HbParams {
     uint32_t *pair_counter;
 };
 
-__global__ void __launch_bounds__(128) hbond_kernel(const HbParams P) {
+__global__ void __launch_bounds__(kPrefThreads) hbond_kernel(const HbParams P) {
+    __shared__ int s_list[kPrefCap * kPrefThreads];
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)P.n_frames * P.n_acc) return;
     const int f = (int)(g / P.n_acc);
@@ -299,7 +349,10 @@ __global__ void __launch_bounds__(128) hbond_kernel(const HbParams P) {
     const int cx = cell_coord(ax, b.iLx, P.grid.nc0), cy = cell_coord(ay, b.iLy, P.grid.nc1),
               cz = cell_coord(az, b.iLz, P.grid.nc2);
     int count = 0;
-    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+    const FloatBox fb = float_box(b.Lx, b.Ly, b.Lz);
+    const float thr2 = float_margin_thr2(sqrt(P.cutsq), fmax(b.Lx, fmax(b.Ly, b.Lz)));
+    sweep_stencil1_pref(P.grid, f, cx, cy, cz, wrapped_coord(ax, b.Lx, b.iLx), wrapped_coord(ay, b.Ly, b.iLy),
+                        wrapped_coord(az, b.Lz, b.iLz), fb, thr2, s_list + threadIdx.x, [&](int j) {
         double dxp, dyp, dzp;
         int jd;
         RecTraits<double>::load(P.grid.recs, (size_t)j, dxp, dyp, dzp, jd);
@@ -368,7 +421,8 @@ struct ShellParams {
     int32_t *mask;  // [F][n_pos], set to 1 (caller zero-fills)
 };
 
-__global__ void __launch_bounds__(128) shell_kernel(const ShellParams P) {
+__global__ void __launch_bounds__(kPrefThreads) shell_kernel(const ShellParams P) {
+    __shared__ int s_list[kPrefCap * kPrefThreads];
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)P.n_frames * P.n_sol) return;
     const int f = (int)(g / P.n_sol);
@@ -377,7 +431,10 @@ __global__ void __launch_bounds__(128) shell_kernel(const ShellParams P) {
     load3<double>(P.sol, P.sol_dtype, g, sx, sy, sz);
     const int cx = cell_coord(sx, b.iLx, P.grid.nc0), cy = cell_coord(sy, b.iLy, P.grid.nc1),
               cz = cell_coord(sz, b.iLz, P.grid.nc2);
-    sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
+    const FloatBox fb = float_box(b.Lx, b.Ly, b.Lz);
+    const float thr2 = float_margin_thr2(sqrt(P.highsq), fmax(b.Lx, fmax(b.Ly, b.Lz)));
+    sweep_stencil1_pref(P.grid, f, cx, cy, cz, wrapped_coord(sx, b.Lx, b.iLx), wrapped_coord(sy, b.Ly, b.iLy),
+                        wrapped_coord(sz, b.Lz, b.iLz), fb, thr2, s_list + threadIdx.x, [&](int j) {
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
@@ -423,6 +480,8 @@ __global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
     int k = 0, n_next = 0, next_idx = 0;
     double next_raw = 0.0, next_min = 0.0;
     bool over = false;
+    // no float prefilter here: a sixth of the stencil lies inside the reach, so every lane does exact work most of the
+    // time anyway and a uniform exact sweep beats a divergent two-step one (measured: 7 ms vs 100 ms per 1M waters)
     sweep_stencil1(P.grid, f, cx, cy, cz, [&](int j) {
         double px, py, pz;
         int id;
@@ -489,6 +548,7 @@ static CellGrid make_grid(void *workspace, const WorkspaceLayout &lay, const int
     CellGrid g;
     g.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
     g.recs = ws + lay.off_recs;
+    g.wrapped = reinterpret_cast<const float4 *>(ws + lay.off_wrapped);
     g.nc0 = nc[0];
     g.nc1 = nc[1];
     g.nc2 = nc[2];

@@ -8,12 +8,6 @@
 
 namespace wol {
 
-struct PGrid {
-    const uint32_t *cell_start;
-    const void *recs;
-    int nc0, nc1, nc2;
-};
-
 struct PBox {
     double L[3], iL[3];
 };
@@ -25,6 +19,38 @@ __device__ __forceinline__ PBox load_pbox(const double *b) {
         o.iL[k] = (b[k] >= 0.0) ? __ddiv_rn(1.0, b[k]) : 0.0;
     }
     return o;
+}
+
+struct PGrid {
+    const uint32_t *cell_start;
+    const void *recs;
+    const float4 *wrapped;  // box-wrapped float coordinates in record order (float prefilter)
+    int nc0, nc1, nc2;
+};
+
+// Float prefilter shared by the sweeps below: true when the record's float minimum-image distance^2 from the wrapped
+// point w0 is within thr2 (a bound widened so that nothing inside the exact range can be rejected; everything that
+// decides a result is recomputed exactly afterwards).
+struct PFloat {
+    float wx, wy, wz, Lx, Ly, Lz, iLx, iLy, iLz, thr2;
+};
+__device__ __forceinline__ PFloat make_pfloat(double x, double y, double z, const PBox &b, double reach) {
+    PFloat p;
+    p.wx = wrapped_coord(x, b.L[0], b.iL[0]);
+    p.wy = wrapped_coord(y, b.L[1], b.iL[1]);
+    p.wz = wrapped_coord(z, b.L[2], b.iL[2]);
+    p.Lx = (float)b.L[0]; p.Ly = (float)b.L[1]; p.Lz = (float)b.L[2];
+    p.iLx = 1.0f / p.Lx; p.iLy = 1.0f / p.Ly; p.iLz = 1.0f / p.Lz;
+    const double m = reach + 16.0 * 5.9604644775390625e-8 * fmax(b.L[0], fmax(b.L[1], b.L[2]));
+    p.thr2 = __double2float_ru(m * m * (1.0 + 1e-6));
+    return p;
+}
+__device__ __forceinline__ bool pfloat_near(const PFloat &p, const float4 w) {
+    float dx = w.x - p.wx, dy = w.y - p.wy, dz = w.z - p.wz;
+    dx -= p.Lx * rintf(dx * p.iLx);
+    dy -= p.Ly * rintf(dy * p.iLy);
+    dz -= p.Lz * rintf(dz * p.iLz);
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= p.thr2;
 }
 
 template <typename T>
@@ -75,6 +101,23 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
         const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
         const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
                   zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+        // (no float prefilter: a sixth of the stencil lies inside the histogram range, so a uniform exact sweep beats a
+        // divergent two-step one -- measured 12 ms vs 110 ms per 1M waters at 15 A)
+        auto exact = [&](int j) {
+            double px, py, pz;
+            int id;
+            RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
+            if (P.mode == 1 && id <= g) return;  // do j = i + 1, NPos
+            // distVec = jPos - iPos, minimum image (:213-214)
+            const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
+            const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
+            const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
+            const double dist = __dsqrt_rn(sumsq3<double>(dx, dy, dz));
+            const double nb = ceil(__ddiv_rn(dist, P.binwidth));
+            if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) return;  // bin 0 (dist == 0) is out of bounds in the Fortran
+            if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
+            else atomicAdd(P.counts + (int)nb - 1, 1ull);
+        };
         for (int iz = 0; iz < cntz; ++iz) {
             const int z = (zs + iz) % nc2;
             for (int iy = 0; iy < cnty; ++iy) {
@@ -84,21 +127,7 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
                     const int x = (xs + ix) % nc0;
                     const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
                     const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
-                    for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
-                        double px, py, pz;
-                        int id;
-                        RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-                        if (P.mode == 1 && id <= g) continue;  // do j = i + 1, NPos
-                        // distVec = jPos - iPos, minimum image (:213-214)
-                        const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
-                        const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
-                        const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
-                        const double dist = __dsqrt_rn(sumsq3<double>(dx, dy, dz));
-                        const double nb = ceil(__ddiv_rn(dist, P.binwidth));
-                        if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) continue;  // bin 0 (dist == 0) is out of bounds in the Fortran
-                        if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
-                        else atomicAdd(P.counts + (int)nb - 1, 1ull);
-                    }
+                    for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) exact(j);
                 }
             }
         }
@@ -155,6 +184,7 @@ __global__ void __launch_bounds__(kPsiThreads) psi_kernel(const PsiParams P) {
         const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
                   zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
         const size_t cell_base = (size_t)f * nc0 * nc1 * nc2;
+        const PFloat pf = make_pfloat(rx, ry, rz, b, sqrt(P.highsq));
         __syncwarp();
         if (lane == 0) W.n = 0;
         __syncwarp();
@@ -163,6 +193,7 @@ __global__ void __launch_bounds__(kPsiThreads) psi_kernel(const PsiParams P) {
             const size_t c = cell_base + ((size_t)((zs + iz) % nc2) * nc1 + (ys + iy) % nc1) * nc0 + (xs + ix) % nc0;
             const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
             for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) {
+                if (!pfloat_near(pf, __ldg(P.grid.wrapped + j))) continue;  // certainly beyond highCut
                 double px, py, pz;
                 int id;
                 RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
@@ -215,6 +246,7 @@ static PGrid make_pgrid(void *workspace, const WorkspaceLayout &lay, const int32
     PGrid g;
     g.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
     g.recs = ws + lay.off_recs;
+    g.wrapped = reinterpret_cast<const float4 *>(ws + lay.off_wrapped);
     g.nc0 = nc[0];
     g.nc1 = nc[1];
     g.nc2 = nc[2];

@@ -150,15 +150,13 @@ __global__ void __launch_bounds__(kPrefThreads) angles_fill_kernel(const MatPara
     const size_t total = (size_t)P.n_frames * P.n_centres;
     if (g >= total) return;
     const int f = (int)(g / P.n_centres);
-    const int m = (int)(g - (size_t)f * P.n_centres);
     const BoxD b = load_box(P.box + (size_t)f * 3);
     double rx, ry, rz;
-    if (P.centres) load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);
-    else load3<double>(P.centres, 0, 0, rx, ry, rz);  // unreachable: centres are always given (see launcher)
-    (void)m;
+    load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);  // centres are always given (checked by the launcher)
     const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
               cz = cell_coord(rz, b.iLz, P.grid.nc2);
     int idx[kMatCap];
+    idx[0] = 0;
     double ex[kMatCap], ey[kMatCap], ez[kMatCap], en[kMatCap];
     int K = 0;
     bool over = false;
@@ -477,6 +475,7 @@ __global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
     const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
               cz = cell_coord(rz, b.iLz, P.grid.nc2);
     double dist[kLsiCap];
+    dist[0] = 0.0;
     int k = 0, n_next = 0, next_idx = 0;
     double next_raw = 0.0, next_min = 0.0;
     bool over = false;

@@ -251,7 +251,6 @@ int wol_q3b_frames(const wol_q3b_args *a, void *stream) {
     int rc = check_shape(a->n_frames, a->n_pos, n_centres, a->nc, a->workspace, a->workspace_bytes, &lay);
     if (rc != WOL_OK) return rc;
     if (!(a->edge_min > 0.0)) return set_error(WOL_ERR_INVALID, "edge_min must come from wol_plan_grid");
-    const bool full1 = a->nc[0] <= 3 && a->nc[1] <= 3 && a->nc[2] <= 3;
     if (a->do_3body) {
         if (!(a->high3 >= 0.0) || !(a->low3 >= 0.0) || !isfinite(a->high3))
             return set_error(WOL_ERR_INVALID, "three-body cutoffs must be finite and non-negative");
@@ -269,7 +268,6 @@ int wol_q3b_frames(const wol_q3b_args *a, void *stream) {
             return set_error(WOL_ERR_INVALID, "q cutoffs must be finite and non-negative");
         if (a->q_hist && a->q_nbins < 1) return set_error(WOL_ERR_INVALID, "bad q histogram spec");
     }
-    (void)full1;
     if (n_centres == 0 || a->n_pos == 0) return WOL_OK;
     return q3b_launch(*a, lay, (cudaStream_t)stream);
 }

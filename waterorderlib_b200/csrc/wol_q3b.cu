@@ -493,7 +493,6 @@ __global__ void __launch_bounds__(kFastThreads) q3b_fast_kernel(const __grid_con
     const long long t_begin = chunk * blockIdx.x;
     const long long t_end = min(P.total_tiles, t_begin + chunk);
     int cur_f = -1;
-    const int ncell_xy = P.nc0 * P.nc1;
     for (long long tile = t_begin; tile < t_end; ++tile) {
         const int f = (int)(tile / P.tiles_per_frame);
         const int m = (int)(tile - (long long)f * P.tiles_per_frame) * kGroups + group;
@@ -534,7 +533,6 @@ __global__ void __launch_bounds__(kFastThreads) q3b_fast_kernel(const __grid_con
             cy = cell_coord((double)ry, __ddiv_rn(1.0, bx[1]), P.nc1);
             cz = cell_coord((double)rz, __ddiv_rn(1.0, bx[2]), P.nc2);
         }
-        (void)ncell_xy;
         worker.run(valid, f, rx, ry, rz, cx, cy, cz, out_index, P.do_3b != 0, P.do_q != 0, 1, fb_id,
                    smem_hist ? s_hist : nullptr, tab, st);
     }
@@ -724,14 +722,12 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     // thread-per-centre fast path: fp64 mode, >= 4 cells per axis
     P.wrapped = reinterpret_cast<const float4 *>(ws + lay.off_wrapped);
     P.cellpack = reinterpret_cast<const uint32_t *>(ws + lay.off_recs + (size_t)lay.n_atoms_total * sizeof(RecF));
-    P.skip_q_only = 0;
     P.ev_begin = a.timing_event_begin;
     P.ev_end = a.timing_event_end;
     {
-        double lmax = 0.0;  // upper bound of the box edges: every cell edge is < 2 * edge of the smallest frame ... use nc * edge bound
         // edge_min * nc underestimates L for the larger frames of an NPT batch; the caller-provided
-        // box_max (>= every edge of every frame) is what the margin needs
-        lmax = a.box_max > 0.0 ? a.box_max : 0.0;
+        // box_max (>= every edge of every frame) is what the rounding margin needs
+        const double lmax = a.box_max > 0.0 ? a.box_max : 0.0;
         const bool last1 = P.wq_max <= 1;
         const double rsel = a.do_q ? (last1 ? a.highq : fmin(a.highq, P.rc1)) : 0.0;
         const double rthr = fmax(a.do_3body ? a.high3 : 0.0, rsel);

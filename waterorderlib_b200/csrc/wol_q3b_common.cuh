@@ -45,7 +45,6 @@ struct Q3bParams {
     const float4 *wrapped;  // box-wrapped float coordinates in record order (nullptr: not built)
     const uint32_t *cellpack;  // FP32 mode: packed cell coordinates in record order
     float pre_thr2;         // prefilter acceptance threshold on the float squared distance
-    int skip_q_only;        // large-capacity pass: 1 = leave q-only items to the light instantiation
     void *ev_begin, *ev_end;  // optional cudaEvent_t around the dominant kernel
     // which queue a large-capacity / widened launch walks
     const uint32_t *list;     // entries

@@ -244,3 +244,22 @@ def test_lsiCalc_and_hexOrderCalc_match_reference_loops(in_tmp):
     got = np.loadtxt("psiDistribution_0.txt")
     want = np.histogram(np.concatenate(pooled[0]), bins=500, range=[0.0, 1.0])[0]
     assert abs(got[:, 1] - want).sum() <= 2  # psi values agree to ~1e-12: a value on a bin edge may move one bin
+
+
+def test_drivers_on_amber_files(in_tmp):
+    """tetOrderCalc / hbCalc fed from parm7 + NetCDF files through the built-in readers give what the in-memory
+    trajectory gives (frames are float32 in the file; the synthetic coordinates are float32-representable)."""
+    from waterorderlib_b200.structureLibs import amber_io
+    top, traj = make_system(3, 20, n_sol=3, seed0=1300)
+    amber_io.write_parm7("sys.parm7", top)
+    amber_io.write_netcdf("sys.nc", traj.xyz, traj.boxes)
+    np.random.seed(3)
+    a_mem = opl.tetOrderCalc(top, traj)
+    hb_mem = opl.hbCalc(top, traj)
+    q_mem = np.loadtxt("qDistribution_0.txt")
+    np.random.seed(3)
+    a_file = opl.tetOrderCalc("sys.parm7", "sys.nc")
+    hb_file = opl.hbCalc("sys.parm7", "sys.nc")
+    # (double atomics make the per-frame sums order-dependent in the last bits)
+    assert np.allclose(a_mem[0][0], a_file[0][0], rtol=1e-12) and np.allclose(a_mem[1][0], a_file[1][0], rtol=1e-10)
+    assert hb_mem == hb_file and np.array_equal(q_mem, np.loadtxt("qDistribution_0.txt"))

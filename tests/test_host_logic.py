@@ -131,3 +131,29 @@ def test_reduce_rejects_non_integer_histograms_single_rank():
     assert wdist.world() == (0, 1)
     rows = torch.ones((3, 2))
     assert wdist.gather_frame_rows(rows, 3) is rows
+
+
+def test_amber_parm7_and_netcdf_readers(tmp_path):
+    """TrajObject on AMBER files without parmed / pytraj: parm7 topology + NetCDF-3 trajectory round trip."""
+    from waterorderlib_b200.structureLibs import amber_io
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    top = small_top()
+    rng = np.random.default_rng(0)
+    xyz = (rng.random((7, 18, 3)) * 20.0).astype(np.float32)
+    boxes = np.array([[20.0, 21.0, 22.0]] * 7) + np.arange(7)[:, None] * 0.125
+    amber_io.write_parm7(tmp_path / "sys.parm7", top)
+    amber_io.write_netcdf(str(tmp_path / "sys.nc"), xyz, boxes)
+    obj = TrajObject(str(tmp_path / "sys.parm7"), str(tmp_path / "sys.nc"), stride=2)
+    assert list(obj.top.names) == list(top.names) and list(obj.top.resnames) == list(top.resnames)
+    assert sorted(map(tuple, obj.top.bonds.tolist())) == sorted(map(tuple, top.bonds.tolist()))
+    assert list(obj.getWatInds()[0]) == [6, 10, 14] and [list(s) for s in obj.getSolInds()][0] == [0, 1, 3, 5]
+    assert len(obj.traj) == 4
+    for k, frame in enumerate(obj.traj):
+        assert frame.xyz.dtype == np.float32 and frame.xyz.dtype.isnative and np.array_equal(frame.xyz, xyz[2 * k])
+        assert np.array_equal(frame.box.values[:3], boxes[2 * k]) and list(frame.box.values[3:]) == [90.0, 90.0, 90.0]
+    block = obj.traj.xyz[1:3]
+    assert block.shape == (2, 18, 3) and block.dtype.isnative and np.array_equal(block, xyz[[2, 4]])
+    assert np.array_equal(obj.traj.xyz[1:3, [6, 10]], xyz[[2, 4]][:, [6, 10]])
+    hbO, _ = opl.getHBInds(obj.top, obj.traj[0], [6, 10, 14], [7, 8, 11, 12, 15, 16], [], [6, 10, 14])
+    assert list(hbO[1]) == [6, 6, 10, 10, 14, 14]
+    obj.traj.close()

@@ -7,6 +7,8 @@ the hot path, which only consumes ``frame.xyz`` (natom,3), ``frame.box.values[:3
 
   * in-memory objects (``Topology`` / ``ArrayTrajectory``), the form synthetic benchmarks and tests use,
   * ``.npz`` files written by ``Topology.save`` / ``ArrayTrajectory.save``,
+  * AMBER ``.parm7`` / ``.prmtop`` topologies and ``.nc`` NetCDF trajectories through the built-in readers of
+    ``amber_io`` (orthorhombic boxes),
   * anything else is handed to parmed / pytraj exactly as the reference does (ImportError if absent).
 
 Trajectory I/O is outside the hot path: nothing here touches the GPU.
@@ -223,7 +225,10 @@ class TrajObject:
             return topFile
         if isinstance(topFile, str) and topFile.endswith(".npz"):
             return Topology.load(topFile)
-        import parmed as pmd  # AMBER / GROMACS / ... topologies, as the reference does (TrajObject.py:30)
+        if isinstance(topFile, str) and topFile.lower().endswith((".parm7", ".prmtop", ".top")):
+            from .amber_io import read_parm7  # built-in reader for the fields the hot path needs
+            return read_parm7(topFile)
+        import parmed as pmd  # anything else: as the reference does (TrajObject.py:30)
         return pmd.load_file(topFile)
 
     def _load_traj(self, trajFile, stride):
@@ -234,6 +239,9 @@ class TrajObject:
             return ArrayTrajectory(trajFile[0], trajFile[1], top=self.top, stride=stride)
         if isinstance(trajFile, str) and trajFile.endswith(".npz"):
             return ArrayTrajectory.load(trajFile, top=self.top, stride=stride)
+        if isinstance(trajFile, str) and trajFile.lower().endswith((".nc", ".ncdf", ".netcdf")) and isinstance(self.top, Topology):
+            from .amber_io import NetCDFTrajectory  # built-in AMBER NetCDF reader (scipy.io.netcdf_file, memory-mapped)
+            return NetCDFTrajectory(trajFile, top=self.top, stride=stride)
         import pytraj as pt  # TrajObject.py:33
         return pt.iterload(trajFile, pt.load_parmed(self.top, traj=False), stride=stride)
 

@@ -310,6 +310,16 @@ int wol_willard_density(const double *points, int64_t n_points, const double *gr
                         void *stream);
 
 /*
+ * DensityField (fortran/waterlib.f90:1219-1268; called at structureLibs/surface_library.py:239): at every grid point the
+ * number of waters inside the cube of edge binwidth (= gridx[1] - gridx[0], passed by the caller) centred on it, faces
+ * included, minimum image, divided by binwidth**3.0.  densvals [nx][ny][nz] row-major.  workspace: cell list over the
+ * waters with r_cell >= binwidth / 2.
+ */
+int wol_density_field(const double *gridx, const double *gridy, const double *gridz, int32_t nx, int32_t ny, int32_t nz, double binwidth,
+                      const double *box, int32_t n_pos, const int32_t nc[3], double edge_min, void *workspace, size_t workspace_bytes,
+                      double *densvals, void *stream);
+
+/*
  * InterfaceWater (fortran/waterlib.f90:1414-1469): for every water the nearest interface point (0-based,
  * first index on ties, -1 if none within distance^2 < 1000 -- the Fortran leaves that entry unwritten) and
  * its signed depth allwatdists = (water - point) . normal; for every interface point the nearest water;

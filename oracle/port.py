@@ -283,3 +283,13 @@ def getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
     _lib().wol_oracle_psi(_ptr(sub, _dp), sub.shape[0], _ptr(pos, _dp), pos.shape[0], _ptr(box, _dp), ctypes.c_double(lowCut),
                           ctypes.c_double(highCut), _ptr(psi, _dp))
     return psi
+
+
+def density_field(pos, gridx, gridy, gridz, BoxL):
+    """DensityField (fortran/waterlib.f90:1219-1268) -> (nx, ny, nz) float64."""
+    p, box = _pos(pos), _box(BoxL)
+    gx, gy, gz = (_c(g).reshape(-1) for g in (gridx, gridy, gridz))
+    out = np.zeros((gx.size, gy.size, gz.size), dtype=np.float64)
+    _lib().wol_oracle_density_field(_ptr(p, _dp), p.shape[0], _ptr(gx, _dp), gx.size, _ptr(gy, _dp), gy.size, _ptr(gz, _dp), gz.size,
+                                    _ptr(box, _dp), _ptr(out, _dp))
+    return out

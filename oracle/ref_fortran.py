@@ -185,6 +185,16 @@ class RefWaterlib:
             ctypes.byref(ctypes.c_int32(ny)), ctypes.byref(ctypes.c_int32(nz)))
         return np.ascontiguousarray(dens), np.ascontiguousarray(norms)
 
+    # fortran/waterlib.f90:1219-1268 -> densvals (nx,ny,nz), C-ordered copy
+    def densityfield(self, pos, gridx, gridy, gridz, boxl):
+        pos = _f64(pos)
+        gx, gy, gz = (np.ascontiguousarray(np.asarray(g, dtype=np.float64).reshape(-1)) for g in (gridx, gridy, gridz))
+        dens = np.zeros((gx.size, gy.size, gz.size), dtype=np.float64, order="F")
+        self._lib.densityfield_(_dp(pos), _dp(gx), _dp(gy), _dp(gz), _dp(_box(boxl)), _dp(dens),
+                                ctypes.byref(ctypes.c_int32(pos.shape[0])), ctypes.byref(ctypes.c_int32(gx.size)),
+                                ctypes.byref(ctypes.c_int32(gy.size)), ctypes.byref(ctypes.c_int32(gz.size)))
+        return np.ascontiguousarray(dens)
+
     # fortran/waterlib.f90:1351-1398
     def willarddensitypoints(self, pos, denspts, boxl, smoothlen):
         pos, pts = _f64(pos), _f64(denspts)

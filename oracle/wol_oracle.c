@@ -721,3 +721,30 @@ int wol_oracle_psi(const double *sub, int m, const double *pos, int n, const dou
     free(img);
     return 0;
 }
+
+/* DensityField (waterlib.f90:1219-1268): number of waters inside the cube of edge binwidth = gridx(2) - gridx(1)
+ * centred on each grid point (inclusive faces, minimum image), divided by binwidth**3.0.  densvals[nx][ny][nz]. */
+int wol_oracle_density_field(const double *pos, int n, const double *gx, int nx, const double *gy, int ny, const double *gz,
+                             int nz, const double *boxl, double *densvals) {
+    box_t b;
+    box_init(&b, boxl);
+    const double binwidth = gx[1] - gx[0];
+    const double h = binwidth / 2.0, vol = pow(binwidth, 3.0);
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+            for (int k = 0; k < nz; ++k) {
+                const double a[3] = {gx[i], gy[j], gz[k]};
+                double dens = 0.0, v[3];
+                for (int l = 0; l < n; ++l) {
+                    min_image(&b, pos + 3 * (size_t)l, a, v); /* thisvec = watpos - apos */
+                    int in = 1;
+                    for (int c = 0; c < 3; ++c) {
+                        const double w = a[c] + v[c];
+                        if (w < (a[c] - h) || w > (a[c] + h)) in = 0;
+                    }
+                    if (in) dens = dens + 1.0;
+                }
+                densvals[((size_t)i * ny + j) * nz + k] = dens / vol;
+            }
+    return 0;
+}

@@ -124,7 +124,8 @@ def main():
     pdens, pnorms = wl.willarddensitypoints(pos, pts, box, 2.4)
     gp, gn = synth.plane_interface(box, z_lo, z_hi, spacing=2.0)
     watclose, surfclose, numwater, dists = wl.interfacewater(pos, gp, gn, 3.0, box)
-    np.savez_compressed(os.path.join(OUT, "slab_n256.npz"), pos=pos, box=box, z_lo=z_lo, z_hi=z_hi, gx=gx, gy=gy, gz=gz,
+    voxel = wl.densityfield(pos, gx + 0.3, gy, gz, box)  # DensityField (waterlib.f90:1219-1268), cubes of edge gx[1] - gx[0]
+    np.savez_compressed(os.path.join(OUT, "slab_n256.npz"), pos=pos, box=box, z_lo=z_lo, z_hi=z_hi, gx=gx, gy=gy, gz=gz, voxel=voxel,
                         smoothlen=2.4, dens=dens, norms=norms, pts=pts, pdens=pdens, pnorms=pnorms, gridpos=gp, gridnorm=gn,
                         cutoff=3.0, watclose=watclose, surfclose=surfclose, numwater=np.int64(numwater), allwatdists=dists)
     print("slab", pos.shape[0], "waters", gp.shape[0], "interface points", numwater, "within cutoff")

@@ -115,3 +115,17 @@ def test_density_field_of_densityGrid():
     assert dens.shape == (20, 20, 20) and norms.shape == (20, 20, 20, 3)
     ref_d, ref_n = port.willard_density_field(pos, spans[0].ravel(), spans[1].ravel(), spans[2].ravel(), box, 2.4)
     check_density(dens, norms, ref_d, ref_n)
+
+
+def test_density_field_golden_and_voxel_grid(golden_dir):
+    """DensityField (fortran/waterlib.f90:1219-1268): counts per cube, bit-exact (integer counts / pow(binwidth, 3.0))."""
+    g = load(golden_dir, "slab_n256")
+    d = wl.densityfield(g["pos"], g["gx"] + 0.3, g["gy"], g["gz"], g["box"])
+    assert d.shape == g["voxel"].shape and np.array_equal(d, g["voxel"]) and d.max() > 0
+    pos, box, _, _ = synth.slab_box(6, 6, 3, sigma=0.3, seed=5)
+    dv = sl.densityVoxel(pos[:40], pos, box)
+    spans = []
+    for k in range(3):
+        s = np.linspace(0.8 * pos[:40, k].min(), 1.2 * pos[:40, k].max(), 11)
+        spans.append(s[:-1] + (s[1] - s[0]))
+    assert dv.shape == (10, 10, 10) and np.array_equal(dv, port.density_field(pos, spans[0], spans[1], spans[2], box))

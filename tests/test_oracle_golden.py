@@ -119,3 +119,8 @@ def test_pairs_against_golden(golden_dir):
     assert np.array_equal(port.pairdistancehistogram(g["sol"], g["pos"], 0.25, 40, g["box"]), g["pdh"])
     assert np.allclose(port.getOrderParamPsi(g["pos"], g["pos"], g["box"], 0.0, 4.5), g["psi_all"], rtol=1e-10, atol=1e-14)
     assert np.allclose(port.getOrderParamPsi(g["sol"], g["pos"], g["box"], 1.0, 6.0), g["psi_sub"], rtol=1e-10, atol=1e-14)
+
+
+def test_density_field_against_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "slab_n256.npz"))
+    assert np.array_equal(port.density_field(g["pos"], g["gx"] + 0.3, g["gy"], g["gz"], g["box"]), g["voxel"])

@@ -168,3 +168,13 @@ def test_psi_matches_live(ref):
         want = fn["getOrderParamPsi"](sub, pos, box, lo, hi)
         got = port.getOrderParamPsi(sub, pos, box, lo, hi)
         assert np.allclose(got, want, rtol=1e-10, atol=1e-14) and want.max() > 0.05
+
+
+def test_density_field_matches_live(ref):
+    wl, _ = ref
+    pos, box, z_lo, z_hi = slab_case(7)
+    gx = np.linspace(0.0, box[0], 9, endpoint=False) + 0.3
+    gy = np.linspace(0.0, box[1], 7, endpoint=False)
+    gz = np.linspace(0.0, box[2], 15, endpoint=False)
+    want = wl.densityfield(pos, gx, gy, gz, box)
+    assert want.max() > 0 and np.array_equal(port.density_field(pos, gx, gy, gz, box), want)

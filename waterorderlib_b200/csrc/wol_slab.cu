@@ -1,6 +1,7 @@
 // Slab / interface routines (BASELINE config 4) and the all-Fortran triplet histogram, sm_100a, fp64 in the
 // reference's operation order:
 //   willard_kernel        WillardDensityField / WillardDensityPoints   fortran/waterlib.f90:1286-1341, :1351-1398
+//   voxel_density_kernel  DensityField                                   fortran/waterlib.f90:1219-1268
 //   iface_nearest_kernel  InterfaceWater: nearest surface point per water (+ signed depth) and nearest water per
 //                         surface point                                 fortran/waterlib.f90:1431-1468
 //   profile_kernel        depth-binned profile of a per-water observable (the cfg-4 composition; the reference
@@ -99,6 +100,51 @@ __global__ void __launch_bounds__(128) willard_kernel(const WillardParams P) {
         P.norms[3 * g + 1] = __ddiv_rn(nvy, nn);
         P.norms[3 * g + 2] = __ddiv_rn(nvz, nn);
     }
+}
+
+// ---- DensityField: waters inside the cube of edge binwidth around each grid point ------------------------------
+
+struct VoxelParams {
+    CellGridS grid;  // cell list over the waters, cell edge >= binwidth / 2
+    const double *box;
+    const double *gx, *gy, *gz;
+    int nx, ny, nz;
+    double half, vol;  // binwidth / 2, binwidth ** 3.0
+    double *dens;
+};
+
+__global__ void __launch_bounds__(128) voxel_density_kernel(const VoxelParams P) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P.nx * P.ny * P.nz) return;
+    const int k = (int)(g % P.nz), j = (int)((g / P.nz) % P.ny), i = (int)(g / ((long long)P.nz * P.ny));
+    const double ax = P.gx[i], ay = P.gy[j], az = P.gz[k];
+    const Box3 b = load_box3(P.box);
+    const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+    const int cx = cell_coord(ax, b.iL[0], nc0), cy = cell_coord(ay, b.iL[1], nc1), cz = cell_coord(az, b.iL[2], nc2);
+    const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+    const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+              zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+    const double lox = __dsub_rn(ax, P.half), hix = __dadd_rn(ax, P.half), loy = __dsub_rn(ay, P.half), hiy = __dadd_rn(ay, P.half),
+                 loz = __dsub_rn(az, P.half), hiz = __dadd_rn(az, P.half);
+    double dens = 0.0;
+    for (int iz = 0; iz < cntz; ++iz)
+        for (int iy = 0; iy < cnty; ++iy)
+            for (int ix = 0; ix < cntx; ++ix) {
+                const size_t c = ((size_t)((zs + iz) % nc2) * nc1 + (ys + iy) % nc1) * nc0 + (xs + ix) % nc0;
+                const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
+                for (int jj = (int)__ldg(P.grid.cell_start + c); jj < j1; ++jj) {
+                    double px, py, pz;
+                    int id;
+                    RecTraits<double>::load(P.grid.recs, (size_t)jj, px, py, pz, id);
+                    // thisvec = watpos - apos, minimum image; watpos = apos + thisvec (:1247-1249)
+                    const double wx = __dadd_rn(ax, min_image_1<double, true>(px, ax, b.L[0], b.iL[0]));
+                    const double wy = __dadd_rn(ay, min_image_1<double, true>(py, ay, b.L[1], b.iL[1]));
+                    const double wz = __dadd_rn(az, min_image_1<double, true>(pz, az, b.L[2], b.iL[2]));
+                    if (wx < lox || wx > hix || wy < loy || wy > hiy || wz < loz || wz > hiz) continue;
+                    dens += 1.0;
+                }
+            }
+    P.dens[g] = __ddiv_rn(dens, P.vol);
 }
 
 // ---- InterfaceWater -----------------------------------------------------------------------------------
@@ -400,6 +446,36 @@ int wol_willard_density(const double *points, int64_t n_points, const double *gr
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_willard_density", e);
+    return WOL_OK;
+}
+
+int wol_density_field(const double *gridx, const double *gridy, const double *gridz, int32_t nx, int32_t ny, int32_t nz, double binwidth,
+                      const double *box, int32_t n_pos, const int32_t nc[3], double edge_min, void *workspace, size_t workspace_bytes,
+                      double *densvals, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!gridx || !gridy || !gridz || !box || !nc || !workspace || !densvals || nx < 0 || ny < 0 || nz < 0)
+        return set_error(WOL_ERR_INVALID, "wol_density_field: bad argument");
+    if (!(binwidth > 0.0)) return set_error(WOL_ERR_INVALID, "wol_density_field: binwidth (gridx[1] - gridx[0]) must be positive");
+    for (int k = 0; k < 3; ++k)
+        if (nc[k] > 3 && 0.5 * binwidth * (1.0 + 1e-9) > edge_min)
+            return set_error(WOL_ERR_INVALID, "half bin width %.6g exceeds the planned cell edge %.6g", 0.5 * binwidth, edge_min);
+    const WorkspaceLayout lay = workspace_layout(1, n_pos, n_pos, nc);
+    if (workspace_bytes < lay.total) return set_error(WOL_ERR_WORKSPACE, "workspace holds %zu bytes, %zu needed", workspace_bytes, lay.total);
+    VoxelParams P;
+    P.grid = make_grid_s(workspace, lay, nc);
+    P.box = box;
+    P.gx = gridx; P.gy = gridy; P.gz = gridz;
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.half = binwidth / 2.0;
+    P.vol = pow(binwidth, 3.0);  // binwidth**3.0 through the host libm, like the Fortran runtime
+    P.dens = densvals;
+    const long long n = (long long)nx * ny * nz;
+    if (n > 0) {
+        voxel_density_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_density_field", e);
     return WOL_OK;
 }
 

@@ -474,3 +474,26 @@ def psi(sub, pos, box, low=0.0, high=10.0, device=None):
                             _vp(out.data_ptr()), _stream()), "wol_psi")
         cells.status()
     return out
+
+
+def density_field(pos, box, grid, device=None):
+    """DensityField (fortran/waterlib.f90:1219-1268): waters per cube of edge gridx[1] - gridx[0] around each grid point,
+    divided by the cube volume -> f64 CUDA tensor (nx, ny, nz)."""
+    device = _device(device, pos)
+    gx, gy, gz = (_f64(np.asarray(g, dtype=np.float64).reshape(-1) if not isinstance(g, torch.Tensor) else g.reshape(-1), device) for g in grid)
+    if gx.numel() < 2:
+        raise ValueError("gridx needs at least two points (the bin width is gridx[1] - gridx[0])")
+    binwidth = float((gx[1] - gx[0]).item())
+    if not binwidth > 0.0:
+        raise ValueError("gridx must be ascending")
+    cells = CellList(pos, box, 0.5 * binwidth * (1.0 + 1e-9), device=device)
+    if cells.F != 1:
+        raise ValueError("the density field is evaluated one frame at a time")
+    nx, ny, nz = int(gx.numel()), int(gy.numel()), int(gz.numel())
+    dens = torch.empty((nx, ny, nz), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_density_field(_vp(gx.data_ptr()), _vp(gy.data_ptr()), _vp(gz.data_ptr()), nx, ny, nz, binwidth,
+                                      _vp(cells.box_d.data_ptr()), cells.N, ctypes.byref(cells.nc), cells.edge_min, _vp(cells.ws_ptr),
+                                      cells.ws_bytes, _vp(dens.data_ptr()), _stream()), "wol_density_field")
+        torch.cuda.current_stream().synchronize()
+    return dens

@@ -58,3 +58,16 @@ def depthBinnedQ(watPos, thisbox, gridpos, gridnorm, binWidth=1.0, depthRange=(-
         var = np.maximum(s2_h / count_h - mean * mean, 0.0)
     return {"depth_edges": depthRange[0] + binWidth * np.arange(nb + 1), "count": count_h, "q_mean": mean, "q_var": var,
             "q": q, "depth": depth, "numwater": int(iw["numwater"].item())}
+
+
+def densityVoxel(heavyPos, watPos, thisbox):
+    """Plain voxel density of the waters on the reference's 10^3 grid around heavyPos (surface_library.py:213-241)."""
+    heavyPos = np.asarray(heavyPos, dtype=np.float64)
+    nBins = 11
+    spans = []
+    for d in range(3):
+        span = np.linspace(0.8 * np.min(heavyPos[:, d]), 1.2 * np.max(heavyPos[:, d]), nBins).reshape(1, nBins)
+        width = span[:, 1] - span[:, 0]
+        spans.append(span[:, :-1] + width)
+    from . import waterlib as wl
+    return wl.densityfield(watPos, spans[0], spans[1], spans[2], thisbox)

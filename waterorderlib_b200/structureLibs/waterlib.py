@@ -110,3 +110,8 @@ def pairdistancehistogram(pos1, pos2, binwidth, totbins, boxl):
     """hist = pairdistancehistogram(pos1,pos2,binwidth,totbins,boxl)   (fortran/waterlib.f90:358-389), 3-D positions"""
     counts = routines.pair_hist(2, _check_pos(pos1, "pos1"), _check_pos(pos2, "pos2"), boxl, binwidth, totbins)
     return counts.cpu().numpy().astype(np.float64)
+
+
+def densityfield(pos, gridx, gridy, gridz, boxl):
+    """densvals = densityfield(pos,gridx,gridy,gridz,boxl)   (fortran/waterlib.f90:1219-1268)"""
+    return _np(routines.density_field(_check_pos(pos, "pos"), boxl, (gridx, gridy, gridz)))

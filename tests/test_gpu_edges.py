@@ -122,3 +122,24 @@ def test_error_paths():
     blob = np.random.default_rng(0).random((1500, 3)) * 2.0 + 9.0
     with pytest.raises(WolError):
         engine.q3b_frames(np.concatenate([blob, pos]), box, high3=3.4)
+
+
+def test_one_workspace_across_batch_shapes():
+    """A driver reuses its workspace for a shorter last batch and for other system sizes: the status counters sit at a
+    fixed offset, so no stale bytes are mistaken for an overflow flag, and a real overflow is still reported later."""
+    ws = engine.Workspace(torch.device("cuda"))
+    pos, box = synth.trajectory(5, 5, sigma=0.4, seed0=70)
+    for sl in (slice(0, 5), slice(0, 2), slice(3, 4)):
+        r = engine.q3b_frames(pos[sl], box[sl], workspace=ws, hist_per_frame=True)
+        for k, f in enumerate(range(*sl.indices(5))):
+            tb = port.three_body(pos[f], pos[f], box[f], materialize=False)
+            assert np.array_equal(r.ang_hist.cpu().numpy()[k], tb["hist"])
+    small, sbox = synth.water_box(3, sigma=0.3, seed=1)
+    engine.q3b_frames(small, sbox, workspace=ws)          # other N, other grid: same workspace
+    big, bbox = synth.trajectory(7, 3, sigma=0.3, seed0=5)
+    engine.q3b_frames(big, bbox, workspace=ws)            # grows the buffer: counters are carried over
+    blob = np.concatenate([np.random.default_rng(0).random((1500, 3)) * 2.0 + 9.0, small])
+    engine.q3b_frames(blob, sbox, workspace=ws, check_status=False, high3=3.4)   # overflows, not checked yet
+    with pytest.raises(WolError):
+        engine.q3b_frames(small, sbox, workspace=ws)      # the sticky flag surfaces at the next checked call
+    engine.q3b_frames(small, sbox, workspace=ws)          # and is cleared by having been read

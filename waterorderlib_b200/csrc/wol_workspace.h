@@ -42,13 +42,13 @@ constexpr uint32_t kFbNeed3b = 1u << 31;
 constexpr uint32_t kFbIdMask = (1u << 30) - 1u;
 
 struct WorkspaceLayout {
+    size_t off_counters;    // uint32[kNumCounters], always at offset 0
     size_t off_cell_start;  // uint32[F*ncell + 1]  counts during the build, exclusive starts afterwards
     size_t off_block_sums;  // uint32[scan blocks + 1]
     size_t off_cell_id;     // uint32[F*N]
     size_t off_slot;        // uint32[F*N]  rank of the atom inside its cell
     size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
     size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates + atom index, same order as recs
-    size_t off_counters;    // uint32[kNumCounters]
     size_t off_fb_list;     // uint32[2*F*M]  centres the fast path handed on; second half = second level
     size_t total;
     int64_t n_cells_total;
@@ -67,7 +67,11 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     w.n_atoms_total = (int64_t)n_pos * n_frames;
     w.n_centres_total = (int64_t)(n_centres_max > n_pos ? n_centres_max : n_pos) * n_frames;
     w.scan_blocks = (int32_t)((w.n_cells_total + 1 + kScanTile - 1) / kScanTile);
+    // the counters come first: their address does not move when the batch shape changes, so the sticky overflow flag
+    // survives a caller that reuses one workspace for batches of different sizes (e.g. a shorter last batch)
     size_t o = 0;
+    w.off_counters = o;
+    o = align_up(o + kNumCounters * 4, 256);
     w.off_cell_start = o;
     o = align_up(o + (size_t)(w.n_cells_total + 1) * 4, 256);
     w.off_block_sums = o;
@@ -80,8 +84,6 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     o = align_up(o + (size_t)w.n_atoms_total * sizeof(RecD), 256);
     w.off_wrapped = o;
     o = align_up(o + (size_t)w.n_atoms_total * 16, 256);
-    w.off_counters = o;
-    o = align_up(o + kNumCounters * 4, 256);
     w.off_fb_list = o;
     o = align_up(o + (size_t)w.n_centres_total * 8, 256);
     w.total = o;

@@ -100,9 +100,13 @@ class Workspace:
         self.buf = None
 
     def get(self, nbytes):
-        if self.buf is None or self.buf.numel() < nbytes:
-            self.buf = None
-            self.buf = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        if self.buf is None or self.buf.numel() < nbytes + 256:
+            old = self.buf
+            self.buf = torch.zeros(int(nbytes) + 512, dtype=torch.uint8, device=self.device)
+            if old is not None:
+                # the device counters (first 256 bytes, incl. the sticky overflow flag) move with the workspace
+                o0, o1 = (-old.data_ptr()) % 256, (-self.buf.data_ptr()) % 256
+                self.buf[o1:o1 + 256].copy_(old[o0:o0 + 256])
         off = (-self.buf.data_ptr()) % 256
         return self.buf.data_ptr() + off, self.buf.numel() - off
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WOL_ABI_VERSION 1
+#define WOL_ABI_VERSION 2
 
 enum {
     WOL_OK = 0,
@@ -162,6 +162,10 @@ typedef struct wol_q3b_args {
      * of the dominant evaluation kernel, so a caller can time that kernel alone (bench roofline). */
     void *timing_event_begin;
     void *timing_event_end;
+    /* Optional ragged centres: device array [n_frames]; frame f evaluates only its first n_valid[f] centres (the
+     * drivers' sub-populations change size from frame to frame, structureLibs/orderParam_lib.py:1343-1346); outputs of
+     * the padded slots are left untouched.  NULL: all n_centres of every frame. */
+    const int32_t *n_valid;
 } wol_q3b_args;
 
 int wol_q3b_frames(const wol_q3b_args *args, void *stream);

@@ -28,7 +28,7 @@ def test_exports_every_declared_symbol(L):
     for name in sorted(declared):
         assert hasattr(L, name), "libwol.so does not export " + name
     assert declared == set(_capi.SIGNATURES), "ctypes binding and header disagree: %s" % (declared ^ set(_capi.SIGNATURES))
-    assert L.wol_abi_version() == 1
+    assert L.wol_abi_version() == 2
     assert ctypes.sizeof(_capi.Q3bArgs) % 8 == 0
 
 

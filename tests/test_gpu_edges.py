@@ -143,3 +143,31 @@ def test_one_workspace_across_batch_shapes():
     with pytest.raises(WolError):
         engine.q3b_frames(small, sbox, workspace=ws)      # the sticky flag surfaces at the next checked call
     engine.q3b_frames(small, sbox, workspace=ws)          # and is cleared by having been read
+
+
+def test_ragged_centres_batched_with_reused_cells():
+    """n_valid: frame f evaluates only its first n_valid[f] centres; the cell list of a previous call on the same batch
+    is reused.  Per-frame outputs must equal the oracle's on exactly the valid centres; padded slots stay untouched."""
+    pos, box = synth.trajectory(5, 4, sigma=0.5, seed0=90)
+    rng = np.random.default_rng(1)
+    counts = np.array([17, 0, 63, 5], dtype=np.int32)
+    cen = np.zeros((4, 63, 3))
+    for f, c in enumerate(counts):
+        cen[f, :c] = pos[f][rng.choice(pos.shape[1], c, replace=False)] + rng.normal(0, 0.2, size=(c, 3))
+    cen = cen.astype(np.float32).astype(np.float64)
+    ws = engine.Workspace(torch.device("cuda"))
+    engine.q3b_frames(pos, box, workspace=ws)  # builds the cell list for this batch
+    q = torch.full((4, 63), -7.0, dtype=torch.float64, device="cuda")
+    n3 = torch.full((4, 63), -7, dtype=torch.int32, device="cuda")
+    r = engine.q3b_frames(pos, box, cen, n_valid=counts, reuse_cells=True, workspace=ws, hist_per_frame=True,
+                          out={"q": q, "n3": n3}, highq=8.0)
+    for f, c in enumerate(counts):
+        qr, nn4, _ = port.order_param_q(cen[f, :c], pos[f], box[f], 0.0, 8.0)
+        tb = port.three_body(cen[f, :c], pos[f], box[f], materialize=False)
+        assert np.allclose(r.q.cpu().numpy()[f, :c], qr, rtol=1e-6, atol=1e-9) and np.all(r.q.cpu().numpy()[f, c:] == -7.0)
+        assert np.array_equal(r.n3.cpu().numpy()[f, :c], tb["numAngs"]) and np.all(r.n3.cpu().numpy()[f, c:] == -7)
+        assert np.array_equal(r.nn_idx.cpu().numpy()[f, :c], nn4)
+        assert np.array_equal(r.ang_hist.cpu().numpy()[f], tb["hist"])
+        assert r.frame_stats[f, 2].item() == c
+    with pytest.raises(ValueError):
+        engine.q3b_frames(pos, box, cen, reuse_cells=True, workspace=engine.Workspace(torch.device("cuda")))

@@ -27,7 +27,7 @@ class Q3bArgs(ctypes.Structure):
         ("lowq", ctypes.c_double), ("highq", ctypes.c_double), ("do_q", c_i32), ("do_3body", c_i32),
         ("nbins", c_i32), ("q_nbins", c_i32), ("hist_lo", ctypes.c_double), ("hist_hi", ctypes.c_double),
         ("angle_table", c_vp), ("q", c_vp), ("nn_idx", c_vp), ("n3", c_vp), ("ang_hist", c_vp), ("q_hist", c_vp),
-        ("frame_stats", c_vp), ("timing_event_begin", c_vp), ("timing_event_end", c_vp),
+        ("frame_stats", c_vp), ("timing_event_begin", c_vp), ("timing_event_end", c_vp), ("n_valid", c_vp),
     ]
 
 

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(kFastThreads) q3b_fast_kernel(const __grid_con
             }
             cur_f = f;
         }
-        const bool valid = m < P.n_centres;
+        const bool valid = m < P.n_centres && (P.n_valid == nullptr || m < __ldg(P.n_valid + f));
         T rx = 0, ry = 0, rz = 0;
         int cx = 0, cy = 0, cz = 0;
         size_t out_index = 0;
@@ -669,6 +669,7 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     P.cell_start = reinterpret_cast<const uint32_t *>(ws + lay.off_cell_start);
     P.box = a.box;
     P.centres = a.centres;
+    P.n_valid = a.centres ? a.n_valid : nullptr;
     P.centre_dtype = a.centre_dtype;
     P.n_frames = a.n_frames;
     P.n_pos = a.n_pos;

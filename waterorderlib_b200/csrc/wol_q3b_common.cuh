@@ -18,6 +18,7 @@ struct Q3bParams {
     const uint32_t *cell_start;
     const double *box;
     const void *centres;  // nullptr: every atom is a centre (visited in cell order)
+    const int32_t *n_valid;  // optional [n_frames]: only the first n_valid[f] centres of frame f are evaluated
     int centre_dtype;
     int n_frames, n_pos, n_centres;
     int nc0, nc1, nc2;

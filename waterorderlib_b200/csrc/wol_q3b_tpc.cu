@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_co
             iLy = __ddiv_rn(1.0, Ly);
             iLz = __ddiv_rn(1.0, Lz);
         }
-        const bool valid = m < P.n_centres;
+        const bool valid = m < P.n_centres && (P.n_valid == nullptr || m < __ldg(P.n_valid + f));
         double rx = 0, ry = 0, rz = 0;
         float wx = 0, wy = 0, wz = 0;
         int cx = 0, cy = 0, cz = 0, self_j = -1;

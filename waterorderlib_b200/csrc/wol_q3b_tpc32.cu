@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kT32Threads, 3) q3b_tpc32_kernel(const __grid_
             Lyf = (float)P.box[(size_t)f * 3 + 1];
             Lzf = (float)P.box[(size_t)f * 3 + 2];
         }
-        const bool valid = m < P.n_centres;
+        const bool valid = m < P.n_centres && (P.n_valid == nullptr || m < __ldg(P.n_valid + f));
         float wx = 0, wy = 0, wz = 0;
         int cx = 0, cy = 0, cz = 0, self_j = -1;
         size_t out_index = 0;

@@ -114,7 +114,7 @@ class Workspace:
 def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, high3=3.413, lowq=0.0, highq=10.0,
                nbins=500, bin_range=(0.0, 180.0), q_nbins=500, precision="fp64", hist_per_frame=False, r_cell=None,
                want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), out=None, workspace=None,
-               device=None, check_status=True, timing_events=None, box_device=None):
+               device=None, check_status=True, timing_events=None, box_device=None, n_valid=None, reuse_cells=False):
     """Fused tetrahedral q + three-body angle histogram for a batch of frames.
 
     pos      (F,N,3) positions of all atoms that can be neighbours (reference: `Pos`)
@@ -122,6 +122,8 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     centres  None = every atom of pos is a centre (reference: subPos is Pos); else (F,M,3) (`subPos`)
     out      optional dict of preallocated output tensors to accumulate into / overwrite
     box_device  optional (F,3) float64 CUDA tensor holding the same boxes (skips the upload)
+    n_valid  optional (F,) counts: frame f evaluates only its first n_valid[f] centres (ragged sub-populations padded to M)
+    reuse_cells  the workspace already holds the cell list of exactly these pos / box / r_cell (skip the build)
     Returns a Q3bResult of device tensors; histograms and frame_stats ACCUMULATE into `out` if given.
     """
     if device is None:
@@ -146,13 +148,16 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     nc, edge_min, box_max = plan_grid(box_h, r_cell)
     ws = workspace if workspace is not None else Workspace(device)
     need = L.wol_workspace_bytes(F, N, M, ctypes.byref(nc))
+    if reuse_cells and (ws.buf is None or ws.buf.numel() < need + 256):
+        raise ValueError("reuse_cells: this workspace does not hold a cell list for a batch of this shape")
     ws_ptr, ws_bytes = ws.get(need)
     stream = _stream_ptr()
     launches = 0
     with torch.cuda.device(device):
-        check(L.wol_cell_build(_ptr(pos_d), _dtype_code(pos_d), _ptr(box_d), F, N, ctypes.byref(nc), prec,
-                               ctypes.c_void_p(ws_ptr), ws_bytes, stream), "wol_cell_build")
-        launches += L.wol_last_launch_count()
+        if not reuse_cells:
+            check(L.wol_cell_build(_ptr(pos_d), _dtype_code(pos_d), _ptr(box_d), F, N, ctypes.byref(nc), prec,
+                                   ctypes.c_void_p(ws_ptr), ws_bytes, stream), "wol_cell_build")
+            launches += L.wol_last_launch_count()
         res = Q3bResult()
         out = out or {}
         qdtype = torch.float64 if prec == WOL_PREC_FP64 else torch.float32
@@ -194,6 +199,15 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
         a.angle_table = table.data_ptr() if table is not None else None
         for name, t in (("q", q), ("nn_idx", nn), ("n3", n3), ("ang_hist", ah), ("q_hist", qh), ("frame_stats", fs)):
             setattr(a, name, t.data_ptr() if t is not None else None)
+        nv_d = None
+        if n_valid is not None:
+            if cen_d is None:
+                raise ValueError("n_valid needs explicit centres")
+            nv_d = n_valid if isinstance(n_valid, torch.Tensor) else torch.as_tensor(np.asarray(n_valid, dtype=np.int32))
+            nv_d = nv_d.to(device=device, dtype=torch.int32).contiguous()
+            if nv_d.numel() != F:
+                raise ValueError("n_valid must hold one count per frame")
+            a.n_valid = nv_d.data_ptr()
         if timing_events is not None:  # (begin, end) torch.cuda.Event pair, already recorded once
             a.timing_event_begin, a.timing_event_end = timing_events[0].cuda_event, timing_events[1].cuda_event
         check(L.wol_q3b_frames(ctypes.byref(a), stream), "wol_q3b_frames")
@@ -206,7 +220,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
             check(L.wol_status(ctypes.c_void_p(ws_ptr), F, N, M, ctypes.byref(nc), stream, ctypes.byref(st)), "wol_status")
             res["n_widened"], res["n_overflow"] = int(st[0]), int(st[1])
     # keep inputs alive until the stream has consumed them
-    res["_keep"] = (pos_d, box_d, cen_d, ws, table)
+    res["_keep"] = (pos_d, box_d, cen_d, ws, table, nv_d)
     return res
 
 

@@ -109,9 +109,9 @@ def _batches(begin, end, n_atoms):
 
 
 def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
-    """Shared core of tetOrderCalc / threeBodyCalc: every frame of this rank's shard through the fused kernel,
-    population 0 (all waters) a whole batch of frames per call, sub-populations frame by frame (their
-    centres change every frame, structureLibs/orderParam_lib.py:1343-1346, :1475-1478).
+    """Shared core of tetOrderCalc / threeBodyCalc: every frame of this rank's shard through the fused kernel, a whole
+    batch of frames per call: population 0 (all waters) builds the cell list, each sub-population (ragged: its members
+    change every frame, structureLibs/orderParam_lib.py:1343-1346, :1475-1478) reuses it with padded centres.
     Returns numpy arrays holding ALL frames on every rank: stats (T, P, NSTATS) f64, per-frame angle
     histograms (T, P, nBins) i64 or None, pooled q histograms (P, 500) i64 or None, members (T, P)."""
     traj = obj.traj
@@ -124,7 +124,7 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
     ang_hist = torch.zeros((P, Tl, nBins), dtype=torch.int64, device=dev) if do_3body else None
     q_hist = torch.zeros((P, 1, 500), dtype=torch.int64, device=dev) if do_q else None
     members = torch.zeros((Tl, P), dtype=torch.float64, device=dev)
-    ws, sub_ws = engine.Workspace(dev), engine.Workspace(dev)
+    ws = engine.Workspace(dev)
     # angle histograms are kept per frame (the drivers report per-frame entropies), q histograms are pooled;
     # the two never run together here
     kw = dict(do_q=do_q, do_3body=do_3body, nbins=nBins, device=dev, hist_per_frame=do_3body)
@@ -145,16 +145,21 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
         o = outputs(0, l0, l1)
         engine.q3b_frames(watPos, box, None, out=o, want=tuple(o.keys()), workspace=ws, **kw)
         members[l0:l1, 0] = float(len(watInds))
-        for t in range(b0, b1):
-            for j in range(1, P):
-                inds = np.asarray(subInds[t][j - 1], dtype=np.int64)
-                members[t - begin, j] = float(len(inds))
-                if len(inds) == 0:
-                    continue
-                cen = torch.from_numpy(np.ascontiguousarray(xyz[t - b0][inds])).to(dev)
-                o = outputs(j, t - begin, t - begin + 1)
-                engine.q3b_frames(watPos[t - b0], box[t - b0], cen, out=o, want=tuple(o.keys()), workspace=sub_ws,
-                                  **kw)
+        # sub-populations: their centres change from frame to frame, so each population is padded to the batch's
+        # largest member count and evaluated in ONE call against the cell list population 0 just built
+        for j in range(1, P):
+            inds = [np.asarray(subInds[t][j - 1], dtype=np.int64) for t in range(b0, b1)]
+            counts = np.array([len(i) for i in inds], dtype=np.int32)
+            members[l0:l1, j] = torch.from_numpy(counts.astype(np.float64)).to(dev)
+            m_max = int(counts.max()) if len(counts) else 0
+            if m_max == 0:
+                continue
+            cen = np.zeros((b1 - b0, m_max, 3), dtype=xyz.dtype)
+            for k, i in enumerate(inds):
+                cen[k, :len(i)] = xyz[k][i]
+            o = outputs(j, l0, l1)
+            engine.q3b_frames(watPos, box, torch.from_numpy(cen).to(dev), out=o, want=tuple(o.keys()), workspace=ws,
+                              n_valid=counts, reuse_cells=True, **kw)
     # ---- combine ranks: one all-reduce of the integer histograms, one all-gather of the per-frame rows ----
     rows = [stats.permute(1, 0, 2).reshape(Tl, P * NS), members]
     if do_3body:

@@ -253,13 +253,18 @@ def threeBodyCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)'
     return pTet, avgCos, varCos, entropy, nWats
 
 
-def _hb_sums(acc, don, donh, box, dist, ang):
-    """(row sums, column sums) of generalhbonds(acc, don, donh) for a batch of frames, as int64 numpy (F, n)."""
+def _hb_sums(acc, don, donh, box, dist, ang, cells=None):
+    """(row sums, column sums) of generalhbonds(acc, don, donh) for a batch of frames, as int64 numpy (F, n).
+    cells: a routines.CellList already built over `don` (the same donors serve several acceptor sets)."""
     F = acc.shape[0]
     if acc.shape[1] == 0 or don.shape[1] == 0:
         return np.zeros((F, acc.shape[1]), dtype=np.int64), np.zeros((F, don.shape[1]), dtype=np.int64)
-    r = routines.hbond_counts(acc, don, donh, box, dist, ang)
+    r = routines.hbond_counts(acc, don, donh, box, dist, ang, cells=cells)
     return r["acc_count"].cpu().numpy().astype(np.int64), r["don_count"].cpu().numpy().astype(np.int64)
+
+
+def _donor_cells(don, box, dist):
+    return routines.CellList(don, box, max(float(dist), 1e-3)) if don.shape[1] else None
 
 
 def hbCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', stride=1):
@@ -285,15 +290,18 @@ def hbCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', stride=
         xyz = np.asarray(xyz)
         g = lambda idx: np.ascontiguousarray(xyz[:, idx])  # noqa: E731
         D, A = 3.5, 120.0
-        ww_a, ww_d = _hb_sums(g(wAcc), g(wDon), g(wDonH), box, D, A)
-        wsO_a, wsO_d = _hb_sums(g(wAcc), g(sDonO), g(sDonHO), box, D, A)
-        swO_a, swO_d = _hb_sums(g(sAccO), g(wDon), g(wDonH), box, D, A)
-        wsN_a, wsN_d = _hb_sums(g(wAcc), g(sDonN), g(sDonHN), box, D, A)
-        swN_a, swN_d = _hb_sums(g(sAccN), g(wDon), g(wDonH), box, D, A)
-        OO_a, OO_d = _hb_sums(g(sAccO), g(sDonO), g(sDonHO), box, D, A)
-        ON_a, ON_d = _hb_sums(g(sAccO), g(sDonN), g(sDonHN), box, D, A)
-        NO_a, NO_d = _hb_sums(g(sAccN), g(sDonO), g(sDonHO), box, D, A)
-        NN_a, NN_d = _hb_sums(g(sAccN), g(sDonN), g(sDonHN), box, D, A)
+        # the nine generalhbonds calls of the reference (:805-834) share three donor sets: one cell list each
+        pw, pO, pN = g(wDon), g(sDonO), g(sDonN)
+        cw, cO, cN = _donor_cells(pw, box, D), _donor_cells(pO, box, D), _donor_cells(pN, box, D)
+        ww_a, ww_d = _hb_sums(g(wAcc), pw, g(wDonH), box, D, A, cw)
+        wsO_a, wsO_d = _hb_sums(g(wAcc), pO, g(sDonHO), box, D, A, cO)
+        swO_a, swO_d = _hb_sums(g(sAccO), pw, g(wDonH), box, D, A, cw)
+        wsN_a, wsN_d = _hb_sums(g(wAcc), pN, g(sDonHN), box, D, A, cN)
+        swN_a, swN_d = _hb_sums(g(sAccN), pw, g(wDonH), box, D, A, cw)
+        OO_a, OO_d = _hb_sums(g(sAccO), pO, g(sDonHO), box, D, A, cO)
+        ON_a, ON_d = _hb_sums(g(sAccO), pN, g(sDonHN), box, D, A, cN)
+        NO_a, NO_d = _hb_sums(g(sAccN), pO, g(sDonHO), box, D, A, cO)
+        NN_a, NN_d = _hb_sums(g(sAccN), pN, g(sDonHN), box, D, A, cN)
         # per water molecule (reference :867-884); donors are listed once per hydrogen, two per water
         fold = lambda d: d[:, ::2] + d[:, 1::2]  # noqa: E731
         wat_rows.append(ww_a + fold(ww_d) + wsO_a + fold(swO_d) + wsN_a + fold(swN_d))

@@ -58,3 +58,14 @@ def test_fp32_mode_subpopulation_and_widening():
     torch.cuda.synchronize()
     compare(r, 0, pos, box, sub=sub, highq=9.0)
     assert r.n_widened > 0
+
+
+def test_fp32_mode_small_box_generic_path():
+    """Fewer than 4 cells per axis: the group-per-centre generic kernel runs the float arithmetic."""
+    rng = np.random.default_rng(6)
+    box = np.array([12.0, 13.0, 11.5])
+    pos = (rng.random((70, 3)) * box).astype(np.float32).astype(np.float64)
+    r = engine.q3b_frames(pos.astype(np.float32), box, precision="fp32", highq=5.5)
+    torch.cuda.synchronize()
+    assert r.nc[0] < 4
+    compare(r, 0, pos, box, highq=5.5)

@@ -390,6 +390,14 @@ int wol_psi(const void *centres, int32_t centre_dtype, const double *box, int32_
             const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes, double *psi,
             void *stream);
 
+/*
+ * Connected components of a SYMMETRIC 0/1 adjacency matrix adj[n][n] (int32, as wol_neighbor_matrix and the residue
+ * H-bond matrices of getHBClusterStats produce): labels[i] = smallest vertex index of i's component.  Replaces the
+ * recursive depthFirstSort (fortran/sortlib.f90:26-72) behind getClusters (structureLibs/orderParam_lib.py:123-156).
+ * `changed`: one int32 of device scratch.  Synchronises the stream (the sweep count depends on the graph).
+ */
+int wol_components(const int32_t *adj, int32_t n, int32_t *labels, int32_t *changed, void *stream);
+
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);
 

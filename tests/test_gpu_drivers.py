@@ -263,3 +263,61 @@ def test_drivers_on_amber_files(in_tmp):
     # (double atomics make the per-frame sums order-dependent in the last bits)
     assert np.allclose(a_mem[0][0], a_file[0][0], rtol=1e-12) and np.allclose(a_mem[1][0], a_file[1][0], rtol=1e-10)
     assert hb_mem == hb_file and np.array_equal(q_mem, np.loadtxt("qDistribution_0.txt"))
+
+
+def _components_ref(mat):
+    """Plain union-find reference for getClusters' output convention."""
+    n = mat.shape[0]
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for i, j in zip(*np.nonzero(mat == 1)):
+        a, b = find(i), find(j)
+        if a != b:
+            parent[max(a, b)] = min(a, b)
+    roots = np.array([find(i) for i in range(n)])
+    out = []
+    for r in np.unique(roots):
+        out.append(np.nonzero(roots == r)[0])
+        if len(out[-1]) == n:
+            break
+    return out
+
+
+def test_getClusters_and_cluster_stats(in_tmp):
+    rng = np.random.default_rng(2)
+    for n, p in ((1, 0.0), (7, 0.0), (40, 0.03), (200, 0.004), (60, 0.5)):
+        m = (rng.random((n, n)) < p).astype(int)
+        m = np.triu(m, 1); m = m + m.T
+        got, want = opl.getClusters(m), _components_ref(m)
+        assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    chain = np.zeros((300, 300), dtype=int)  # a path graph: the slowest case for label propagation
+    idx = np.arange(299); chain[idx, idx + 1] = 1; chain[idx + 1, idx] = 1
+    c = opl.getClusters(chain)
+    assert len(c) == 1 and len(c[0]) == 300
+    # drivers: ion contacts and residue H-bond clusters against matrices from the oracle
+    top, traj = make_system(3, 3, n_sol=4, seed0=1500)
+    obj = TrajObject(top, traj)
+    watInds, watHInds, _ = obj.getWatInds()
+    got = opl.getIonClusterStats(top, traj, watInds, np.ones(len(watInds)), distCut=3.0)
+    sizes = []
+    for t in range(3):
+        sizes += [len(x) for x in _components_ref(port.neighbor_matrix(traj.xyz[t][watInds], traj.xyz[t][watInds], traj.boxes[t], 0.0, 3.0))]
+    assert got == np.mean(sizes) and os.path.exists("clusterDistribution.txt")
+    (wAcc, wDon, wDonH), _ = opl.getHBInds(top, traj[0], watInds, watHInds, [], watInds)
+    got = opl.getHBClusterStats(top, traj, wAcc, wDon, wDonH, distCut=3.5, angCut=120.0)
+    sizes = []
+    res = np.asarray(top.resids)
+    for t in range(3):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        mat = port.hbonds(pos[wAcc], pos[wDon], pos[wDonH], box, 3.5, 120.0, dense=True)[2]
+        hb = np.zeros((top.n_residues(), top.n_residues()), dtype=int)
+        ai, dj = np.nonzero(mat)
+        hb[res[wAcc][ai], res[wDonH][dj]] = 1; hb[res[wDonH][dj], res[wAcc][ai]] = 1
+        sizes += [len(x) for x in _components_ref(hb) if len(x) != 1]
+    assert got == np.mean(sizes)

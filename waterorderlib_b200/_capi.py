@@ -78,6 +78,7 @@ SIGNATURES = {
     "wol_angle_table_ceil": (ctypes.c_int, [c_f64, c_i32, c_vp]),
     "wol_histrr3b": (ctypes.c_int, [c_vp, c_i32, _NC, c_f64, c_f64, c_i32, c_f64, c_i32, c_vp, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "wol_pair_hist": (ctypes.c_int, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, _NC, c_f64, c_f64, c_i32, c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "wol_components": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "wol_psi": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "wol_status": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_vp, ctypes.POINTER(c_i32 * 4)]),
 }

@@ -241,6 +241,33 @@ __global__ void __launch_bounds__(kPsiThreads) psi_kernel(const PsiParams P) {
     }
 }
 
+// ---- connected components of a symmetric 0/1 adjacency matrix (replaces sortlib's recursive depthFirstSort) ----------
+// Minimum-label propagation with pointer jumping: every vertex repeatedly takes the smallest label among itself and
+// its neighbours' labels, then shortcuts label chains; the host relaunches until nothing changes.
+
+__global__ void components_init_kernel(int32_t *labels, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[i] = i;
+}
+
+__global__ void __launch_bounds__(128) components_step_kernel(const int32_t *__restrict__ adj, int n, int32_t *labels, int32_t *changed) {
+    // one warp per vertex: the lanes share its row
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= n) return;
+    int best = labels[v];
+    const int32_t *row = adj + (size_t)v * n;
+    for (int j = lane; j < n; j += 32)
+        if (row[j] == 1) best = min(best, labels[j]);
+    best = __reduce_min_sync(kFullMask, best);
+    if (lane == 0) {
+        while (labels[best] < best) best = labels[best];  // pointer jumping
+        if (best < labels[v]) {
+            atomicMin(labels + v, best);
+            *changed = 1;
+        }
+    }
+}
+
 static PGrid make_pgrid(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
     char *ws = reinterpret_cast<char *>(workspace);
     PGrid g;
@@ -288,6 +315,26 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_pair_hist", e);
+    return WOL_OK;
+}
+
+int wol_components(const int32_t *adj, int32_t n, int32_t *labels, int32_t *changed, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || !labels || !changed || (!adj && n > 0)) return set_error(WOL_ERR_INVALID, "wol_components: bad argument");
+    if (n == 0) return WOL_OK;
+    components_init_kernel<<<(n + 127) / 128, 128, 0, stream>>>(labels, n);
+    add_launches(1);
+    for (int it = 0; it < n + 1; ++it) {  // converges in O(diameter) sweeps; n + 1 is the hard bound
+        int32_t flag = 0;
+        cudaError_t e = cudaMemsetAsync(changed, 0, sizeof(int32_t), stream);
+        if (e != cudaSuccess) return set_cuda_error("wol_components", e);
+        components_step_kernel<<<(unsigned)(((long long)n * 32 + 127) / 128), 128, 0, stream>>>(adj, n, labels, changed);
+        add_launches(1);
+        e = cudaMemcpyAsync(&flag, changed, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return set_cuda_error("wol_components", e);
+        if (!flag) break;
+    }
     return WOL_OK;
 }
 

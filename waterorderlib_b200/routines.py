@@ -497,3 +497,18 @@ def density_field(pos, box, grid, device=None):
                                       cells.ws_bytes, _vp(dens.data_ptr()), _stream()), "wol_density_field")
         torch.cuda.current_stream().synchronize()
     return dens
+
+
+def components(adj, device=None):
+    """Connected components of a symmetric 0/1 matrix -> int32 CUDA tensor labels (n,), labels[i] = smallest member."""
+    device = _device(device, adj)
+    a = adj if isinstance(adj, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(adj)))
+    a = (a == 1).to(device=device, dtype=torch.int32).contiguous()
+    if a.dim() != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("adjacency matrix must be square")
+    n = int(a.shape[0])
+    labels = torch.empty(n, dtype=torch.int32, device=device)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_components(_vp(a.data_ptr()), n, _vp(labels.data_ptr()), _vp(flag.data_ptr()), _stream()), "wol_components")
+    return labels

@@ -15,6 +15,7 @@ Same names, positional order, keyword names, defaults, return values and output 
     hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, endResName, stride=1,
                  lowCut=0.0, highCut=7.0)                                                            reference :1505-1584
     blockAverage(vals, nBlocks=20), getCI(means)                                                     reference :386-417
+    getClusters(hbMat), getHBClusterStats(...), getIonClusterStats(...)                              reference :123-311
 
 ``topFile`` / ``trajFile`` are whatever ``TrajObject`` accepts (in-memory objects, .npz, or AMBER files when
 parmed/pytraj are installed).  Where the reference loops over frames calling f2py routines per water, these
@@ -471,3 +472,77 @@ def hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)',
         return wp.getOrderParamPsi(sub, pos, box)
 
     return _value_driver(obj, endInds, subInds, nPops, per_frame, (0.0, 1.0), 'psiDistribution_%d.txt', 'psiVal    frequency')
+
+
+# ---- cluster analysis (reference orderParam_lib.py:123-311 over sortlib.depthfirstsort) -------------------------------
+
+def getClusters(hbMat):
+    """Clusters (connected components) of a symmetric residue-connectivity matrix, as a list of index arrays in the
+    reference's order: by smallest member, members ascending, an unconnected residue as a cluster of one; stops after
+    a cluster that spans every residue (reference orderParam_lib.py:123-156)."""
+    hbMat = np.asarray(hbMat)
+    n = hbMat.shape[0]
+    if n == 0:
+        return []
+    labels = routines.components(hbMat).cpu().numpy()
+    clusters = []
+    for root in np.unique(labels):  # ascending smallest member = the order the reference's loop meets them in
+        members = np.nonzero(labels == root)[0]
+        clusters.append(members)
+        if len(members) == n:
+            break
+    return clusters
+
+
+def _residue_index(top, atom_indices):
+    if hasattr(top, "resids"):
+        return np.asarray(top.resids)[np.asarray(atom_indices, dtype=int)]
+    return np.array([top.atoms[int(i)].residue.idx for i in atom_indices], dtype=int)  # parmed topology
+
+
+def _n_residues(top):
+    return top.n_residues() if hasattr(top, "n_residues") else len(top.residues)
+
+
+def getHBClusterStats(topFile, trajFile, acceptorInds, donorInds, donorHInds, stride=1, distCut=3.0, angCut=150.0):
+    """Mean size of the hydrogen-bonded residue clusters with more than one member (reference
+    orderParam_lib.py:158-233)."""
+    obj = TrajObject(topFile, trajFile=trajFile, stride=stride, solResName=None, watResName=None)
+    top = obj.top
+    acceptorInds, donorInds, donorHInds = (np.asarray(x, dtype=int) for x in (acceptorInds, donorInds, donorHInds))
+    resAccept, resDonorH = _residue_index(top, acceptorInds), _residue_index(top, donorHInds)
+    nRes = _n_residues(top)
+    clusters = []
+    for frame in obj.traj:
+        thisbox = np.reshape(np.array(frame.box.values[:3]), (1, 3))
+        thispos = np.array(frame.xyz)
+        allHB = wl.generalhbonds(thispos[acceptorInds], thispos[donorInds], thispos[donorHInds], thisbox, distCut, angCut)
+        # residue i is linked to every residue it accepts from or donates to (reference :209-224)
+        ai, dj = np.nonzero(allHB == 1)
+        hbMat = np.zeros((nRes, nRes))
+        hbMat[resAccept[ai], resDonorH[dj]] = 1
+        hbMat[resDonorH[dj], resAccept[ai]] = 1
+        iClusters = getClusters(hbMat)
+        clusters.append(np.array([len(c) for c in iClusters if len(c) != 1]))
+    clusters = np.concatenate(clusters)
+    return np.mean(clusters)
+
+
+def getIonClusterStats(topFile, trajFile, Inds, chargeAssign, stride=1, distCut=3.4):
+    """Mean size of the contact clusters among the atoms Inds (reference orderParam_lib.py:235-311); writes
+    clusterDistribution.txt."""
+    obj = TrajObject(topFile, trajFile=trajFile, stride=stride, solResName=None, watResName=None)
+    Inds = np.asarray(Inds, dtype=int)
+    clusters = []
+    for frame in obj.traj:
+        thisbox = np.reshape(np.array(frame.box.values[:3]), (1, 3))
+        subPos = np.array(frame.xyz)[Inds]
+        pairMat = wl.allnearneighbors(subPos, thisbox, 0.0, distCut)
+        tClusters = getClusters(pairMat)
+        clusters.append(np.array([len(c) for c in tClusters]))
+    clusters = np.concatenate(clusters)
+    meanCluster = np.mean(clusters)
+    clusterDist, bins = np.histogram(clusters, bins=[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10], density=False)
+    np.savetxt('clusterDistribution.txt', np.stack([0.5 * (bins[:-1] + bins[1:]), clusterDist], axis=1),
+               header='# clusters    frequency', fmt="%.3e")
+    return meanCluster

@@ -326,6 +326,23 @@ int wol_density_field(const double *gridx, const double *gridy, const double *gr
                       double *densvals, void *stream);
 
 /*
+ * Iso-surface vertices of a scalar field on a rectilinear grid: for every grid edge from node (i, j, k) to (i+1, j, k),
+ * (i, j+1, k) and (i, j, k+1) whose end values va, vb straddle `level` ((va > level) != (vb > level)) the point
+ * a + t (b - a), t = (level - va) / (vb - va).  This is the vertex set of the marching-cubes mesh densityGrid takes from
+ * skimage.measure.marching_cubes (structureLibs/surface_library.py:202; un-vendored, version unpinned, so parity is
+ * pinned on this rule, not on skimage); together with wol_willard_density in points mode (the normals at the
+ * vertices) it feeds wol_interface_water without leaving the device.  No periodic wrap of the grid, as in skimage.
+ *   points[capacity][3] : vertices in ascending node index ((i * ny + j) * nz + k), then axis x, y, z; only the
+ *                         first `capacity` are written (capacity 0 / points NULL: count only)
+ *   n_total             : device int32, the number of crossing edges (may exceed capacity)
+ *   scratch             : wol_iso_scratch_bytes(nx, ny, nz) bytes of device memory, 16-byte aligned
+ */
+size_t wol_iso_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);
+int wol_iso_points(const double *densvals, const double *gridx, const double *gridy, const double *gridz, int32_t nx, int32_t ny,
+                   int32_t nz, double level, uint32_t *scratch, size_t scratch_bytes, double *points, int64_t capacity,
+                   int32_t *n_total, void *stream);
+
+/*
  * InterfaceWater (fortran/waterlib.f90:1414-1469): for every water the nearest interface point (0-based,
  * first index on ties, -1 if none within distance^2 < 1000 -- the Fortran leaves that entry unwritten) and
  * its signed depth allwatdists = (water - point) . normal; for every interface point the nearest water;

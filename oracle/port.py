@@ -293,3 +293,35 @@ def density_field(pos, gridx, gridy, gridz, BoxL):
     _lib().wol_oracle_density_field(_ptr(p, _dp), p.shape[0], _ptr(gx, _dp), gx.size, _ptr(gy, _dp), gy.size, _ptr(gz, _dp), gz.size,
                                     _ptr(box, _dp), _ptr(out, _dp))
     return out
+
+
+def iso_points(dens, gridx, gridy, gridz, level):
+    """Iso-surface vertices: one per grid edge whose end values straddle the level ((va > level) != (vb > level)),
+    at a + t (b - a), t = (level - va) / (vb - va); ordered by node index ((i * ny + j) * nz + k), then axis.  This is
+    the rule marching cubes places its vertices with (skimage.measure.marching_cubes at
+    structureLibs/surface_library.py:202 is un-vendored and not installed: PARITY UNPINNED for this step -- the
+    restatement is pinned by its own properties in tests/test_oracle_golden.py)."""
+    dens = np.asarray(dens, dtype=np.float64)
+    gx, gy, gz = (np.asarray(g, dtype=np.float64).reshape(-1) for g in (gridx, gridy, gridz))
+    nx, ny, nz = dens.shape
+    above = dens > level
+    node = np.arange(nx * ny * nz).reshape(nx, ny, nz)
+    keys, pts = [], []
+    for ax, g in enumerate((gx, gy, gz)):
+        lo = [slice(None)] * 3
+        hi = [slice(None)] * 3
+        lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+        lo, hi = tuple(lo), tuple(hi)
+        cross = above[lo] != above[hi]
+        ijk = np.nonzero(cross)
+        va, vb = dens[lo][cross], dens[hi][cross]
+        t = (level - va) / (vb - va)
+        p = np.stack([gx[ijk[0]], gy[ijk[1]], gz[ijk[2]]], axis=1)
+        a = g[ijk[ax]]
+        p[:, ax] = a + t * (g[ijk[ax] + 1] - a)
+        keys.append(node[lo][cross] * 3 + ax)
+        pts.append(p)
+    keys = np.concatenate(keys)
+    pts = np.concatenate(pts)
+    order = np.argsort(keys, kind="stable")
+    return pts[order]

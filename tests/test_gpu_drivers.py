@@ -321,3 +321,25 @@ def test_getClusters_and_cluster_stats(in_tmp):
         hb[res[wAcc][ai], res[wDonH][dj]] = 1; hb[res[wDonH][dj], res[wAcc][ai]] = 1
         sizes += [len(x) for x in _components_ref(hb) if len(x) != 1]
     assert got == np.mean(sizes)
+
+
+def test_rdfCalc_matches_reference_golden(in_tmp, golden_dir):
+    """rdfCalc against the fixture made by running the reference's own rdfCalc body over the same trajectory with its
+    compiled Fortran (tests/golden/make_golden_rdfcalc.py): return values to 1e-10 relative (the g(r) per frame are
+    bit-exact; the Simpson sums are restated), the two written tables to the 3 digits they are printed with."""
+    g = np.load(os.path.join(golden_dir, "rdfcalc_n512.npz"))
+    xyz, boxes, n_sol = g["xyz"], g["boxes"], int(g["n_sol"])
+    n_wat = xyz.shape[1] - n_sol
+    top = Topology(["C1"] * n_sol + ["O"] * n_wat, ["SOL"] * n_sol + ["WAT"] * n_wat)
+    ret = opl.rdfCalc(top, (xyz, boxes), binwidth=0.1, totbins=110)
+    ref = g["ret_sol"]
+    assert np.allclose(np.asarray(ret, dtype=np.float64), ref, rtol=1e-10, atol=0)
+    for name in ("rdf", "coord"):
+        tab, tab_ref = np.loadtxt(name + ".txt"), g[name + "_txt_sol"]
+        assert tab.shape == tab_ref.shape and np.allclose(tab, tab_ref, rtol=2.1e-3, atol=1e-12)
+        assert np.mean(tab == tab_ref) > 0.999
+    # no solute selected: the reference returns (n1_OwOw, index of the last frame of a chunk)
+    top_w = Topology(["O"] * n_wat, ["WAT"] * n_wat)
+    n1, t = opl.rdfCalc(top_w, (xyz[:, n_sol:], boxes), binwidth=0.1, totbins=110)
+    assert np.isclose(n1, g["ret_nosol"][0], rtol=1e-10) and t == int(g["ret_nosol"][1])
+    assert np.allclose(np.loadtxt("rdf.txt"), g["rdf_txt_nosol"], rtol=2.1e-3, atol=1e-12)

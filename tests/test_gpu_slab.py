@@ -129,3 +129,87 @@ def test_density_field_golden_and_voxel_grid(golden_dir):
         s = np.linspace(0.8 * pos[:40, k].min(), 1.2 * pos[:40, k].max(), 11)
         spans.append(s[:-1] + (s[1] - s[0]))
     assert dv.shape == (10, 10, 10) and np.array_equal(dv, port.density_field(pos, spans[0], spans[1], spans[2], box))
+
+
+def test_iso_points_vs_oracle_analytic_and_density():
+    """wol_iso_points against the numpy restatement: bit-exact vertices, same order, on an analytic field with
+    anisotropic grid spacing and on a Willard density field; count-only and truncated-capacity behaviour."""
+    gx, gy, gz = np.linspace(-2.0, 2.0, 23), np.linspace(-2.1, 2.2, 17), np.linspace(-1.9, 2.0, 31)
+    X, Y, Z = np.meshgrid(gx, gy, gz, indexing="ij")
+    field = np.sqrt(X * X + 1.3 * Y * Y + 0.8 * Z * Z) + 0.05 * np.sin(3 * X) * np.cos(2 * Z)
+    for level in (1.3, 0.4, 5.0):
+        ref = port.iso_points(field, gx, gy, gz, level)
+        got = routines.iso_points(field, (gx, gy, gz), level).cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert routines.iso_points(field, (gx, gy, gz), 5.0).shape == (0, 3)
+    pos, box, z_lo, z_hi = synth.slab_box(4, 4, 2, sigma=0.3, seed=2)
+    grid = [(np.arange(n) + 0.5) * (box[d] / n) for d, n in enumerate((12, 12, 19))]
+    dens, _ = routines.willard_density(pos, box, 2.4, grid=grid)
+    ref = port.iso_points(dens.cpu().numpy(), grid[0], grid[1], grid[2], 0.016)
+    got = routines.iso_points(dens, grid, 0.016).cpu().numpy()
+    assert np.array_equal(got, ref) and len(ref) > 200
+    # a grid with a single node along an axis has no edges along it
+    one = routines.iso_points(field[:, :1, :], (gx, gy[:1], gz), 1.3).cpu().numpy()
+    assert np.array_equal(one, port.iso_points(field[:, :1, :], gx, gy[:1], gz, 1.3))
+
+
+def test_iso_points_capacity_and_errors():
+    import ctypes
+    from waterorderlib_b200._capi import lib
+    gx = np.linspace(0.0, 1.0, 9)
+    field = np.add.outer(np.add.outer(gx, gx), gx)  # x + y + z
+    ref = port.iso_points(field, gx, gx, gx, 1.45)
+    d = torch.from_numpy(field).cuda()
+    g = torch.from_numpy(gx).cuda()
+    nbytes = lib().wol_iso_scratch_bytes(9, 9, 9)
+    scratch = torch.empty(nbytes // 4 + 4, dtype=torch.int32, device="cuda")
+    n_total = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cap = 10
+    pts = torch.full((cap + 2, 3), -7.0, dtype=torch.float64, device="cuda")
+    vp = ctypes.c_void_p
+    s = vp(torch.cuda.current_stream().cuda_stream)
+    rc = lib().wol_iso_points(vp(d.data_ptr()), vp(g.data_ptr()), vp(g.data_ptr()), vp(g.data_ptr()), 9, 9, 9, 1.45, vp(scratch.data_ptr()),
+                              nbytes, vp(pts.data_ptr()), cap, vp(n_total.data_ptr()), s)
+    assert rc == 0 and int(n_total.item()) == len(ref) > cap
+    out = pts.cpu().numpy()
+    assert np.array_equal(out[:cap], ref[:cap]) and np.all(out[cap:] == -7.0)  # nothing past the capacity
+    rc = lib().wol_iso_points(vp(d.data_ptr()), vp(g.data_ptr()), vp(g.data_ptr()), vp(g.data_ptr()), 9, 9, 9, 1.45, vp(scratch.data_ptr()),
+                              16, vp(pts.data_ptr()), cap, vp(n_total.data_ptr()), s)
+    assert rc != 0 and b"scratch" in lib().wol_last_error()
+
+
+def test_instantaneous_interface_slab_end_to_end():
+    """cfg4 without the analytic planes: density -> iso-surface -> normals -> depth -> q profile on the device.  The
+    Willard-Chandler surface of a slab sits near the ideal faces, its normals are close to +-z and point out of the
+    liquid, and the depth profile agrees with the analytic-plane one up to the surface's roughness."""
+    pos, box, z_lo, z_hi = synth.slab_box(6, 6, 3, sigma=0.3, seed=9)
+    gp, gn = sl.instantaneousInterface(pos, box, spacing=1.5)
+    assert gp.shape == gn.shape and gp.shape[0] > 500
+    top = gp[:, 2] > 0.5 * (z_lo + z_hi)
+    assert np.all(np.abs(gp[top, 2] - z_hi) < 3.0) and np.all(np.abs(gp[~top, 2] - z_lo) < 3.0)
+    assert np.allclose(np.linalg.norm(gn, axis=1), 1.0, atol=1e-12)
+    assert np.all(gn[top, 2] > 0.5) and np.all(gn[~top, 2] < -0.5)
+    # the vertices lie on the iso-surface of the exact field up to the linear-interpolation error
+    d_at, _ = routines.willard_density(pos, box, 2.4, points=gp)
+    assert np.all(np.abs(d_at.cpu().numpy() - 0.016) < 2e-3)
+    # vertices and normals are what the oracle's restatements give for the same grid
+    grid = [(np.arange(n) + 0.5) * (box[d] / n) for d, n in enumerate(int(np.ceil(b / 1.5)) for b in box)]
+    dens_ref, _ = port.willard_density_field(pos, grid[0], grid[1], grid[2], box, 2.4)
+    dens_gpu, _ = routines.willard_density(pos, box, 2.4, grid=grid)
+    ref_pts = port.iso_points(dens_gpu.cpu().numpy(), grid[0], grid[1], grid[2], 0.016)
+    # (a second density evaluation: the cell list orders atoms within a cell by atomics, so sums differ by ulps)
+    assert gp.shape == ref_pts.shape and np.allclose(gp, ref_pts, rtol=0, atol=1e-9)
+    assert np.allclose(dens_gpu.cpu().numpy(), dens_ref, rtol=DENS_RTOL, atol=1e-18)
+    _, n_ref = port.willard_density_points(pos, gp, box, 2.4)
+    assert np.allclose(gn, -n_ref, rtol=0, atol=NORM_ATOL)
+    out = sl.depthBinnedQ(pos, box, binWidth=1.0, depthRange=(-12.0, 4.0), spacing=1.5)
+    assert out["n_surface"] == gp.shape[0]
+    _, _, nw, depth = port.interface_water(pos, gp, gn, 0.0, box)
+    given = sl.depthBinnedQ(pos, box, gp, gn, binWidth=1.0, depthRange=(-12.0, 4.0))
+    assert np.array_equal(given["depth"].cpu().numpy(), depth) and given["numwater"] == nw
+    # the self-computed interface is a fresh density evaluation (ulps apart, see above)
+    assert np.mean(np.abs(out["depth"].cpu().numpy() - depth) < 1e-6) > 0.999 and abs(out["numwater"] - nw) <= 2
+    gp0, gn0 = synth.plane_interface(box, z_lo, z_hi, spacing=2.0)
+    flat = sl.depthBinnedQ(pos, box, gp0, gn0, binWidth=1.0, depthRange=(-12.0, 4.0))
+    assert np.abs(np.median(out["depth"].cpu().numpy() - flat["depth"].cpu().numpy())) < 3.0
+    assert out["count"].sum() > 0.9 * len(pos)

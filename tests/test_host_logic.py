@@ -157,3 +157,36 @@ def test_amber_parm7_and_netcdf_readers(tmp_path):
     hbO, _ = opl.getHBInds(obj.top, obj.traj[0], [6, 10, 14], [7, 8, 11, 12, 15, 16], [], [6, 10, 14])
     assert list(hbO[1]) == [6, 6, 10, 10, 14, 14]
     obj.traj.close()
+
+
+def test_legacy_simps_and_trajectory_slices(tmp_path):
+    """rdfCalc's host pieces: the SciPy < 1.11 ``simps`` rule (even='avg') and pytraj-style traj[a:b] slicing."""
+    from scipy.integrate import simpson
+    from waterorderlib_b200.structureLibs.amber_io import NetCDFTrajectory, write_netcdf
+    from waterorderlib_b200.structureLibs.orderParam_lib import simps
+    from waterorderlib_b200.structureLibs.TrajObject import ArrayTrajectory
+    rng = np.random.default_rng(3)
+    for n in (3, 7, 151):
+        x, y = np.cumsum(rng.uniform(0.5, 1.5, n)), rng.normal(size=n)
+        assert np.isclose(simps(y, x), simpson(y, x=x), rtol=1e-12)
+    for n in (2, 4, 150):
+        x, y = np.cumsum(rng.uniform(0.5, 1.5, n)), rng.normal(size=n)
+        first, last = 0.5 * (x[1] - x[0]) * (y[1] + y[0]), 0.5 * (x[-1] - x[-2]) * (y[-1] + y[-2])
+        a = (simpson(y[:-1], x=x[:-1]) if n > 2 else 0.0) + last
+        b = (simpson(y[1:], x=x[1:]) if n > 2 else 0.0) + first
+        assert np.isclose(simps(y, x), 0.5 * (a + b), rtol=1e-12)
+    assert np.isclose(simps(np.arange(6.0) ** 2, np.arange(6.0)), 125.0 / 3.0, rtol=0.01)
+    xyz = rng.normal(size=(7, 5, 3)).astype(np.float32)
+    boxes = np.tile(np.array([10.0, 11.0, 12.0]), (7, 1)) + np.arange(7)[:, None]
+    t = ArrayTrajectory(xyz, boxes)
+    sub = t[2:5]
+    assert len(sub) == 3 and np.array_equal(sub[0].xyz, xyz[2]) and np.array_equal(sub[2].box.values[:3], boxes[4])
+    assert [f.box.values[0] for f in t[5:99]] == [15.0, 16.0]
+    path = str(tmp_path / "t.nc")
+    write_netcdf(path, xyz, boxes)
+    nc = NetCDFTrajectory(path)
+    sub = nc[1:4]
+    assert len(sub) == 3 and np.array_equal(sub[1].xyz, xyz[2]) and np.array_equal(sub[1].box.values[:3], boxes[2])
+    nc.close()
+    with pytest.raises(TypeError):
+        t["a"]

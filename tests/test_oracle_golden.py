@@ -124,3 +124,25 @@ def test_pairs_against_golden(golden_dir):
 def test_density_field_against_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "slab_n256.npz"))
     assert np.array_equal(port.density_field(g["pos"], g["gx"] + 0.3, g["gy"], g["gz"], g["box"]), g["voxel"])
+
+
+def test_iso_points_properties():
+    """The iso-surface restatement (parity unpinned: skimage is not installed) pinned by its own properties: every
+    vertex lies on a grid edge, between two nodes whose values straddle the level, at the linear interpolation; a
+    linear field is interpolated exactly; one vertex per straddling edge."""
+    from oracle import port
+    g = np.linspace(0.0, 1.0, 9)
+    field = np.add.outer(np.add.outer(g, 2.0 * g), 3.0 * g)  # x + 2y + 3z
+    pts = port.iso_points(field, g, g, g, 2.2)
+    assert np.allclose(pts[:, 0] + 2.0 * pts[:, 1] + 3.0 * pts[:, 2], 2.2, atol=1e-12)
+    on_node = np.isclose(pts[:, :, None], g[None, None, :], atol=1e-12).any(axis=2)
+    assert np.all(on_node.sum(axis=1) >= 2)  # at most one coordinate is off the grid lines
+    above = field > 2.2
+    n_edges = sum(int(np.sum(np.diff(above, axis=a) != 0)) for a in range(3))
+    assert len(pts) == n_edges > 0
+    X, Y, Z = np.meshgrid(g - 0.5, g - 0.5, g - 0.5, indexing="ij")
+    r = np.sqrt(X * X + Y * Y + Z * Z)
+    sph = port.iso_points(r, g, g, g, 0.3)
+    rr = np.linalg.norm(sph - 0.5, axis=1)
+    assert len(sph) > 50 and np.all(rr <= 0.3 + 1e-12) and np.all(rr > 0.27)  # chords of a convex field lie inside
+    assert port.iso_points(r, g, g, g, 5.0).shape == (0, 3)

@@ -297,6 +297,64 @@ __global__ void __launch_bounds__(256) profile_kernel(const double *__restrict__
     }
 }
 
+// ---- iso-surface vertices -------------------------------------------------------------------------------
+// Every grid edge node -> next node along x, y, z whose end values straddle the level carries one vertex at the
+// linear interpolation -- the vertex set a marching-cubes mesh of the field has (structureLibs/surface_library.py:202).
+// Two passes around an exclusive scan so that the output order is deterministic: ascending node index
+// ((i * ny + j) * nz + k), then axis.
+
+struct IsoParams {
+    const double *dens;  // [nx][ny][nz]
+    const double *gx, *gy, *gz;
+    int nx, ny, nz;
+    long long n_nodes;
+    double level;
+    uint32_t *offs;      // [n_nodes + 1]
+    long long capacity;  // vertices `points` holds
+    double *points;      // [capacity][3]
+    int32_t *n_total;
+};
+
+__device__ __forceinline__ bool iso_above(double v, double level) { return v > level; }
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) iso_kernel(const IsoParams P) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > P.n_nodes) return;
+    if (g == P.n_nodes) {  // sentinel: the scan turns it into the total
+        if (!FILL) P.offs[g] = 0u;
+        else *P.n_total = (int32_t)P.offs[g];
+        return;
+    }
+    const int k = (int)(g % P.nz), j = (int)((g / P.nz) % P.ny), i = (int)(g / ((long long)P.nz * P.ny));
+    const double va = P.dens[g];
+    const bool a = iso_above(va, P.level);
+    const long long step[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1ll};
+    const bool has[3] = {i + 1 < P.nx, j + 1 < P.ny, k + 1 < P.nz};
+    uint32_t n = 0;
+    long long o = FILL ? (long long)P.offs[g] : 0ll;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!has[ax]) continue;
+        const double vb = P.dens[g + step[ax]];
+        if (iso_above(vb, P.level) == a) continue;
+        ++n;
+        if (FILL) {
+            if (o < P.capacity) {
+                const double t = __ddiv_rn(__dsub_rn(P.level, va), __dsub_rn(vb, va));
+                double p[3] = {P.gx[i], P.gy[j], P.gz[k]};
+                const double nxt = ax == 0 ? P.gx[i + 1] : (ax == 1 ? P.gy[j + 1] : P.gz[k + 1]);
+                p[ax] = __dadd_rn(p[ax], __dmul_rn(t, __dsub_rn(nxt, p[ax])));
+                P.points[3 * o + 0] = p[0];
+                P.points[3 * o + 1] = p[1];
+                P.points[3 * o + 2] = p[2];
+            }
+            ++o;
+        }
+    }
+    if (!FILL) P.offs[g] = n;
+}
+
 // ---- histrr3b ---------------------------------------------------------------------------------------------
 // One warp per centre.  The lanes walk the candidates of the 27-cell stencil (cell edge >= dNum * distWidth),
 // keep those whose distance bin is inside the histogram in a shared list, then spread the list's pairs over
@@ -498,6 +556,42 @@ int wol_interface_water(const double *pos, int32_t n_pos, const double *gridpos,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_interface_water", e);
     return WOL_OK;
+}
+
+int wol_iso_points(const double *densvals, const double *gridx, const double *gridy, const double *gridz, int32_t nx, int32_t ny,
+                   int32_t nz, double level, uint32_t *scratch, size_t scratch_bytes, double *points, int64_t capacity,
+                   int32_t *n_total, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!densvals || !gridx || !gridy || !gridz || !scratch || !n_total) return set_error(WOL_ERR_INVALID, "wol_iso_points: null argument");
+    if (nx < 1 || ny < 1 || nz < 1 || capacity < 0 || (capacity > 0 && !points)) return set_error(WOL_ERR_INVALID, "wol_iso_points: bad size");
+    const long long n = (long long)nx * ny * nz;
+    if (3 * n > 0x7fffffffll) return set_error(WOL_ERR_INVALID, "wol_iso_points: grid of %lld nodes is too large", n);
+    const size_t need = wol_iso_scratch_bytes(nx, ny, nz);
+    if (scratch_bytes < need) return set_error(WOL_ERR_WORKSPACE, "scratch holds %zu bytes, %zu needed", scratch_bytes, need);
+    IsoParams P;
+    P.dens = densvals;
+    P.gx = gridx; P.gy = gridy; P.gz = gridz;
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.n_nodes = n;
+    P.level = level;
+    P.offs = scratch;
+    P.capacity = capacity;
+    P.points = points;
+    P.n_total = n_total;
+    const unsigned blocks = (unsigned)((n + 1 + 255) / 256);
+    iso_kernel<false><<<blocks, 256, 0, stream>>>(P);
+    exclusive_scan_u32(scratch, (size_t)n + 1, scratch + (((size_t)n + 1 + 3) & ~(size_t)3), stream);
+    iso_kernel<true><<<blocks, 256, 0, stream>>>(P);
+    add_launches(2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_iso_points", e);
+    return WOL_OK;
+}
+
+size_t wol_iso_scratch_bytes(int32_t nx, int32_t ny, int32_t nz) {
+    if (nx < 1 || ny < 1 || nz < 1) return 0;
+    const size_t n = (size_t)nx * ny * nz + 1;
+    return sizeof(uint32_t) * (((n + 3) & ~(size_t)3) + n / kScanTile + 2);
 }
 
 int wol_profile_bins(const double *value, const double *coord, int64_t n, double lo, double width, int32_t nbins, int64_t *count,

@@ -331,6 +331,35 @@ def willard_density(pos, box, smoothlen=2.4, grid=None, points=None, want_normal
     return dens, norms
 
 
+def iso_points(dens, grid, level, device=None):
+    """Vertices of the iso-surface dens == level on the rectilinear grid (gridx, gridy, gridz): one per grid edge whose
+    end values straddle the level, linearly interpolated -- the vertex set skimage.measure.marching_cubes gives
+    densityGrid (structureLibs/surface_library.py:202).  Returns a CUDA tensor (n, 3) f64, ordered by node index then axis."""
+    device = _device(device, dens)
+    gx, gy, gz = (_f64(np.asarray(g, dtype=np.float64).reshape(-1) if not isinstance(g, torch.Tensor) else g.reshape(-1), device)
+                  for g in grid)
+    nx, ny, nz = int(gx.numel()), int(gy.numel()), int(gz.numel())
+    d = _f64(dens, device).reshape(-1)
+    if int(d.numel()) != nx * ny * nz:
+        raise ValueError("dens has %d values, the grid %d x %d x %d nodes" % (d.numel(), nx, ny, nz))
+    if nx * ny * nz == 0:
+        return torch.zeros((0, 3), dtype=torch.float64, device=device)
+    nbytes = int(lib().wol_iso_scratch_bytes(nx, ny, nz))
+    scratch = torch.empty(nbytes // 4 + 4, dtype=torch.int32, device=device)
+    n_total = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        def run(points, cap):
+            check(lib().wol_iso_points(_vp(d.data_ptr()), _vp(gx.data_ptr()), _vp(gy.data_ptr()), _vp(gz.data_ptr()), nx, ny, nz,
+                                       float(level), _vp(scratch.data_ptr()), nbytes, _vp(points.data_ptr()) if points is not None else None,
+                                       cap, _vp(n_total.data_ptr()), _stream()), "wol_iso_points")
+        run(None, 0)
+        n = int(n_total.item())  # the vertex count sizes the output: one host read
+        pts = torch.empty((n, 3), dtype=torch.float64, device=device)
+        if n:
+            run(pts, n)
+    return pts
+
+
 def interface_water(pos, gridpos, gridnorm, cutoff, box, want_surfclose=True, device=None):
     """InterfaceWater (fortran/waterlib.f90:1414-1469) -> dict(watclose int32 (n,) 0-based / -1, surfclose int32
     (ng,), numwater int, allwatdists f64 (n,))."""

@@ -191,7 +191,9 @@ class ArrayTrajectory:
     def __getitem__(self, i):
         if isinstance(i, (int, np.integer)):
             return Frame(self.xyz[i], self.boxes[i])
-        raise TypeError("only integer frame indices are supported")
+        if isinstance(i, slice):  # a sub-trajectory, as pytraj's traj[a:b] (rdfCalc's chunks, orderParam_lib.py:617)
+            return ArrayTrajectory(self.xyz[i], self.boxes[i], top=self.top)
+        raise TypeError("frame indices must be integers or slices")
 
     def __iter__(self):
         for i in range(len(self)):

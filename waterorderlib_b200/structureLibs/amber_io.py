@@ -115,7 +115,9 @@ class NetCDFTrajectory(ArrayTrajectory):
     def __getitem__(self, i):
         if isinstance(i, (int, np.integer)):
             return Frame(self.xyz[int(i)], self.boxes[int(i)])
-        raise TypeError("only integer frame indices are supported")
+        if isinstance(i, slice):  # a sub-trajectory (copied out of the map), as pytraj's traj[a:b]
+            return ArrayTrajectory(self.xyz[i], self.boxes[i], top=self.top)
+        raise TypeError("frame indices must be integers or slices")
 
     def close(self):
         """Release the memory map (frames already handed out are copies and stay valid)."""

@@ -14,6 +14,7 @@ Same names, positional order, keyword names, defaults, return values and output 
     lsiCalc(topFile, trajFile, subInds=None, nPops=0, solResName, watResName, stride=1)            reference :1586-1663
     hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, endResName, stride=1,
                  lowCut=0.0, highCut=7.0)                                                            reference :1505-1584
+    rdfCalc(topFile, trajFile, solResName, watResName, binwidth=0.1, totbins=150, stride=1)         reference :575-727
     blockAverage(vals, nBlocks=20), getCI(means)                                                     reference :386-417
     getClusters(hbMat), getHBClusterStats(...), getIonClusterStats(...)                              reference :123-311
 
@@ -472,6 +473,98 @@ def hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)',
         return wp.getOrderParamPsi(sub, pos, box)
 
     return _value_driver(obj, endInds, subInds, nPops, per_frame, (0.0, 1.0), 'psiDistribution_%d.txt', 'psiVal    frequency')
+
+
+# ---- radial distribution functions (reference orderParam_lib.py:575-727) --------------------------------------------------
+
+def _basic_simps(y, start, stop, x):
+    h = np.diff(x)
+    h0, h1 = h[start:stop:2], h[start + 1:stop + 1:2]
+    hsum, hprod, h0divh1 = h0 + h1, h0 * h1, h0 / h1
+    return np.sum(hsum / 6.0 * (y[start:stop:2] * (2.0 - 1.0 / h0divh1) + y[start + 1:stop + 1:2] * hsum * hsum / hprod
+                                + y[start + 2:stop + 2:2] * (2.0 - h0divh1)))
+
+
+def simps(y, x):
+    """Composite Simpson rule over samples y(x) as ``scipy.integrate.simps`` computed it when the reference was written
+    (orderParam_lib.py:19; SciPy < 1.11, default even='avg'): with an even number of samples, the mean of (Simpson over
+    the first N-1 samples + a trapezoid on the last interval) and (a trapezoid on the first interval + Simpson over the
+    last N-1 samples).  Today's ``scipy.integrate.simpson`` treats that case differently and has no ``simps`` name."""
+    y, x = np.asarray(y, dtype=np.float64), np.asarray(x, dtype=np.float64)
+    N = y.shape[0]
+    if N % 2 == 1:
+        return _basic_simps(y, 0, N - 2, x)
+    val = 0.5 * (x[-1] - x[-2]) * (y[-1] + y[-2])
+    result = _basic_simps(y, 0, N - 3, x)
+    val += 0.5 * (x[1] - x[0]) * (y[1] + y[0])
+    result += _basic_simps(y, 1, N - 2, x)
+    return result / 2.0 + val / 2.0
+
+
+def rdfCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', binwidth=0.1, totbins=150, stride=1):
+    """Ow-Ow, solute-solute and solute-Ow radial distribution functions over five trajectory chunks, their running
+    coordination numbers (Simpson), the first-shell coordination n1 at the first RDF minimum and the translational
+    parameter (reference orderParam_lib.py:575-727).  Writes rdf.txt and coord.txt; returns
+    ([n1_OwOw, se], [n1_SolOw, se], [tParam, se]) with a solute, (n1_OwOw, last frame index of a chunk) without, as the
+    reference does.  The pair histograms come from wol_pair_hist (bit-exact g(r) per frame, summed in frame order).
+    The reference's ``solInds==[]`` tests (:633,:660,:673,:724) are read as "no solute atoms selected"."""
+    from scipy.signal import argrelmin
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    traj = obj.traj
+    watInds, _watHInds, _lenWat = obj.getWatInds()
+    solInds = obj.getSolInds()[0]
+    has_sol = len(solInds) > 0
+    tot_rdf = {k: [] for k in ("OwOw", "SolOw", "SolSol")}
+    tot_coord = {k: [] for k in ("OwOw", "SolOw", "SolSol")}
+    tot_n1_OwOw, tot_n1_SolOw, tot_tParam = [], [], []
+    nChunks = 5
+    chunkSize = int(len(traj) / nChunks)
+    dist = np.linspace(0, (totbins - 1) * binwidth, totbins) + binwidth
+    bulkdens = 1.0  # local densities, as in the reference (:630)
+    t = -1
+    for c in range(nChunks):
+        rdf_OwOw, rdf_SolOw, rdf_SolSol = np.zeros(totbins), np.zeros(totbins), np.zeros(totbins)
+        for t, frame in enumerate(traj[int(c * chunkSize):int((c + 1) * chunkSize)]):
+            thispos = np.asarray(frame.xyz)
+            thisbox = np.reshape(np.array(frame.box.values[:3]), (1, 3))
+            thisWat, thisSol = thispos[watInds], thispos[solInds]
+            rdf_OwOw = rdf_OwOw + wl.radialdistsame(thisWat, binwidth, totbins, bulkdens, thisbox)
+            if has_sol:
+                rdf_SolSol = rdf_SolSol + wl.radialdistsame(thisSol, binwidth, totbins, bulkdens, thisbox)
+                rdf_SolOw = rdf_SolOw + wl.radialdist(thisSol, thisWat, binwidth, totbins, bulkdens, thisbox)
+        rdf_OwOw, rdf_SolSol, rdf_SolOw = rdf_OwOw / (1.0 + t), rdf_SolSol / (1.0 + t), rdf_SolOw / (1.0 + t)
+        tot_rdf["OwOw"].append(rdf_OwOw); tot_rdf["SolSol"].append(rdf_SolSol); tot_rdf["SolOw"].append(rdf_SolOw)
+        coord_OwOw, coord_SolOw, coord_SolSol = np.zeros(len(dist) - 2), np.zeros(len(dist) - 2), np.zeros(len(dist) - 2)
+        for j in range(2, len(dist)):
+            coord_OwOw[j - 2] = 8.0 * np.pi * simps(rdf_OwOw[:j] * (dist[:j]) ** 2.0, dist[:j])
+            if has_sol:
+                coord_SolOw[j - 2] = 4.0 * np.pi * simps(rdf_SolOw[:j] * (dist[:j]) ** 2.0, dist[:j])
+                coord_SolSol[j - 2] = 8.0 * np.pi * simps(rdf_SolSol[:j] * (dist[:j]) ** 2.0, dist[:j])
+        tot_coord["OwOw"].append(coord_OwOw); tot_coord["SolSol"].append(coord_SolSol); tot_coord["SolOw"].append(coord_SolOw)
+        if has_sol:
+            tot_n1_SolOw.append(coord_SolOw[argrelmin(rdf_SolOw)[0][0] - 2])
+        first_min = argrelmin(rdf_OwOw)[0][0]
+        n1_OwOw = coord_OwOw[first_min - 2]
+        rdf = rdf_OwOw[:first_min] / rdf_OwOw[-1]
+        tParam = simps(rdf, dist[:first_min]) / dist[first_min]
+        tot_n1_OwOw.append(n1_OwOw)
+        tot_tParam.append(tParam)
+
+    def se(a, axis=None):
+        return np.std(np.array(a), axis=axis, ddof=1) / np.sqrt(nChunks - 1)
+
+    rdf_se = {k: se(v, 0) for k, v in tot_rdf.items()}
+    coord_se = {k: se(v, 0) for k, v in tot_coord.items()}
+    # as in the reference, the value columns are the LAST chunk's curves, the error columns the spread over chunks
+    np.savetxt('rdf.txt', np.stack([dist, rdf_OwOw, rdf_se["OwOw"], rdf_SolSol, rdf_se["SolSol"], rdf_SolOw, rdf_se["SolOw"]], axis=1),
+               header='pair distance (A)     Ow-Ow rdf     err     Sol-Sol rdf     err     Sol-Ow rdf     err', fmt="%.3e")
+    np.savetxt('coord.txt', np.stack([dist[2:], coord_OwOw, coord_se["OwOw"], coord_SolSol, coord_se["SolSol"], coord_SolOw,
+                                      coord_se["SolOw"]], axis=1),
+               header='pair distance (A)     Ow-Ow n1     err     Sol-Sol n1     err     Sol-Ow n1     err', fmt="%.3e")
+    n1_OwOw, tParam = np.mean(tot_n1_OwOw), np.mean(tot_tParam)
+    if has_sol:
+        return [n1_OwOw, se(tot_n1_OwOw)], [np.mean(tot_n1_SolOw), se(tot_n1_SolOw)], [tParam, se(tot_tParam)]
+    return n1_OwOw, t
 
 
 # ---- cluster analysis (reference orderParam_lib.py:123-311 over sortlib.depthfirstsort) -------------------------------

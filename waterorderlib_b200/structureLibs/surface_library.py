@@ -3,9 +3,10 @@ density field of ``densityGrid`` (:170-210) and the slab composition BASELINE co
 ("instantaneous-interface depth-binned q profiles"), which the reference has the ingredients for
 (``wl.willarddensityfield``, ``wl.interfacewater``, ``wp.getOrderParamq``) but no function.
 
-Iso-surface extraction (``skimage.measure.marching_cubes``, surface_library.py:202), meshing and plotting are
-third-party work outside the hot path: ``densityGrid`` here returns the density field on the reference's grid
-and hands it to skimage only if that package is installed.
+``instantaneousInterface`` extracts the iso-surface on the device (the vertex set marching cubes would produce, with
+the exact Willard-Chandler normals at the vertices) so that the slab pipeline density -> interface -> depth -> profile
+never leaves the GPU.  Triangulation (``skimage.measure.marching_cubes``, surface_library.py:202), meshing and plotting
+stay third-party work outside the hot path: ``densityGrid`` hands the density field to skimage only if it is installed.
 """
 import numpy as np
 import torch
@@ -38,16 +39,45 @@ def densityGrid(heavyPos, watPos, thisbox, level=0.016, minFrac=0.7):
     return verts, faces
 
 
-def depthBinnedQ(watPos, thisbox, gridpos, gridnorm, binWidth=1.0, depthRange=(-30.0, 10.0), lowCut=0.0, highCut=10.0,
-                 cutoff=0.0):
+def instantaneousInterface(watPos, thisbox, grid=None, spacing=2.0, level=0.016, smoothlen=2.4, outward=True):
+    """Willard-Chandler instantaneous interface of one frame as the point set InterfaceWater consumes
+    (fortran/waterlib.f90:1414-1469): density field on `grid` (default: the whole box at about `spacing` Angstrom,
+    nodes at cell centres) -> vertices of the iso-surface dens == level (the marching-cubes vertex rule of
+    surface_library.py:202) -> density gradient at the vertices (WillardDensityPoints, fortran/waterlib.f90:1351-1398).
+    `outward` normals point towards lower density, so that the depth (water - point) . normal is negative inside the
+    liquid.  Returns (gridpos (n,3), gridnorm (n,3)): CUDA tensors for tensor input, numpy arrays otherwise."""
+    box = np.asarray(thisbox.detach().cpu() if isinstance(thisbox, torch.Tensor) else thisbox, dtype=np.float64).reshape(-1)[:3]
+    if grid is None:
+        grid = []
+        for d in range(3):
+            n = max(int(np.ceil(box[d] / float(spacing))), 1)
+            grid.append((np.arange(n) + 0.5) * (box[d] / n))
+    dens, _ = routines.willard_density(watPos, box, smoothlen, grid=grid, want_normals=False)
+    pts = routines.iso_points(dens, grid, level)
+    if pts.shape[0]:
+        _, norms = routines.willard_density(watPos, box, smoothlen, points=pts)
+        if outward:
+            norms = -norms
+    else:
+        norms = torch.zeros_like(pts)
+    if isinstance(watPos, torch.Tensor):
+        return pts, norms
+    return pts.cpu().numpy(), norms.cpu().numpy()
+
+
+def depthBinnedQ(watPos, thisbox, gridpos=None, gridnorm=None, binWidth=1.0, depthRange=(-30.0, 10.0), lowCut=0.0, highCut=10.0,
+                 cutoff=0.0, **interface_kw):
     """Config-4 composition for one frame: tetrahedral q of every water (getOrderParamq), its signed depth below
     the instantaneous interface (InterfaceWater: (water - nearest surface point) . normal, negative inside the
-    liquid for outward normals), and the profile of q against depth.
-    Returns dict(depth_edges, count, q_mean, q_var, q (n,), depth (n,), numwater)."""
+    liquid for outward normals), and the profile of q against depth.  Without gridpos / gridnorm the interface is
+    the frame's own Willard-Chandler surface (instantaneousInterface(**interface_kw)).
+    Returns dict(depth_edges, count, q_mean, q_var, q (n,), depth (n,), numwater, n_surface)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     pos = torch.as_tensor(np.ascontiguousarray(np.asarray(watPos, dtype=np.float64))).to(dev) if not isinstance(watPos, torch.Tensor) else watPos
     r = engine.q3b_frames(pos, thisbox, None, do_q=True, do_3body=False, lowq=lowCut, highq=highCut, want=("q",))
     q = r["q"][0]
+    if gridpos is None:
+        gridpos, gridnorm = instantaneousInterface(pos, thisbox, **interface_kw)
     iw = routines.interface_water(pos, gridpos, gridnorm, cutoff, thisbox, want_surfclose=False)
     depth = iw["allwatdists"]
     nb = int(np.ceil((depthRange[1] - depthRange[0]) / binWidth))
@@ -57,7 +87,7 @@ def depthBinnedQ(watPos, thisbox, gridpos, gridnorm, binWidth=1.0, depthRange=(-
         mean = s1_h / count_h
         var = np.maximum(s2_h / count_h - mean * mean, 0.0)
     return {"depth_edges": depthRange[0] + binWidth * np.arange(nb + 1), "count": count_h, "q_mean": mean, "q_var": var,
-            "q": q, "depth": depth, "numwater": int(iw["numwater"].item())}
+            "q": q, "depth": depth, "numwater": int(iw["numwater"].item()), "n_surface": int(gridpos.shape[0])}
 
 
 def densityVoxel(heavyPos, watPos, thisbox):

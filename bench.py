@@ -344,6 +344,26 @@ def main():
     f1.record()
     barrier()
     e2e_ms_total = f0.elapsed_time(f1)
+
+    # the same leg fed float32 host frames -- the values an AMBER NetCDF trajectory stores (amber_io.NetCDFTrajectory
+    # hands them on without upcasting); arithmetic stays fp64, results are identical; half the host->device bytes
+    pipe32 = FramePipeline(n_waters, max(1, min(B, args.e2e_batch)), dtype=np.float32, device=dev)
+    pos_h32 = torch.empty((B, n_waters, 3), dtype=torch.float32, pin_memory=True)
+    pos_h32.copy_(pos_h)
+    q_h32 = torch.empty((B, n_waters), dtype=torch.float64, pin_memory=True)
+    for _ in range(2):
+        pipe32.run(pos_h32, box, out_q=q_h32, out_n3=n3_h)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        r32 = pipe32.run(pos_h32, box, out_q=q_h32, out_n3=n3_h)
+        e2e_launches += pipe32.launches
+    if world > 1:
+        dist.all_reduce(r32["_device"]["ang_hist"])
+    g1.record()
+    barrier()
+    e2e32_ms_total = g0.elapsed_time(g1)
     sampler.stop_flag = True
     sampler.join(timeout=2.0)
 
@@ -357,6 +377,7 @@ def main():
     ms_total = max_over_ranks(ms_total)
     ms32 = max_over_ranks(ms32)
     e2e_ms_total = max_over_ranks(e2e_ms_total)
+    e2e32_ms_total = max_over_ranks(e2e32_ms_total)
     kernel_ms = max_over_ranks(kernel_ms)
     wf_per_step = float(world) * B * n_waters
     value = wf_per_step * args.steps / (ms_total * 1e-3)
@@ -364,6 +385,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_WF_FP64 * B * n_waters / (kernel_ms * 1e-3) / 1e9
     q_ok = bool(torch.equal(q_h.to(dev), out["q"]))
+    q32_ok = bool(torch.equal(q_h32.to(dev), out["q"]))
 
     # FP roofline of the dominant kernel: 17 flop per candidate pair evaluation + 37 per angle, candidates
     # = 27 cells * cell volume * number density, angles = three-body angles (measured) + 6 for q
@@ -381,6 +403,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / args.steps,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "api": "waterorderlib_b200.pipeline.FramePipeline.run", "matches_device_run": q_ok},
+            "e2e_f32_host_frames": {"value": wf_per_step * args.steps / (e2e32_ms_total * 1e-3), "unit": UNIT,
+                                    "ms_per_step": e2e32_ms_total / args.steps, "h2d_bytes_per_step": pipe32.h2d_bytes,
+                                    "d2h_bytes_per_step": pipe32.d2h_bytes, "matches_device_run": q32_ok,
+                                    "note": "float32 host frames as a NetCDF trajectory stores them; fp64 arithmetic, identical results"},
             "gpu_launches": int(launches_per_step * args.steps + e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": kernel_traffic(n_waters, B), "kernel": "wol::q3b_tpc_kernel",

@@ -561,12 +561,10 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
     const uint32_t n_items = P.counters[P.list_counter];
     if (CAP == kBigCap && P.counters[kCntOverflow] == 0u) return;  // nothing overflowed: no list to redo
     const uint32_t warps_total = gridDim.x * (kBigThreads / 32);
-    for (uint32_t it = blockIdx.x * (kBigThreads / 32) + warp; it < n_items; it += warps_total) {
+    auto process = [&](uint32_t e) {
         st.reset();
-        const uint32_t e = P.list[it];
         const uint32_t id = e & kFbIdMask;
         const bool do3 = (e & kFbNeed3b) != 0, doq = (e & kFbNeedQ) != 0;
-        if (do3 != (CAP == kBigCap)) continue;
         T rx, ry, rz;
         size_t out_index;
         int f;
@@ -587,6 +585,27 @@ __global__ void __launch_bounds__(kBigThreads) q3b_big_kernel(const __grid_const
         // a centre queued only for q already failed at half-width 1; an overflowed one starts over
         worker.run(true, f, rx, ry, rz, cx, cy, cz, out_index, do3, doq, do3 ? 1 : P.list_w_start, id, nullptr, P.table, st);
         flush_stats(P, f, st);
+    };
+    if (CAP == kBigCap) {
+        // overflowed centres are rare entries of a queue that is mostly q-only work: the lanes read 32 entries at a
+        // time and the warp handles the matches one by one (a dependent load per entry would cost ~0.5 us each)
+        const int lane = threadIdx.x & 31;
+        for (uint32_t base = (blockIdx.x * (kBigThreads / 32) + warp) * 32u; base < n_items; base += warps_total * 32u) {
+            const uint32_t it = base + lane;
+            const uint32_t e_l = it < n_items ? P.list[it] : 0u;
+            unsigned m = __ballot_sync(kFullMask, it < n_items && (e_l & kFbNeed3b) != 0u);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                process(__shfl_sync(kFullMask, e_l, src));
+            }
+        }
+    } else {
+        for (uint32_t it = blockIdx.x * (kBigThreads / 32) + warp; it < n_items; it += warps_total) {
+            const uint32_t e = P.list[it];
+            if ((e & kFbNeed3b) != 0u) continue;
+            process(e);
+        }
     }
 }
 

@@ -178,8 +178,8 @@ int wol_q3b_frames(const wol_q3b_args *args, void *stream);
  *   status_host[2]  non-zero: a neighbour list overflowed even the large-capacity path -> results invalid;
  *                   this one is sticky across evaluations on the workspace and cleared by this call
  *   status_host[3]  reserved
- * Returns WOL_ERR_CAPACITY when status_host[2] != 0.  A fresh workspace must be zero-filled by the caller.  The
- * counters live in the first 256 bytes of the workspace whatever the batch shape, so one workspace can serve batches
+ * Returns WOL_ERR_CAPACITY when status_host[2] != 0.  The first 256 bytes of a fresh workspace must be zero (the rest
+ * may hold anything).  The counters live in those first 256 bytes of the workspace whatever the batch shape, so one workspace can serve batches
  * of different sizes (a shorter last batch) without the flag moving.
  */
 int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3],

@@ -145,6 +145,28 @@ def test_one_workspace_across_batch_shapes():
     engine.q3b_frames(small, sbox, workspace=ws)          # and is cleared by having been read
 
 
+def test_workspace_needs_only_zero_counters():
+    """Only the first 256 bytes of a workspace (the counters) must start at zero: everything behind them is rebuilt by
+    every call, so a buffer full of stale bytes gives the same answers on every path (fast sweep, widened search,
+    overflow pass, H-bonds)."""
+    dev = torch.device("cuda")
+    pos, box = synth.trajectory(5, 3, sigma=0.6, seed0=21)   # liquid-like: widened centres and some list overflows
+    ref = engine.q3b_frames(pos, box)
+    ws = engine.Workspace(dev)
+    engine.q3b_frames(pos, box, workspace=ws)
+    ws.buf[512:].fill_(0xAB)
+    r = engine.q3b_frames(pos, box, workspace=ws)
+    assert torch.equal(r.q, ref.q) and torch.equal(r.nn_idx, ref.nn_idx) and torch.equal(r.ang_hist, ref.ang_hist)
+    assert r["n_widened"] == ref["n_widened"] > 0
+    ws.buf[512:].fill_(0xFF)
+    hyd = synth.add_hydrogens(pos[0], seed=4)
+    don = np.repeat(pos[0], 2, axis=0)
+    cells = routines.CellList(don, box[0], 3.5, workspace=ws)
+    hb_poisoned = routines.hbond_counts(pos[0], don, hyd, box[0], 3.5, 120.0, cells=cells)
+    hb = routines.hbond_counts(pos[0], don, hyd, box[0], 3.5, 120.0)
+    assert torch.equal(hb_poisoned["acc_count"], hb["acc_count"]) and torch.equal(hb_poisoned["don_count"], hb["don_count"])
+
+
 def test_ragged_centres_batched_with_reused_cells():
     """n_valid: frame f evaluates only its first n_valid[f] centres; the cell list of a previous call on the same batch
     is reused.  Per-frame outputs must equal the oracle's on exactly the valid centres; padded slots stay untouched."""

@@ -102,7 +102,8 @@ class Workspace:
     def get(self, nbytes):
         if self.buf is None or self.buf.numel() < nbytes + 256:
             old = self.buf
-            self.buf = torch.zeros(int(nbytes) + 512, dtype=torch.uint8, device=self.device)
+            self.buf = torch.empty(int(nbytes) + 512, dtype=torch.uint8, device=self.device)
+            self.buf[:512].zero_()  # only the counters (first 256 bytes after alignment) must start at zero
             if old is not None:
                 # the device counters (first 256 bytes, incl. the sticky overflow flag) move with the workspace
                 o0, o1 = (-old.data_ptr()) % 256, (-self.buf.data_ptr()) % 256

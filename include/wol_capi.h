@@ -43,6 +43,7 @@ enum {
 };
 
 enum { WOL_F64 = 0, WOL_F32 = 1 };            /* storage dtype of a position array               */
+enum { WOL_SUM_I64 = 0, WOL_SUM_F64 = 1 };    /* element type of wol_hist_allreduce              */
 enum { WOL_PREC_FP64 = 0, WOL_PREC_FP32 = 1 }; /* arithmetic mode of the evaluation kernels       */
 
 /* Number of doubles per frame in `frame_stats` (see wol_q3b_args). */
@@ -414,6 +415,16 @@ int wol_psi(const void *centres, int32_t centre_dtype, const double *box, int32_
  * `changed`: one int32 of device scratch.  Synchronises the stream (the sweep count depends on the graph).
  */
 int wol_components(const int32_t *adj, int32_t n, int32_t *labels, int32_t *changed, void *stream);
+
+/*
+ * Multi-GPU combine for frame sharding (the reference has no parallel path at all,
+ * structureLibs/orderParam_lib.py:1312-1353 loops over frames in one process): in-place sum over the ranks of an NCCL
+ * communicator the CALLER owns of `count` int64 histogram bins (WOL_SUM_I64: angle, q, H-bond histograms -- integer
+ * sums, so the result is bit-identical for any number of ranks) or doubles (WOL_SUM_F64), enqueued on `stream`.
+ * nccl_comm is an ncclComm_t.  NCCL is looked up at run time in the host process (libnccl.so.2 already loaded, e.g. by
+ * torch, else the library search path): libwol.so does not link it.  WOL_ERR_UNSUPPORTED if none is found.
+ */
+int wol_hist_allreduce(void *nccl_comm, void *buf, size_t count, int32_t dtype, void *stream);
 
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);

@@ -52,5 +52,29 @@ if rank == 0:
     for n, want in ref_files.items():
         ok &= np.array_equal(np.loadtxt(n), want)
     print("dist_check world=%d: %s  <q>=%.6f  pTet=%.6f  HB/water=%.4f" % (world, "OK" if ok else "MISMATCH", got_q[0][0][0], got_3b[0][0][0], got_hb[0]))
+
+# the C-ABI combine over a communicator the host owns (what a native, non-torch host would do): same sums as NCCL via torch
+import ctypes  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "tools"))
+import raw_nccl  # noqa: E402
+from waterorderlib_b200._capi import lib  # noqa: E402
+nccl = raw_nccl.load()
+uid = raw_nccl.unique_id(nccl) if rank == 0 else raw_nccl.UniqueId()
+t = torch.tensor(list(bytes(uid)) if rank == 0 else [0] * 128, dtype=torch.uint8, device="cuda")
+dist.broadcast(t, 0)
+uid = raw_nccl.UniqueId.from_buffer_copy(bytes(t.cpu().tolist()))
+comm = raw_nccl.comm_init(nccl, uid, world, rank)
+hist = (torch.arange(1011, dtype=torch.int64, device="cuda") + rank) * 1_000_003
+via_torch = hist.clone()
+dist.all_reduce(via_torch)
+rc = lib().wol_hist_allreduce(comm, ctypes.c_void_p(hist.data_ptr()), hist.numel(), 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+ok2 = rc == 0 and torch.equal(hist, via_torch)
+nccl.ncclCommDestroy(comm)
+flag = torch.tensor([1 if ok2 else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("wol_hist_allreduce over a raw ncclComm_t, world=%d: %s" % (world, "OK" if flag.item() == 1 else "MISMATCH"))
+ok = ok and flag.item() == 1
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -249,3 +249,30 @@ def test_integration_md_ctypes_stub_runs(golden_dir):
     g = load(golden_dir, "cfg1_n512_liq")
     q, n3, hist = ns["q_and_three_body"](g["pos"], g["box"])
     assert np.allclose(q, g["q"], rtol=Q_RTOL, atol=1e-9) and np.array_equal(n3, g["n3"]) and np.array_equal(hist, g["hist"])
+
+
+def test_hist_allreduce_over_a_caller_owned_nccl_communicator():
+    """wol_hist_allreduce with a raw ncclComm_t (single rank here; scripts/dist_check.py covers two GPUs): the sum over
+    one rank is the input, in place, for int64 bins and for doubles; bad arguments are refused."""
+    import ctypes
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    import raw_nccl
+    from waterorderlib_b200._capi import lib
+    nccl = raw_nccl.load()
+    torch.cuda.set_device(0)
+    comm = raw_nccl.comm_init(nccl, raw_nccl.unique_id(nccl), 1, 0)
+    try:
+        hist = torch.arange(1011, dtype=torch.int64, device="cuda") * 3_000_000_007
+        rows = torch.linspace(-1.0, 1.0, 77, dtype=torch.float64, device="cuda")
+        h0, r0 = hist.clone(), rows.clone()
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert lib().wol_hist_allreduce(comm, ctypes.c_void_p(hist.data_ptr()), hist.numel(), 0, s) == 0
+        assert lib().wol_hist_allreduce(comm, ctypes.c_void_p(rows.data_ptr()), rows.numel(), 1, s) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(hist, h0) and torch.equal(rows, r0)
+        assert lib().wol_hist_allreduce(comm, None, 0, 0, s) == 0
+        assert lib().wol_hist_allreduce(None, ctypes.c_void_p(hist.data_ptr()), 4, 0, s) != 0
+        assert lib().wol_hist_allreduce(comm, ctypes.c_void_p(hist.data_ptr()), 4, 7, s) != 0
+    finally:
+        nccl.ncclCommDestroy(comm)

@@ -1,5 +1,6 @@
 // Entry points of libwol.so (see include/wol_capi.h): argument validation, error strings, the grid
 // plan, the angle-bin table and the launches.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -110,6 +111,39 @@ extern "C" {
 const char *wol_version(void) { return "waterorderlib_b200 0.1 (sm_100a)"; }
 const char *wol_last_error(void) { return g_error; }
 int wol_abi_version(void) { return WOL_ABI_VERSION; }
+// ---- multi-GPU combine (frames sharded over ranks) ------------------------------------------------------
+// NCCL is resolved at run time from the library the host process already uses (torch's, an MPI program's): libwol.so
+// itself links only the CUDA runtime.
+
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_fn)(int);
+
+static void *nccl_symbol(const char *name) {
+    static const char *const kNames[] = {"libnccl.so.2", "libnccl.so"};
+    for (int pass = 0; pass < 2; ++pass)      // first a library that is already loaded, then the default search path
+        for (const char *lib : kNames) {
+            void *h = dlopen(lib, pass == 0 ? (RTLD_NOW | RTLD_NOLOAD) : (RTLD_NOW | RTLD_GLOBAL));
+            if (!h) continue;
+            if (void *sym = dlsym(h, name)) return sym;
+        }
+    return dlsym(RTLD_DEFAULT, name);         // statically linked into the host, or loaded under another name
+}
+
+int wol_hist_allreduce(void *nccl_comm, void *buf, size_t count, int32_t dtype, void *stream) {
+    if (!nccl_comm || (!buf && count > 0)) return set_error(WOL_ERR_INVALID, "wol_hist_allreduce: null argument");
+    if (dtype != WOL_SUM_I64 && dtype != WOL_SUM_F64) return set_error(WOL_ERR_INVALID, "wol_hist_allreduce: unknown dtype %d", dtype);
+    if (count == 0) return WOL_OK;
+    static nccl_allreduce_fn allreduce = reinterpret_cast<nccl_allreduce_fn>(nccl_symbol("ncclAllReduce"));
+    if (!allreduce) return set_error(WOL_ERR_UNSUPPORTED, "wol_hist_allreduce: no NCCL library (libnccl.so.2) in this process or on the search path");
+    // ncclDataType_t: ncclInt64 = 4, ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0 (stable across NCCL 2.x)
+    const int rc = allreduce(buf, buf, count, dtype == WOL_SUM_I64 ? 4 : 8, 0, nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) {
+        static nccl_errstr_fn errstr = reinterpret_cast<nccl_errstr_fn>(nccl_symbol("ncclGetErrorString"));
+        return set_error(WOL_ERR_CUDA, "ncclAllReduce failed: %s", errstr ? errstr(rc) : "unknown NCCL error");
+    }
+    return WOL_OK;
+}
+
 int wol_last_launch_count(void) { return g_launches; }
 
 int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3], double *edge_min_out,

@@ -211,6 +211,23 @@ int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box
                     size_t workspace_bytes, const uint32_t *offsets, double *angles, void *stream);
 
 /*
+ * Neighbour lists in CSR form: what allNearNeighbors / nearNeighbors (fortran/waterlib.f90:830-862, :710-743) mark in
+ * their dense N x N / M x N logical matrices, for sizes where that matrix cannot exist (3.6 TiB at 10^6 waters).
+ * For centre g = f * n_centres + i its neighbours j with lowcut^2 < r^2 <= highcut^2 (minimum image) are
+ * indices[offsets[g] .. offsets[g + 1]), frame-local atom indices in ASCENDING order (the order of the reference's
+ * boolean-mask gathers, structureLibs/water_properties.py:243,372).
+ *   workspace : cell list of wol_cell_build(FP64) over pos with r_cell >= highcut
+ *   offsets   : [n_frames * n_centres + 1] uint32; offsets[last] = number of pairs
+ *   scratch   : at least (n_frames * n_centres / 2048 + 2) uint32
+ *   indices   : [capacity] int32; a centre whose segment ends beyond capacity is not written (call with capacity 0
+ *               and indices NULL to get the offsets only, read offsets[last], allocate, call again)
+ */
+int wol_neighbors_csr(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos,
+                      int32_t n_centres, const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace,
+                      size_t workspace_bytes, uint32_t *offsets, uint32_t *scratch, int32_t *indices, int64_t capacity,
+                      void *stream);
+
+/*
  * np.histogram(x, bins=nbins, range=[lo, hi]) counts (ACCUMULATED into hist) plus the sums
  * tetrahedralMetrics takes over the window tet_lo <= x <= tet_hi (water_properties.py:328-335):
  * tet_sums[0] += count, [1] += sum cos(x pi/180), [2] += sum cos^2.  tet_sums may be NULL.

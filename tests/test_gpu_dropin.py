@@ -276,3 +276,53 @@ def test_hist_allreduce_over_a_caller_owned_nccl_communicator():
         assert lib().wol_hist_allreduce(comm, ctypes.c_void_p(hist.data_ptr()), 4, 7, s) != 0
     finally:
         nccl.ncclCommDestroy(comm)
+
+
+def _csr_from_dense(mat):
+    off = np.concatenate([[0], np.cumsum(mat.sum(axis=1))])
+    return off, np.nonzero(mat)[1].astype(np.int32)
+
+
+def test_neighbors_csr_matches_dense_reference_matrices():
+    """wol_neighbors_csr against the dense matrices of allNearNeighbors / nearNeighbors (oracle restatement, pinned on
+    the compiled Fortran): same pairs, ascending atom index within a centre; several frames, sub-populations, float32
+    centres, cut-offs from 3.4 to 10 A, boxes below four cells per edge, empty inputs."""
+    pos, box = synth.water_box(4, sigma=0.4, seed=12)
+    for low, high in ((0.0, 3.413), (0.0, 10.0), (2.8, 5.5)):
+        off, idx = routines.neighbors_csr(None, pos, box, low, high)
+        ro, ri = _csr_from_dense(port.neighbor_matrix(pos, pos, box, low, high))
+        assert np.array_equal(off.cpu().numpy(), ro) and np.array_equal(idx.cpu().numpy(), ri)
+    rng = np.random.default_rng(5)
+    sub = (rng.random((37, 3)) * box).astype(np.float32)
+    off, idx = routines.neighbors_csr(torch.from_numpy(sub).cuda(), pos, box, 0.0, 4.0)
+    ro, ri = _csr_from_dense(port.neighbor_matrix(sub.astype(np.float64), pos, box, 0.0, 4.0))
+    assert np.array_equal(off.cpu().numpy(), ro) and np.array_equal(idx.cpu().numpy(), ri)
+    xyz, boxes = synth.trajectory(3, 4, sigma=0.5, seed0=8)     # 216 waters: three cells per edge at 6 A
+    off, idx = routines.neighbors_csr(None, xyz, boxes, 0.0, 6.0)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    n = xyz.shape[1]
+    for f in range(4):
+        ro, ri = _csr_from_dense(port.neighbor_matrix(xyz[f], xyz[f], boxes[f], 0.0, 6.0))
+        seg = off[f * n:(f + 1) * n + 1]
+        assert np.array_equal(seg - seg[0], ro) and np.array_equal(idx[seg[0]:seg[-1]], ri)
+    off, idx = routines.neighbors_csr(np.zeros((0, 3)), pos, box, 0.0, 3.5)
+    assert off.tolist() == [0] and idx.numel() == 0
+
+
+def test_neighbors_csr_large_counts_agree_with_the_fused_sweep():
+    pos, box = synth.water_box(30, sigma=0.3, seed=2)            # 216 000 waters
+    off, idx = routines.neighbors_csr(None, pos, box, 0.0, 3.413)
+    r = engine_q3b(pos, box)
+    counts = (off[1:] - off[:-1]).to(torch.int32)
+    assert torch.equal(counts, r["n3"][0]) and int(off[-1]) == idx.numel()
+    seg = torch.repeat_interleave(torch.arange(counts.numel(), device=idx.device), counts.to(torch.int64))
+    i = idx.to(torch.int64)
+    assert bool(((i[1:] > i[:-1]) | (seg[1:] != seg[:-1])).all())   # ascending atom index inside every segment
+    for c in (0, 777, 215_999):                                  # a few centres against the oracle's dense row
+        row = port.neighbor_matrix(pos[c:c + 1], pos, box, 0.0, 3.413)[0]
+        assert np.array_equal(idx[off[c]:off[c + 1]].cpu().numpy(), np.nonzero(row)[0])
+
+
+def engine_q3b(pos, box):
+    from waterorderlib_b200 import engine
+    return engine.q3b_frames(pos, box, do_q=False, want=("n3",))

@@ -120,6 +120,37 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
     return angles, n3, offsets.to(torch.int64) & 0xFFFFFFFF
 
 
+def neighbors_csr(sub, pos, box, low=0.0, high=3.413, device=None):
+    """Neighbour lists of allNearNeighbors (sub is None) / nearNeighbors (fortran/waterlib.f90:830-862, :710-743) in CSR
+    form instead of the dense logical matrix: returns (offsets int64 (F*M+1,), indices int32 (n_pairs,)); the neighbours
+    of centre i of frame f are indices[offsets[f*M+i]:offsets[f*M+i+1]], frame-local atom indices, ascending."""
+    device = _device(device, pos, sub)
+    cells = CellList(pos, box, max(float(high), 1e-3), device=device,
+                     n_centres_max=0 if sub is None else int(np.shape(sub)[-2]))
+    cen_d = cells.pos if sub is None else engine.as_device_positions(sub, device)
+    if cen_d.shape[0] != cells.F:
+        raise ValueError("sub and pos must hold the same number of frames")
+    F, N, M = cells.F, cells.N, int(cen_d.shape[1])
+    total = F * M
+    offsets = torch.zeros(total + 1, dtype=torch.int32, device=device)
+    if total == 0 or N == 0:
+        return offsets.to(torch.int64), torch.zeros(0, dtype=torch.int32, device=device)
+    scratch = torch.empty(total // 2048 + 8, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        def run(indices, cap):
+            check(lib().wol_neighbors_csr(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
+                                          ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr),
+                                          cells.ws_bytes, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()),
+                                          _vp(indices.data_ptr()) if indices is not None else None, cap, _stream()), "wol_neighbors_csr")
+        run(None, 0)
+        n_pairs = int(offsets[-1].item()) & 0xFFFFFFFF  # sizes the output: one host read
+        indices = torch.empty(n_pairs, dtype=torch.int32, device=device)
+        if n_pairs:
+            run(indices, n_pairs)
+        torch.cuda.current_stream().synchronize()  # the cell list dies with this call
+    return offsets.to(torch.int64) & 0xFFFFFFFF, indices
+
+
 def histogram(x, nbins=500, bin_range=(0.0, 180.0), tet_window=(100.0, 120.0), device=None):
     """np.histogram(x, bins=nbins, range=bin_range) counts (int64 CUDA tensor) and the
     (count, sum cos, sum cos^2) of tetrahedralMetrics' window (water_properties.py:328-335)."""

@@ -69,3 +69,19 @@ def test_pipeline_timeline_trace():
     tl = pipe.timeline()
     assert tl.shape == (3, 6) and np.all(tl[:, 1] >= tl[:, 0]) and np.all(tl[:, 3] >= tl[:, 2]) and np.all(tl[:, 5] >= tl[:, 4])
     assert np.all(tl[:, 2] >= tl[:, 1] - 1e-3) and np.all(tl[:, 4] >= tl[:, 3] - 1e-3)  # copy-in -> kernels -> copy-out per batch
+
+
+def test_pipeline_fp32_arithmetic_mode():
+    """precision="fp32" through the pipeline: float results identical to the device-resident fp32 call, and within the
+    1e-4 bar of the fp64 oracle wherever both modes picked the same four neighbours."""
+    xyz, boxes = frames(5)
+    F, N = xyz.shape[:2]
+    dev = engine.q3b_frames(torch.from_numpy(xyz).cuda(), boxes, precision="fp32")
+    pipe = FramePipeline(N, 2, dtype=np.float32, precision="fp32", want_nn=True)
+    r = pipe.run(torch.from_numpy(xyz.astype(np.float32)).pin_memory(), boxes)
+    torch.cuda.synchronize()
+    assert r["q"].dtype == torch.float32 and torch.equal(r["q"], dev["q"].cpu()) and torch.equal(r["nn_idx"], dev["nn_idx"].cpu())
+    assert torch.equal(r["ang_hist"], dev["ang_hist"].cpu()) and torch.equal(r["n3"], dev["n3"].cpu())
+    q64, nn64, _ = port.order_param_q(xyz[0], xyz[0], boxes[0], 0.0, 10.0)
+    same = np.all(r["nn_idx"][0].numpy() == nn64, axis=1)
+    assert same.mean() > 0.99 and np.max(np.abs(r["q"][0].numpy()[same] - q64[same])) < 1e-4

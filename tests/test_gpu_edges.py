@@ -193,3 +193,34 @@ def test_ragged_centres_batched_with_reused_cells():
         assert r.frame_stats[f, 2].item() == c
     with pytest.raises(ValueError):
         engine.q3b_frames(pos, box, cen, reuse_cells=True, workspace=engine.Workspace(torch.device("cuda")))
+
+
+def test_reentrant_from_several_host_threads():
+    """The library keeps no global state beyond thread-local error / launch bookkeeping: host threads working on their
+    own streams and workspaces at the same time get the answers of a serial run (ctypes releases the GIL in the calls)."""
+    import threading
+    cases = [synth.water_box(m, sigma=s, seed=k) for k, (m, s) in enumerate(((5, 0.3), (6, 0.5), (4, 0.6), (7, 0.25)))]
+    serial = [engine.q3b_frames(p, b) for p, b in cases]
+    got, errors = [None] * len(cases), []
+
+    def work(k):
+        try:
+            stream = torch.cuda.Stream()
+            ws = engine.Workspace(torch.device("cuda"))
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    r = engine.q3b_frames(cases[k][0], cases[k][1], workspace=ws)
+                stream.synchronize()
+            got[k] = r
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for r, s in zip(got, serial):
+        assert torch.equal(r.q, s.q) and torch.equal(r.nn_idx, s.nn_idx) and torch.equal(r.ang_hist, s.ang_hist)
+        assert torch.equal(r.n3, s.n3)

@@ -224,3 +224,29 @@ def test_reentrant_from_several_host_threads():
     for r, s in zip(got, serial):
         assert torch.equal(r.q, s.q) and torch.equal(r.nn_idx, s.nn_idx) and torch.equal(r.ang_hist, s.ang_hist)
         assert torch.equal(r.n3, s.n3)
+
+
+def test_generic_kernels_agree_with_the_fast_path_at_size(monkeypatch):
+    """The group-per-centre kernels normally serve only boxes below four cells per edge; forced on a larger liquid-like
+    box (WOL_NO_TPC, read per call) they must reproduce the thread-per-centre path: same neighbours, counts and angle bins, q to rounding (fp64); within the fp32 bar in float mode."""
+    pos, box = synth.trajectory(9, 2, sigma=0.6, seed0=31)     # 5832 waters per frame, widened and overflowing centres
+    sub = pos[:, ::7]
+    for prec in ("fp64", "fp32"):
+        fast = engine.q3b_frames(pos, box, precision=prec)
+        fast_sub = engine.q3b_frames(pos, box, sub, precision=prec, highq=7.0)
+        monkeypatch.setenv("WOL_NO_TPC", "1")
+        slow = engine.q3b_frames(pos, box, precision=prec)
+        slow_sub = engine.q3b_frames(pos, box, sub, precision=prec, highq=7.0)
+        monkeypatch.delenv("WOL_NO_TPC")
+        for a, b in ((fast, slow), (fast_sub, slow_sub)):
+            if prec == "fp64":
+                assert torch.equal(a.nn_idx, b.nn_idx) and torch.equal(a.n3, b.n3) and torch.equal(a.ang_hist, b.ang_hist)
+                d = (a.q - b.q).abs().max().item()
+                assert d < 1e-12, d
+                assert (a.q_hist - b.q_hist).abs().sum().item() <= 2
+            else:
+                # float arithmetic in a different order (wrapped vs raw coordinates): decisions agree except on the boundary
+                same = (a.nn_idx == b.nn_idx).all(dim=-1)
+                assert same.double().mean().item() > 0.999 and (a.n3 == b.n3).double().mean().item() > 0.999
+                assert torch.allclose(a.q[same], b.q[same], rtol=0, atol=1e-4)
+                assert (a.ang_hist - b.ang_hist).abs().sum().item() < 2e-3 * a.ang_hist.sum().item()

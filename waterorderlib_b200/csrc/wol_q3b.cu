@@ -769,6 +769,8 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     P.list2 = P.fb_list + lay.n_centres_total;
     P.list_counter = kCntFallback;
     P.list_w_start = 2;
+    // WOL_NO_TPC / WOL_NO_TPC32 (environment, read per call): route to the generic group-per-centre kernels that
+    // otherwise only serve boxes below four cells per edge -- a test switch (tests/test_gpu_edges.py), not a tuning knob
     const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
     if (a.precision == WOL_PREC_FP64)
         return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);

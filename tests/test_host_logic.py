@@ -190,3 +190,33 @@ def test_legacy_simps_and_trajectory_slices(tmp_path):
     nc.close()
     with pytest.raises(TypeError):
         t["a"]
+
+
+def test_product_never_touches_the_oracle_and_has_no_cpu_fallback():
+    """The oracle is test infrastructure: nothing under waterorderlib_b200/ may import it (only tests/, smoke() and
+    bench.py's CPU legs do), and without a CUDA device the product path raises instead of computing on the CPU."""
+    import ast
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parents[1]
+    offenders = []
+    for path in (root / "waterorderlib_b200").rglob("*.py"):
+        for node in ast.walk(ast.parse(path.read_text())):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                offenders.append(str(path))
+    assert not offenders
+    for path in (root / "waterorderlib_b200" / "csrc").glob("*"):
+        assert "oracle" not in path.read_text(), path          # the kernels do not include or link it either
+    import torch
+    if not torch.cuda.is_available():
+        from waterorderlib_b200 import synth
+        from waterorderlib_b200.structureLibs import water_properties as wp
+        pos, box = synth.water_box(3, sigma=0.3, seed=1)
+        with pytest.raises(Exception):
+            wp.getOrderParamq(pos, pos, box)
+        with pytest.raises(Exception):
+            wp.getCosAngs(pos, pos, box)

@@ -434,6 +434,26 @@ int wol_psi(const void *centres, int32_t centre_dtype, const double *box, int32_
 int wol_components(const int32_t *adj, int32_t n, int32_t *labels, int32_t *changed, void *stream);
 
 /*
+ * watOrient (fortran/waterlib.f90:973-1011; called at structureLibs/water_properties.py:605,636): per water the angle
+ * in degrees (AngBetween, :954-965) between refvec and the dipole direction (sum of the two minimum-imaged O->H
+ * vectors, imaged once more) and between refvec and the normal of the molecular plane (cross product of the O->H vectors).
+ * opos [n_frames][n_waters][3], hpos [n_frames][2 n_waters][3] (H1, H2 of water i at rows 2i, 2i+1), box [n_frames][3]:
+ * device, fp64.  refvec_host: 3 doubles on the HOST (normalised here like the Fortran does).  Out: [n_frames][n_waters].
+ */
+int wol_water_orient(const double *opos, const double *hpos, const double *box, int32_t n_frames, int32_t n_waters,
+                     const double refvec_host[3], double *angdip, double *angplane, void *stream);
+
+/*
+ * binOnGrid (fortran/waterlib.f90:1047-1099; called at structureLibs/water_properties.py:668): number of atoms in every
+ * cubic bin of the grid (left edge inclusive, atoms outside the grid ignored, no periodic wrap), counting only those inside
+ * the sphere of diameter binwidth centred in the bin.  x/y/zbins: bin EDGES on the device (nx, ny, nz of them, uniform
+ * spacing binwidth = xbins[1] - xbins[0] passed by the caller, who also checks that the bins are cubes -- the Fortran
+ * STOPs otherwise).  outhist [nx-1][ny-1][nz-1] int32 row-major, overwritten.
+ */
+int wol_bin_on_grid(const double *opos, int64_t n, const double *xbins, const double *ybins, const double *zbins, int32_t nx, int32_t ny,
+                    int32_t nz, double binwidth, int32_t *outhist, void *stream);
+
+/*
  * Multi-GPU combine for frame sharding (the reference has no parallel path at all,
  * structureLibs/orderParam_lib.py:1312-1353 loops over frames in one process): in-place sum over the ranks of an NCCL
  * communicator the CALLER owns of `count` int64 histogram bins (WOL_SUM_I64: angle, q, H-bond histograms -- integer

@@ -6,11 +6,14 @@
  * there is no Fortran compiler, so the oracle loads the reference binary on top of this stub.  The
  * routines on the water-structure hot path (allnearneighbors_, nearneighbors_, reimage_,
  * tetracosang_, cosangle3_, generalhbonds_, lsidists_, histrr3b_, interfacewater_) never reach a
- * libgfortran entry point except through Fortran `stop` / `print`, so I/O entries are no-ops and
- * everything else aborts loudly.
+ * libgfortran entry point except through Fortran `stop` / `print`, so I/O entries are no-ops; the array
+ * (un)packing helpers are implemented (watorient_ passes strided sections through them) and everything else
+ * aborts loudly.
  */
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define WOL_NOOP(name) void name(void *a) { (void)a; }
 #define WOL_FATAL(name) \
@@ -24,8 +27,60 @@ void _gfortran_transfer_real_write(void *a, void *b, int c) { (void)a; (void)b; 
 
 WOL_FATAL(_gfortran_stop_string)
 WOL_FATAL(_gfortran_stop_numeric_f08)
-WOL_FATAL(_gfortran_internal_pack)
-WOL_FATAL(_gfortran_internal_unpack)
+
+/* Array descriptor of GCC 5's libgfortran ABI (the reference binary was built with GCC 5.4): strides in elements,
+ * rank in the low 3 bits of dtype, element size in dtype >> 6.  internal_pack hands an explicit-shape dummy a
+ * contiguous copy of a strided section (or the section itself when it already is contiguous); internal_unpack copies
+ * the values back.  The caller frees the copy.  Reached from watorient_ (fortran/waterlib.f90:973-1011). */
+typedef struct { ptrdiff_t stride, lbound, ubound; } wol_dim_t;
+typedef struct { char *base_addr; size_t offset; ptrdiff_t dtype; wol_dim_t dim[7]; } wol_desc_t;
+
+static ptrdiff_t wol_desc_walk(const wol_desc_t *d, char *packed, int to_packed) {
+    const int rank = (int)(d->dtype & 7);
+    const ptrdiff_t size = d->dtype >> 6;
+    ptrdiff_t extent[7], idx[7], total = 1;
+    for (int n = 0; n < rank; ++n) {
+        extent[n] = d->dim[n].ubound - d->dim[n].lbound + 1;
+        if (extent[n] <= 0) return 0;
+        total *= extent[n];
+        idx[n] = 0;
+    }
+    if (!packed) return total;
+    for (ptrdiff_t k = 0; k < total; ++k) {
+        ptrdiff_t off = 0;
+        for (int n = 0; n < rank; ++n) off += idx[n] * d->dim[n].stride;
+        if (to_packed) memcpy(packed + k * size, d->base_addr + off * size, (size_t)size);
+        else memcpy(d->base_addr + off * size, packed + k * size, (size_t)size);
+        for (int n = 0; n < rank; ++n) {
+            if (++idx[n] < extent[n]) break;
+            idx[n] = 0;
+        }
+    }
+    return total;
+}
+
+void *_gfortran_internal_pack(wol_desc_t *d) {
+    const int rank = (int)(d->dtype & 7);
+    ptrdiff_t expect = 1;
+    int contiguous = 1;
+    for (int n = 0; n < rank; ++n) {
+        const ptrdiff_t extent = d->dim[n].ubound - d->dim[n].lbound + 1;
+        if (extent <= 0) return d->base_addr;
+        if (d->dim[n].stride != expect) contiguous = 0;
+        expect *= extent;
+    }
+    if (contiguous) return d->base_addr;
+    char *packed = malloc((size_t)(expect * (d->dtype >> 6)));
+    if (!packed) { fprintf(stderr, "oracle gfortran stub: out of memory in internal_pack\n"); abort(); }
+    wol_desc_walk(d, packed, 1);
+    return packed;
+}
+
+void _gfortran_internal_unpack(wol_desc_t *d, const void *src) {
+    if (!src || src == (const void *)d->base_addr) return;
+    wol_desc_walk(d, (char *)src, 0);
+}
+
 WOL_FATAL(_gfortran_matmul_r8)
 WOL_FATAL(_gfortran_random_r4)
 WOL_FATAL(_gfortran_random_seed_i4)

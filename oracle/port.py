@@ -325,3 +325,26 @@ def iso_points(dens, gridx, gridy, gridz, level):
     pts = np.concatenate(pts)
     order = np.argsort(keys, kind="stable")
     return pts[order]
+
+
+def watorient(opos, hpos, refvec, boxl):
+    """watOrient (fortran/waterlib.f90:973-1011) -> (angDip, angPlane) in degrees, one per water."""
+    o, h, box = _pos(opos), _pos(hpos), _box(boxl)
+    if h.shape[0] != 2 * o.shape[0]:
+        raise ValueError("Number of hydrogens must be two times number of oxygens.")
+    ref = _c(np.asarray(refvec, dtype=np.float64).reshape(-1))
+    a, b = np.zeros(o.shape[0]), np.zeros(o.shape[0])
+    _lib().wol_oracle_watorient(_ptr(o, _dp), o.shape[0], _ptr(h, _dp), _ptr(ref, _dp), _ptr(box, _dp), _ptr(a, _dp), _ptr(b, _dp))
+    return a, b
+
+
+def binongrid(opos, xbins, ybins, zbins):
+    """binOnGrid (fortran/waterlib.f90:1047-1099) -> int32 (nx-1, ny-1, nz-1)."""
+    o = _pos(opos)
+    xb, yb, zb = (_c(np.asarray(g, dtype=np.float64).reshape(-1)) for g in (xbins, ybins, zbins))
+    out = np.zeros((xb.size - 1, yb.size - 1, zb.size - 1), dtype=np.int32)
+    rc = _lib().wol_oracle_binongrid(_ptr(o, _dp), o.shape[0], _ptr(xb, _dp), xb.size, _ptr(yb, _dp), yb.size, _ptr(zb, _dp), zb.size,
+                                     _ptr(out, _ip))
+    if rc != 0:
+        raise ValueError("Must break volume into CUBES. Currently, bin-widths do not match.")
+    return out

@@ -260,6 +260,31 @@ class RefWaterlib:
         return watclose, surfclose, int(numwater.value), allwatdists
 
 
+    # fortran/waterlib.f90:973-1011
+    def watorient(self, opos, hpos, refvec, boxl):
+        opos, hpos = _f64(opos), _f64(hpos)
+        no, nh = opos.shape[0], hpos.shape[0]
+        if nh != 2 * no:
+            raise ValueError("Number of hydrogens must be two times number of oxygens.")  # the Fortran STOPs here
+        ref = np.ascontiguousarray(np.asarray(refvec, dtype=np.float64).reshape(-1))
+        angdip, angplane = np.zeros(no), np.zeros(no)
+        self._lib.watorient_(_dp(opos), _dp(hpos), _dp(ref), _dp(_box(boxl)), _dp(angdip), _dp(angplane),
+                             ctypes.byref(ctypes.c_int32(no)), ctypes.byref(ctypes.c_int32(nh)))
+        return angdip, angplane
+
+    # fortran/waterlib.f90:1047-1099
+    def binongrid(self, opos, xbins, ybins, zbins):
+        opos = _f64(opos)
+        xb, yb, zb = (np.ascontiguousarray(np.asarray(g, dtype=np.float64).reshape(-1)) for g in (xbins, ybins, zbins))
+        if (yb[1] - yb[0]) != (xb[1] - xb[0]) or (zb[1] - zb[0]) != (xb[1] - xb[0]):
+            raise ValueError("Must break volume into CUBES. Currently, bin-widths do not match.")  # the Fortran STOPs here
+        out = np.zeros((xb.size - 1, yb.size - 1, zb.size - 1), dtype=np.int32, order="F")
+        self._lib.binongrid_(_dp(opos), _dp(xb), _dp(yb), _dp(zb), _ip(out), ctypes.byref(ctypes.c_int32(opos.shape[0])),
+                             ctypes.byref(ctypes.c_int32(xb.size)), ctypes.byref(ctypes.c_int32(yb.size)),
+                             ctypes.byref(ctypes.c_int32(zb.size)))
+        return out
+
+
 _WP_FUNCS = ("getCosAngs", "getOrderParamq", "tetrahedralMetrics", "getLSI", "HBondsGeneral", "getOrderParamPsi")
 
 

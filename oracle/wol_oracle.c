@@ -748,3 +748,52 @@ int wol_oracle_density_field(const double *pos, int n, const double *gx, int nx,
             }
     return 0;
 }
+
+/* watOrient (fortran/waterlib.f90:973-1011): per water the angles (degrees, AngBetween) between refvec and the dipole
+ * direction (sum of the two minimum-imaged O->H vectors, imaged once more) and between refvec and the normal of the
+ * molecular plane (cross product of the O->H vectors). hpos holds H1, H2 of water i at rows 2i, 2i+1. */
+int wol_oracle_watorient(const double *opos, int no, const double *hpos, const double *refvec, const double *boxl, double *angdip,
+                         double *angplane) {
+    box_t b;
+    box_init(&b, boxl);
+    const double rn = sqrt((refvec[0] * refvec[0] + refvec[1] * refvec[1]) + refvec[2] * refvec[2]);
+    const double ref[3] = {refvec[0] / rn, refvec[1] / rn, refvec[2] / rn};
+    for (int i = 0; i < no; ++i) {
+        double v1[3], v2[3], dip[3], pl[3], u[3];
+        min_image(&b, hpos + 3 * (size_t)(2 * i), opos + 3 * (size_t)i, v1);
+        min_image(&b, hpos + 3 * (size_t)(2 * i + 1), opos + 3 * (size_t)i, v2);
+        for (int k = 0; k < 3; ++k) {
+            const double t = v1[k] + v2[k];
+            dip[k] = t - b.L[k] * round(t * b.iL[k]);
+        }
+        double n = sqrt(sumsq(dip));
+        for (int k = 0; k < 3; ++k) u[k] = dip[k] / n;
+        angdip[i] = ang_between(u, ref);
+        pl[0] = v1[1] * v2[2] - v1[2] * v2[1]; /* crossProd3, waterlib.f90:26-28 */
+        pl[1] = v1[2] * v2[0] - v1[0] * v2[2];
+        pl[2] = v1[0] * v2[1] - v1[1] * v2[0];
+        n = sqrt(sumsq(pl));
+        for (int k = 0; k < 3; ++k) u[k] = pl[k] / n;
+        angplane[i] = ang_between(u, ref);
+    }
+    return 0;
+}
+
+/* binOnGrid (fortran/waterlib.f90:1047-1099): atoms per cubic bin (left edge inclusive), counted only inside the sphere
+ * of diameter binwidth centred in the bin; no periodic wrap. outhist [nx-1][ny-1][nz-1] row-major. */
+int wol_oracle_binongrid(const double *opos, int n, const double *xb, int nx, const double *yb, int ny, const double *zb, int nz,
+                         int32_t *outhist) {
+    const double binwidth = xb[1] - xb[0];
+    if (yb[1] - yb[0] != binwidth || zb[1] - zb[0] != binwidth) return -1;
+    const double radsq = binwidth * binwidth / 4.0;
+    for (size_t i = 0; i < (size_t)(nx - 1) * (ny - 1) * (nz - 1); ++i) outhist[i] = 0;
+    for (int i = 0; i < n; ++i) {
+        const double *p = opos + 3 * (size_t)i;
+        const double fx = floor((p[0] - xb[0]) / binwidth), fy = floor((p[1] - yb[0]) / binwidth), fz = floor((p[2] - zb[0]) / binwidth);
+        if (!(fx >= 0 && fx < nx - 1) || !(fy >= 0 && fy < ny - 1) || !(fz >= 0 && fz < nz - 1)) continue;
+        const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+        const double v[3] = {p[0] - (xb[ix] + binwidth * 0.5), p[1] - (yb[iy] + binwidth * 0.5), p[2] - (zb[iz] + binwidth * 0.5)};
+        if (sumsq(v) <= radsq) outhist[((size_t)ix * (ny - 1) + iy) * (nz - 1) + iz] += 1;
+    }
+    return 0;
+}

@@ -161,6 +161,18 @@ def main():
                         hist=np.ascontiguousarray(h).astype(np.int64))
     print("histrr3b", int(h.sum()))
 
+    # watOrient / binOnGrid (waterlib.f90:973-1011, :1047-1099): water orientation angles and sphere-in-cube occupancy
+    o, box = synth.water_box(4, sigma=0.4, seed=3)
+    h = synth.add_hydrogens(o, seed=3)
+    h[::5] += box
+    refvec = np.array([1.0, 2.0, -0.5])
+    dip, plane = wl.watorient(o, h, refvec, box)
+    edges = np.arange(0.0, 24.0, 3.0)
+    occ = wl.binongrid(o, edges + 0.7, edges, edges - 1.0)
+    np.savez_compressed(os.path.join(OUT, "orient_n512.npz"), opos=o, hpos=h, box=box, refvec=refvec, angdip=dip, angplane=plane,
+                        xbins=edges + 0.7, ybins=edges, zbins=edges - 1.0, occupancy=np.ascontiguousarray(occ))
+    print("orient: <dip> %.3f <plane> %.3f, %d atoms inside spheres" % (dip.mean(), plane.mean(), int(occ.sum())))
+
 
 if __name__ == "__main__":
     main()

@@ -326,3 +326,37 @@ def test_neighbors_csr_large_counts_agree_with_the_fused_sweep():
 def engine_q3b(pos, box):
     from waterorderlib_b200 import engine
     return engine.q3b_frames(pos, box, do_q=False, want=("n3",))
+
+
+def test_water_orientation_and_sphere_occupancy(golden_dir):
+    """watorient / binongrid and their callers waterOrientation, waterOrientationBinZ, binnedVolumePofN
+    (reference water_properties.py:578-676): golden values from the reference's compiled Fortran, the oracle at a larger
+    size and over several frames.  Angles to 1e-12 degrees (device acos vs glibc's), occupancy counts exact."""
+    from waterorderlib_b200.structureLibs import water_properties as wp
+    from waterorderlib_b200.structureLibs import waterlib as wl
+    g = np.load(os.path.join(golden_dir, "orient_n512.npz"))
+    dip, plane = wl.watorient(g["opos"], g["hpos"], g["refvec"], g["box"])
+    assert np.allclose(dip, g["angdip"], rtol=0, atol=1e-12) and np.allclose(plane, g["angplane"], rtol=0, atol=1e-12)
+    occ = wl.binongrid(g["opos"], g["xbins"], g["ybins"], g["zbins"])
+    assert occ.dtype == np.int32 and np.array_equal(occ, g["occupancy"])
+    xyz, boxes = synth.trajectory(6, 3, sigma=0.5, seed0=60)
+    hyd = np.stack([synth.add_hydrogens(xyz[f], seed=60 + f) for f in range(3)])
+    d, p = routines.water_orient(xyz, hyd, boxes, (0.3, -1.0, 2.0))
+    for f in range(3):
+        rd, rp = port.watorient(xyz[f], hyd[f], (0.3, -1.0, 2.0), boxes[f])
+        assert np.allclose(d[f].cpu().numpy(), rd, rtol=0, atol=1e-12) and np.allclose(p[f].cpu().numpy(), rp, rtol=0, atol=1e-12)
+    da, pa = wp.waterOrientation(xyz[0], hyd[0], boxes[0])
+    rd, rp = port.watorient(xyz[0], hyd[0], (0.0, 0.0, 1.0), boxes[0])
+    assert isinstance(da, np.ndarray) and np.allclose(da, rd, atol=1e-12) and np.allclose(pa, rp, atol=1e-12)
+    plane2d, dip2d = wp.waterOrientationBinZ(xyz[0], hyd[0], boxes[0], angBins=np.arange(0.0, 180.001, 5.0))
+    z = xyz[0][:, 2]
+    want, _, _ = np.histogram2d(rd, z, bins=[np.arange(0.0, 180.001, 5.0), np.arange(z.min(), z.max(), 0.2)])
+    assert np.array_equal(dip2d, want) and plane2d.shape == want.shape and plane2d.sum() == dip2d.sum()
+    edges = np.linspace(0.0, boxes[0][0], 9)
+    pn = wp.binnedVolumePofN(xyz[0], (edges, edges, edges), np.arange(0, 12))
+    ref_occ = port.binongrid(xyz[0], edges, edges, edges)
+    assert np.array_equal(pn, np.histogram(ref_occ.flatten(), bins=np.arange(0, 12))[0]) and pn.sum() == 8 ** 3
+    with pytest.raises(ValueError):
+        wl.binongrid(xyz[0], edges, edges * 1.1, edges)
+    with pytest.raises(ValueError):
+        wl.watorient(xyz[0], hyd[0][:-1], (0, 0, 1.0), boxes[0])

@@ -146,3 +146,15 @@ def test_iso_points_properties():
     rr = np.linalg.norm(sph - 0.5, axis=1)
     assert len(sph) > 50 and np.all(rr <= 0.3 + 1e-12) and np.all(rr > 0.27)  # chords of a convex field lie inside
     assert port.iso_points(r, g, g, g, 5.0).shape == (0, 3)
+
+
+def test_watorient_and_binongrid_golden(golden_dir):
+    from oracle import port
+    g = np.load(os.path.join(golden_dir, "orient_n512.npz"))
+    dip, plane = port.watorient(g["opos"], g["hpos"], g["refvec"], g["box"])
+    assert np.array_equal(dip, g["angdip"]) and np.array_equal(plane, g["angplane"])
+    assert np.array_equal(port.binongrid(g["opos"], g["xbins"], g["ybins"], g["zbins"]), g["occupancy"])
+    with pytest.raises(ValueError):
+        port.binongrid(g["opos"], g["xbins"], g["ybins"] * 1.5, g["zbins"])
+    with pytest.raises(ValueError):
+        port.watorient(g["opos"], g["hpos"][:-1], g["refvec"], g["box"])

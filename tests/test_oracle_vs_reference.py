@@ -178,3 +178,19 @@ def test_density_field_matches_live(ref):
     gz = np.linspace(0.0, box[2], 15, endpoint=False)
     want = wl.densityfield(pos, gx, gy, gz, box)
     assert want.max() > 0 and np.array_equal(port.density_field(pos, gx, gy, gz, box), want)
+
+
+def test_watorient_and_binongrid_match_live(ref):
+    """watOrient (through the stub's internal_pack: the Fortran passes strided sections) and binOnGrid, bit for bit."""
+    wl, _ = ref
+    o, box = synth.water_box(4, sigma=0.4, seed=3)
+    h = synth.add_hydrogens(o, seed=3)
+    h[::5] += box          # some hydrogens stored in the neighbouring image: the minimum image must bring them back
+    for refvec in ([0.0, 0.0, 1.0], [1.0, 2.0, -0.5], [0.0, -3.0, 0.0]):
+        a, b = wl.watorient(o, h, refvec, box)
+        pa, pb = port.watorient(o, h, refvec, box)
+        assert np.array_equal(a, pa) and np.array_equal(b, pb) and a.min() >= 0.0 and a.max() <= 180.0
+    edges = np.arange(0.0, 24.0, 3.0)
+    for shift in (0.0, 0.7):
+        r = wl.binongrid(o, edges + shift, edges, edges - 1.0)
+        assert np.array_equal(np.ascontiguousarray(r), port.binongrid(o, edges + shift, edges, edges - 1.0)) and r.sum() > 50

@@ -75,6 +75,8 @@ SIGNATURES = {
     "wol_density_field": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f64, c_vp, c_i32, _NC, c_f64, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "wol_neighbors_csr": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, _NC, c_f64, c_f64, c_f64, c_vp, ctypes.c_size_t, c_vp, c_vp, c_vp,
                                          c_i64, c_vp]),
+    "wol_water_orient": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "wol_bin_on_grid": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp]),
     "wol_hist_allreduce": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_i32, c_vp]),
     "wol_iso_scratch_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
     "wol_iso_points": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f64, c_vp, ctypes.c_size_t, c_vp, ctypes.c_int64, c_vp, c_vp]),

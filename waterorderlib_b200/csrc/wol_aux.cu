@@ -272,6 +272,62 @@ __global__ void __launch_bounds__(kPrefThreads) neighbors_csr_kernel(const CsrPa
     if (!FILL) P.offsets[g] = K;
 }
 
+// ---- water orientation (watOrient) and cube/sphere occupancy (binOnGrid) ---------------------------------------------------
+
+// AngBetween of the unit vector v / n with the unit reference (fortran/waterlib.f90:954-965): dot product of the
+// normalised components summed left to right, clamped, then the same acos -> degrees chain as CosAngle3
+__device__ __forceinline__ double ang_between_unit(double vx, double vy, double vz, double n, double rx, double ry, double rz) {
+    const double ux = __ddiv_rn(vx, n), uy = __ddiv_rn(vy, n), uz = __ddiv_rn(vz, n);
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ux, rx), __dmul_rn(uy, ry)), __dmul_rn(uz, rz));
+    return angle_deg_from_cos(fmin(1.0, fmax(-1.0, dot)));
+}
+
+__global__ void __launch_bounds__(256) water_orient_kernel(const double *__restrict__ opos, const double *__restrict__ hpos,
+                                                           const double *__restrict__ box, int n_frames, int n_waters, double rx,
+                                                           double ry, double rz, double *__restrict__ angdip,
+                                                           double *__restrict__ angplane) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)n_frames * n_waters) return;
+    const BoxD b = load_box(box + (g / n_waters) * 3);
+    const double L[3] = {b.Lx, b.Ly, b.Lz}, iL[3] = {b.iLx, b.iLy, b.iLz};
+    const double *o = opos + 3 * g, *h1 = hpos + 6 * g, *h2 = hpos + 6 * g + 3;
+    double v1[3], v2[3], dip[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // vecoh = hpos - opos, minimum image; the dipole (their sum) is imaged once more (waterlib.f90:998-1004)
+        double t = __dsub_rn(h1[k], o[k]);
+        v1[k] = __dsub_rn(t, __dmul_rn(L[k], anint_exact<double>(__dmul_rn(t, iL[k]))));
+        t = __dsub_rn(h2[k], o[k]);
+        v2[k] = __dsub_rn(t, __dmul_rn(L[k], anint_exact<double>(__dmul_rn(t, iL[k]))));
+        t = __dadd_rn(v1[k], v2[k]);
+        dip[k] = __dsub_rn(t, __dmul_rn(L[k], anint_exact<double>(__dmul_rn(t, iL[k]))));
+    }
+    angdip[g] = ang_between_unit(dip[0], dip[1], dip[2], __dsqrt_rn(sumsq3<double>(dip[0], dip[1], dip[2])), rx, ry, rz);
+    // crossProd3 (waterlib.f90:26-28)
+    const double px = __dsub_rn(__dmul_rn(v1[1], v2[2]), __dmul_rn(v1[2], v2[1]));
+    const double py = __dsub_rn(__dmul_rn(v1[2], v2[0]), __dmul_rn(v1[0], v2[2]));
+    const double pz = __dsub_rn(__dmul_rn(v1[0], v2[1]), __dmul_rn(v1[1], v2[0]));
+    angplane[g] = ang_between_unit(px, py, pz, __dsqrt_rn(sumsq3<double>(px, py, pz)), rx, ry, rz);
+}
+
+__global__ void __launch_bounds__(256) bin_on_grid_kernel(const double *__restrict__ opos, long long n, const double *__restrict__ xb,
+                                                          const double *__restrict__ yb, const double *__restrict__ zb, int nx,
+                                                          int ny, int nz, double binwidth, int32_t *__restrict__ hist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = opos[3 * i], y = opos[3 * i + 1], z = opos[3 * i + 2];
+    // thisbin = floor((pos - bins(1)) / binwidth) + 1, left edge inclusive; outside the bins: not counted
+    const double fx = floor(__ddiv_rn(__dsub_rn(x, xb[0]), binwidth)), fy = floor(__ddiv_rn(__dsub_rn(y, yb[0]), binwidth)),
+                 fz = floor(__ddiv_rn(__dsub_rn(z, zb[0]), binwidth));
+    if (!(fx >= 0.0 && fx < (double)(nx - 1)) || !(fy >= 0.0 && fy < (double)(ny - 1)) || !(fz >= 0.0 && fz < (double)(nz - 1))) return;
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const double half = __dmul_rn(binwidth, 0.5);
+    const double vx = __dsub_rn(x, __dadd_rn(xb[ix], half)), vy = __dsub_rn(y, __dadd_rn(yb[iy], half)),
+                 vz = __dsub_rn(z, __dadd_rn(zb[iz], half));
+    if (sumsq3<double>(vx, vy, vz) <= __ddiv_rn(__dmul_rn(binwidth, binwidth), 4.0))
+        atomicAdd(hist + ((size_t)ix * (ny - 1) + iy) * (nz - 1) + iz, 1);
+}
+
 // ---- np.histogram + tetrahedral-window sums over an array of angles --------------------------------
 
 __global__ void __launch_bounds__(256) histogram_kernel(const double *__restrict__ x, size_t n, double lo, double hi, int nbins,
@@ -707,6 +763,41 @@ int wol_neighbors_csr(const void *centres, int32_t centre_dtype, const double *b
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_neighbors_csr", e);
+    return WOL_OK;
+}
+
+int wol_water_orient(const double *opos, const double *hpos, const double *box, int32_t n_frames, int32_t n_waters,
+                     const double refvec_host[3], double *angdip, double *angplane, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!box || !refvec_host || !angdip || !angplane || n_frames < 1 || n_waters < 0 || ((!opos || !hpos) && n_waters > 0))
+        return set_error(WOL_ERR_INVALID, "wol_water_orient: bad argument");
+    // refvecnorm = refvec / sqrt(sum(refvec * refvec))  (waterlib.f90:993)
+    const double rn = sqrt((refvec_host[0] * refvec_host[0] + refvec_host[1] * refvec_host[1]) + refvec_host[2] * refvec_host[2]);
+    const size_t total = (size_t)n_frames * n_waters;
+    if (total > 0) {
+        water_orient_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(opos, hpos, box, n_frames, n_waters, refvec_host[0] / rn,
+                                                                             refvec_host[1] / rn, refvec_host[2] / rn, angdip, angplane);
+        add_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_water_orient", e);
+    return WOL_OK;
+}
+
+int wol_bin_on_grid(const double *opos, int64_t n, const double *xbins, const double *ybins, const double *zbins, int32_t nx, int32_t ny,
+                    int32_t nz, double binwidth, int32_t *outhist, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!xbins || !ybins || !zbins || !outhist || nx < 2 || ny < 2 || nz < 2 || n < 0 || (!opos && n > 0) || !(binwidth > 0.0))
+        return set_error(WOL_ERR_INVALID, "wol_bin_on_grid: bad argument");
+    cudaError_t e = cudaMemsetAsync(outhist, 0, sizeof(int32_t) * (size_t)(nx - 1) * (ny - 1) * (nz - 1), stream);  // outhist = 0 (:1064)
+    if (e != cudaSuccess) return set_cuda_error("wol_bin_on_grid", e);
+    if (n > 0) {
+        bin_on_grid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(opos, (long long)n, xbins, ybins, zbins, nx, ny, nz, binwidth,
+                                                                          outhist);
+        add_launches(1);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_bin_on_grid", e);
     return WOL_OK;
 }
 

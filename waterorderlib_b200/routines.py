@@ -559,6 +559,49 @@ def density_field(pos, box, grid, device=None):
     return dens
 
 
+def water_orient(opos, hpos, box, refvec=(0.0, 0.0, 1.0), device=None):
+    """watOrient (fortran/waterlib.f90:973-1011) for one frame (N,3)/(2N,3) or several (F,N,3)/(F,2N,3):
+    -> (angDip, angPlane) float64 CUDA tensors (F, N): angles in degrees of the water dipoles / molecular-plane normals
+    with refvec.  hpos rows 2i, 2i+1 are the hydrogens of oxygen i."""
+    device = _device(device, opos, hpos)
+    o = _f64(opos, device, (3,))
+    h = _f64(hpos, device, (3,))
+    o = o.reshape(1, -1, 3) if o.dim() == 2 else o
+    h = h.reshape(1, -1, 3) if h.dim() == 2 else h
+    F, N = int(o.shape[0]), int(o.shape[1])
+    if h.shape[0] != F or h.shape[1] != 2 * N:
+        raise ValueError("Number of hydrogens must be two times number of oxygens.")  # the Fortran STOPs here (:988-991)
+    box_d = torch.from_numpy(engine.as_host_boxes(box, F).copy()).to(device)
+    ref = (ctypes.c_double * 3)(*[float(v) for v in np.asarray(refvec, dtype=np.float64).reshape(-1)[:3]])
+    dip = torch.empty((F, N), dtype=torch.float64, device=device)
+    plane = torch.empty((F, N), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_water_orient(_vp(o.data_ptr()), _vp(h.data_ptr()), _vp(box_d.data_ptr()), F, N, ref, _vp(dip.data_ptr()),
+                                     _vp(plane.data_ptr()), _stream()), "wol_water_orient")
+    return dip, plane
+
+
+def bin_on_grid(opos, xbins, ybins, zbins, device=None):
+    """binOnGrid (fortran/waterlib.f90:1047-1099): atoms per cubic bin, counted inside the bin's inscribed sphere only
+    -> int32 CUDA tensor (nx-1, ny-1, nz-1).  The bins must be uniform cubes."""
+    device = _device(device, opos)
+    o = _f64(opos, device, (3,)).reshape(-1, 3)
+    edges = [np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64).reshape(-1) for b in (xbins, ybins, zbins)]
+    if any(e.size < 2 for e in edges):
+        raise ValueError("each axis needs at least two bin edges")
+    binwidth = edges[0][1] - edges[0][0]
+    if edges[1][1] - edges[1][0] != binwidth or edges[2][1] - edges[2][0] != binwidth:
+        raise ValueError("Must break volume into CUBES. Currently, bin-widths do not match.")  # the Fortran STOPs here (:1060-1063)
+    xb, yb, zb = (torch.from_numpy(np.ascontiguousarray(e)).to(device) for e in edges)
+    nx, ny, nz = (int(e.size) for e in edges)
+    out = torch.empty((nx - 1, ny - 1, nz - 1), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_bin_on_grid(_vp(o.data_ptr()), int(o.shape[0]), _vp(xb.data_ptr()), _vp(yb.data_ptr()), _vp(zb.data_ptr()), nx, ny,
+                                    nz, float(binwidth), _vp(out.data_ptr()), _stream()), "wol_bin_on_grid")
+        torch.cuda.current_stream().synchronize()  # xb, yb, zb die with this call
+    return out
+
+
 def components(adj, device=None):
     """Connected components of a symmetric 0/1 matrix -> int32 CUDA tensor labels (n,), labels[i] = smallest member."""
     device = _device(device, adj)

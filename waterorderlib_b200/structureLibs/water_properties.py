@@ -9,6 +9,10 @@ Same names, positional order, keyword names, defaults and return values:
                   distCut=3.5, angCut=150.0)                                         reference :681-719
     getLSI(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.7)                            reference :252-311
     getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0)                 reference :393-433
+    waterOrientation(Opos, Hpos, boxDim, refVec=[0.0, 0.0, 1.0])                     reference :622-638
+    waterOrientationBinZ(Opos, Hpos, boxDim, refVec=[0.0, 0.0, 1.0], refBins=None,
+                         angBins=None)                                               reference :578-619
+    binnedVolumePofN(Opos, volBins, numBins, binMask=None)                           reference :641-676
 
 numpy arrays in -> numpy arrays out; torch CUDA tensors in -> torch CUDA tensors out (zero copy).  The
 per-water Python loops and f2py calls of the reference are replaced by one pass of the cell-list kernels in
@@ -144,3 +148,45 @@ def getOrderParamPsi(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
     _pos2(subPos, "subPos"); _pos2(Pos, "Pos")
     r = routines.psi(None if _same(subPos, Pos) else subPos, Pos, BoxDims, lowCut, highCut)
     return _out(r[0], tor)
+
+
+def waterOrientation(Opos, Hpos, boxDim, refVec=[0.0, 0.0, 1.0]):
+    """(dipAngs, planeAngs): angles in degrees between refVec and each water's dipole / molecular-plane normal
+    (reference water_properties.py:622-638 over wl.watorient)."""
+    like_torch = _is_torch(Opos, Hpos)
+    dip, plane = routines.water_orient(Opos, Hpos, boxDim, refVec)
+    return _out(dip[0], like_torch), _out(plane[0], like_torch)
+
+
+def waterOrientationBinZ(Opos, Hpos, boxDim, refVec=[0.0, 0.0, 1.0], refBins=None, angBins=None):
+    """(plane2Dhist, dip2Dhist): 2-D histograms of the plane-normal and dipole angles against the oxygen coordinate along
+    refVec (reference water_properties.py:578-619).  One deliberate difference: the reference bins the N plane angles
+    against a 2N-long coordinate array (``zOposforH``, :600,:617), which ``np.histogram2d`` rejects (unequal lengths), so
+    that line cannot run as written; here the plane angles are binned against the per-water coordinate like the dipole
+    angles.  ``normed=False`` (removed from numpy) is dropped."""
+    refVec = np.asarray(refVec, dtype=np.float64)
+    refVec = refVec / np.linalg.norm(refVec)
+    Opos_h = Opos.detach().cpu().numpy() if isinstance(Opos, torch.Tensor) else np.asarray(Opos, dtype=np.float64)
+    zOpos = np.dot(Opos_h, refVec)
+    angDip, angPlane = routines.water_orient(Opos, Hpos, boxDim, refVec)
+    angDip, angPlane = angDip[0].cpu().numpy(), angPlane[0].cpu().numpy()
+    if refBins is None:
+        refBins = np.arange(np.min(zOpos), np.max(zOpos), 0.2)
+    if angBins is None:
+        angBins = np.arange(0.0, 180.001, 180.0 / 500.0)
+    plane2Dhist, _a, _r = np.histogram2d(angPlane, zOpos, bins=[angBins, refBins])
+    dip2Dhist, _a, _r = np.histogram2d(angDip, zOpos, bins=[angBins, refBins])
+    return plane2Dhist, dip2Dhist
+
+
+def binnedVolumePofN(Opos, volBins, numBins, binMask=None):
+    """P(N) counts: histogram over the spatial bins of the number of oxygens inside each bin's inscribed sphere
+    (reference water_properties.py:641-676 over wl.binongrid)."""
+    shape = (len(volBins[0]) - 1, len(volBins[1]) - 1, len(volBins[2]) - 1)
+    if binMask is None:
+        binMask = np.ones(shape, dtype=bool)
+    elif np.shape(binMask) != shape:
+        raise ValueError("Dimensions of mask for spatial bins does not match dimensions of spatial bins.")  # reference: sys.exit(2)
+    hist = routines.bin_on_grid(Opos, volBins[0], volBins[1], volBins[2]).cpu().numpy()
+    numWatHist, _edges = np.histogram(hist[np.asarray(binMask, dtype=bool)].flatten(), bins=numBins)
+    return numWatHist

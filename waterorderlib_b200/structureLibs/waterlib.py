@@ -115,3 +115,14 @@ def pairdistancehistogram(pos1, pos2, binwidth, totbins, boxl):
 def densityfield(pos, gridx, gridy, gridz, boxl):
     """densvals = densityfield(pos,gridx,gridy,gridz,boxl)   (fortran/waterlib.f90:1219-1268)"""
     return _np(routines.density_field(_check_pos(pos, "pos"), boxl, (gridx, gridy, gridz)))
+
+
+def watorient(opos, hpos, refvec, boxl):
+    """angdip,angplane = watorient(opos,hpos,refvec,boxl)   (fortran/waterlib.f90:973-1011)"""
+    dip, plane = routines.water_orient(_check_pos(opos, "opos"), _check_pos(hpos, "hpos"), boxl, refvec)
+    return _np(dip[0]), _np(plane[0])
+
+
+def binongrid(opos, xbins, ybins, zbins):
+    """outhist = binongrid(opos,xbins,ybins,zbins)   (fortran/waterlib.f90:1047-1099)"""
+    return _np(routines.bin_on_grid(_check_pos(opos, "opos"), xbins, ybins, zbins))

@@ -343,3 +343,36 @@ def test_rdfCalc_matches_reference_golden(in_tmp, golden_dir):
     n1, t = opl.rdfCalc(top_w, (xyz[:, n_sol:], boxes), binwidth=0.1, totbins=110)
     assert np.isclose(n1, g["ret_nosol"][0], rtol=1e-10) and t == int(g["ret_nosol"][1])
     assert np.allclose(np.loadtxt("rdf.txt"), g["rdf_txt_nosol"], rtol=2.1e-3, atol=1e-12)
+
+
+def test_drivers_accept_pinned_and_cuda_trajectories_and_small_staging_batches(in_tmp, monkeypatch):
+    """The batched drivers stage numpy frames through page-locked buffers (several batches, one staged ahead) and take
+    torch tensors (pinned host or CUDA) as they are: same numbers whichever way the frames arrive, sub-populations included."""
+    T = 23
+    top, traj = make_system(4, T)
+    obj = TrajObject(top, traj)
+    watInds, _, _ = obj.getWatInds()
+    rng = np.random.default_rng(5)
+    subInds = [[np.sort(rng.choice(watInds, 40, replace=False))] for _ in range(T)]
+    monkeypatch.setattr(opl, "_MAX_ATOMS_PER_BATCH", 5 * len(watInds))   # five frames per batch: 5 batches, the last ragged
+    results = []
+    for kind in ("numpy64", "numpy32", "pinned", "cuda"):
+        xyz = traj.xyz
+        if kind == "numpy32":
+            xyz = xyz.astype(np.float32)
+        elif kind == "pinned":
+            xyz = torch.from_numpy(xyz).pin_memory()
+        elif kind == "cuda":
+            xyz = torch.from_numpy(xyz).cuda()
+        tr = ArrayTrajectory(xyz, traj.boxes, top=top)
+        np.random.seed(11)
+        q = opl.tetOrderCalc(top, tr, subInds=subInds, nPops=1)
+        qd = np.loadtxt("qDistribution_1.txt")
+        np.random.seed(11)
+        tb = opl.threeBodyCalc(top, tr, subInds=subInds, nPops=1)
+        results.append((q, qd, tb, np.loadtxt("3bDistribution_0.txt")))
+    for r in results[1:]:
+        for a, b in zip(results[0][0] + results[0][2], r[0] + r[2]):
+            # per-frame sums are accumulated with double atomics: equal to rounding, not bit for bit
+            assert np.allclose(a[0], b[0], rtol=1e-12, atol=0) and np.allclose(a[1], b[1], rtol=1e-9, atol=1e-15)
+        assert np.array_equal(results[0][1], r[1]) and np.array_equal(results[0][3], r[3])

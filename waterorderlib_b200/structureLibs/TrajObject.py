@@ -40,6 +40,7 @@ class Topology:
         self.resids = np.arange(n) if resids is None else np.asarray(resids, dtype=np.int64)
         self.bonds = np.zeros((0, 2), dtype=np.int64) if bonds is None else np.asarray(bonds, dtype=np.int64).reshape(-1, 2)
         self._atoms = None
+        self._selections = {}
 
     @property
     def n_atoms(self):
@@ -60,6 +61,9 @@ class Topology:
 
     def select(self, mask):
         """Indices (ascending int array) of the atoms matching an Amber mask, like pytraj's top.select."""
+        cached = self._selections.get(mask)
+        if cached is not None:     # string matching over 10^6 atoms costs ~0.1 s; the drivers ask for the same masks again
+            return cached.copy()
         tokens = []
         pos = 0
         mask = mask.strip()
@@ -73,7 +77,9 @@ class Topology:
         sel = self._parse_or()
         if self._i != len(tokens):
             raise ValueError("unbalanced mask %r" % mask)
-        return np.nonzero(sel)[0]
+        out = np.nonzero(sel)[0]
+        self._selections[mask] = out
+        return out.copy()
 
     def _peek(self):
         return self._tok[self._i] if self._i < len(self._tok) else None
@@ -172,10 +178,12 @@ class Frame:
 class ArrayTrajectory:
     """In-memory trajectory with the slice of pytraj's TrajectoryIterator interface the drivers use:
     len(), iteration, integer indexing, ``.top.select(mask)``; plus the whole-array views (``xyz``, ``boxes``)
-    the batched GPU path reads directly."""
+    the batched GPU path reads directly.  ``xyz`` may also be a torch tensor (page-locked host memory or CUDA): the
+    batched drivers (tetOrderCalc, threeBodyCalc) then skip the staging copy numpy frames need."""
 
     def __init__(self, xyz, box, top=None, stride=1):
-        xyz = np.asarray(xyz)
+        if not (hasattr(xyz, "is_cuda") and hasattr(xyz, "ndim")):   # torch tensors (pinned host or CUDA) are kept as they are:
+            xyz = np.asarray(xyz)                                    # the batched drivers move them without a staging copy
         if xyz.ndim != 3 or xyz.shape[2] != 3:
             raise ValueError("xyz must have shape (frames, atoms, 3)")
         box = np.asarray(box, dtype=np.float64)

@@ -104,6 +104,46 @@ def _frame_arrays(traj, begin, end):
     return np.stack(xyz), np.stack(box)
 
 
+class _FrameStager:
+    """Moves batches of whole frames to the device.  numpy frames live in pageable memory: each batch is copied into one
+    of two page-locked buffers (a plain, multi-threaded host memcpy) and sent from there on a side stream, so the host copy
+    of batch k+1 runs while the kernels of batch k do, and the transfer itself runs at full PCIe rate.  torch tensors are
+    passed through: CUDA tensors as they are, (pinned) CPU tensors with one asynchronous copy."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [None, None]
+        self.sent = [None, None]
+        self.k = 0
+
+    def put(self, xyz):
+        """-> (device tensor (f, natom, 3), event recorded when it is complete)."""
+        done = torch.cuda.Event()
+        if isinstance(xyz, torch.Tensor):
+            if xyz.is_cuda:
+                done.record(torch.cuda.current_stream(self.dev))
+                return xyz, done
+            src = xyz
+        else:
+            a = np.ascontiguousarray(np.asarray(xyz))
+            if not a.dtype.isnative:
+                a = a.astype(a.dtype.newbyteorder("="))
+            i = self.k & 1
+            self.k += 1
+            if self.sent[i] is not None:
+                self.sent[i].synchronize()          # the previous transfer out of this buffer
+            if self.bufs[i] is None or self.bufs[i].numel() < a.size or self.bufs[i].dtype != torch.from_numpy(a[:0]).dtype:
+                self.bufs[i] = torch.empty(a.size, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+            src = self.bufs[i][:a.size].view(a.shape)
+            src.copy_(torch.from_numpy(a))
+            self.sent[i] = done
+        with torch.cuda.stream(self.stream):
+            out = src.to(self.dev, non_blocking=True)
+            done.record(self.stream)
+        return out, done
+
+
 def _batches(begin, end, n_atoms):
     per = max(1, _MAX_ATOMS_PER_BATCH // max(n_atoms, 1))
     for b in range(begin, end, per):
@@ -139,10 +179,27 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
             o["q_hist"] = q_hist[j]
         return o
 
-    for b0, b1 in _batches(begin, end, len(watInds)):
-        xyz, box = _frame_arrays(traj, b0, b1)
-        xyz = np.asarray(xyz)
-        watPos = torch.from_numpy(np.ascontiguousarray(xyz[:, watInds])).to(dev)
+    wat_d = torch.from_numpy(np.ascontiguousarray(np.asarray(watInds, dtype=np.int64))).to(dev)
+    stager = _FrameStager(dev)
+    batches = list(_batches(begin, end, len(watInds)))
+    if not (isinstance(getattr(traj, "xyz", None), torch.Tensor) and traj.xyz.is_cuda) and Tl > 0:
+        # host frames: batches of at most ~64 MB, so that little of the staging is exposed before the first kernels start
+        # and the page-locked buffers stay small
+        first = _frame_arrays(traj, begin, begin + 1)[0]
+        frame_bytes = int(np.prod(first.shape[1:])) * (first.element_size() if isinstance(first, torch.Tensor) else first.dtype.itemsize)
+        per = max(1, min(batches[0][1] - batches[0][0], (64 << 20) // max(frame_bytes, 1)))
+        batches = [(b, min(end, b + per)) for b in range(begin, end, per)]
+    # whole frames go to the device as they are and the water oxygens are gathered THERE: a host-side fancy-index
+    # gather of 10^6 waters costs 40-90 ms per frame, a hundred times the kernels.  One batch is staged ahead.
+    ahead = None
+    for n, (b0, b1) in enumerate(batches):
+        if ahead is None:
+            xyz, box = _frame_arrays(traj, b0, b1)
+            ahead = (stager.put(xyz), box)
+        (xyz_d, ready), box = ahead
+        torch.cuda.current_stream(dev).wait_event(ready)
+        xyz_d.record_stream(torch.cuda.current_stream(dev))
+        watPos = xyz_d.index_select(1, wat_d)
         l0, l1 = b0 - begin, b1 - begin
         o = outputs(0, l0, l1)
         engine.q3b_frames(watPos, box, None, out=o, want=tuple(o.keys()), workspace=ws, **kw)
@@ -156,12 +213,17 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
             m_max = int(counts.max()) if len(counts) else 0
             if m_max == 0:
                 continue
-            cen = np.zeros((b1 - b0, m_max, 3), dtype=xyz.dtype)
+            pad = np.zeros((b1 - b0, m_max), dtype=np.int64)   # padded member indices; rows beyond n_valid are ignored
             for k, i in enumerate(inds):
-                cen[k, :len(i)] = xyz[k][i]
+                pad[k, :len(i)] = i
+            cen = torch.gather(xyz_d, 1, torch.from_numpy(pad).to(dev)[:, :, None].expand(-1, -1, 3))
             o = outputs(j, l0, l1)
-            engine.q3b_frames(watPos, box, torch.from_numpy(cen).to(dev), out=o, want=tuple(o.keys()), workspace=ws,
-                              n_valid=counts, reuse_cells=True, **kw)
+            engine.q3b_frames(watPos, box, cen, out=o, want=tuple(o.keys()), workspace=ws, n_valid=counts, reuse_cells=True,
+                              **kw)
+        ahead = None
+        if n + 1 < len(batches):   # the kernels of this batch are queued: stage the next one while they run
+            nxt, nbox = _frame_arrays(traj, *batches[n + 1])
+            ahead = (stager.put(nxt), nbox)
     # ---- combine ranks: one all-reduce of the integer histograms, one all-gather of the per-frame rows ----
     rows = [stats.permute(1, 0, 2).reshape(Tl, P * NS), members]
     if do_3body:

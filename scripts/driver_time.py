@@ -40,3 +40,12 @@ for name, fn in (("tetOrderCalc", opl.tetOrderCalc), ("threeBodyCalc", opl.three
     dtm = time.perf_counter() - t0
     print("%-14s %d waters x %d frames (%s, %s): %.1f ms per frame, %.3g water-frames/s; first value %.6f"
           % (name, n_w, frames, np.dtype(dt).name, where, dtm / frames * 1e3, n_w * frames / dtm, r[0][0][0]))
+if len(sys.argv) > 5 and sys.argv[5] == "hb":
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = opl.hbCalc(top, traj)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+    print("hbCalc         %d waters x %d frames (%s, %s): %.1f ms per frame, %.3g water-frames/s; H-bonds per water %.4f"
+          % (n_w, frames, np.dtype(dt).name, where, dtm / frames * 1e3, n_w * frames / dtm, r[0]))

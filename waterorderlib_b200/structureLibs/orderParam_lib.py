@@ -70,6 +70,8 @@ def _mean_ci(series):
 def getHBInds(top, frame, solInds, solHInds, solNInds, solOInds):
     """Acceptor / donor / donor-hydrogen index lists from the bonded topology (reference :46-120):
     every O (N) in solOInds (solNInds) is an acceptor and appears once per bonded hydrogen as a donor."""
+    if hasattr(top, "bonds") and hasattr(top, "names") and not hasattr(top, "residues"):
+        return _hb_inds_from_arrays(top, solOInds, solNInds)   # same lists without a Python loop over every atom
     solO, solN = set(int(i) for i in solOInds), set(int(i) for i in solNInds)
     acc = {"O": [], "N": []}
     don = {"O": [], "N": []}
@@ -88,6 +90,31 @@ def getHBInds(top, frame, solInds, solHInds, solNInds, solOInds):
     hbOInds = [np.array(acc["O"], dtype=int), np.array(don["O"], dtype=int), np.array(donH["O"], dtype=int)]
     hbNInds = [np.array(acc["N"], dtype=int), np.array(don["N"], dtype=int), np.array(donH["N"], dtype=int)]
     return hbOInds, hbNInds
+
+
+def _hb_inds_from_arrays(top, solOInds, solNInds):
+    """getHBInds for the built-in Topology (arrays of names and bonds): acceptors ascending; a donor entry per bonded atom
+    whose name contains 'H', in the order the reference meets them -- atoms ascending, each atom's partners in bond-list
+    order (Atom.bond_partners is filled bond by bond)."""
+    is_h = getattr(top, "_name_has_h", None)
+    if is_h is None:
+        is_h = np.char.find(top.names, "H") >= 0
+        top._name_has_h = is_h
+    bonds = np.asarray(top.bonds, dtype=np.int64).reshape(-1, 2)
+    k = np.arange(bonds.shape[0])
+    heavy = np.concatenate([bonds[:, 0], bonds[:, 1]])
+    other = np.concatenate([bonds[:, 1], bonds[:, 0]])
+    when = np.concatenate([k, k])
+    out = []
+    for inds in (solOInds, solNInds):
+        member = np.zeros(top.n_atoms, dtype=bool)
+        inds = np.asarray(inds, dtype=np.int64)
+        member[inds] = True
+        sel = member[heavy] & is_h[other]
+        h, o, w = heavy[sel], other[sel], when[sel]
+        order = np.lexsort((w, h))
+        out.append([np.nonzero(member)[0].astype(int), h[order].astype(int), o[order].astype(int)])
+    return out[0], out[1]
 
 
 # ---- frame batching ----------------------------------------------------------------------------------
@@ -349,10 +376,21 @@ def hbCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', stride=
     begin, end = wdist.shard_frames(T)
     dev = torch.device("cuda", torch.cuda.current_device())
     wat_rows, sol_rows = [], []
+    stager = _FrameStager(dev)
+    on_dev = {}
+
+    def dev_index(idx):   # each index list goes to the device once; the gathers run there (see _run_populations)
+        key = id(idx)
+        if key not in on_dev:
+            on_dev[key] = (idx, torch.from_numpy(np.ascontiguousarray(np.asarray(idx, dtype=np.int64))).to(dev))
+        return on_dev[key][1]
+
     for b0, b1 in _batches(begin, end, 3 * len(watInds) + len(solInds)):
         xyz, box = _frame_arrays(traj, b0, b1)
-        xyz = np.asarray(xyz)
-        g = lambda idx: np.ascontiguousarray(xyz[:, idx])  # noqa: E731
+        xyz_d, ready = stager.put(xyz)
+        torch.cuda.current_stream(dev).wait_event(ready)
+        xyz_d.record_stream(torch.cuda.current_stream(dev))
+        g = lambda idx: xyz_d.index_select(1, dev_index(idx))  # noqa: E731
         D, A = 3.5, 120.0
         # the nine generalhbonds calls of the reference (:805-834) share three donor sets: one cell list each
         pw, pO, pN = g(wDon), g(sDonO), g(sDonN)

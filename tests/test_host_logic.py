@@ -220,3 +220,42 @@ def test_product_never_touches_the_oracle_and_has_no_cpu_fallback():
             wp.getOrderParamq(pos, pos, box)
         with pytest.raises(Exception):
             wp.getCosAngs(pos, pos, box)
+
+
+def test_vectorised_getHBInds_equals_the_per_atom_loop():
+    """getHBInds over the built-in Topology avoids the reference's Python loop over every atom (orderParam_lib.py:46-120);
+    the lists must come out identical, whatever the order and orientation of the bond list."""
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    from waterorderlib_b200.structureLibs.TrajObject import Topology
+    rng = np.random.default_rng(2)
+    n_sol, n_w = 6, 40
+    names, resn, bonds = [], [], []
+    for s in range(n_sol):                       # C, O-H, N-H2 cosolvent
+        b = 6 * s
+        names += ["C1", "O1", "HO1", "N1", "HN1", "HN2"]
+        resn += ["SOL"] * 6
+        bonds += [(b, b + 1), (b + 1, b + 2), (b, b + 3), (b + 3, b + 4), (b + 3, b + 5)]
+    top0 = Topology.water_box(n_w)
+    off = len(names)
+    names += list(top0.names)
+    resn += list(top0.resnames)
+    bonds += [(int(a) + off, int(b) + off) for a, b in top0.bonds]
+    bonds = np.array(bonds)
+    perm = rng.permutation(len(bonds))
+    bonds = bonds[perm]
+    flip = rng.random(len(bonds)) < 0.5
+    bonds[flip] = bonds[flip][:, ::-1]
+    top = Topology(names, resn, None, bonds)
+    solO, solN = top.select("(!:WAT)&(@O=)"), top.select("(!:WAT)&(@N=)")
+    wat = top.select("(:WAT)&(!@H=)")
+
+    class LoopTop:                               # anything without arrays takes the reference-style loop
+        atoms, residues = top.atoms, ()
+
+    for o_set, n_set in ((solO, solN), (wat, []), (np.concatenate([solO, wat]), solN)):
+        fast = opl.getHBInds(top, None, None, None, n_set, o_set)
+        slow = opl.getHBInds(LoopTop, None, None, None, n_set, o_set)
+        for a, b in zip(fast, slow):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+    assert len(fast[1][1]) == 2 * n_sol and len(fast[0][1]) == n_sol + 2 * n_w

@@ -507,25 +507,32 @@ def getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1
 def _value_driver(obj, centreInds, subInds, nPops, per_frame, hist_range, fname, header):
     """Shared frame loop of lsiCalc / hexOrderCalc (reference orderParam_lib.py:1617-1661, :1537-1582): a per-centre
     observable for all centres and for nPops sub-populations, per-frame mean / variance, bootstrap CIs, pooled 500-bin
-    histograms written as two-column text.  per_frame(j, sub, pos, box) -> 1-D numpy array of values (j = population)."""
+    histograms written as two-column text.  per_frame(j, sub, pos, box) -> 1-D array of values (j = population); it is
+    handed CUDA tensors."""
     traj = obj.traj
     T, P = len(traj), nPops + 1
     dev = torch.device("cuda", torch.cuda.current_device())
     begin, end = wdist.shard_frames(T)
     rows = np.zeros((end - begin, 2 * P))
     hists = torch.zeros((P, 500), dtype=torch.int64, device=dev)
+    cen_d = torch.from_numpy(np.ascontiguousarray(np.asarray(centreInds, dtype=np.int64))).to(dev)
     for t in range(begin, end):
         frame = traj[t]
-        pos = np.array(frame.xyz)
         thisbox = np.array(frame.box.values[:3])
-        cenPos = pos[centreInds]
+        # the frame goes to the device once; centres and sub-populations are gathered there (a host-side gather of 10^6
+        # atoms costs more than the kernels, see _run_populations)
+        xyz = frame.xyz if isinstance(frame.xyz, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(frame.xyz)))
+        pos_d = xyz.to(dev)
+        cenPos = pos_d.index_select(0, cen_d)
         for j in range(P):
-            sub = cenPos if j == 0 else pos[np.asarray(subInds[t][j - 1], dtype=np.int64)]
-            vals = per_frame(j, sub, cenPos, thisbox)
+            sub = cenPos if j == 0 else pos_d.index_select(
+                0, torch.from_numpy(np.ascontiguousarray(np.asarray(subInds[t][j - 1], dtype=np.int64))).to(dev))
+            vals_d = per_frame(j, sub, cenPos, thisbox)
+            vals = vals_d.cpu().numpy() if isinstance(vals_d, torch.Tensor) else np.asarray(vals_d)
             with np.errstate(all="ignore"):
                 rows[t - begin, 2 * j], rows[t - begin, 2 * j + 1] = np.mean(vals), np.var(vals)
             if vals.size:
-                h, _ = routines.histogram(vals, 500, hist_range)
+                h, _ = routines.histogram(vals_d, 500, hist_range)
                 hists[j] += h
     rows = wdist.gather_frame_rows(torch.from_numpy(rows).to(dev), T).cpu().numpy()
     wdist.reduce_histograms(hists)

@@ -78,6 +78,11 @@ class _NativeFrames:
     def __len__(self):
         return self.shape[0]
 
+    def raw(self, begin, end):
+        """Frames [begin, end) exactly as the file stores them (big-endian float32, a view of the memory map): the
+        batched drivers upload these bytes and swap them on the device."""
+        return self._v[begin * self._stride:end * self._stride:self._stride]
+
     def __getitem__(self, key):
         if isinstance(key, tuple):
             head, rest = key[0], key[1:]

@@ -122,6 +122,8 @@ def _hb_inds_from_arrays(top, solOInds, solNInds):
 def _frame_arrays(traj, begin, end):
     """(xyz (f, natom, 3), box (f, 3)) of frames [begin, end) of an ArrayTrajectory or any pytraj-like iterable."""
     if hasattr(traj, "boxes") and hasattr(traj, "xyz") and getattr(traj.xyz, "ndim", 0) == 3:
+        if hasattr(traj.xyz, "raw"):   # file-backed frames in the file's own byte order (amber_io.NetCDFTrajectory)
+            return traj.xyz.raw(begin, end), traj.boxes[begin:end, :3]
         return traj.xyz[begin:end], traj.boxes[begin:end, :3]
     xyz, box = [], []
     for t in range(begin, end):
@@ -154,17 +156,25 @@ class _FrameStager:
             src = xyz
         else:
             a = np.ascontiguousarray(np.asarray(xyz))
-            if not a.dtype.isnative:
-                a = a.astype(a.dtype.newbyteorder("="))
+            swap = not a.dtype.isnative         # e.g. the big-endian floats of a NetCDF-3 file: bytes go up as they are
+            native = a.dtype.newbyteorder("=")  # and are swapped on the device, which saves a pass over them on the host
+            raw = a.reshape(-1).view(np.uint8)
             i = self.k & 1
             self.k += 1
             if self.sent[i] is not None:
                 self.sent[i].synchronize()          # the previous transfer out of this buffer
-            if self.bufs[i] is None or self.bufs[i].numel() < a.size or self.bufs[i].dtype != torch.from_numpy(a[:0]).dtype:
-                self.bufs[i] = torch.empty(a.size, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
-            src = self.bufs[i][:a.size].view(a.shape)
-            src.copy_(torch.from_numpy(a))
+            if self.bufs[i] is None or self.bufs[i].numel() < raw.size:
+                self.bufs[i] = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+            src = self.bufs[i][:raw.size]
+            src.copy_(torch.from_numpy(raw))
             self.sent[i] = done
+            with torch.cuda.stream(self.stream):
+                up = src.to(self.dev, non_blocking=True)
+                if swap:
+                    up = up.view(-1, native.itemsize).flip(1).contiguous().view(-1)
+                out = up.view(torch.from_numpy(np.zeros(0, dtype=native)).dtype).view(a.shape)
+                done.record(self.stream)
+            return out, done
         with torch.cuda.stream(self.stream):
             out = src.to(self.dev, non_blocking=True)
             done.record(self.stream)

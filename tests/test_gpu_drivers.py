@@ -376,3 +376,46 @@ def test_drivers_accept_pinned_and_cuda_trajectories_and_small_staging_batches(i
             # per-frame sums are accumulated with double atomics: equal to rounding, not bit for bit
             assert np.allclose(a[0], b[0], rtol=1e-12, atol=0) and np.allclose(a[1], b[1], rtol=1e-9, atol=1e-15)
         assert np.array_equal(results[0][1], r[1]) and np.array_equal(results[0][3], r[3])
+
+
+def test_chemPotCalc_matches_reference_loop(in_tmp):
+    """Hard-sphere insertion statistics: same np.random call sequence as the reference (orderParam_lib.py:1757-1772 and
+    the shell variant :1709-1731), overlap counts from the kernel = row sums of the dense nearNeighbors matrix."""
+    T = 3
+    top, traj = make_system(3, T, n_sol=4)
+    obj = TrajObject(top, traj)
+    heavy = top.select('(!@H=)&(!@EPW)')
+    sol = obj.getSolInds()[0]
+    np.random.seed(21)
+    want = np.zeros(100)
+    for t in range(T):
+        pos, box = traj.xyz[t], traj.boxes[t]
+        hs = np.zeros((10000, 3))
+        for k in range(3):
+            hs[:, k] = np.random.random(10000) * box[k]
+        tot = port.neighbor_matrix(hs, pos[heavy], box, 0.0, 3.3).sum(axis=1).astype(int)
+        want[np.arange(tot.max() + 1)] += np.bincount(tot)
+    np.random.seed(21)
+    mu, avgN, avgN2 = opl.chemPotCalc(top, traj)
+    got = np.loadtxt("HS-solute_overlap_hist.txt")
+    assert np.array_equal(got[:, 1], want) and np.array_equal(got[:, 0], np.arange(100)) and want.sum() == T * 10000
+    with np.errstate(divide="ignore"):   # no empty 3.3 A cavity among 30 000 insertions in dense water: mu = inf, as in the reference
+        assert np.isclose(mu, -np.log(want[0] / want.sum())) and np.isclose(avgN, np.dot(np.arange(100), want) / want.sum())
+    assert np.isclose(avgN2, np.dot(np.arange(100) ** 2.0, want) / want.sum()) and 0.5 < avgN < 6.0
+    # shell variant on one frame: the reference's rejection loop, call for call
+    one = ArrayTrajectory(traj.xyz[:1], traj.boxes[:1], top=top)
+    np.random.seed(5)
+    pos, box = traj.xyz[0], traj.boxes[0]
+    hs, count = np.zeros((100000, 3)), 0
+    while count < 100000:
+        rx, ry, rz = (2.0 * (np.random.random(1) - 0.5) * 4.2 for _ in range(3))
+        if np.sqrt(rx[0] ** 2.0 + ry[0] ** 2.0 + rz[0] ** 2.0) > 4.2:
+            continue
+        hs[count] = pos[np.random.choice(sol)] + np.array([rx[0], ry[0], rz[0]])
+        count += 1
+    tot = port.neighbor_matrix(hs, pos[heavy], box, 0.0, 3.3).sum(axis=1).astype(int)
+    want = np.zeros(100)
+    want[np.arange(tot.max() + 1)] += np.bincount(tot)
+    np.random.seed(5)
+    mu_s, _, _ = opl.chemPotCalc(top, one, keyword=True)
+    assert np.array_equal(np.loadtxt("HS-solute_overlap_hist_Shell.txt")[:, 1], want) and want[0] < want.sum()

@@ -15,6 +15,7 @@ Same names, positional order, keyword names, defaults, return values and output 
     hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, endResName, stride=1,
                  lowCut=0.0, highCut=7.0)                                                            reference :1505-1584
     rdfCalc(topFile, trajFile, solResName, watResName, binwidth=0.1, totbins=150, stride=1)         reference :575-727
+    chemPotCalc(topFile, trajFile, solResName, watResName, probeRadius=3.3, keyword=False, stride=1)  reference :1666-1791
     blockAverage(vals, nBlocks=20), getCI(means)                                                     reference :386-417
     getClusters(hbMat), getHBClusterStats(...), getIonClusterStats(...)                              reference :123-311
 
@@ -682,6 +683,64 @@ def rdfCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', binwid
     if has_sol:
         return [n1_OwOw, se(tot_n1_OwOw)], [np.mean(tot_n1_SolOw), se(tot_n1_SolOw)], [tParam, se(tot_tParam)]
     return n1_OwOw, t
+
+
+# ---- hard-sphere insertion (reference orderParam_lib.py:1666-1791) -----------------------------------------------------
+
+def chemPotCalc(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', probeRadius=3.3, keyword=False, stride=1):
+    """Hard-sphere solute insertion statistics: the distribution of the number of heavy atoms overlapping a probe sphere
+    of radius probeRadius placed at random -- anywhere in the box, or (keyword=True) inside the 4.2 A shell of a random
+    solute atom -- and from it mu = -ln P(0), <N>, <N^2> (reference orderParam_lib.py:1666-1791).  Writes
+    HS-solute_overlap_hist.txt / HS-solute_overlap_hist_Shell.txt.  The random insertions are drawn with the same
+    np.random calls in the same order as the reference (so a seeded run reproduces it); the overlap counts -- the row sums
+    of wl.nearneighbors(hsPos, heavyPos, thisbox, 0.0, probeRadius) (:1727,:1770) -- come from the cell-list kernel."""
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    traj = obj.traj
+    solInds = obj.getSolInds()[0]
+    heavyInds = traj.top.select('(!@H=)&(!@EPW)')
+    cutoff = 4.2
+    numOverlap = np.arange(100)
+    countOverlap = np.zeros(len(numOverlap))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    heavy_d = torch.from_numpy(np.ascontiguousarray(np.asarray(heavyInds, dtype=np.int64))).to(dev)
+    ws = engine.Workspace(dev)
+    for t, frame in enumerate(traj):
+        pos = np.array(frame.xyz)
+        thisbox = np.array(frame.box.values[:3])
+        if keyword:
+            count, numIns = 0, 100000
+            hsPos = np.zeros((numIns, 3))
+            while count < numIns:   # the reference's rejection loop, call for call (:1709-1722)
+                randX = 2.0 * (np.random.random(1) - 0.5) * cutoff
+                randY = 2.0 * (np.random.random(1) - 0.5) * cutoff
+                randZ = 2.0 * (np.random.random(1) - 0.5) * cutoff
+                randSq = np.sqrt(randX[0] ** 2.0 + randY[0] ** 2.0 + randZ[0] ** 2.0)
+                if randSq > cutoff:
+                    continue
+                randSolPos = pos[np.random.choice(solInds)]
+                hsPos[count, 0] = randSolPos[0] + randX[0]
+                hsPos[count, 1] = randSolPos[1] + randY[0]
+                hsPos[count, 2] = randSolPos[2] + randZ[0]
+                count += 1
+        else:
+            numIns = 10000
+            hsPos = np.zeros((numIns, 3))
+            hsPos[:, 0] = np.random.random(numIns) * thisbox[0]
+            hsPos[:, 1] = np.random.random(numIns) * thisbox[1]
+            hsPos[:, 2] = np.random.random(numIns) * thisbox[2]
+        heavyPos = torch.from_numpy(np.ascontiguousarray(pos)).to(dev).index_select(0, heavy_d)
+        r = engine.q3b_frames(heavyPos[None], thisbox, torch.from_numpy(hsPos).to(dev)[None], do_q=False, low3=0.0,
+                              high3=float(probeRadius), want=("n3",), workspace=ws, device=dev)
+        thisTotOverlap = r["n3"][0].cpu().numpy().astype(int)
+        thisBins = np.arange(np.max(thisTotOverlap) + 1)
+        countOverlap[thisBins] += np.bincount(thisTotOverlap)
+    np.savetxt('HS-solute_overlap_hist_Shell.txt' if keyword else 'HS-solute_overlap_hist.txt', np.vstack((numOverlap, countOverlap)).T,
+               header='Number of non-solute atoms overlapping           Histogram count')
+    with np.errstate(all="ignore"):
+        muHS = -np.log(countOverlap[0] / np.sum(countOverlap))
+    avgN = np.dot(numOverlap, countOverlap) / np.sum(countOverlap)
+    avgN2 = np.dot(numOverlap ** 2.0, countOverlap) / np.sum(countOverlap)
+    return muHS, avgN, avgN2
 
 
 # ---- cluster analysis (reference orderParam_lib.py:123-311 over sortlib.depthfirstsort) -------------------------------

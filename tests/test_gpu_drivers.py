@@ -419,3 +419,30 @@ def test_chemPotCalc_matches_reference_loop(in_tmp):
     np.random.seed(5)
     mu_s, _, _ = opl.chemPotCalc(top, one, keyword=True)
     assert np.array_equal(np.loadtxt("HS-solute_overlap_hist_Shell.txt")[:, 1], want) and want[0] < want.sum()
+
+
+def test_boundWrapPopulations_cache_and_use_as_subInds(in_tmp, monkeypatch):
+    """The reference script's subInds workflow (orderParam_lib.py:2010-2036): populations from getBoundWrap per frame,
+    cached in boundFile.npy, reused when the cache fits the trajectory, rebuilt when it does not; usable as subInds."""
+    T = 6
+    top, traj = make_system(4, T, n_sol=3)
+    sub = opl.boundWrapPopulations(top, traj)
+    assert len(sub) == T and all(len(row) == 4 for row in sub) and os.path.exists("boundFile.npy")
+    obj = TrajObject(top, traj)
+    watInds = obj.getWatInds()[0]
+    for row in sub:
+        bound, wrap, shell, rest = row
+        assert np.array_equal(np.sort(np.concatenate([bound, wrap])), np.sort(shell))
+        assert np.array_equal(np.sort(np.concatenate([shell, rest])), watInds) and len(shell) > 0
+    calls = []
+    real = opl.getBoundWrap
+    monkeypatch.setattr(opl, "getBoundWrap", lambda *a, **k: calls.append(1) or real(*a, **k))
+    again = opl.boundWrapPopulations(top, traj)                       # served from the cache
+    assert not calls and all(np.array_equal(a, b) for ra, rb in zip(sub, again) for a, b in zip(ra, rb))
+    shorter = ArrayTrajectory(traj.xyz[:4], traj.boxes[:4], top=top)  # cache does not fit: rebuilt
+    assert len(opl.boundWrapPopulations(top, shorter)) == 4 and len(calls) == 4
+    assert len(np.load("boundFile.npy", allow_pickle=True)) == 4
+    np.random.seed(2)
+    avgQ, _ = opl.tetOrderCalc(top, traj, subInds=sub, nPops=4)
+    # (a frame without bound waters gives that population a NaN mean, as in the reference)
+    assert avgQ[0].shape == (5,) and np.all(np.isfinite(avgQ[0][[0, 3, 4]]))

@@ -11,6 +11,7 @@ Same names, positional order, keyword names, defaults, return values and output 
     getNeighborStats(topFile, trajFile, Inds1, Inds2, nAtoms1, nAtoms2, stride=1, distCut=3.4,
                      switch=False)                                                                   reference :313-384
     getHBInds(top, frame, solInds, solHInds, solNInds, solOInds)                                     reference :46-120
+    boundWrapPopulations(topFile, trajFile, ..., cutoff=4.6, nPops=4, cacheFile='boundFile.npy')     reference :2010-2036 (script)
     lsiCalc(topFile, trajFile, subInds=None, nPops=0, solResName, watResName, stride=1)            reference :1586-1663
     hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName, endResName, stride=1,
                  lowCut=0.0, highCut=7.0)                                                            reference :1505-1584
@@ -591,6 +592,37 @@ def hexOrderCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)',
         return wp.getOrderParamPsi(sub, pos, box)
 
     return _value_driver(obj, endInds, subInds, nPops, per_frame, (0.0, 1.0), 'psiDistribution_%d.txt', 'psiVal    frequency')
+
+
+def boundWrapPopulations(topFile, trajFile, solResName='(!:WAT)', watResName='(:WAT)', stride=1, cutoff=4.6, nPops=4,
+                         cacheFile='boundFile.npy'):
+    """Per-frame water populations [bound, wrap, shell, non-shell] for the subInds argument of the frame drivers, cached
+    in cacheFile: the workflow of the reference's driver script (orderParam_lib.py:2010-2036) -- an existing cache is
+    reused when it holds nPops populations for every frame of the trajectory and discarded otherwise; a fresh one is
+    built with getBoundWrap (cutoff 4.6 A there) and saved as a pickled object array.  Returns the list of per-frame lists."""
+    import os
+    obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
+    traj = obj.traj
+    watInds, watHInds, _lenWat = obj.getWatInds()
+    solInds, solHInds, solCInds, solNInds, solOInds, solSInds = obj.getSolInds()
+    if cacheFile and os.path.exists(cacheFile):
+        trial = np.load(cacheFile, allow_pickle=True)
+        if len(trial) != len(traj) or len(trial) == 0 or len(trial[0]) != nPops:
+            os.remove(cacheFile)
+        else:
+            return [list(row) for row in trial]
+    subInds = []
+    for frame in traj:
+        boundInds, wrapInds, shellInds, nonShellInds = getBoundWrap(obj.top, frame, watInds, watHInds, solInds, solHInds, solCInds,
+                                                                    solOInds, solNInds, solSInds, cutoff=cutoff)
+        subInds.append([boundInds, wrapInds, shellInds, nonShellInds][:nPops])
+    if cacheFile and wdist.world()[0] == 0:
+        arr = np.empty((len(subInds), nPops), dtype=object)
+        for t, row in enumerate(subInds):
+            for j, v in enumerate(row):
+                arr[t, j] = v
+        np.save(cacheFile, arr, allow_pickle=True)
+    return subInds
 
 
 # ---- radial distribution functions (reference orderParam_lib.py:575-727) --------------------------------------------------

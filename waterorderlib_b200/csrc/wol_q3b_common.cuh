@@ -147,8 +147,12 @@ __device__ __forceinline__ float shfl_t(float v, int src, int w) { return __shfl
 // the search.
 __device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
     if (c == -1.0) return (int)tab[nbins + 1];
-    const float th = acosf((float)c) * 57.29577951308232f;
-    int k = (int)(((double)th - lo) * inv_width);
+    // seed: acos(|x|) ~ sqrt(1 - |x|) * cubic(|x|) (Abramowitz & Stegun 4.4.45, |error| < 7e-5 rad = 0.004 degrees, a
+    // hundredth of a default bin); the exact position comes from the table below whatever the seed is
+    const float x = (float)c, ax = fabsf(x);
+    float r = fmaf(fmaf(fmaf(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f) * sqrtf(fmaxf(1.0f - ax, 0.f));
+    r = x < 0.f ? 3.14159265f - r : r;
+    int k = (int)((r * 57.29577951f - (float)lo) * (float)inv_width);
     k = min(max(k, 0), nbins);
     while (k < nbins && c <= tab[k + 1]) ++k;
     while (k >= 0 && !(c <= tab[k])) --k;

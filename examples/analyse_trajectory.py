@@ -4,11 +4,12 @@
 
 Without arguments a small synthetic water box with a cosolvent is generated in memory.  Needs a CUDA device.
 """
+import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from waterorderlib_b200 import synth  # noqa: E402
 from waterorderlib_b200.structureLibs import orderParam_lib as opl  # noqa: E402  (was: import orderParam_lib as opl)
 from waterorderlib_b200.structureLibs import water_properties as wp  # noqa: E402  (was: import water_properties as wp)

@@ -153,9 +153,16 @@ __device__ __forceinline__ int angle_position(double c, const double *tab, int n
     float r = fmaf(fmaf(fmaf(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f) * sqrtf(fmaxf(1.0f - ax, 0.f));
     r = x < 0.f ? 3.14159265f - r : r;
     int k = (int)((r * 57.29577951f - (float)lo) * (float)inv_width);
-    k = min(max(k, 0), nbins);
-    while (k < nbins && c <= tab[k + 1]) ++k;
-    while (k >= 0 && !(c <= tab[k])) --k;
+    k = min(max(k, 0), nbins - 1);
+    const double t0 = tab[k], t1 = tab[k + 1];  // both thresholds of the seeded bin at once: the usual case ends here
+    if (c <= t0 && !(c <= t1)) return k;
+    if (c <= t1) {
+        ++k;
+        while (k < nbins && c <= tab[k + 1]) ++k;
+    } else {
+        --k;
+        while (k >= 0 && !(c <= tab[k])) --k;
+    }
     return k;
 }
 

@@ -145,14 +145,14 @@ __device__ __forceinline__ float shfl_t(float v, int src, int w) { return __shfl
 // 0..nbins-1 a bin, nbins above the range.  tab[k] (decreasing in k) is the largest c whose angle sits
 // at or beyond bin k, so the position is the largest k with c <= tab[k]; the float acos only seeds
 // the search.
-__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
+__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, float lo, float inv_width) {
     if (c == -1.0) return (int)tab[nbins + 1];
     // seed: acos(|x|) ~ sqrt(1 - |x|) * cubic(|x|) (Abramowitz & Stegun 4.4.45, |error| < 7e-5 rad = 0.004 degrees, a
     // hundredth of a default bin); the exact position comes from the table below whatever the seed is
     const float x = (float)c, ax = fabsf(x);
     float r = fmaf(fmaf(fmaf(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f) * sqrtf(fmaxf(1.0f - ax, 0.f));
     r = x < 0.f ? 3.14159265f - r : r;
-    int k = (int)((r * 57.29577951f - (float)lo) * (float)inv_width);
+    int k = (int)((r * 57.29577951f - lo) * inv_width);
     k = min(max(k, 0), nbins - 1);
     const double t0 = tab[k], t1 = tab[k + 1];  // both thresholds of the seeded bin at once: the usual case ends here
     if (c <= t0 && !(c <= t1)) return k;
@@ -164,6 +164,10 @@ __device__ __forceinline__ int angle_position(double c, const double *tab, int n
         while (k >= 0 && !(c <= tab[k])) --k;
     }
     return k;
+}
+
+__device__ __forceinline__ int angle_position(double c, const double *tab, int nbins, double lo, double inv_width) {
+    return angle_position(c, tab, nbins, (float)lo, (float)inv_width);
 }
 
 struct LaneStats {

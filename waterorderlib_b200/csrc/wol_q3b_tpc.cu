@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_co
     __syncthreads();
     const double *tab = smem_tab ? s_tab : P.table;
     const double inv_width = (double)P.nbins / (P.hist_hi - P.hist_lo);
+    const float hist_lo_f = (float)P.hist_lo, inv_width_f = (float)inv_width;  // the bin search is seeded in float
     const double tet_c_hi = P.do_3b ? tab[P.nbins + 3] : 0.0, tet_c_lo = P.do_3b ? tab[P.nbins + 4] : 0.0;  // cosines of the tetrahedral window
     const bool do3 = P.do_3b != 0, doq = P.do_q != 0;
     const double low3sq = P.low3sq, high3sq = P.high3sq, lowqsq = P.lowqsq, highqsq = P.highqsq;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_co
                 } else {
                     const double dot = dot3<double>(va.x, va.y, va.z, vb.x, vb.y, vb.z);
                     const double c = clamped_cos<double>(dot, va.w, vb.w);
-                    pos = angle_position(c, tab, P.nbins, P.hist_lo, inv_width);
+                    pos = angle_position(c, tab, P.nbins, hist_lo_f, inv_width_f);
                     if (c != -1.0 && c <= tet_c_hi && c >= tet_c_lo) {
                         st.tet_count += 1u;
                         st.tet_cos += c;

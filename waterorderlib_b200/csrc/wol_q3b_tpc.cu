@@ -312,11 +312,16 @@ __global__ void __launch_bounds__(kTpcThreads, 2) q3b_tpc_kernel(const __grid_co
             __syncwarp();
             const int *woff = S.woff[warp];
             for (int w = lane; w < total; w += 32) {
-                int t = 0;
+                int t = 0, base = 0;  // woff[0] == 0; the search keeps woff[t] so that no load follows it
 #pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (woff[t + step] <= w) t += step;
-                const int p = w - woff[t];
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = woff[t + step];
+                    if (v <= w) {
+                        t += step;
+                        base = v;
+                    }
+                }
+                const int p = w - base;
                 const int ab = S.pair_ab[p];
                 const int col = warp * 32 + t;
                 const Vec4<double> va = S.ent[ab & 15][col], vb = S.ent[ab >> 4][col];

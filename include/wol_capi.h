@@ -30,6 +30,7 @@
 extern "C" {
 #endif
 
+/* bumped when a struct layout or an existing signature changes (2: wol_q3b_args.n_valid); added entry points do not bump it */
 #define WOL_ABI_VERSION 2
 
 enum {

@@ -321,7 +321,7 @@ int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n
     status_host[0] = (int32_t)c[kCntWidened];
     status_host[1] = (int32_t)c[kCntOverflow];
     status_host[2] = (int32_t)c[kCntFatal];
-    status_host[3] = 0;
+    status_host[3] = (int32_t)c[kCntSlowPair];  /* brick path: pairs re-evaluated in exact arithmetic */
     if (c[kCntFatal] != 0)
         return set_error(WOL_ERR_CAPACITY, "%u centres have more neighbours than the large-capacity path holds", c[kCntFatal]);
     return WOL_OK;

@@ -629,12 +629,15 @@ static int launch_big(const Q3bParams &P, cudaStream_t stream) {
 }
 
 template <typename T, bool EXACT>
-static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc) {
+static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc, double brick_box_max = 0.0) {
     typedef GroupWorker<T, kFastG, kFastCap, kFastMaxSeg, EXACT, false> FastWorker;
     reset_counters_kernel<<<1, 32, 0, stream>>>(P.counters);
     add_launches(1);
     if (P.ev_begin) cudaEventRecord((cudaEvent_t)P.ev_begin, stream);
-    if (use_tpc) {
+    if (brick_box_max > 0.0) {
+        int rc = q3b_brick_launch(P, brick_box_max, stream);
+        if (rc != WOL_OK) return rc;
+    } else if (use_tpc) {
         int rc = (sizeof(T) == 8) ? q3b_tpc_launch(P, stream, EXACT) : q3b_tpc32_launch(P, stream);
         if (rc != WOL_OK) return rc;
     } else {
@@ -772,8 +775,11 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     // WOL_NO_TPC / WOL_NO_TPC32 (environment, read per call): route to the generic group-per-centre kernels that
     // otherwise only serve boxes below four cells per edge -- a test switch (tests/test_gpu_edges.py), not a tuning knob
     const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
-    if (a.precision == WOL_PREC_FP64)
+    if (a.precision == WOL_PREC_FP64) {
+        // large batches where every atom is a centre: brick path (wol_q3b_brick.cu); it feeds the same queues
+        if (use_tpc && q3b_brick_supported(P, exact)) return launch_typed<double, false>(P, stream, true, a.box_max);
         return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);
+    }
     const bool use_tpc32 = use_tpc && getenv("WOL_NO_TPC32") == nullptr;
     return exact ? launch_typed<float, true>(P, stream, false) : launch_typed<float, false>(P, stream, use_tpc32);
 }

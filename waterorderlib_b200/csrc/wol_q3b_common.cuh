@@ -305,5 +305,7 @@ int q3b_tpc32_launch(const Q3bParams &P, cudaStream_t stream);
 int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact, bool f32);
 bool q3b_tpc_widen_supported(const Q3bParams &P);
 bool q3b_tpc_supported(const Q3bParams &P);
+bool q3b_brick_supported(const Q3bParams &P, bool exact);
+int q3b_brick_launch(const Q3bParams &P, double box_max, cudaStream_t stream);
 
 }  // namespace wol

@@ -33,6 +33,9 @@ enum {
     kCntOverflow = 2,  // centres whose list overflowed the fast path
     kCntFatal = 3,     // centres whose list overflowed the large-capacity path
     kCntLevel2 = 4,    // entries in the second-level list (widened search at half-width 2 was not enough)
+    kCntBrick = 5,     // brick path: next brick to hand out
+    kCntSlowPair = 6,  // brick path: three-body pairs re-evaluated in exact arithmetic (decision too close to call)
+    kCntBrickFb = 7,   // brick path: one-cell-wide sub-bricks too dense to stage (their centres went to the queue)
     kNumCounters = 8
 };
 

@@ -220,6 +220,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
             st = (ctypes.c_int32 * 4)()
             check(L.wol_status(ctypes.c_void_p(ws_ptr), F, N, M, ctypes.byref(nc), stream, ctypes.byref(st)), "wol_status")
             res["n_widened"], res["n_overflow"] = int(st[0]), int(st[1])
+            res["n_slow_pairs"] = int(st[3])  # brick path: pairs decided by the exact re-evaluation
     # keep inputs alive until the stream has consumed them
     res["_keep"] = (pos_d, box_d, cen_d, ws, table, nv_d)
     return res

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
                 w.x = wrapped_coord((double)x, s_L[0], s_iL[0]);
                 w.y = wrapped_coord((double)y, s_L[1], s_iL[1]);
                 w.z = wrapped_coord((double)z, s_L[2], s_iL[2]);
-                w.w = __int_as_float(a0 + t);
+                w.w = __int_as_float((int)dst);  // fp64 records: the atom's place in the cell-sorted arrays (brick sweep)
                 p.wrapped[dst] = w;
             }
         } else {

@@ -1,39 +1,40 @@
 // K2, brick path (sm_100a): the dominant kernel for large frames, fp64 mode, every atom a centre.
 //
 // One persistent CTA per SM: 15 consumer warps + 1 producer warp.  The unit of work is a BRICK of cells
-// (about 16 x 4 x 4) plus its one-cell halo.
+// (about 15 x 4 x 4) plus its one-cell halo.
 //
 //   producer   takes the next brick from a device counter, reads the cell starts at the ends of the
 //              (y, z) rows of brick + halo (every row is one contiguous x-run of the cell-sorted arrays,
-//              plus one cell from the other end of the box where the run wraps), and stages the rows into
-//              shared memory with 1-D bulk async copies (cp.async.bulk -> mbarrier complete_tx): the float
-//              prefilter coordinates (`wrapped`, 16 B per atom, double-buffered: the next brick lands while
-//              this one is swept) and the fp64 records (32 B per atom, needed from phase 2 on, so their copy
-//              overlaps phase 1).  Once the float rows have landed it rewrites them in place as coordinates
-//              relative to the brick origin with the periodic image already applied, so the sweep has no
-//              image logic at all.  A brick whose halo does not fit the stage is split along x on the spot.
-//   consumers  warps take chunks of 32 consecutive centres of the brick from a shared counter (a warp that
-//              finds none left moves on to the next brick, whose floats are already staged).
+//              plus one cell from the other end of the box where the run wraps), and stages the rows' float
+//              prefilter coordinates (`wrapped`, 16 B per atom) into one of three shared-memory stages with
+//              1-D bulk async copies (cp.async.bulk -> mbarrier complete_tx), up to two bricks ahead of
+//              the consumers.  Rows (or row ends) that come from the other side of the box are shifted by
+//              the box edge in place once they have landed, so the sweep has no image logic at all; .w of a
+//              staged atom is its position in the cell-sorted arrays (written by the cell build).  A brick
+//              whose halo does not fit a stage is split along x on the spot.
+//   consumers  warps take chunks of 32 consecutive centres of a brick from a shared counter; a warp that
+//              finds none left moves on to the next brick, so no warp ever waits for another.
 //     phase 1  float prefilter over the 9 stencil rows, all operands from shared memory (LDS.128 per
-//              candidate, 3 FADD + 1 FMUL + 2 FFMA + compare).  A min/max network keeps the four smallest
-//              float distances; a candidate beyond the three-body cutoff is only kept while it can still be
-//              one of the four nearest (4th smallest so far + rounding slack), which cuts the survivors
-//              from ~8 to ~5.5.
-//     phase 2  exact re-evaluation of the survivors in the reference's fp64 operation order (cutoff
-//              tests and neighbour counts are bit-exact by construction); the UNIT vector of every kept
-//              neighbour goes to a per-thread shared-memory column.
+//              candidate, 3 FADD + 1 FMUL + 2 FFMA + compare); a survivor costs one predicated store of
+//              (distance^2 | stage slot) -- nothing else is allowed inside this loop, because with 32 lanes some
+//              lane has a survivor in nearly every iteration.
+//     phase 1b dense pass over the ~9 survivors: min/max network for the four smallest float distances; a
+//              survivor beyond the three-body cutoff is kept only while it can still be one of the four
+//              nearest (4th smallest so far + rounding slack): ~5.5 remain.
+//     phase 2  exact re-evaluation of those in the reference's fp64 operation order from the fp64 records
+//              (gathered from L2, next one in flight): cutoff tests and neighbour counts are bit-exact by
+//              construction; the UNIT vector of every kept neighbour goes to a per-thread shared column.
 //     phase 3a three-body pairs flattened over the warp; cosine = dot of two unit vectors (3 DFMA).
 //     phase 3b q from the four winners' unit vectors.
 //
 // "Certified" decisions.  The reference computes the cosine as dot / sqrt(n1 * n2) from vectors
 // (r + d) - r, every operation rounded (waterlib.f90:694-698); the unit-vector cosine differs from it by
-// at most eps_c = O(2^-50 (|r| + cutoff) / |d|) (derivation at bk_eps below, a few 1e-12 for a 310 A
+// at most eps_c = O(2^-50 (|r| + cutoff) / |d|) (derivation in q3b_brick_launch, a few 1e-12 for a 310 A
 // box).  A histogram bin, the tetrahedral-window test, the order of the four nearest and the q bin are
 // taken from the fast value only when it is farther than that bound from every decision boundary;
-// otherwise the pair is re-evaluated in the reference's exact arithmetic from the staged records
-// (bk_exact_pair), or the centre's q is handed to the exact widened-search kernel.  Outputs are therefore
-// bit-identical to the exact path; the slow paths fire for ~1e-8 of the angles (counted in
-// counters[kCntSlowPair]).
+// otherwise the pair is re-evaluated in the reference's exact arithmetic (bk_exact_pair), or the centre's
+// q is handed to the exact widened-search kernel.  Outputs are therefore bit-identical to the exact path;
+// the slow paths fire for ~1e-8 of the angles (counted in counters[kCntSlowPair]).
 #include <math.h>
 #include <stdlib.h>
 
@@ -45,16 +46,19 @@ constexpr int kBkWarps = 15;                    // consumer warps (16 warps with
                                                 // a 17th warp would be charged as 20 -- warps are allocated in fours)
 constexpr int kBkConsumers = kBkWarps * 32;
 constexpr int kBkThreads = kBkConsumers + 32;   // + one producer warp
-constexpr int kBkAtomCap = 1536;                // atoms of brick + halo per stage
+constexpr int kBkStages = 3;
+constexpr int kBkAtomCap = 1536;                // atoms of brick + halo per stage (slot fits 11 bits)
 constexpr int kBkRowCap = 49;                   // (y, z) rows of brick + halo: (nby + 2) (nbz + 2), nby, nbz <= 5
 constexpr int kBkCsW = 32;                      // cell starts per row: nbx + 3 <= 32
 constexpr int kBkMaxBx = kBkCsW - 3;
 constexpr int kBkMaxByz = 5;
 constexpr int kBkCRowCap = kBkMaxByz * kBkMaxByz;
-constexpr int kBkListCap = 14;                  // prefilter survivors per centre
+constexpr int kBkListCap = 12;                  // prefilter survivors per centre (self included)
 constexpr int kBkEntCap = 8;                    // unit vectors per centre (three-body neighbours from the front,
                                                 // q-only candidates from the back)
 constexpr int kBkMaxPairs = kBkEntCap * (kBkEntCap - 1) / 2;
+constexpr unsigned kBkSlotMask = 2047u;         // list entry = float bits of distance^2 with the low 11 bits = slot
+static_assert(kBkAtomCap <= 2048, "slot must fit 11 bits");
 
 struct BrickPlan {
     int nb0, nb1, nb2;        // bricks per axis; brick i covers cells [i nc / nb, (i + 1) nc / nb)
@@ -62,32 +66,35 @@ struct BrickPlan {
     unsigned total;           // bricks in the batch
     float pre_thr3;           // prefilter threshold of the three-body cutoff (< 0: no three-body)
     float pre_cst1;           // slack added to the running 4th-smallest float distance^2
-    double eps_a, eps_b;      // eps_c = eps_a * (max |coordinate| + reach) + eps_b
+    double eps_a, eps_b;      // eps_c = eps_a * (max |coordinate|) + eps_b
     double floor2;            // neighbours closer than this (squared) send the centre to the exact path
 };
 
 struct BkItem {
     int done, frame, n_centres, n_chunks;
-    int nbx, nby, n_crows, pad;
+    int nbx, nby, n_crows, next;             // next: chunk counter
     double L[3], iL[3];
     int crow_off[kBkCRowCap + 1];            // centres before centre row r
-    int crow_g[kBkCRowCap];                  // its index in the cell-sorted arrays
     unsigned short crow_slot[kBkCRowCap];    // stage slot of the first centre of row r
     unsigned short crow_hrow[kBkCRowCap];    // its row among brick + halo rows
 };
 
+struct BkRowInfo {    // one (y, z) row of brick + halo (producer scratch)
+    int base;         // cell_start index of the row's cell x = 0
+    int delta;        // stage slot - cell-sorted index, for the atoms of the main run
+};
+
 struct BkSmem {
-    float4 loc[2][kBkAtomCap];
-    RecD recs[kBkAtomCap];
+    float4 loc[kBkStages][kBkAtomCap];
     double ent[kBkEntCap][3][kBkConsumers];
-    unsigned short ent_slot[kBkEntCap][kBkConsumers];
-    unsigned short lj[kBkListCap][kBkConsumers];
-    unsigned short cslot[kBkConsumers];
-    unsigned short cs[2][kBkRowCap * kBkCsW];
+    int ent_g[kBkEntCap][kBkConsumers];          // where the entry's fp64 record is
+    unsigned lj[kBkListCap + 1][kBkConsumers];   // survivor lists (+ one row that absorbs overflowing stores)
+    unsigned short cs[kBkStages][kBkRowCap * kBkCsW];
+    int cgj[kBkConsumers];                       // where the centre's fp64 record is
     int woff[kBkWarps][33];
-    BkItem item[2];
-    unsigned long long bar_full_w[2], bar_raw_w[2], bar_empty_w[2], bar_full_r, bar_empty_r;
-    int next[2];
+    BkItem item[kBkStages];
+    BkRowInfo rows[kBkRowCap];
+    unsigned long long bar_full[kBkStages], bar_raw[kBkStages], bar_empty[kBkStages];
     unsigned char pair_ab[kBkMaxPairs + 4];
 };
 
@@ -104,20 +111,26 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t a, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return done != 0u;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     const uint32_t a = smem_addr(bar);
-    unsigned done, polls = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
+    if (mbar_try(a, parity)) return;
+    unsigned polls = 0;
+    while (!mbar_try(a, parity)) {
+        __nanosleep(40);  // leave the issue slots to the warps that have work (the producer shares a scheduler with three consumers)
         // a wait that never completes becomes a launch failure the host sees, not a hung device
-        if (!done && ++polls > (1u << 24)) __trap();
-    } while (!done);
+        if (++polls > (1u << 24)) __trap();
+    }
 }
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
@@ -129,13 +142,12 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 
 // ---- producer ------------------------------------------------------------------------------------------------------
 
-struct BkRow {        // one (y, z) row of brick + halo, as the lane that owns it sees it
-    int gA, gM, gB;   // global index of the first atom of the piece: image at x - L, main run, image at x + L
-    int cA, cM, cB;   // atoms per piece
+struct BkRow {        // as the lane that measures the row sees it
+    int gA, gM, gB, cA, cM, cB;
     int cc, gc;       // centres of the row (0 for halo rows), cell_start index of the first centre cell
-    int base;         // cell_start index of the row's cell x = 0
-    float sy, sz;     // what to add to y, z to reach the image next to the brick
-    int off;          // stage slot of the row's first atom
+    int base;
+    float sy, sz;
+    int off;
 };
 
 __device__ __forceinline__ void bk_measure_row(const Q3bParams &P, int f, int rr, int nby, int nbz, int by0, int bz0, int xa, int w,
@@ -181,7 +193,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
 }
 
 // centres of a sub-brick that cannot be staged even one cell wide: hand them to the large-capacity pass
-__device__ void bk_route_to_fallback(const Q3bParams &P, const BkRow &R, int f, int lane) {
+__device__ void bk_route_to_fallback(const Q3bParams &P, const BkRow &R) {
     const uint32_t flags = (P.do_3b ? kFbNeed3b : 0u) | (P.do_q ? kFbNeedQ : 0u);
     const int g0 = (int)__ldg(P.cell_start + R.gc);
     for (int k = 0; k < R.cc; ++k) {
@@ -189,8 +201,6 @@ __device__ void bk_route_to_fallback(const Q3bParams &P, const BkRow &R, int f, 
         P.fb_list[at] = (uint32_t)(g0 + k) | flags;
         atomicAdd(P.counters + kCntOverflow, 1u);
     }
-    (void)f;
-    (void)lane;
 }
 
 __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, BkSmem &S, int lane) {
@@ -198,30 +208,35 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, BkSmem &S, i
     unsigned it = 0;
     int xa = 0, xb = 0, w = 0, f = 0, by0 = 0, nby = 0, bz0 = 0, nbz = 0;
     double Lx = 1, Ly = 1, Lz = 1;
+    int box_f = -1;
+    unsigned next_id = 0;  // the next brick id is fetched one brick ahead: the atomic's round trip is off the critical path
+    if (lane == 0) next_id = atomicAdd(P.counters + kCntBrick, 1u);
     for (;;) {
         if (xa >= xb) {  // next brick
-            unsigned id = 0;
-            if (lane == 0) id = atomicAdd(P.counters + kCntBrick, 1u);
-            id = __shfl_sync(kFullMask, id, 0);
+            const unsigned id = __shfl_sync(kFullMask, next_id, 0);
             if (id >= B.total) break;
+            if (lane == 0) next_id = atomicAdd(P.counters + kCntBrick, 1u);
             f = (int)(id / (unsigned)B.bricks_per_frame);
             const int r = (int)(id - (unsigned)f * (unsigned)B.bricks_per_frame);
             const int ibx = r % B.nb0, iby = (r / B.nb0) % B.nb1, ibz = r / (B.nb0 * B.nb1);
-            xa = (int)((long long)ibx * nc0 / B.nb0);
-            xb = (int)((long long)(ibx + 1) * nc0 / B.nb0);
-            by0 = (int)((long long)iby * nc1 / B.nb1);
-            nby = (int)((long long)(iby + 1) * nc1 / B.nb1) - by0;
-            bz0 = (int)((long long)ibz * nc2 / B.nb2);
-            nbz = (int)((long long)(ibz + 1) * nc2 / B.nb2) - bz0;
+            xa = ibx * nc0 / B.nb0;  // nc <= 1024
+            xb = (ibx + 1) * nc0 / B.nb0;
+            by0 = iby * nc1 / B.nb1;
+            nby = (iby + 1) * nc1 / B.nb1 - by0;
+            bz0 = ibz * nc2 / B.nb2;
+            nbz = (ibz + 1) * nc2 / B.nb2 - bz0;
             w = xb - xa;
-            Lx = P.box[(size_t)f * 3 + 0];
-            Ly = P.box[(size_t)f * 3 + 1];
-            Lz = P.box[(size_t)f * 3 + 2];
+            if (f != box_f) {
+                Lx = P.box[(size_t)f * 3 + 0];
+                Ly = P.box[(size_t)f * 3 + 1];
+                Lz = P.box[(size_t)f * 3 + 2];
+                box_f = f;
+            }
             if (w <= 0 || nby <= 0 || nbz <= 0) { xa = xb; continue; }
         }
         const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
         const int nrows = (nby + 2) * (nbz + 2);
-        // ---- measure the sub-brick [xa, xa + w): atoms per row, centres per row --------------------------
+        // ---- measure the sub-brick [xa, xa + w): atoms per row, centres per row (lane <-> rows lane, lane + 32) -----
         BkRow R0, R1;
         R0.cA = R0.cM = R0.cB = R0.cc = 0;
         R1.cA = R1.cM = R1.cB = R1.cc = 0;
@@ -236,18 +251,20 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, BkSmem &S, i
         if (n_centres == 0) { xa += w; w = min(w, xb - xa); continue; }
         if (n_atoms > kBkAtomCap - 1) {
             if (w > 1) { w = (w + 1) / 2; continue; }
-            if (R0.cc > 0) bk_route_to_fallback(P, R0, f, lane);
-            if (R1.cc > 0) bk_route_to_fallback(P, R1, f, lane);
+            if (R0.cc > 0) bk_route_to_fallback(P, R0);
+            if (R1.cc > 0) bk_route_to_fallback(P, R1);
             if (lane == 0) atomicAdd(P.counters + kCntBrickFb, 1u);
             xa += 1;
             w = min(w, xb - xa);
             continue;
         }
         // ---- stage it ---------------------------------------------------------------------------------------
-        const int s = (int)(it & 1u);
-        if (it >= 2) mbar_wait(&S.bar_empty_w[s], ((it >> 1) + 1u) & 1u);
+        const int s = (int)(it % kBkStages);
+        const unsigned round = it / kBkStages;
+        if (round >= 1) mbar_wait(&S.bar_empty[s], (round + 1u) & 1u);
         BkItem &I = S.item[s];
         unsigned short *cst = S.cs[s];
+        float4 *stage = S.loc[s];
         if (lane == 0) {
             I.done = 0;
             I.frame = f;
@@ -256,107 +273,99 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, BkSmem &S, i
             I.nbx = w;
             I.nby = nby;
             I.n_crows = nby * nbz;
+            I.next = 0;
             I.L[0] = Lx; I.L[1] = Ly; I.L[2] = Lz;
             I.iL[0] = __ddiv_rn(1.0, Lx);
             I.iL[1] = __ddiv_rn(1.0, Ly);
             I.iL[2] = __ddiv_rn(1.0, Lz);
             I.crow_off[nby * nbz] = n_centres;
-            S.next[s] = 0;
+            mbar_arrive_expect_tx(&S.bar_raw[s], (unsigned)n_atoms * 16u);
         }
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const BkRow &R = h ? R1 : R0;
             const int rr = lane + 32 * h;
             if (rr >= nrows) continue;
-            // slot of every cell start of the row: entry i <-> cell xa - 1 + i, entry w + 2 = end of the row
-            unsigned short *row = cst + rr * kBkCsW;
-            for (int i0 = 0; i0 <= w + 2; i0 += 4) {
-                int v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {  // four independent loads in flight
-                    const int i = i0 + u, gx = xa - 1 + i;
-                    v[u] = (i <= w + 1 && gx >= 0 && gx < nc0) ? (int)__ldg(P.cell_start + R.base + gx) : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u, gx = xa - 1 + i;
-                    if (i > w + 2) break;
-                    int o;
-                    if (i == w + 2) o = R.off + R.cA + R.cM + R.cB;
-                    else if (gx < 0) o = R.off;                      // the single cell at x - L
-                    else if (gx < nc0) o = R.off + R.cA + v[u] - R.gM;
-                    else o = R.off + R.cA + R.cM;                    // the single cell at x + L
-                    row[i] = (unsigned short)o;
-                }
-            }
-            {
-                const int hz = rr / (nby + 2), hy = rr - hz * (nby + 2);
-                if (hy >= 1 && hy <= nby && hz >= 1 && hz <= nbz) {
-                    const int r = (hz - 1) * nby + (hy - 1);
-                    I.crow_off[r] = h ? coff1 : coff0;
-                    const int g0 = (int)__ldg(P.cell_start + R.gc);
-                    I.crow_g[r] = g0;
-                    I.crow_slot[r] = (unsigned short)(R.off + R.cA + g0 - R.gM);
-                    I.crow_hrow[r] = (unsigned short)rr;
-                }
+            if (R.cA > 0) bulk_g2s(stage + R.off, P.wrapped + R.gA, (unsigned)R.cA * 16u, &S.bar_raw[s]);
+            if (R.cM > 0) bulk_g2s(stage + R.off + R.cA, P.wrapped + R.gM, (unsigned)R.cM * 16u, &S.bar_raw[s]);
+            if (R.cB > 0) bulk_g2s(stage + R.off + R.cA + R.cM, P.wrapped + R.gB, (unsigned)R.cB * 16u, &S.bar_raw[s]);
+            S.rows[rr].base = R.base;
+            S.rows[rr].delta = R.off + R.cA - R.gM;
+            const int hz = rr / (nby + 2), hy = rr - hz * (nby + 2);
+            if (hy >= 1 && hy <= nby && hz >= 1 && hz <= nbz) {
+                const int r = (hz - 1) * nby + (hy - 1);
+                I.crow_off[r] = h ? coff1 : coff0;
+                I.crow_slot[r] = (unsigned short)(R.off + R.cA + (int)__ldg(P.cell_start + R.gc) - R.gM);
+                I.crow_hrow[r] = (unsigned short)rr;
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_arrive_expect_tx(&S.bar_raw_w[s], (unsigned)n_atoms * 16u);
         __syncwarp();
-        float4 *stage = S.loc[s];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const BkRow &R = h ? R1 : R0;
-            if (R.cA > 0) bulk_g2s(stage + R.off, P.wrapped + R.gA, (unsigned)R.cA * 16u, &S.bar_raw_w[s]);
-            if (R.cM > 0) bulk_g2s(stage + R.off + R.cA, P.wrapped + R.gM, (unsigned)R.cM * 16u, &S.bar_raw_w[s]);
-            if (R.cB > 0) bulk_g2s(stage + R.off + R.cA + R.cM, P.wrapped + R.gB, (unsigned)R.cB * 16u, &S.bar_raw_w[s]);
-        }
-        mbar_wait(&S.bar_raw_w[s], (it >> 1) & 1u);
-        // ---- in place: coordinates relative to the brick origin, periodic image applied --------------------
+        // ---- while the copies fly: stage slot of every cell start.  Entry i of a row <-> cell xa - 1 + i, entry
+        // w + 2 = end of the row.  Lane <-> cell, one coalesced load per row, eight rows in flight; the entries of
+        // the image cells and the row ends are patched afterwards by the lane that measured the row.
         {
-            const float ox = (float)((double)xa * (Lx / (double)nc0));
-            const float oy = (float)((double)by0 * (Ly / (double)nc1));
-            const float oz = (float)((double)bz0 * (Lz / (double)nc2));
+            const int gx = min(max(xa - 1 + lane, 0), nc0 - 1);
+            const bool act = lane <= w + 1;
+            for (int r0 = 0; r0 < nrows; r0 += 8) {
+                int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < nrows && act) v[u] = (int)__ldg(P.cell_start + S.rows[r0 + u].base + gx);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < nrows && act) cst[(r0 + u) * kBkCsW + lane] = (unsigned short)(v[u] + S.rows[r0 + u].delta);
+            }
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const BkRow &R = h ? R1 : R0;
-                const int n = R.cA + R.cM + R.cB;
-                for (int k = 0; k < n; ++k) {
-                    float4 v = stage[R.off + k];
-                    const float sx = k < R.cA ? -Lxf : (k < R.cA + R.cM ? 0.f : Lxf);
-                    v.x = (v.x + sx) - ox;
-                    v.y = (v.y + R.sy) - oy;
-                    v.z = (v.z + R.sz) - oz;
-                    stage[R.off + k] = v;
-                }
+                const int rr = lane + 32 * h;
+                if (rr >= nrows) continue;
+                unsigned short *row = cst + rr * kBkCsW;
+                row[w + 2] = (unsigned short)(R.off + R.cA + R.cM + R.cB);
+                if (xa - 1 < 0) row[0] = (unsigned short)R.off;                          // the single cell at x - L
+                if (xa + w >= nc0) row[w + 1] = (unsigned short)(R.off + R.cA + R.cM);   // the single cell at x + L
             }
         }
-        mbar_arrive(&S.bar_full_w[s]);  // 32 arrivals: every lane's metadata and rewritten rows are published
-        // ---- the fp64 records of the same rows, once every warp is done with the previous brick's ----------
-        if (it >= 1) mbar_wait(&S.bar_empty_r, (it + 1u) & 1u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_arrive_expect_tx(&S.bar_full_r, (unsigned)n_atoms * 32u);
-        __syncwarp();
+        mbar_wait(&S.bar_raw[s], round & 1u);
+        // ---- periodic images: rows (or row ends) that come from the other side of the box are shifted in place, so
+        // the sweep has no image logic.  Interior bricks have none.
         {
-            const RecD *g = reinterpret_cast<const RecD *>(P.recs);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const BkRow &R = h ? R1 : R0;
-                if (R.cA > 0) bulk_g2s(S.recs + R.off, g + R.gA, (unsigned)R.cA * 32u, &S.bar_full_r);
-                if (R.cM > 0) bulk_g2s(S.recs + R.off + R.cA, g + R.gM, (unsigned)R.cM * 32u, &S.bar_full_r);
-                if (R.cB > 0) bulk_g2s(S.recs + R.off + R.cA + R.cM, g + R.gB, (unsigned)R.cB * 32u, &S.bar_full_r);
+                const bool mine = (lane + 32 * h < nrows) && (R.sy != 0.f || R.sz != 0.f || R.cA > 0 || R.cB > 0);
+                unsigned todo = __ballot_sync(kFullMask, mine);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int off = __shfl_sync(kFullMask, R.off, src), cA = __shfl_sync(kFullMask, R.cA, src);
+                    const int cM = __shfl_sync(kFullMask, R.cM, src), cB = __shfl_sync(kFullMask, R.cB, src);
+                    const float sy = __shfl_sync(kFullMask, R.sy, src), sz = __shfl_sync(kFullMask, R.sz, src);
+                    const int n = cA + cM + cB;
+                    for (int k = lane; k < n; k += 32) {
+                        float4 v = stage[off + k];
+                        v.x += k < cA ? -Lxf : (k >= cA + cM ? Lxf : 0.f);
+                        v.y += sy;
+                        v.z += sz;
+                        stage[off + k] = v;
+                    }
+                }
             }
         }
+        mbar_arrive(&S.bar_full[s]);  // 32 arrivals: every lane's metadata and rewritten rows are published
         ++it;
         xa += w;
         w = min(w, xb - xa);
     }
     // no more bricks: publish the end marker in the next stage
-    const int s = (int)(it & 1u);
-    if (it >= 2) mbar_wait(&S.bar_empty_w[s], ((it >> 1) + 1u) & 1u);
+    const int s = (int)(it % kBkStages);
+    const unsigned round = it / kBkStages;
+    if (round >= 1) mbar_wait(&S.bar_empty[s], (round + 1u) & 1u);
     if (lane == 0) S.item[s].done = 1;
-    mbar_arrive(&S.bar_full_w[s]);
+    mbar_arrive(&S.bar_full[s]);
 }
 
 // ---- consumers -----------------------------------------------------------------------------------------------------
@@ -386,10 +395,10 @@ struct Top4S {
     }
 };
 
-// The reference's clamped cosine and bin for one pair, from the staged records, every operation as the
-// Fortran performs it (waterlib.f90:880-883 second reimage is the identity here: |v| < L / 2).
-static __device__ __noinline__ double bk_exact_pair(const RecD *recs, int cslot, int sa, int sb, const double *L, const double *iL) {
-    const RecD c = recs[cslot], a = recs[sa], b = recs[sb];
+// The reference's clamped cosine for one pair, from the fp64 records, every operation as the Fortran
+// performs it (waterlib.f90:880-883 second reimage is the identity here: |v| < L / 2).
+static __device__ __noinline__ double bk_exact_pair(const RecD *recs, int gc, int ga, int gb, const double *L, const double *iL) {
+    const RecD c = recs[gc], a = recs[ga], b = recs[gb];
     double va[3], vb[3];
     const double r[3] = {c.x, c.y, c.z}, pa[3] = {a.x, a.y, a.z}, pb[3] = {b.x, b.y, b.z};
 #pragma unroll
@@ -428,6 +437,15 @@ __device__ __forceinline__ void bk_push_q(const Q3bParams &P, uint32_t fb_id) {
     atomicAdd(P.counters + kCntWidened, 1u);
 }
 
+__device__ __forceinline__ void bk_load_rec(const void *recs, int g, double &x, double &y, double &z, int &idx) {
+    const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + g);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    x = __hiloint2double(a.y, a.x);
+    y = __hiloint2double(a.w, a.z);
+    z = __hiloint2double(b.y, b.x);
+    idx = b.z;
+}
+
 __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_constant__ Q3bParams P, const __grid_constant__ BrickPlan B) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BkSmem &S = *reinterpret_cast<BkSmem *>(smem_raw);
@@ -450,13 +468,11 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
         S.pair_ab[tid] = (unsigned char)((tid - b * (b - 1) / 2) | (b << 4));
     }
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&S.bar_full_w[s], 32);
-            mbar_init(&S.bar_raw_w[s], 1);
-            mbar_init(&S.bar_empty_w[s], kBkWarps);
+        for (int s = 0; s < kBkStages; ++s) {
+            mbar_init(&S.bar_full[s], 32);
+            mbar_init(&S.bar_raw[s], 1);
+            mbar_init(&S.bar_empty[s], kBkWarps);
         }
-        mbar_init(&S.bar_full_r, 1);
-        mbar_init(&S.bar_empty_r, kBkWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -476,14 +492,15 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
     const float pre_thr2 = P.pre_thr2, pre_thr3 = B.pre_thr3, pre_cst1 = B.pre_cst1, lowq_hi2 = P.lowq_hi2;
     const float kInf = __int_as_float(0x7f800000);
     const HistSpec qhs = hist_spec(0.0, 1.0, P.q_nbins);
+    unsigned *const my_list = &S.lj[0][tid];
 
     LaneStats st;
     st.reset();
     int cur_f = -1;
     for (unsigned it = 0;; ++it) {
-        const int s = (int)(it & 1u);
-        mbar_wait(&S.bar_full_w[s], (it >> 1) & 1u);
-        const BkItem &I = S.item[s];
+        const int s = (int)(it % kBkStages);
+        mbar_wait(&S.bar_full[s], (it / kBkStages) & 1u);
+        BkItem &I = S.item[s];
         if (I.done) break;
         const int f = I.frame;
         if (f != cur_f) {
@@ -501,16 +518,14 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
         const float4 *loc = S.loc[s];
         const unsigned short *cst = S.cs[s];
         const int nbx = I.nbx, rstride = I.nby + 2, n_centres = I.n_centres, n_chunks = I.n_chunks, n_crows = I.n_crows;
-        bool recs_ready = false;
         for (;;) {
             int chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&S.next[s], 1);
+            if (lane == 0) chunk = atomicAdd(&I.next, 1);
             chunk = __shfl_sync(kFullMask, chunk, 0);
             if (chunk >= n_chunks) break;
             const int ci = chunk * 32 + lane;
             const bool valid = ci < n_centres;
             int slot = 0, hx1 = 1, hrow = rstride + 1;
-            uint32_t fb_id = 0;  // the centre's index in the cell-sorted arrays = its id in the queues
             if (valid) {
                 int r = 0;
 #pragma unroll
@@ -519,7 +534,6 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     if (t < n_crows && I.crow_off[t] <= ci) r = t;
                 }
                 slot = I.crow_slot[r] + (ci - I.crow_off[r]);
-                fb_id = (uint32_t)(I.crow_g[r] + (ci - I.crow_off[r]));
                 hrow = I.crow_hrow[r];
                 const unsigned short *row = cst + hrow * kBkCsW;
 #pragma unroll
@@ -528,13 +542,19 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     if (t <= nbx && (int)row[t] <= slot) hx1 = t;
                 }
             }
-            S.cslot[tid] = (unsigned short)slot;
+            const float4 me = loc[slot];
+            const int gj = __float_as_int(me.w);  // the centre's place in the cell-sorted arrays = its id in the queues
+            S.cgj[tid] = gj;
+            // the centre's fp64 record is needed from phase 2 on: in flight during the sweep
+            double rx = 0, ry = 0, rz = 0;
+            int my_idx = 0;
+            if (valid) bk_load_rec(P.recs, gj, rx, ry, rz, my_idx);
 
             // ---------------- phase 1: float prefilter over the 9 rows of the stencil ---------------------
+            // A survivor is ONE predicated store (distance^2 with the slot in its low mantissa bits); the centre itself
+            // passes (distance 0) and is dropped in phase 1b.
             int nl = 0;
             if (valid) {
-                const float4 me = loc[slot];
-                float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
                 const unsigned short *row = cst + (hrow - rstride - 1) * kBkCsW + hx1 - 1;
 #pragma unroll 1
                 for (int r9 = 0; r9 < 9; ++r9) {
@@ -543,59 +563,72 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     row += (r9 == 2 || r9 == 5) ? (rstride - 2) * kBkCsW : kBkCsW;
                     float4 w = loc[j];
                     while (j < jend) {
-                        const float4 wn = loc[j + 1];  // stage holds one spare entry
+                        const float4 wn = loc[j + 1];  // a stage holds one spare entry
                         const float dx = w.x - me.x, dy = w.y - me.y, dz = w.z - me.z;
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        if (r2 <= pre_thr2 && j != slot) {
-                            const bool keep = r2 <= pre_thr3 || r2 <= a3 + pre_cst1;
-                            if (r2 > lowq_hi2) {
-                                float v = r2, m;
-                                m = fminf(a0, v); v = fmaxf(a0, v); a0 = m;
-                                m = fminf(a1, v); v = fmaxf(a1, v); a1 = m;
-                                m = fminf(a2, v); v = fmaxf(a2, v); a2 = m;
-                                a3 = fminf(a3, v);
-                            }
-                            if (keep) {
-                                if (nl < kBkListCap) S.lj[nl][tid] = (unsigned short)j;
-                                ++nl;
-                            }
+                        if (r2 <= pre_thr2) {
+                            my_list[min(nl, kBkListCap) * kBkConsumers] = (__float_as_uint(r2) & ~kBkSlotMask) | (unsigned)j;
+                            ++nl;
                         }
                         w = wn;
                         ++j;
                     }
                 }
             }
-            if (!recs_ready) {
-                mbar_wait(&S.bar_full_r, it & 1u);
-                recs_ready = true;
+            bool overflow = nl > kBkListCap;
+
+            // ---------------- phase 1b: which survivors can matter -------------------------------------------
+            // Four smallest distances^2 (truncated to 12 mantissa bits: the slack pre_cst1 covers that) among the
+            // survivors certainly beyond lowCut; a survivor is kept if it can be a three-body neighbour or one of the
+            // four nearest.  Kept entries become positions in the cell-sorted arrays (the stage is not needed again).
+            int nk = 0;
+            if (valid && !overflow) {
+                float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
+                for (int k = 0; k < nl; ++k) {
+                    const unsigned e = my_list[k * kBkConsumers];
+                    const int j = (int)(e & kBkSlotMask);
+                    const float r2 = __uint_as_float(e & ~kBkSlotMask);
+                    if (j == slot) continue;
+                    const bool keep = r2 <= pre_thr3 || r2 <= a3 + pre_cst1;
+                    if (r2 > lowq_hi2) {
+                        float v = r2, m;
+                        m = fminf(a0, v); v = fmaxf(a0, v); a0 = m;
+                        m = fminf(a1, v); v = fmaxf(a1, v); a1 = m;
+                        m = fminf(a2, v); v = fmaxf(a2, v); a2 = m;
+                        a3 = fminf(a3, v);
+                    }
+                    if (keep) {
+                        my_list[nk * kBkConsumers] = (unsigned)__float_as_int(loc[j].w);
+                        ++nk;
+                    }
+                }
             }
 
             // ---------------- phase 2: exact fp64 re-evaluation, unit vectors ---------------------------------
-            bool overflow = nl > kBkListCap;
             Top4S top;
             top.reset();
             double rej_min = Ops<double>::inf();
-            int K3 = 0, Kb = 0, nq = 0, my_idx = 0;
-            double rx = 0, ry = 0, rz = 0;
+            int K3 = 0, Kb = 0, nq = 0;
             float bmax = 0.f;
-            if (valid) {
-                const int4 *rp = reinterpret_cast<const int4 *>(S.recs + slot);
-                const int4 a = rp[0], b = rp[1];
-                rx = __hiloint2double(a.y, a.x);
-                ry = __hiloint2double(a.w, a.z);
-                rz = __hiloint2double(b.y, b.x);
-                my_idx = b.z;
-                bmax = __double2float_ru(fmax(fmax(fabs(rx), fabs(ry)), fabs(rz)));
-            }
+            if (valid) bmax = __double2float_ru(fmax(fmax(fabs(rx), fabs(ry)), fabs(rz)));
             if (valid && !overflow) {
                 const double Lx = I.L[0], Ly = I.L[1], Lz = I.L[2], iLx = I.iL[0], iLy = I.iL[1], iLz = I.iL[2];
-                for (int k = 0; k < nl; ++k) {
-                    const int j = S.lj[k][tid];
-                    const int4 *np = reinterpret_cast<const int4 *>(S.recs + j);
-                    const int4 a = np[0], b = np[1];
-                    const double dx = min_image_1<double, false>(__hiloint2double(a.y, a.x), rx, Lx, iLx);
-                    const double dy = min_image_1<double, false>(__hiloint2double(a.w, a.z), ry, Ly, iLy);
-                    const double dz = min_image_1<double, false>(__hiloint2double(b.y, b.x), rz, Lz, iLz);
+                double nx = 0, ny = 0, nz = 0;
+                int nidx = 0, ng = 0;
+                if (nk > 0) {
+                    ng = (int)my_list[0];
+                    bk_load_rec(P.recs, ng, nx, ny, nz, nidx);
+                }
+                for (int k = 0; k < nk; ++k) {
+                    const int g = ng;
+                    const double px = nx, py = ny, pz = nz;
+                    if (k + 1 < nk) {  // next survivor's record is in flight while this one is evaluated
+                        ng = (int)my_list[(k + 1) * kBkConsumers];
+                        bk_load_rec(P.recs, ng, nx, ny, nz, nidx);
+                    }
+                    const double dx = min_image_1<double, false>(px, rx, Lx, iLx);
+                    const double dy = min_image_1<double, false>(py, ry, Ly, iLy);
+                    const double dz = min_image_1<double, false>(pz, rz, Lz, iLz);
                     const double sq = sumsq3<double>(dx, dy, dz);
                     const bool in3 = do3 && (sq > low3sq) && (sq <= high3sq);
                     const bool inq = doq && (sq > lowqsq) && (sq <= selsq1);
@@ -613,7 +646,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                             S.ent[e][0][tid] = dx * rs;
                             S.ent[e][1][tid] = dy * rs;
                             S.ent[e][2][tid] = dz * rs;
-                            S.ent_slot[e][tid] = (unsigned short)j;
+                            S.ent_g[e][tid] = g;
                             if (want_q) {
                                 rej_min = fmin(rej_min, top.d[3]);
                                 top.insert(sq, e);
@@ -630,7 +663,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
             const size_t out_index = (size_t)f * P.n_pos + my_idx;
             if (valid && overflow) {
                 const uint32_t at = atomicAdd(P.counters + kCntFallback, 1u);
-                P.fb_list[at] = fb_id | (do3 ? kFbNeed3b : 0u) | (doq ? kFbNeedQ : 0u);
+                P.fb_list[at] = (uint32_t)gj | (do3 ? kFbNeed3b : 0u) | (doq ? kFbNeedQ : 0u);
                 atomicAdd(P.counters + kCntOverflow, 1u);
             }
             if (q_go) {
@@ -645,7 +678,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     if (nq > 4 && !(rej_min - top.d[3] > band * rej_min)) requeue = true;
                 }
                 if (requeue) {
-                    bk_push_q(P, fb_id);
+                    bk_push_q(P, (uint32_t)gj);
                     q_go = false;
                 }
             }
@@ -688,7 +721,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     if (pos < nbins && !(clo > tab[pos + 1])) sure = false;
                     if ((chi >= tet_c_hi && clo <= tet_c_hi) || (chi >= tet_c_lo && clo <= tet_c_lo)) sure = false;
                     if (!sure) {
-                        c = bk_exact_pair(S.recs, S.cslot[col], S.ent_slot[ea][col], S.ent_slot[eb][col], I.L, I.iL);
+                        c = bk_exact_pair(reinterpret_cast<const RecD *>(P.recs), S.cgj[col], S.ent_g[ea][col], S.ent_g[eb][col], I.L, I.iL);
                         pos = bk_exact_position(c, tab, nbins, hist_lo_f, inv_width_f);
                         atomicAdd(P.counters + kCntSlowPair, 1u);
                     }
@@ -750,15 +783,16 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     }
                 }
                 if (!sure) {
-                    bk_push_q(P, fb_id);
+                    bk_push_q(P, (uint32_t)gj);
                 } else {
                     if (P.q) reinterpret_cast<double *>(P.q)[out_index] = qv;
                     if (P.nn_idx) {
+                        const RecD *recs = reinterpret_cast<const RecD *>(P.recs);
                         int4 o;
-                        o.x = (nf > 0) ? S.recs[S.ent_slot[top.p[0]][tid]].idx : -1;
-                        o.y = (nf > 1) ? S.recs[S.ent_slot[top.p[1]][tid]].idx : -1;
-                        o.z = (nf > 2) ? S.recs[S.ent_slot[top.p[2]][tid]].idx : -1;
-                        o.w = (nf > 3) ? S.recs[S.ent_slot[top.p[3]][tid]].idx : -1;
+                        o.x = (nf > 0) ? __ldg(&recs[S.ent_g[top.p[0]][tid]].idx) : -1;
+                        o.y = (nf > 1) ? __ldg(&recs[S.ent_g[top.p[1]][tid]].idx) : -1;
+                        o.z = (nf > 2) ? __ldg(&recs[S.ent_g[top.p[2]][tid]].idx) : -1;
+                        o.w = (nf > 3) ? __ldg(&recs[S.ent_g[top.p[3]][tid]].idx) : -1;
                         reinterpret_cast<int4 *>(P.nn_idx)[out_index] = o;
                     }
                     if (bin >= 0) atomicAdd(s_qhist + bin, 1u);
@@ -768,12 +802,8 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                 }
             }
         }
-        if (!recs_ready) mbar_wait(&S.bar_full_r, it & 1u);  // keeps every warp in step with the barrier's phases
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&S.bar_empty_w[s]);
-            mbar_arrive(&S.bar_empty_r);
-        }
+        if (lane == 0) mbar_arrive(&S.bar_empty[s]);
     }
     if (cur_f >= 0) bk_flush_stats(P, cur_f, st);
     if (use_hist || use_qhist) {
@@ -854,14 +884,15 @@ int q3b_brick_launch(const Q3bParams &P, double box_max, cudaStream_t stream) {
     const double rthr = fmax(P.do_3b ? high3 : 0.0, rsel);
     B.pre_thr3 = P.do_3b ? nextafterf((float)((high3 + margin) * (high3 + margin) * (1.0 + 1e-6)), INFINITY) : -1.0f;
     const double cst = (4.0 * margin * (rthr + margin) + 4.0 * margin * margin) * (1.0 + 1e-6) + 1e-6 * rthr * rthr;
-    B.pre_cst1 = nextafterf((float)cst, INFINITY);
+    // + what dropping 11 mantissa bits of a survivor's distance^2 can hide (phase 1b)
+    B.pre_cst1 = nextafterf((float)(cst + 2.0 * ldexp(1.0, -12) * (rthr + margin) * (rthr + margin) * (1.0 + 1e-6)), INFINITY);
     // eps_c (bk header): the reference's vectors (r + d) - r differ from d by at most delta = 2^-51 (|r| + reach) per
     // component; two such vectors of length >= r_floor turn the cosine by at most 2 sqrt(3) delta / r_floor; the
     // roundings of either evaluation add less than 2^-48.  Factor 4 of safety on the first term.
     const double r_floor = 0.25, reach = rthr + margin + 1.0;
     B.floor2 = r_floor * r_floor;
     B.eps_a = 4.0 * 2.0 * sqrt(3.0) * ldexp(1.0, -51) / r_floor;
-    B.eps_b = B.eps_a * reach + ldexp(1.0, -46);
+    B.eps_b = B.eps_a * reach + ldexp(1.0, -46);  // eps_c = eps_a (max |coordinate| + reach) + 2^-46
     const size_t smem = brick_smem_bytes(P);
     cudaError_t e = cudaFuncSetAttribute(q3b_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(brick)", e);

@@ -51,7 +51,8 @@ struct WorkspaceLayout {
     size_t off_cell_id;     // uint32[F*N]
     size_t off_slot;        // uint32[F*N]  rank of the atom inside its cell
     size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
-    size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates + atom index, same order as recs
+    size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates, same order as recs; .w = the atom's place in
+                            // this array (fp64 records) or its original index (fp32 records)
     size_t off_fb_list;     // uint32[2*F*M]  centres the fast path handed on; second half = second level
     size_t total;
     int64_t n_cells_total;

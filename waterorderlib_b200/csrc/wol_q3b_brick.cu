@@ -423,6 +423,16 @@ static __device__ __noinline__ int bk_exact_position(double c, const double *tab
     return angle_position(c, tab, nbins, lo_f, invw_f);
 }
 
+// float seed of the bin of cosine c, always a valid bin index (see angle_position, which it mirrors)
+__device__ __forceinline__ int bk_seed_position(double c, int nbins, float lo, float inv_width) {
+    const float x = (float)c, ax = fabsf(x);
+    const float t = fmaxf(1.0f - ax, 1e-30f);
+    float r = fmaf(fmaf(fmaf(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f) * (t * rsqrtf(t));
+    r = x < 0.f ? 3.14159265f - r : r;
+    const int k = (int)((r * 57.29577951f - lo) * inv_width);
+    return min(max(k, 0), nbins - 1);
+}
+
 __device__ __forceinline__ void bk_flush_bins(unsigned *s_bins, unsigned long long *g_bins, int nbins, bool clear, int tid) {
     for (int i = tid; i < nbins; i += kBkConsumers) {
         const unsigned v = s_bins[i];
@@ -486,6 +496,9 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
     const double inv_width = (double)nbins / (P.hist_hi - P.hist_lo);
     const float hist_lo_f = (float)P.hist_lo, inv_width_f = (float)inv_width;
     const double tet_c_hi = do3 ? tab[nbins + 3] : 0.0, tet_c_lo = do3 ? tab[nbins + 4] : 0.0;
+    // bins that hold the ends of the tetrahedral window (exact positions of the two cosines)
+    const int tet_pos_hi = do3 ? angle_position(tet_c_hi, tab, nbins, hist_lo_f, inv_width_f) : -2;
+    const int tet_pos_lo = do3 ? angle_position(tet_c_lo, tab, nbins, hist_lo_f, inv_width_f) : -2;
     const double low3sq = P.low3sq, high3sq = P.high3sq, lowqsq = P.lowqsq, highqsq = P.highqsq;
     const bool last1 = P.wq_max <= 1;
     const double selsq1 = last1 ? highqsq : fmin(highqsq, fmin(P.highq, P.rc1) * fmin(P.highq, P.rc1));
@@ -579,26 +592,31 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
 
             // ---------------- phase 1b: which survivors can matter -------------------------------------------
             // Four smallest distances^2 (truncated to 12 mantissa bits: the slack pre_cst1 covers that) among the
-            // survivors certainly beyond lowCut; a survivor is kept if it can be a three-body neighbour or one of the
-            // four nearest.  Kept entries become positions in the cell-sorted arrays (the stage is not needed again).
+            // survivors certainly beyond lowCut.  A survivor is kept if it can be a three-body neighbour, or MARKED (bit 31)
+            // if it can be one of the four nearest.  Two passes, so that what is kept does not depend on the order of the
+            // atoms inside a cell (the cell build hands out slots with an atomic).  Kept entries become positions in the
+            // cell-sorted arrays: the stage is not needed again.
             int nk = 0;
             if (valid && !overflow) {
                 float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
                 for (int k = 0; k < nl; ++k) {
                     const unsigned e = my_list[k * kBkConsumers];
-                    const int j = (int)(e & kBkSlotMask);
                     const float r2 = __uint_as_float(e & ~kBkSlotMask);
-                    if (j == slot) continue;
-                    const bool keep = r2 <= pre_thr3 || r2 <= a3 + pre_cst1;
-                    if (r2 > lowq_hi2) {
+                    if ((int)(e & kBkSlotMask) != slot && r2 > lowq_hi2) {
                         float v = r2, m;
                         m = fminf(a0, v); v = fmaxf(a0, v); a0 = m;
                         m = fminf(a1, v); v = fmaxf(a1, v); a1 = m;
                         m = fminf(a2, v); v = fmaxf(a2, v); a2 = m;
                         a3 = fminf(a3, v);
                     }
-                    if (keep) {
-                        my_list[nk * kBkConsumers] = (unsigned)__float_as_int(loc[j].w);
+                }
+                const float thr_q = doq ? a3 + pre_cst1 : -1.f, thr_keep = fmaxf(pre_thr3, thr_q);
+                for (int k = 0; k < nl; ++k) {
+                    const unsigned e = my_list[k * kBkConsumers];
+                    const int j = (int)(e & kBkSlotMask);
+                    const float r2 = __uint_as_float(e & ~kBkSlotMask);
+                    if (j != slot && r2 <= thr_keep) {
+                        my_list[nk * kBkConsumers] = (unsigned)__float_as_int(loc[j].w) | (r2 <= thr_q ? 0x80000000u : 0u);
                         ++nk;
                     }
                 }
@@ -607,24 +625,26 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
             // ---------------- phase 2: exact fp64 re-evaluation, unit vectors ---------------------------------
             Top4S top;
             top.reset();
-            double rej_min = Ops<double>::inf();
+            double rej_min = Ops<double>::inf();  // smallest distance^2 among the marked candidates that did not make the four
             int K3 = 0, Kb = 0, nq = 0;
             float bmax = 0.f;
             if (valid) bmax = __double2float_ru(fmax(fmax(fabs(rx), fabs(ry)), fabs(rz)));
             if (valid && !overflow) {
                 const double Lx = I.L[0], Ly = I.L[1], Lz = I.L[2], iLx = I.iL[0], iLy = I.iL[1], iLz = I.iL[2];
                 double nx = 0, ny = 0, nz = 0;
-                int nidx = 0, ng = 0;
+                int nidx = 0;
+                unsigned ne = 0;
                 if (nk > 0) {
-                    ng = (int)my_list[0];
-                    bk_load_rec(P.recs, ng, nx, ny, nz, nidx);
+                    ne = my_list[0];
+                    bk_load_rec(P.recs, (int)(ne & 0x7fffffffu), nx, ny, nz, nidx);
                 }
                 for (int k = 0; k < nk; ++k) {
-                    const int g = ng;
+                    const int g = (int)(ne & 0x7fffffffu);
+                    const bool marked = (ne >> 31) != 0u;
                     const double px = nx, py = ny, pz = nz;
                     if (k + 1 < nk) {  // next survivor's record is in flight while this one is evaluated
-                        ng = (int)my_list[(k + 1) * kBkConsumers];
-                        bk_load_rec(P.recs, ng, nx, ny, nz, nidx);
+                        ne = my_list[(k + 1) * kBkConsumers];
+                        bk_load_rec(P.recs, (int)(ne & 0x7fffffffu), nx, ny, nz, nidx);
                     }
                     const double dx = min_image_1<double, false>(px, rx, Lx, iLx);
                     const double dy = min_image_1<double, false>(py, ry, Ly, iLy);
@@ -632,11 +652,9 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     const double sq = sumsq3<double>(dx, dy, dz);
                     const bool in3 = do3 && (sq > low3sq) && (sq <= high3sq);
                     const bool inq = doq && (sq > lowqsq) && (sq <= selsq1);
-                    if (inq) {
-                        ++nq;
-                        if (!(sq < top.d[3])) rej_min = fmin(rej_min, sq);
-                    }
-                    const bool want_q = inq && sq < top.d[3];
+                    nq += inq ? 1 : 0;
+                    // an unmarked candidate is farther than four others by more than the float arithmetic can hide
+                    const bool want_q = inq && marked;
                     if (in3 || want_q) {
                         const int e = in3 ? K3++ : kBkEntCap - 1 - Kb++;
                         if (K3 + Kb > kBkEntCap || sq < B.floor2) {
@@ -648,8 +666,12 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                             S.ent[e][2][tid] = dz * rs;
                             S.ent_g[e][tid] = g;
                             if (want_q) {
-                                rej_min = fmin(rej_min, top.d[3]);
-                                top.insert(sq, e);
+                                if (sq < top.d[3]) {
+                                    rej_min = fmin(rej_min, top.d[3]);
+                                    top.insert(sq, e);
+                                } else {
+                                    rej_min = fmin(rej_min, sq);
+                                }
                             }
                         }
                     }
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         if (k + 1 < nf && !(top.d[k + 1] - top.d[k] > band * top.d[k + 1])) requeue = true;
-                    if (nq > 4 && !(rej_min - top.d[3] > band * rej_min)) requeue = true;
+                    if (rej_min < Ops<double>::inf() && !(rej_min - top.d[3] > band * rej_min)) requeue = true;
                 }
                 if (requeue) {
                     bk_push_q(P, (uint32_t)gj);
@@ -712,18 +734,27 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     const int col = warp * 32 + t, ea = ab & 15, eb = ab >> 4;
                     double c = fma(S.ent[ea][0][col], S.ent[eb][0][col],
                                    fma(S.ent[ea][1][col], S.ent[eb][1][col], S.ent[ea][2][col] * S.ent[eb][2][col]));
-                    c = fmin(1.0, fmax(-1.0, c));
-                    // bin of the fast value, then the certificate: the reference's cosine lies within eps_c of c
-                    int pos = angle_position(c, tab, nbins, hist_lo_f, inv_width_f);
+                    // Bin of the fast value with its certificate: the reference's (clamped) cosine lies within eps_c of c, so
+                    // the bin is settled when [c - eps_c, c + eps_c] sits inside one bin's cosine interval and away from -1
+                    // (whose angle the reference turns into -180 degrees).  No clamp: a |c| beyond 1 fails the certificate.
                     const double chi = c + eps_c, clo = c - eps_c;
-                    bool sure = clo > -1.0;
-                    if (pos >= 0 && !(chi <= tab[pos])) sure = false;
-                    if (pos < nbins && !(clo > tab[pos + 1])) sure = false;
-                    if ((chi >= tet_c_hi && clo <= tet_c_hi) || (chi >= tet_c_lo && clo <= tet_c_lo)) sure = false;
+                    int pos = bk_seed_position(c, nbins, hist_lo_f, inv_width_f);
+                    bool sure = clo > -1.0 && chi <= tab[pos] && clo > tab[pos + 1];
+                    if (pos == tet_pos_hi || pos == tet_pos_lo)  // the tetrahedral window's ends fall inside these two bins
+                        if ((chi >= tet_c_hi && clo <= tet_c_hi) || (chi >= tet_c_lo && clo <= tet_c_lo)) sure = false;
                     if (!sure) {
-                        c = bk_exact_pair(reinterpret_cast<const RecD *>(P.recs), S.cgj[col], S.ent_g[ea][col], S.ent_g[eb][col], I.L, I.iL);
-                        pos = bk_exact_position(c, tab, nbins, hist_lo_f, inv_width_f);
-                        atomicAdd(P.counters + kCntSlowPair, 1u);
+                        // seeded one bin off (2 % of the pairs), outside the histogram range, or really too close to call
+                        c = fmin(1.0, fmax(-1.0, c));
+                        pos = angle_position(c, tab, nbins, hist_lo_f, inv_width_f);
+                        sure = clo > -1.0;
+                        if (pos >= 0 && !(chi <= tab[pos])) sure = false;
+                        if (pos < nbins && !(clo > tab[pos + 1])) sure = false;
+                        if ((chi >= tet_c_hi && clo <= tet_c_hi) || (chi >= tet_c_lo && clo <= tet_c_lo)) sure = false;
+                        if (!sure) {
+                            c = bk_exact_pair(reinterpret_cast<const RecD *>(P.recs), S.cgj[col], S.ent_g[ea][col], S.ent_g[eb][col], I.L, I.iL);
+                            pos = bk_exact_position(c, tab, nbins, hist_lo_f, inv_width_f);
+                            atomicAdd(P.counters + kCntSlowPair, 1u);
+                        }
                     }
                     if (c != -1.0 && c <= tet_c_hi && c >= tet_c_lo) {
                         st.tet_count += 1u;

@@ -41,7 +41,8 @@ def test_cfg5_conservation_laws(million):
     s = torch.sort(nn, dim=-1).values
     assert bool((s[..., 1:] != s[..., :-1]).all())                                        # four distinct neighbours
     assert float(r.q.max()) <= 1.0 and float(r.q.min()) >= -3.0
-    assert r["n_overflow"] < 100 and 0 < r["n_widened"] < 0.05 * 2 * N
+    # (the brick path keeps 8 unit vectors per centre: the few liquid-like centres with more go to the large-capacity pass)
+    assert r["n_overflow"] < 0.002 * 2 * N and 0 < r["n_widened"] < 0.05 * 2 * N
 
 
 def test_cfg5_q_histogram_counts_every_value_in_range(million):

@@ -1,12 +1,13 @@
 // K1: cell-list build for a batch of frames (sm_100a).
 //
-//   cell_count  : one thread per atom; positions are staged through shared memory with 16-byte
-//                 vector loads and binned; the atomicAdd that counts the cell also hands the atom its
-//                 rank ("slot") inside the cell.
+//   count pass  : one thread per atom; positions are staged through shared memory with 16-byte
+//                 vector loads and binned; one atomicAdd per atom counts its cell.
 //   scan_*      : exclusive prefix sum over all F*ncell counters (reduce / scan-of-sums / apply, the
 //                 in-block part is a warp shuffle scan).
-//   cell_scatter: each atom writes its record (original coordinates, index, cell) to
-//                 cell_start[cell] + slot with 16-byte stores.
+//   scatter pass: each atom is binned again and takes the next free place of its cell with an atomicAdd on
+//                 the scanned counter, then writes its record (original coordinates, index, cell) and its
+//                 box-wrapped float coordinates there with 16-byte stores.  No per-atom scratch between the
+//                 passes: 24 + 24 B read and 48 B written per atom (fp64 positions and records).
 //
 // The reference has no counterpart: its neighbour search is the O(N^2) double loop of
 // fortran/waterlib.f90:846-861 writing an N x N logical matrix.
@@ -42,16 +43,17 @@ struct BuildParams {
     int nc0, nc1, nc2;
     int tiles_per_frame;
     uint32_t *cell_start;
-    uint32_t *cell_id;
-    uint32_t *slot;
     void *recs;
     float4 *wrapped;
     uint32_t *cellpack;  // FP32 records only: packed cell coordinates per sorted atom (RecD carries them itself)
 };
 
 // T = storage type of the input positions, R = record type (RecD keeps doubles, RecF floats).
-// SCATTER = false: bin + count (the counting atomic also hands the atom its slot inside the cell);
-// SCATTER = true : write the record at cell_start[cell] + slot.
+// SCATTER = false: bin + count into cell_start[cell + 1].  The exclusive scan over cell_start[0 .. ncells] (entry 0 is
+//                  zero) then leaves the START of cell c in entry c + 1.
+// SCATTER = true : bin again (same arithmetic, same cell) and take the next free place of the cell with an atomicAdd on
+//                  entry c + 1, which thereby ends up as the cell's END = the start of cell c + 1: afterwards entry c is
+//                  the start of cell c for every c, with no per-atom scratch (cell id, rank) written or re-read.
 template <typename T, typename R, bool SCATTER>
 __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p) {
     __shared__ __align__(16) T s_pos[kBuildThreads * 3];
@@ -72,32 +74,29 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     const int t = threadIdx.x;
     if (t >= n_here) return;
     const T x = s_pos[3 * t + 0], y = s_pos[3 * t + 1], z = s_pos[3 * t + 2];
-    const size_t ga = frame_atom0 + a0 + t;
     const size_t ncell = (size_t)p.nc0 * p.nc1 * p.nc2;
+    double xd = (double)x, yd = (double)y, zd = (double)z;
+    if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
+        xd = (double)(float)x;
+        yd = (double)(float)y;
+        zd = (double)(float)z;
+    }
+    const int cx = cell_coord(xd, s_iL[0], p.nc0);
+    const int cy = cell_coord(yd, s_iL[1], p.nc1);
+    const int cz = cell_coord(zd, s_iL[2], p.nc2);
+    uint32_t *counter = p.cell_start + (size_t)f * ncell + (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx) + 1;
     if (!SCATTER) {
-        double xd = (double)x, yd = (double)y, zd = (double)z;
-        if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
-            xd = (double)(float)x;
-            yd = (double)(float)y;
-            zd = (double)(float)z;
-        }
-        const int cx = cell_coord(xd, s_iL[0], p.nc0);
-        const int cy = cell_coord(yd, s_iL[1], p.nc1);
-        const int cz = cell_coord(zd, s_iL[2], p.nc2);
-        const uint32_t c = (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx);
-        p.cell_id[ga] = c;
-        p.slot[ga] = atomicAdd(&p.cell_start[(size_t)f * ncell + c], 1u);
+        atomicAdd(counter, 1u);
     } else {
-        const uint32_t c = p.cell_id[ga];
-        const uint32_t dst = p.cell_start[(size_t)f * ncell + c] + p.slot[ga];
+        const uint32_t dst = atomicAdd(counter, 1u);
+        const int cellpack = cx | (cy << 10) | (cz << 20);
         if (sizeof(R) == sizeof(RecD)) {
             RecD r;
             r.x = (double)x;
             r.y = (double)y;
             r.z = (double)z;
             r.idx = a0 + t;
-            const int cxy = (int)(c % (uint32_t)(p.nc0 * p.nc1));
-            r.cell = (cxy % p.nc0) | ((cxy / p.nc0) << 10) | ((int)(c / (uint32_t)(p.nc0 * p.nc1)) << 20);
+            r.cell = cellpack;
             int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst);
             const int4 *s4 = reinterpret_cast<const int4 *>(&r);
             d4[0] = s4[0];
@@ -126,8 +125,7 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
                 w.z = wrapped_coord((double)r.z, s_L[2], s_iL[2]);
                 w.w = __int_as_float(a0 + t);
                 p.wrapped[dst] = w;
-                const int cxy = (int)(c % (uint32_t)(p.nc0 * p.nc1));
-                p.cellpack[dst] = (uint32_t)((cxy % p.nc0) | ((cxy / p.nc0) << 10) | ((int)(c / (uint32_t)(p.nc0 * p.nc1)) << 20));
+                p.cellpack[dst] = (uint32_t)cellpack;
             }
         }
     }
@@ -276,8 +274,6 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     p.nc2 = nc[2];
     p.tiles_per_frame = (n_pos + kBuildThreads - 1) / kBuildThreads;
     p.cell_start = reinterpret_cast<uint32_t *>(ws + lay.off_cell_start);
-    p.cell_id = reinterpret_cast<uint32_t *>(ws + lay.off_cell_id);
-    p.slot = reinterpret_cast<uint32_t *>(ws + lay.off_slot);
     p.recs = ws + lay.off_recs;
     p.wrapped = reinterpret_cast<float4 *>(ws + lay.off_wrapped);
     // FP32 records fill only the first half of the record region; the packed cells of the sorted atoms follow

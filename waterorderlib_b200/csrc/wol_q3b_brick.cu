@@ -53,7 +53,7 @@ constexpr int kBkCsW = 32;                      // cell starts per row: nbx + 3 
 constexpr int kBkMaxBx = kBkCsW - 3;
 constexpr int kBkMaxByz = 5;
 constexpr int kBkCRowCap = kBkMaxByz * kBkMaxByz;
-constexpr int kBkListCap = 12;                  // prefilter survivors per centre (self included)
+constexpr int kBkListCap = 16;                  // prefilter survivors per centre (self included)
 constexpr int kBkEntCap = 8;                    // unit vectors per centre (three-body neighbours from the front,
                                                 // q-only candidates from the back)
 constexpr int kBkMaxPairs = kBkEntCap * (kBkEntCap - 1) / 2;
@@ -87,7 +87,7 @@ struct BkRowInfo {    // one (y, z) row of brick + halo (producer scratch)
 struct BkSmem {
     float4 loc[kBkStages][kBkAtomCap];
     double ent[kBkEntCap][3][kBkConsumers];
-    int ent_g[kBkEntCap][kBkConsumers];          // where the entry's fp64 record is
+    unsigned char ent_k[kBkEntCap][kBkConsumers];  // which kept survivor the entry is (its list entry says where the record is)
     unsigned lj[kBkListCap + 1][kBkConsumers];   // survivor lists (+ one row that absorbs overflowing stores)
     unsigned short cs[kBkStages][kBkRowCap * kBkCsW];
     int cgj[kBkConsumers];                       // where the centre's fp64 record is
@@ -639,7 +639,6 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     bk_load_rec(P.recs, (int)(ne & 0x7fffffffu), nx, ny, nz, nidx);
                 }
                 for (int k = 0; k < nk; ++k) {
-                    const int g = (int)(ne & 0x7fffffffu);
                     const bool marked = (ne >> 31) != 0u;
                     const double px = nx, py = ny, pz = nz;
                     if (k + 1 < nk) {  // next survivor's record is in flight while this one is evaluated
@@ -664,7 +663,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                             S.ent[e][0][tid] = dx * rs;
                             S.ent[e][1][tid] = dy * rs;
                             S.ent[e][2][tid] = dz * rs;
-                            S.ent_g[e][tid] = g;
+                            S.ent_k[e][tid] = (unsigned char)k;
                             if (want_q) {
                                 if (sq < top.d[3]) {
                                     rej_min = fmin(rej_min, top.d[3]);
@@ -751,7 +750,8 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                         if (pos < nbins && !(clo > tab[pos + 1])) sure = false;
                         if ((chi >= tet_c_hi && clo <= tet_c_hi) || (chi >= tet_c_lo && clo <= tet_c_lo)) sure = false;
                         if (!sure) {
-                            c = bk_exact_pair(reinterpret_cast<const RecD *>(P.recs), S.cgj[col], S.ent_g[ea][col], S.ent_g[eb][col], I.L, I.iL);
+                            c = bk_exact_pair(reinterpret_cast<const RecD *>(P.recs), S.cgj[col],
+                                              (int)(S.lj[S.ent_k[ea][col]][col] & 0x7fffffffu), (int)(S.lj[S.ent_k[eb][col]][col] & 0x7fffffffu), I.L, I.iL);
                             pos = bk_exact_position(c, tab, nbins, hist_lo_f, inv_width_f);
                             atomicAdd(P.counters + kCntSlowPair, 1u);
                         }
@@ -820,10 +820,10 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     if (P.nn_idx) {
                         const RecD *recs = reinterpret_cast<const RecD *>(P.recs);
                         int4 o;
-                        o.x = (nf > 0) ? __ldg(&recs[S.ent_g[top.p[0]][tid]].idx) : -1;
-                        o.y = (nf > 1) ? __ldg(&recs[S.ent_g[top.p[1]][tid]].idx) : -1;
-                        o.z = (nf > 2) ? __ldg(&recs[S.ent_g[top.p[2]][tid]].idx) : -1;
-                        o.w = (nf > 3) ? __ldg(&recs[S.ent_g[top.p[3]][tid]].idx) : -1;
+                        o.x = (nf > 0) ? __ldg(&recs[my_list[S.ent_k[top.p[0]][tid] * kBkConsumers] & 0x7fffffffu].idx) : -1;
+                        o.y = (nf > 1) ? __ldg(&recs[my_list[S.ent_k[top.p[1]][tid] * kBkConsumers] & 0x7fffffffu].idx) : -1;
+                        o.z = (nf > 2) ? __ldg(&recs[my_list[S.ent_k[top.p[2]][tid] * kBkConsumers] & 0x7fffffffu].idx) : -1;
+                        o.w = (nf > 3) ? __ldg(&recs[my_list[S.ent_k[top.p[3]][tid] * kBkConsumers] & 0x7fffffffu].idx) : -1;
                         reinterpret_cast<int4 *>(P.nn_idx)[out_index] = o;
                     }
                     if (bin >= 0) atomicAdd(s_qhist + bin, 1u);

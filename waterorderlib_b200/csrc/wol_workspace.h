@@ -48,8 +48,6 @@ struct WorkspaceLayout {
     size_t off_counters;    // uint32[kNumCounters], always at offset 0
     size_t off_cell_start;  // uint32[F*ncell + 1]  counts during the build, exclusive starts afterwards
     size_t off_block_sums;  // uint32[scan blocks + 1]
-    size_t off_cell_id;     // uint32[F*N]
-    size_t off_slot;        // uint32[F*N]  rank of the atom inside its cell
     size_t off_recs;        // RecD[F*N] (or RecF) atoms grouped by (frame, cell)
     size_t off_wrapped;     // float4[F*N]  box-wrapped float coordinates, same order as recs; .w = the atom's place in
                             // this array (fp64 records) or its original index (fp32 records)
@@ -80,10 +78,6 @@ inline WorkspaceLayout workspace_layout(int32_t n_frames, int32_t n_pos, int32_t
     o = align_up(o + (size_t)(w.n_cells_total + 1) * 4, 256);
     w.off_block_sums = o;
     o = align_up(o + (size_t)(w.scan_blocks + 1) * 4, 256);
-    w.off_cell_id = o;
-    o = align_up(o + (size_t)w.n_atoms_total * 4, 256);
-    w.off_slot = o;
-    o = align_up(o + (size_t)w.n_atoms_total * 4, 256);
     w.off_recs = o;
     o = align_up(o + (size_t)w.n_atoms_total * sizeof(RecD), 256);
     w.off_wrapped = o;

@@ -464,6 +464,15 @@ int wol_bin_on_grid(const double *opos, int64_t n, const double *xbins, const do
  */
 int wol_hist_allreduce(void *nccl_comm, void *buf, size_t count, int32_t dtype, void *stream);
 
+/*
+ * Measurement aid (no counterpart in the reference): an FMA throughput probe for the FP roofline denominator
+ * (SURVEY.md section 8d asks for a measured one).  Launches `blocks` blocks of 256 threads; every thread runs `iters`
+ * rounds of 8 independent fused multiply-adds in the given dtype (WOL_F64 / WOL_F32) and adds its result to sink[0]
+ * (a device double that only exists to keep the arithmetic alive).  The caller times the launch with events:
+ * flop = 2 * 8 * iters * 256 * blocks.
+ */
+int wol_fma_probe(int32_t dtype, int32_t blocks, int32_t iters, double *sink, void *stream);
+
 /* Number of kernel launches the last wol_* call on this thread enqueued (for bench bookkeeping). */
 int wol_last_launch_count(void);
 

@@ -27,8 +27,7 @@ def test_pipeline_matches_device_run_and_oracle(dtype, batch, slots, streams):
     pipe = FramePipeline(N, batch, dtype=dtype, n_slots=slots, n_run_streams=streams, want_nn=True)
     host = torch.from_numpy(xyz.astype(dtype)).pin_memory()
     for rep in range(2):  # a second run reuses the slots and workspaces
-        r = pipe.run(host, boxes)
-        torch.cuda.synchronize()
+        r = pipe.run(host, boxes)  # no synchronize here: run() returns when the results are in host memory
         assert torch.equal(r["q"], dev["q"].cpu()) and torch.equal(r["n3"], dev["n3"].cpu())
         assert torch.equal(r["nn_idx"], dev["nn_idx"].cpu())
         assert torch.equal(r["ang_hist"], dev["ang_hist"].cpu()) and torch.equal(r["q_hist"], dev["q_hist"].cpu())
@@ -59,6 +58,19 @@ def test_pipeline_per_frame_histograms_pageable_input_and_errors():
         pipe.run(xyz.astype(np.float32), boxes)
     with pytest.raises(ValueError):
         pipe.run(xyz[:, :-1], boxes)
+
+
+def test_pipeline_histograms_only_is_what_the_drivers_consume():
+    """want_q = want_n3 = False: nothing per water comes back, histograms and per-frame sums are unchanged."""
+    xyz, boxes = frames(7)
+    F, N = xyz.shape[:2]
+    full = FramePipeline(N, 2, dtype=np.float32).run(xyz.astype(np.float32), boxes)
+    pipe = FramePipeline(N, 3, dtype=np.float32, want_q=False, want_n3=False)
+    r = pipe.run(torch.from_numpy(xyz.astype(np.float32)).pin_memory(), boxes)
+    assert r["q"] is None and r["n3"] is None
+    assert torch.equal(r["ang_hist"], full["ang_hist"]) and torch.equal(r["q_hist"], full["q_hist"])
+    assert np.allclose(r["frame_stats"].numpy(), full["frame_stats"].numpy(), rtol=1e-12, atol=1e-12)
+    assert pipe.d2h_bytes == (2 * 500 + F * 8) * 8 and r["n_overflow_last_batches"] == 0
 
 
 def test_pipeline_timeline_trace():

@@ -102,6 +102,23 @@ double angle_cos_threshold(double ang_deg, int *minus_one_passes) {
     return last_true([&](double c) { return ref_angle_deg(c) >= ang_deg; });
 }
 
+// FMA throughput probe (wol_fma_probe): 8 independent chains per thread keep the pipe full at any occupancy
+template <typename T>
+__global__ void __launch_bounds__(256) fma_probe_kernel(int iters, double *sink) {
+    T a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (T)(threadIdx.x + k) * (T)1e-3;
+    const T m = (T)0.999999, c = (T)1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] * m + c;
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == (T)-1) atomicAdd(sink, (double)s);  // never true; keeps the loop alive
+}
+
 }  // namespace wol
 
 using namespace wol;
@@ -145,6 +162,17 @@ int wol_hist_allreduce(void *nccl_comm, void *buf, size_t count, int32_t dtype, 
 }
 
 int wol_last_launch_count(void) { return g_launches; }
+
+int wol_fma_probe(int32_t dtype, int32_t blocks, int32_t iters, double *sink, void *stream) {
+    if (!sink || blocks < 1 || iters < 1) return set_error(WOL_ERR_INVALID, "wol_fma_probe: need a sink, blocks >= 1, iters >= 1");
+    if (dtype == WOL_F64) fma_probe_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else if (dtype == WOL_F32) fma_probe_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else return set_error(WOL_ERR_INVALID, "wol_fma_probe: unknown dtype %d", dtype);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_fma_probe", e);
+    g_launches = 1;
+    return WOL_OK;
+}
 
 int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3], double *edge_min_out,
                   double *box_max_out) {

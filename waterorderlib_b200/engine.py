@@ -27,8 +27,8 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def as_device_positions(a, device):
@@ -152,7 +152,7 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     if reuse_cells and (ws.buf is None or ws.buf.numel() < need + 256):
         raise ValueError("reuse_cells: this workspace does not hold a cell list for a batch of this shape")
     ws_ptr, ws_bytes = ws.get(need)
-    stream = _stream_ptr()
+    stream = _stream_ptr(device)
     launches = 0
     with torch.cuda.device(device):
         if not reuse_cells:
@@ -239,14 +239,17 @@ def default_r_cell(do_q, do_3body, high3, highq):
     return max(r, 1e-3)
 
 
-def workspace_status(ws, n_frames, n_pos, n_centres, r_cell, box):
+def workspace_status(ws, n_frames, n_pos, n_centres, r_cell, box, stream=None):
     """(widened, overflow) of the last evaluation on `ws`; raises WolError if a list overflowed the
-    large-capacity path at any point since the previous call.  Synchronises the current stream."""
+    large-capacity path at any point since the previous call (the flag is sticky).  Synchronises `stream`
+    (default: the current stream of the workspace's device)."""
     box_h = as_host_boxes(box, n_frames)
     nc, _edge, _bmax = plan_grid(box_h, r_cell)
     need = lib().wol_workspace_bytes(n_frames, n_pos, n_centres, ctypes.byref(nc))
     ws_ptr, _ = ws.get(need)
     st = (ctypes.c_int32 * 4)()
-    check(lib().wol_status(ctypes.c_void_p(ws_ptr), n_frames, n_pos, n_centres, ctypes.byref(nc), _stream_ptr(),
-                           ctypes.byref(st)), "wol_status")
+    with torch.cuda.device(ws.device):
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream_ptr(ws.device)
+        check(lib().wol_status(ctypes.c_void_p(ws_ptr), n_frames, n_pos, n_centres, ctypes.byref(nc), sp,
+                               ctypes.byref(st)), "wol_status")
     return int(st[0]), int(st[1])

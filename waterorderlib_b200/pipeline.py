@@ -43,8 +43,8 @@ class FramePipeline:
             self.n_slots = max(2, int(n_slots))
             for _ in range(self.n_slots):
                 slot = dict(pos=torch.empty((B, N, 3), dtype=self.tdtype, device=self.device),
-                            q=torch.empty((B, N), dtype=self.qdtype, device=self.device) if do_q else None,
-                            n3=torch.empty((B, N), dtype=torch.int32, device=self.device) if do_3body else None,
+                            q=torch.empty((B, N), dtype=self.qdtype, device=self.device) if self.want_q else None,
+                            n3=torch.empty((B, N), dtype=torch.int32, device=self.device) if self.want_n3 else None,
                             nn=torch.empty((B, N, 4), dtype=torch.int32, device=self.device) if self.want_nn else None,
                             loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event())
                 self.slots.append(slot)
@@ -73,7 +73,10 @@ class FramePipeline:
     def run(self, pos_host, box, out_q=None, out_n3=None, out_nn=None):
         """pos_host (F,N,3) torch CPU tensor (pinned for overlap) or numpy array; box (3,) / (F,3).
         Returns dict(ang_hist, q_hist, frame_stats [, q, n3, nn_idx]) of HOST tensors; per-water arrays
-        are written into out_q / out_n3 / out_nn (pinned CPU tensors) when given."""
+        are written into out_q / out_n3 / out_nn (pinned CPU tensors) when given.  The call returns when every
+        result has landed in host memory (it waits for the last device->host copy); a list that overflowed even
+        the large-capacity path raises WolError, as the per-call API does.  n_widened / n_overflow of the run are
+        in the result."""
         pos_host = pos_host if isinstance(pos_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pos_host))
         if pos_host.dtype != self.tdtype:
             raise ValueError("pipeline was built for %s frames, got %s" % (self.tdtype, pos_host.dtype))
@@ -133,10 +136,12 @@ class FramePipeline:
                     out = {"frame_stats": acc["frame_stats"][f0:f0 + nb]}
                     if self.do_3body:
                         out["ang_hist"] = acc["ang_hist"][f0:f0 + nb] if self.hist_per_frame else acc["ang_hist"]
-                        out["n3"] = slot["n3"][:nb]
+                        if self.want_n3:
+                            out["n3"] = slot["n3"][:nb]
                     if self.do_q:
                         out["q_hist"] = acc["q_hist"][f0:f0 + nb] if self.hist_per_frame else acc["q_hist"]
-                        out["q"] = slot["q"][:nb]
+                        if self.want_q:
+                            out["q"] = slot["q"][:nb]
                         if self.want_nn:
                             out["nn_idx"] = slot["nn"][:nb]
                     if self.trace:
@@ -175,8 +180,24 @@ class FramePipeline:
                     h.copy_(t, non_blocking=True)
                     self.d2h_bytes += t.numel() * t.element_size()
                     res[k] = h
+            done = torch.cuda.Event()
+            done.record(self.s_out)
             for s in [self.s_out, self.s_in] + self.s_runs:
                 main.wait_stream(s)
+            # the returned tensors are host memory filled by asynchronous copies: wait for the last of them
+            done.synchronize()
+            # device-side list capacity: the batches ran with check_status=False (no host sync inside the loop)
+            widened = overflow = 0
+            for k, ws in enumerate(self.wss):
+                nb = [min(self.fpb, F - f0) for i, f0 in enumerate(starts) if i % len(self.s_runs) == k]
+                if not nb:
+                    continue
+                w, o = engine.workspace_status(ws, nb[-1], N, N, self.kw["r_cell"] if self.kw["r_cell"] is not None else
+                                               engine.default_r_cell(self.do_q, self.do_3body, self.kw["high3"], self.kw["highq"]),
+                                               box_h[:nb[-1]], stream=self.s_runs[k])
+                widened += w
+                overflow += o
         res["q"], res["n3"], res["nn_idx"] = out_q, out_n3, out_nn
+        res["n_widened_last_batches"], res["n_overflow_last_batches"] = widened, overflow
         res["_device"] = acc
         return res

@@ -109,3 +109,26 @@ def plane_interface(box, z_lo, z_hi, spacing=2.0):
         pts.append(np.stack([X.ravel(), Y.ravel(), np.full(X.size, z)], axis=1))
         nrm.append(np.tile(np.array([0.0, 0.0, s]), (X.size, 1)))
     return (np.concatenate(pts).astype(np.float32).astype(np.float64), np.concatenate(nrm))
+
+
+def device_frames(m, f0, f1, sigma=0.25, device="cuda", seed_base=17):
+    """Jittered-ice frames f0 .. f1-1 of an m^3-cell box generated ON THE DEVICE (torch): (f1-f0, N, 3) float64 values that
+    are float32-representable, wrapped into [0, L), plus the box (3,) as numpy.  Frame f depends only on its absolute
+    index (generator seeded with 1000003 f + seed_base), so a sharded trajectory does not depend on the number of ranks.
+    Not the same stream of numbers as water_box (numpy PCG64): use one or the other for a given comparison."""
+    import torch
+    lattice, box = diamond_lattice(m)
+    box = box.astype(np.float32).astype(np.float64)
+    lat_d = torch.from_numpy(lattice).to(device)
+    box_d = torch.from_numpy(box).to(device)
+    out = torch.empty((f1 - f0, lattice.shape[0], 3), dtype=torch.float64, device=device)
+    for k, f in enumerate(range(f0, f1)):
+        g = torch.Generator(device=device)
+        g.manual_seed(1_000_003 * f + seed_base)
+        p = lat_d + sigma * torch.randn(lattice.shape, generator=g, device=device, dtype=torch.float64)
+        p = p - box_d * torch.floor(p / box_d)
+        p = p.to(torch.float32)
+        boxf = box_d.to(torch.float32)
+        p = torch.where(p >= boxf, p - boxf, p)  # float32 rounding can land exactly on L
+        out[k] = p.to(torch.float64)
+    return out, box

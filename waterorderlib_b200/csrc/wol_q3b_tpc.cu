@@ -621,6 +621,232 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same search, one WARP per queued centre (fp64 records).  A batch queues a few hundred centres per million;
+// with a thread per centre that is a handful of warps each walking ~150 cells one dependent load after the other --
+// a ~100 us floor per call whatever the count, which a host-fed pipeline pays once per batch.  Here the lanes share
+// the cells: 27 lanes take one cell each for the bound, 25 lanes one row each for the collection, one lane per
+// survivor for the exact arithmetic; the four nearest come out of four warp-wide (distance, index) minima.  Same
+// thresholds, same exact evaluation and the same finish_q as the thread-per-centre version above.
+constexpr int kWidenWarps = 8;        // warps per block
+constexpr int kWidenWarpCap = 32;     // survivors per centre: one lane each
+
+__device__ __forceinline__ void warp_key_min(double &d, int &i, int &p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(kFullMask, d, o);
+        const int oi = __shfl_xor_sync(kFullMask, i, o), op = __shfl_xor_sync(kFullMask, p, o);
+        if (key_less(od, oi, d, i)) { d = od; i = oi; p = op; }
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kWidenWarps * 32) q3b_widen_warp_kernel(const __grid_constant__ Q3bParams P) {
+    __shared__ int s_list[kWidenWarps][kWidenWarpCap];
+    __shared__ int s_count[kWidenWarps];
+    extern __shared__ unsigned s_qhist_dyn[];
+    const uint32_t n_items = P.counters[P.list_counter];
+    if (P.counters[kCntWidened] == 0u) return;
+    unsigned *s_qhist = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? s_qhist_dyn : nullptr;
+    if (s_qhist) {
+        for (int i = threadIdx.x; i < P.q_nbins; i += kWidenWarps * 32) s_qhist[i] = 0u;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
+    const double lowqsq = P.lowqsq, highqsq = P.highqsq;
+    const bool last2 = P.wq_max <= 2;
+    const double rsel = fmin(P.highq, 2.0 * P.rc1);
+    const double selsq2 = last2 ? highqsq : fmin(highqsq, rsel * rsel);
+    const float lowq_hi2 = P.lowq_hi2, thr_cap = P.pre_thr2_w2, cst = P.pre_cst_w2, eps = P.cell_eps;
+    const float kInf = __int_as_float(0x7f800000);
+    const float4 *__restrict__ wr = P.wrapped;
+    int *list = s_list[warp];
+    LaneStats st;  // lane 0 accumulates; flushed when the frame changes
+    st.reset();
+    int st_f = -1;
+    for (uint32_t it = blockIdx.x * kWidenWarps + warp; it < n_items; it += gridDim.x * kWidenWarps) {
+        const uint32_t e = P.list[it];
+        if ((e & kFbNeed3b) != 0u || (e & kFbNeedQ) == 0u) continue;  // list overflows belong to the large-capacity pass
+        const uint32_t id = e & kFbIdMask;
+        double rx, ry, rz;
+        float wx, wy, wz;
+        int cx, cy, cz, self_j = -1, f;
+        size_t out_index;
+        if (P.centres == nullptr) {
+            f = (int)(id / (uint32_t)P.n_pos);
+            const int4 *rp = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(P.recs) + id);
+            const int4 a = __ldg(rp), b = __ldg(rp + 1);
+            rx = __hiloint2double(a.y, a.x);
+            ry = __hiloint2double(a.w, a.z);
+            rz = __hiloint2double(b.y, b.x);
+            cx = b.w & 1023;
+            cy = (b.w >> 10) & 1023;
+            cz = (b.w >> 20) & 1023;
+            const float4 w = __ldg(wr + id);
+            wx = w.x; wy = w.y; wz = w.z;
+            self_j = (int)id;
+            out_index = (size_t)f * P.n_pos + b.z;
+        } else {
+            f = (int)(id / (uint32_t)P.n_centres);
+            load_centre<double>(P, f, (int)(id - (uint32_t)f * P.n_centres), rx, ry, rz);
+            out_index = id;
+        }
+        const double Lx = P.box[(size_t)f * 3 + 0], Ly = P.box[(size_t)f * 3 + 1], Lz = P.box[(size_t)f * 3 + 2];
+        const double iLx = __ddiv_rn(1.0, Lx), iLy = __ddiv_rn(1.0, Ly), iLz = __ddiv_rn(1.0, Lz);
+        if (P.centres != nullptr) {
+            cx = cell_coord(rx, iLx, nc0);
+            cy = cell_coord(ry, iLy, nc1);
+            cz = cell_coord(rz, iLz, nc2);
+            wx = wrapped_coord(rx, Lx, iLx);
+            wy = wrapped_coord(ry, Ly, iLy);
+            wz = wrapped_coord(rz, Lz, iLz);
+        }
+        const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
+        const uint32_t *cs_frame = P.cell_start + (size_t)f * nc0 * nc1 * nc2;
+        if (lane == 0) s_count[warp] = 0;
+        __syncwarp();
+
+        // ---- bound: 4th smallest float distance^2 inside the 27-cell stencil, one cell per lane -------------------
+        float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
+        int nl_unused = 0;
+        if (lane < 27) {
+            const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
+            int y = cy + oy, z = cz + oz;
+            float sy = wy, sz = wz;
+            if (y < 0) { y += nc1; sy += Lyf; } else if (y >= nc1) { y -= nc1; sy -= Lyf; }
+            if (z < 0) { z += nc2; sz += Lzf; } else if (z >= nc2) { z -= nc2; sz -= Lzf; }
+            widen_row<0>(wr, cs_frame + ((size_t)z * nc1 + y) * nc0, nc0, cx, ox, ox, wx, sy, sz, Lxf, lowq_hi2, 0.f, self_j, a0, a1, a2,
+                         a3, list, nl_unused);
+        }
+        float b4 = kInf;  // 4th smallest over the warp: four rounds of "take the minimum of the lanes' heads"
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            float m = a0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(kFullMask, m, o));
+            b4 = m;
+            const unsigned who = __ballot_sync(kFullMask, a0 == m && m < kInf);
+            if (who != 0u && lane == __ffs(who) - 1) { a0 = a1; a1 = a2; a2 = a3; a3 = kInf; }
+        }
+        const float thr = fminf(b4 + cst, thr_cap);
+
+        // ---- collect: the rows of the half-width-2 stencil the bound can reach, one row per lane --------------------
+        if (lane < 25) {
+            const float ex = Lxf / (float)nc0, ey = Lyf / (float)nc1, ez = Lzf / (float)nc2, iex = 1.0f / ex;
+            const float ux = wx - (float)cx * ex, uy = wy - (float)cy * ey, uz = wz - (float)cz * ez;
+            const int oy = lane % 5 - 2, oz = lane / 5 - 2;
+            const float gy = fmaxf(cell_gap(oy, uy, ey) - eps, 0.f), gz = fmaxf(cell_gap(oz, uz, ez) - eps, 0.f);
+            const float left = thr - fmaf(gz, gz, gy * gy);
+            if (left >= 0.f) {
+                const float reach = sqrtf(left) + eps;
+                const int lo = max(-2, (int)floorf((ux - reach) * iex)), hi = min(2, (int)floorf((ux + reach) * iex));
+                int y = cy + oy, z = cz + oz;
+                float sy = wy, sz = wz;
+                if (y < 0) { y += nc1; sy += Lyf; } else if (y >= nc1) { y -= nc1; sy -= Lyf; }
+                if (z < 0) { z += nc2; sz += Lzf; } else if (z >= nc2) { z -= nc2; sz -= Lzf; }
+                const uint32_t *cs = cs_frame + ((size_t)z * nc1 + y) * nc0;
+                // the x-run [cx + lo, cx + hi], split where it wraps around the box (as widen_row does)
+                for (int piece = 0; piece < 3; ++piece) {
+                    const int x0 = cx + lo, x1 = cx + hi;
+                    int j0, j1;
+                    float sx;
+                    if (piece == 0) {
+                        const int m0 = max(x0, 0), m1 = min(x1, nc0 - 1);
+                        if (m0 > m1) continue;
+                        j0 = (int)__ldg(cs + m0); j1 = (int)__ldg(cs + m1 + 1); sx = wx;
+                    } else if (piece == 1) {
+                        if (x0 >= 0) continue;
+                        j0 = (int)__ldg(cs + x0 + nc0); j1 = (int)__ldg(cs + nc0); sx = wx + Lxf;
+                    } else {
+                        if (x1 < nc0) continue;
+                        j0 = (int)__ldg(cs); j1 = (int)__ldg(cs + x1 - nc0 + 1); sx = wx - Lxf;
+                    }
+                    for (int jb = j0; jb < j1; jb += 4) {  // four loads in flight: the run is a chain of cache misses otherwise
+                        float4 w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) w[u] = __ldg(wr + min(jb + u, j1 - 1));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = jb + u;
+                            const float dx = w[u].x - sx, dy = w[u].y - sy, dz = w[u].z - sz;
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (j < j1 && r2 <= thr && j != self_j) {
+                                const int at = atomicAdd(&s_count[warp], 1);
+                                if (at < kWidenWarpCap) list[at] = j;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const int nl = s_count[warp];
+
+        // ---- exact evaluation, one survivor per lane; the four nearest by (distance, atom index) --------------------
+        double key = Ops<double>::inf();
+        int kidx = INT_MAX, kj = -1;
+        bool inq = false;
+        if (nl <= kWidenWarpCap && lane < nl) {
+            const int j = list[lane];
+            double px, py, pz;
+            int idx;
+            RecTraits<double>::load(P.recs, (size_t)j, px, py, pz, idx);
+            const double dx = min_image_1<double, EXACT>(px, rx, Lx, iLx);
+            const double dy = min_image_1<double, EXACT>(py, ry, Ly, iLy);
+            const double dz = min_image_1<double, EXACT>(pz, rz, Lz, iLz);
+            const double s = sumsq3<double>(dx, dy, dz);
+            if ((s > lowqsq) && (s <= selsq2)) {
+                inq = true;
+                const double vx = __dsub_rn(__dadd_rn(rx, dx), rx);
+                const double vy = __dsub_rn(__dadd_rn(ry, dy), ry);
+                const double vz = __dsub_rn(__dadd_rn(rz, dz), rz);
+                key = __dsqrt_rn(sumsq3<double>(vx, vy, vz));
+                kidx = idx;
+                kj = j;
+            }
+        }
+        const int nq = __popc(__ballot_sync(kFullMask, inq));
+        Top4<double> top;
+        top.reset();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double d = key;
+            int i = kidx, pj = kj;
+            warp_key_min(d, i, pj);
+            top.d[k] = d; top.i[k] = i; top.p[k] = pj;
+            if (pj >= 0 && pj == kj) { key = Ops<double>::inf(); kidx = INT_MAX; kj = -1; }  // the winner leaves the pool
+        }
+        if (lane == 0) {
+            if (nl > kWidenWarpCap || (nq < 4 && !last2)) {
+                const uint32_t at = atomicAdd(P.counters + kCntLevel2, 1u);
+                P.list2[at] = id | kFbNeedQ;
+            } else {
+                if (f != st_f) {
+                    if (st_f >= 0 && P.stats) {
+                        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_Q_SUM, st.q_sum);
+                        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_Q_SUMSQ, st.q_sumsq);
+                        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_N_CENTRES, (double)st.n_centres);
+                    }
+                    st.reset();
+                    st_f = f;
+                }
+                finish_q<EXACT>(P, f, rx, ry, rz, Lx, Ly, Lz, iLx, iLy, iLz, top, min(nq, 4), out_index, st, s_qhist);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && st_f >= 0 && P.stats) {
+        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_Q_SUM, st.q_sum);
+        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_Q_SUMSQ, st.q_sumsq);
+        atomicAdd(P.stats + (size_t)st_f * WOL_NSTATS + WOL_STAT_N_CENTRES, (double)st.n_centres);
+    }
+    if (s_qhist) {
+        __syncthreads();
+        flush_bins(s_qhist, P.q_hist, P.q_nbins, false);
+    }
+}
+
 // adjacency image == minimum image needs 3 cell edges < L / 2
 bool q3b_tpc_widen_supported(const Q3bParams &P) {
     return P.wrapped != nullptr && P.nc0 >= 7 && P.nc1 >= 7 && P.nc2 >= 7;
@@ -629,7 +855,12 @@ bool q3b_tpc_widen_supported(const Q3bParams &P) {
 int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact, bool f32) {
     const int grid = sm_count() * 8;
     const size_t smem = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? sizeof(unsigned) * P.q_nbins : 0;
+    // fp64 records: one warp per queued centre (short dependent chains: the pass is a latency floor, not a throughput
+    // problem); WOL_WIDEN_THREAD=1 keeps the thread-per-centre version for comparison
+    const bool per_warp = !f32 && getenv("WOL_WIDEN_THREAD") == nullptr;
     if (f32) q3b_tpc_widen_kernel<false, true><<<grid, kWidenThreads, smem, stream>>>(P);
+    else if (per_warp && exact) q3b_widen_warp_kernel<true><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
+    else if (per_warp) q3b_widen_warp_kernel<false><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
     else if (exact) q3b_tpc_widen_kernel<true, false><<<grid, kWidenThreads, smem, stream>>>(P);
     else q3b_tpc_widen_kernel<false, false><<<grid, kWidenThreads, smem, stream>>>(P);
     add_launches(1);

@@ -455,6 +455,26 @@ int wol_bin_on_grid(const double *opos, int64_t n, const double *xbins, const do
                     int32_t nz, double binwidth, int32_t *outhist, void *stream);
 
 /*
+ * RadialDistPlane (fortran/waterlib.f90:237-314; never called from the reference's Python): atoms of Pos2 inside the slab
+ * |z'| <= 5 of the frame spanned by the three points Pos1, counted on a totbins x totbins grid of (x', y') with the
+ * Fortran's ceiling binning.  pos1 [3][3], pos2 [n][3], box [3] (a negative edge = not periodic), counts
+ * [totbins][totbins] int64 ACCUMULATED, counts[kx][ky] = the Fortran's rdf(kx + 1, ky + 1).  The Fortran writes out of
+ * bounds for any slab atom with x' <= 0 or y' <= 0 (bin <= 0); here those atoms are skipped and their number is added to
+ * *n_out_of_bounds (device int32) -- non-zero means the reference's result for this input is undefined.
+ */
+int wol_radial_dist_plane(const double *pos1, const double *pos2, int32_t n_pos2, const double *box, double binwidth, int32_t totbins,
+                          double bulkdens, int64_t *counts, int32_t *n_out_of_bounds, void *stream);
+
+/*
+ * np.histogram2d(x, y, bins=(xedges, yedges)) on the device (numpy's histogramdd rule: searchsorted from the right, the
+ * last edge belongs to the last bin, samples outside are dropped): the (theta, N_c) histogram of
+ * threeBodyCalc(output2D=True), structureLibs/orderParam_lib.py:1385-1393.  x, y [n] double; edges ascending;
+ * out [(n_xedges - 1)][(n_yedges - 1)] int64, ACCUMULATED.
+ */
+int wol_histogram2d(const double *x, const double *y, int64_t n, const double *xedges, int32_t n_xedges, const double *yedges,
+                    int32_t n_yedges, int64_t *out, void *stream);
+
+/*
  * Multi-GPU combine for frame sharding (the reference has no parallel path at all,
  * structureLibs/orderParam_lib.py:1312-1353 loops over frames in one process): in-place sum over the ranks of an NCCL
  * communicator the CALLER owns of `count` int64 histogram bins (WOL_SUM_I64: angle, q, H-bond histograms -- integer

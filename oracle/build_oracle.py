@@ -2,7 +2,7 @@
 
   oracle/libwol_oracle.so      the C restatement (oracle/wol_oracle.c), OpenMP, no FMA contraction
   oracle/_ref/libgfortran.so.3 the stub runtime the reference's prebuilt f2py module needs
-  oracle/_ref/waterlib.cpython-37m-x86_64-linux-gnu.so   staged only while /root/reference is visible
+  oracle/_ref/{waterlib,sortlib}.cpython-37m-x86_64-linux-gnu.so   staged only while /root/reference is visible
         (build container): the reference's own prebuilt BINARY of fortran/waterlib.f90 (gfortran is not
         in this image, so it cannot be recompiled), so that the reference's compiled arithmetic can also
         run on a GPU box where /root/reference does not exist.  No reference source text is staged.
@@ -20,6 +20,7 @@ REF = os.path.join(HERE, "_ref")
 REFERENCE_ROOT = "/root/reference"
 STAGED = (
     (os.path.join("fortran", "waterlib.cpython-37m-x86_64-linux-gnu.so"), "waterlib.cpython-37m-x86_64-linux-gnu.so"),
+    (os.path.join("fortran", "sortlib.cpython-37m-x86_64-linux-gnu.so"), "sortlib.cpython-37m-x86_64-linux-gnu.so"),
 )
 
 
@@ -40,7 +41,7 @@ def build(verbose=True):
     stub_src = os.path.join(HERE, "gfortran_stub.c")
     stub = os.path.join(REF, "libgfortran.so.3")
     if _newer(stub_src, stub):
-        cmd = ["gcc", "-O1", "-fPIC", "-shared", "-o", stub, stub_src,
+        cmd = ["gcc", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-o", stub, stub_src,
                "-Wl,--version-script=" + os.path.join(HERE, "gfortran_stub.map"),
                "-Wl,-soname,libgfortran.so.3"]
         if verbose:

@@ -81,7 +81,32 @@ void _gfortran_internal_unpack(wol_desc_t *d, const void *src) {
     wol_desc_walk(d, (char *)src, 0);
 }
 
-WOL_FATAL(_gfortran_matmul_r8)
+/* matmul for real(8), rank-2 x rank-1 (RadialDistPlane, fortran/waterlib.f90:278-292, is the only caller on a path the
+ * oracle runs).  Same accumulation order as libgfortran 5's generic matmul_r8: dest(x) starts at zero and receives
+ * a(x, n) * b(n) for n = 1, 2, ... in turn.  An unallocated result descriptor is allocated here (the caller frees it). */
+void _gfortran_matmul_r8(wol_desc_t *ret, const wol_desc_t *a, const wol_desc_t *b, int try_blas, int blas_limit, void *gemm) {
+    (void)try_blas; (void)blas_limit; (void)gemm;
+    if ((a->dtype & 7) != 2 || (b->dtype & 7) != 1) {
+        fprintf(stderr, "oracle gfortran stub: matmul_r8 only handles matrix x vector\n");
+        abort();
+    }
+    const ptrdiff_t rows = a->dim[0].ubound - a->dim[0].lbound + 1, cols = a->dim[1].ubound - a->dim[1].lbound + 1;
+    if (!ret->base_addr) {
+        ret->dim[0].stride = 1;
+        ret->dim[0].lbound = 0;
+        ret->dim[0].ubound = rows - 1;
+        ret->offset = 0;
+        ret->base_addr = malloc((size_t)(rows > 0 ? rows : 1) * sizeof(double));
+        if (!ret->base_addr) { fprintf(stderr, "oracle gfortran stub: out of memory in matmul_r8\n"); abort(); }
+    }
+    double *dest = (double *)ret->base_addr;
+    const double *A = (const double *)a->base_addr, *B = (const double *)b->base_addr;
+    const ptrdiff_t rs = ret->dim[0].stride ? ret->dim[0].stride : 1, as0 = a->dim[0].stride ? a->dim[0].stride : 1;
+    const ptrdiff_t as1 = a->dim[1].stride, bs = b->dim[0].stride ? b->dim[0].stride : 1;
+    for (ptrdiff_t x = 0; x < rows; ++x) dest[x * rs] = 0.0;
+    for (ptrdiff_t n = 0; n < cols; ++n)
+        for (ptrdiff_t x = 0; x < rows; ++x) dest[x * rs] += A[x * as0 + n * as1] * B[n * bs];
+}
 WOL_FATAL(_gfortran_random_r4)
 WOL_FATAL(_gfortran_random_seed_i4)
 WOL_FATAL(_gfortran_system_clock_4)

@@ -348,3 +348,50 @@ def binongrid(opos, xbins, ybins, zbins):
     if rc != 0:
         raise ValueError("Must break volume into CUBES. Currently, bin-widths do not match.")
     return out
+
+
+def _anint(x):
+    """Fortran anint: round half away from zero."""
+    t = np.trunc(x)
+    f = x - t
+    return t + (f >= 0.5) - (f <= -0.5)
+
+
+def radialdistplane(Pos1, Pos2, binwidth, totbins, BulkDens, BoxL):
+    """RadialDistPlane (fortran/waterlib.f90:237-314) operation by operation -> (rdf (totbins, totbins) f64, number of
+    slab atoms whose bin index is <= 0: the Fortran writes out of bounds for those, they are skipped here)."""
+    p1 = np.asarray(Pos1, dtype=np.float64).reshape(3, 3)
+    p2 = np.asarray(Pos2, dtype=np.float64).reshape(-1, 3)
+    L = np.asarray(BoxL, dtype=np.float64).reshape(3)
+    with np.errstate(divide="ignore"):
+        iL = np.where(L >= 0.0, 1.0 / L, 0.0)                      # :261
+    v1 = p1[2] - p1[0]                                                # :264-266
+    v2 = p1[1] - p1[0]
+    v3 = np.array([v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]])
+    v1 = v1 - L * _anint(v1 * iL)                                     # :268-270
+    v2 = v2 - L * _anint(v2 * iL)
+    v3 = v3 - L * _anint(v3 * iL)
+
+    def dot(a, b):
+        return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+    v2 = v2 - (dot(v1, v2) / dot(v1, v1)) * v1                        # :272
+    v1 = v1 / np.sqrt(dot(v1, v1))                                    # :274-276
+    v2 = v2 / np.sqrt(dot(v2, v2))
+    v3 = v3 / np.sqrt(dot(v3, v3))
+    Q = np.stack([v1, v2, v3], axis=1)                                # Q(:, k) = v_k
+    rdf = np.zeros((totbins, totbins))
+    bad = 0
+    for p in p2:
+        q = p * BulkDens / BulkDens                                   # :291
+        q = q - L * _anint(q * iL)
+        r = np.zeros(3)
+        for n in range(3):                                            # libgfortran's matmul: dest(x) += Q(x, n) * q(n)
+            r = r + Q[:, n] * q[n]
+        if -5.0 <= r[2] <= 5.0:                                       # newPos1(1, :) = matmul(Q, 0) = 0
+            bx, by = np.ceil(r[0] / binwidth), np.ceil(r[1] / binwidth)
+            if bx <= totbins and by <= totbins:
+                if bx >= 1 and by >= 1:
+                    rdf[int(bx) - 1, int(by) - 1] += 1.0
+                else:
+                    bad += 1
+    return rdf, bad

@@ -5,6 +5,7 @@ into oracle/_ref/), so the CPU baseline there runs these restatements of
 
     getCosAngs       structureLibs/water_properties.py:210-250
     getOrderParamq   structureLibs/water_properties.py:344-391
+    getClusters      structureLibs/orderParam_lib.py:123-156 (over sortlib.depthfirstsort)
 
 on top of ``RefWaterlib`` (the reference's own compiled ``allnearneighbors`` / ``nearneighbors`` /
 ``reimage`` / ``tetracosang``).  Same call sequence per water, same NumPy calls, so the timing has the
@@ -51,3 +52,23 @@ def get_order_param_q(wl, subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
             vals = np.concatenate((vals, np.full(3, 180.0)))
         q[i] = 1.0 - (3.0 / 8.0) * np.sum((np.cos(vals * np.pi / 180.0) + (1.0 / 3.0)) ** 2)
     return q
+
+
+def get_clusters(sortlib, hbMat):
+    """Clusters of a residue-connectivity matrix through the reference's compiled depth-first search, in the order and
+    with the conventions of the reference's loop: residues already placed are skipped, an unconnected residue is a
+    cluster of one, a cluster that spans everything ends the search."""
+    n = hbMat.shape[0]
+    clusters = []
+    placed = np.zeros(n, dtype=bool)
+    for i in range(n):
+        if placed[i]:
+            continue
+        seen = sortlib.depthfirstsort(i + 1, hbMat, np.zeros(n, dtype=int), np.int64(np.sum(hbMat[i, :])), n)
+        members = np.where(seen == 1)[0]
+        placed[members] = True
+        if len(members) == n:
+            clusters.append(members)
+            break
+        clusters.append(members if len(members) else np.array([i]))
+    return clusters

@@ -216,6 +216,17 @@ class RefWaterlib:
         return rdf
 
     # fortran/waterlib.f90:316-353
+    # fortran/waterlib.f90:237-314 (its matmul goes through the stub runtime's _gfortran_matmul_r8)
+    def radialdistplane(self, pos1, pos2, binwidth, totbins, bulkdens, boxl):
+        p1, p2 = _f64(pos1), _f64(pos2)
+        if p1.shape != (3, 3):
+            raise ValueError("pos1 must be (3, 3)")
+        rdf = np.zeros((totbins, totbins), dtype=np.float64, order="F")
+        self._lib.radialdistplane_(_dp(p1), _dp(p2), ctypes.byref(ctypes.c_double(binwidth)), ctypes.byref(ctypes.c_int32(totbins)),
+                                   ctypes.byref(ctypes.c_double(bulkdens)), _dp(_box(boxl)), _dp(rdf),
+                                   ctypes.byref(ctypes.c_int32(p2.shape[0])))
+        return rdf
+
     def radialdistsame(self, pos, binwidth, totbins, bulkdens, boxl):
         p = _f64(pos)
         rdf = np.zeros(totbins, dtype=np.float64)
@@ -306,4 +317,47 @@ def load_reference_functions(names=_WP_FUNCS, wl=None):
     missing = wanted - set(ns)
     if missing:
         raise RuntimeError("reference functions not found: %s" % sorted(missing))
+    return {k: ns[k] for k in names}
+
+
+_SORT_SO = "sortlib.cpython-37m-x86_64-linux-gnu.so"
+
+
+def sortlib_available():
+    return os.path.exists(os.path.join(_REF_DIR, "libgfortran.so.3")) and _find(os.path.join("fortran", _SORT_SO), _SORT_SO) is not None
+
+
+class RefSortlib:
+    """f2py-compatible face of the reference's compiled sortlib: depthfirstsort (fortran/sortlib.f90:26-72), reached
+    through the wrapper f2py generated for its assumed-shape argument (f2pywrapdepthfirstsort_)."""
+
+    def __init__(self):
+        stub = os.path.join(_REF_DIR, "libgfortran.so.3")
+        so = _find(os.path.join("fortran", _SORT_SO), _SORT_SO)
+        if not os.path.exists(stub) or so is None:
+            raise RuntimeError("reference sortlib unavailable: run `python oracle/build_oracle.py` where /root/reference exists")
+        self._stub = ctypes.CDLL(stub, mode=ctypes.RTLD_GLOBAL)
+        self._lib = ctypes.CDLL(so)
+
+    def depthfirstsort(self, vertex, array, visited, m, n=None):
+        """final_visited = depthfirstsort(vertex, array, visited, m, [n]) -- visited is updated in place like f2py's
+        intent(inout) would; vertex is 1-based."""
+        a = np.asfortranarray(np.asarray(array, dtype=np.int32))
+        n = a.shape[0] if n is None else int(n)
+        vis = np.ascontiguousarray(visited, dtype=np.int32)
+        final = np.zeros(n, dtype=np.int32)  # f2py hands the Fortran a fresh intent(out) array
+        self._lib.f2pywrapdepthfirstsort_(ctypes.byref(ctypes.c_int32(int(vertex))), _ip(a), _ip(vis), ctypes.byref(ctypes.c_int32(int(m))),
+                                          ctypes.byref(ctypes.c_int32(n)), _ip(final), ctypes.byref(ctypes.c_int32(vis.shape[0])))
+        return final
+
+
+def load_reference_driver_functions(names, sortlib):
+    """AST-extract def bodies from the reference's structureLibs/orderParam_lib.py (getClusters, ...) and exec them with
+    np and the given sortlib in scope.  Build container only."""
+    path = os.path.join("/root/reference", "structureLibs", "orderParam_lib.py")
+    tree = ast.parse(open(path).read())
+    ns = {"np": np, "sortlib": sortlib}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return {k: ns[k] for k in names}

@@ -446,3 +446,34 @@ def test_boundWrapPopulations_cache_and_use_as_subInds(in_tmp, monkeypatch):
     avgQ, _ = opl.tetOrderCalc(top, traj, subInds=sub, nPops=4)
     # (a frame without bound waters gives that population a NaN mean, as in the reference)
     assert avgQ[0].shape == (5,) and np.all(np.isfinite(avgQ[0][[0, 3, 4]]))
+
+
+def test_threeBodyCalc_output2D_is_numpy_histogram2d_of_the_reference_lists(in_tmp):
+    """output2D=True: the (N_c - 1, theta) histogram of reference orderParam_lib.py:1329-1335 / :1385-1393, rebuilt here
+    with the reference's own list construction and np.histogram2d over the oracle's angles."""
+    T = 6
+    top, traj = make_system(3, T, sigma=0.45)
+    obj = TrajObject(top, traj)
+    watInds, _, _ = obj.getWatInds()
+    numbers, angles = [], []
+    for t in range(T):
+        watPos = traj.xyz[t][watInds]
+        tb = port.three_body(watPos, watPos, traj.boxes[t])
+        angles.append(tb["angVals"])
+        for n in tb["numAngs"]:
+            count = int(n - 1)
+            while count > 0:
+                numbers.append([int(n - 1) for _ in range(count)])
+                count -= 1
+    numbers = np.concatenate(numbers).astype(float)
+    angles = np.concatenate(angles)
+    H, xe, ye = np.histogram2d(numbers, angles, bins=(np.arange(-1.5, 13.5, 1), np.linspace(0, 180, 500)))
+    H = H / np.sum(H)
+    plain = opl.threeBodyCalc(top, traj)
+    with2d = opl.threeBodyCalc(top, traj, output2D=True)
+    got, gx, gy = opl.threeBodyCalc.last_2d
+    assert got.shape == (14, 499) and np.array_equal(gx, xe) and np.array_equal(gy, ye)
+    assert np.array_equal(got, H) and abs(got.sum() - 1.0) < 1e-12
+    for a, b in zip(plain[:4], with2d[:4]):  # the statistics do not change (the CIs are bootstrap draws)
+        assert np.array_equal(a[0], b[0])
+    assert np.loadtxt("3bDistribution_2D.txt").shape == (14, 499)

@@ -360,3 +360,43 @@ def test_water_orientation_and_sphere_occupancy(golden_dir):
         wl.binongrid(xyz[0], edges, edges * 1.1, edges)
     with pytest.raises(ValueError):
         wl.watorient(xyz[0], hyd[0][:-1], (0, 0, 1.0), boxes[0])
+
+
+def test_getClusters_matches_the_reference_depth_first_search(golden_dir):
+    """Fixture: the reference's own getClusters body (orderParam_lib.py:123-156) over its compiled
+    sortlib.depthfirstsort (fortran/sortlib.f90:26-72): same clusters, same order, members ascending."""
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    g = np.load(os.path.join(golden_dir, "clusters.npz"))
+    for k in range(int(g["n_cases"])):
+        got = opl.getClusters(g["mat%d" % k])
+        sizes, members = g["sizes%d" % k], g["members%d" % k]
+        assert [len(c) for c in got] == list(sizes)
+        assert np.array_equal(np.concatenate(got), members)
+
+
+def test_radialdistplane_matches_the_compiled_fortran(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rdfplane.npz"))
+    for tag in ("a", "b"):
+        rdf = wl.radialdistplane(g["pos1"], g["pos2"], float(g["binwidth_" + tag]), int(g["totbins_" + tag]), float(g["bulkdens"]), g["box"])
+        assert rdf.shape == g["rdf_" + tag].shape and np.array_equal(rdf, g["rdf_" + tag]) and rdf.sum() > 100
+    # an atom behind the plane's origin indexes bin <= 0 in the Fortran (out-of-bounds write): reported, not performed
+    with pytest.raises(ValueError):
+        wl.radialdistplane(g["pos1"], g["pos2"] - 6.0, 0.5, 40, float(g["bulkdens"]), g["box"])
+    with pytest.raises(ValueError):
+        wl.radialdistplane(g["pos1"][:2], g["pos2"], 0.5, 40, 1.0, g["box"])
+
+
+def test_histogram2d_is_numpy_histogram2d():
+    from waterorderlib_b200 import routines
+    rng = np.random.default_rng(5)
+    x = rng.integers(-2, 14, size=20000).astype(float)
+    y = rng.random(20000) * 190.0 - 5.0
+    y[:50] = 180.0          # the last edge belongs to the last bin
+    y[50:100] = 0.0
+    xe, ye = np.arange(-1.5, 13.5, 1), np.linspace(0, 180, 500)
+    y[100:600] = ye[rng.integers(0, 500, size=500)]  # values exactly on edges go to the bin on their right
+    want = np.histogram2d(x, y, bins=(xe, ye))[0]
+    got = routines.histogram2d(x, y, xe, ye)
+    assert np.array_equal(got.cpu().numpy(), want.astype(np.int64))
+    routines.histogram2d(x, y, xe, ye, out=got)
+    assert np.array_equal(got.cpu().numpy(), 2 * want.astype(np.int64))

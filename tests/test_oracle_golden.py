@@ -158,3 +158,21 @@ def test_watorient_and_binongrid_golden(golden_dir):
         port.binongrid(g["opos"], g["xbins"], g["ybins"] * 1.5, g["zbins"])
     with pytest.raises(ValueError):
         port.watorient(g["opos"], g["hpos"][:-1], g["refvec"], g["box"])
+
+
+def test_clusters_and_rdfplane_against_golden(golden_dir):
+    """getClusters through the staged reference DFS (oracle/_ref) and the RadialDistPlane restatement, against fixtures made
+    by the reference's own getClusters body / compiled RadialDistPlane (tests/golden/make_golden_extras.py)."""
+    from oracle import port, ref_driver, ref_fortran
+    g = np.load(os.path.join(golden_dir, "clusters.npz"))
+    if ref_fortran.sortlib_available():
+        sl = ref_fortran.RefSortlib()
+        for k in range(int(g["n_cases"])):
+            cl = ref_driver.get_clusters(sl, g["mat%d" % k])
+            assert [len(c) for c in cl] == list(g["sizes%d" % k]) and np.array_equal(np.concatenate(cl), g["members%d" % k])
+    r = np.load(os.path.join(golden_dir, "rdfplane.npz"))
+    for tag in ("a", "b"):
+        rdf, bad = port.radialdistplane(r["pos1"], r["pos2"], float(r["binwidth_" + tag]), int(r["totbins_" + tag]), float(r["bulkdens"]), r["box"])
+        assert bad == 0 and np.array_equal(rdf, r["rdf_" + tag])
+    _, bad = port.radialdistplane(r["pos1"], r["pos2"] - 6.0, 0.5, 40, float(r["bulkdens"]), r["box"])
+    assert bad > 0

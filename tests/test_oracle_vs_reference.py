@@ -194,3 +194,31 @@ def test_watorient_and_binongrid_match_live(ref):
     for shift in (0.0, 0.7):
         r = wl.binongrid(o, edges + shift, edges, edges - 1.0)
         assert np.array_equal(np.ascontiguousarray(r), port.binongrid(o, edges + shift, edges, edges - 1.0)) and r.sum() > 50
+
+
+def test_clusters_restatement_matches_the_live_getClusters():
+    """oracle/ref_driver.get_clusters against the reference's unmodified getClusters body (orderParam_lib.py:123-156),
+    both over the reference's compiled depthfirstsort (fortran/sortlib.f90:26-72)."""
+    from oracle import ref_driver
+    sl = ref_fortran.RefSortlib()
+    live = ref_fortran.load_reference_driver_functions(["getClusters"], sl)["getClusters"]
+    rng = np.random.default_rng(11)
+    for n, p in ((25, 0.04), (40, 0.03), (16, 0.3), (9, 0.0), (33, 0.06)):
+        m = np.triu((rng.random((n, n)) < p).astype(int), 1)
+        m = m + m.T
+        a, b = live(m), ref_driver.get_clusters(sl, m)
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert sorted(np.concatenate(b).tolist()) == list(range(n)) or len(b[-1]) == n
+
+
+def test_radialdistplane_restatement_matches_live(ref):
+    """RadialDistPlane (fortran/waterlib.f90:237-314; its matmul runs in the stub runtime with libgfortran 5's order)."""
+    wl, _ = ref
+    rng = np.random.default_rng(4)
+    L = np.array([38.0, 41.0, 35.0])
+    p1 = np.array([[2.0, 1.5, 1.0], [2.4, 4.4, 1.2], [5.1, 1.2, 1.5]])
+    p2 = rng.random((800, 3)) * np.array([13.0, 13.0, 11.0]) + np.array([3.5, 3.5, 0.5])
+    for bw, nb in ((0.5, 36), (0.8, 20)):
+        mine, bad = port.radialdistplane(p1, p2, bw, nb, 0.03, L)
+        assert bad == 0 and mine.sum() > 50
+        assert np.array_equal(wl.radialdistplane(p1, p2, bw, nb, 0.03, L), mine)

@@ -284,6 +284,112 @@ static PGrid make_pgrid(void *workspace, const WorkspaceLayout &lay, const int32
 
 using namespace wol;
 
+
+// ---- RadialDistPlane (fortran/waterlib.f90:237-314) -------------------------------------------------------------------
+// The frame: v1 = P3 - P1, v2 = P2 - P1, v3 = v1 x v2, each minimum-imaged, v2 made orthogonal to v1 with the Fortran's
+// expression v2 - (v1.v2) / (sum(v1 ** 2.0)) * v1, all normalised; Q(:, k) = v_k.  Every atom is minimum-imaged about the
+// ORIGIN (Pos2 * BulkDens / BulkDens first: two roundings the reference performs), mapped with matmul(Q, .) -- libgfortran's
+// matmul_r8 accumulates dest(x) += Q(x, n) * p(n) over n from a zeroed dest -- and counted in bin
+// (ceiling(x' / w), ceiling(y' / w)) when |z'| <= 5.  A non-positive x' or y' indexes bin <= 0 in the Fortran, an
+// out-of-bounds write; such atoms are skipped here and COUNTED in *n_bad so the caller can tell.
+struct PlaneParams {
+    const double *pos1;  // [3][3]
+    const double *pos2;  // [n][3]
+    const double *box;
+    double binwidth, bulkdens;
+    int totbins, n;
+    unsigned long long *counts;  // [totbins][totbins], counts[kx][ky] (kx = x bin - 1)
+    unsigned *n_bad;
+};
+
+__device__ __forceinline__ double plane_minimg(double v, double L) {
+    const double iL = (L >= 0.0) ? __ddiv_rn(1.0, L) : 0.0;
+    return __dsub_rn(v, __dmul_rn(L, anint_exact<double>(__dmul_rn(v, iL))));
+}
+
+__global__ void __launch_bounds__(128) radial_dist_plane_kernel(PlaneParams P) {
+    __shared__ double Q[3][3];  // Q[row][col]: Q(row, col) = v_col(row)
+    if (threadIdx.x == 0) {
+        const double *p = P.pos1;
+        double L[3] = {P.box[0], P.box[1], P.box[2]};
+        double v1[3], v2[3], v3[3];
+        for (int k = 0; k < 3; ++k) {
+            v1[k] = __dsub_rn(p[2 * 3 + k], p[k]);
+            v2[k] = __dsub_rn(p[1 * 3 + k], p[k]);
+        }
+        // crossProd3 (waterlib.f90:18-29): v3 = v1 x v2
+        v3[0] = __dsub_rn(__dmul_rn(v1[1], v2[2]), __dmul_rn(v1[2], v2[1]));
+        v3[1] = __dsub_rn(__dmul_rn(v1[2], v2[0]), __dmul_rn(v1[0], v2[2]));
+        v3[2] = __dsub_rn(__dmul_rn(v1[0], v2[1]), __dmul_rn(v1[1], v2[0]));
+        for (int k = 0; k < 3; ++k) {
+            v1[k] = plane_minimg(v1[k], L[k]);
+            v2[k] = plane_minimg(v2[k], L[k]);
+            v3[k] = plane_minimg(v3[k], L[k]);
+        }
+        const double d12 = dot3<double>(v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]);
+        const double n1 = sumsq3<double>(v1[0], v1[1], v1[2]);  // v1 ** 2.0 is compiled as v1 * v1
+        const double fac = __ddiv_rn(d12, n1);
+        for (int k = 0; k < 3; ++k) v2[k] = __dsub_rn(v2[k], __dmul_rn(fac, v1[k]));
+        const double l1 = __dsqrt_rn(sumsq3<double>(v1[0], v1[1], v1[2]));
+        const double l2 = __dsqrt_rn(sumsq3<double>(v2[0], v2[1], v2[2]));
+        const double l3 = __dsqrt_rn(sumsq3<double>(v3[0], v3[1], v3[2]));
+        for (int k = 0; k < 3; ++k) {
+            Q[k][0] = __ddiv_rn(v1[k], l1);
+            Q[k][1] = __ddiv_rn(v2[k], l2);
+            Q[k][2] = __ddiv_rn(v3[k], l3);
+        }
+    }
+    __syncthreads();
+    const double L[3] = {P.box[0], P.box[1], P.box[2]};
+    // newPos1(1, :) = matmul(Q, 0) = 0: the slab is |z'| <= 5
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
+        double q[3];
+        for (int k = 0; k < 3; ++k) {
+            const double scaled = __ddiv_rn(__dmul_rn(P.pos2[(size_t)i * 3 + k], P.bulkdens), P.bulkdens);
+            q[k] = plane_minimg(scaled, L[k]);
+        }
+        double r[3];
+        for (int x = 0; x < 3; ++x) {
+            double acc = 0.0;
+            for (int n = 0; n < 3; ++n) acc = __dadd_rn(acc, __dmul_rn(Q[x][n], q[n]));
+            r[x] = acc;
+        }
+        if (r[2] <= 5.0 && r[2] >= -5.0) {
+            const double bx = ceil(__ddiv_rn(r[0], P.binwidth)), by = ceil(__ddiv_rn(r[1], P.binwidth));
+            if (bx <= (double)P.totbins && by <= (double)P.totbins) {
+                if (bx >= 1.0 && by >= 1.0) atomicAdd(P.counts + ((size_t)((int)bx - 1) * P.totbins + ((int)by - 1)), 1ull);
+                else atomicAdd(P.n_bad, 1u);
+            }
+        }
+    }
+}
+
+// ---- np.histogramdd over two coordinates (numpy/lib/_histograms_impl.py: searchsorted(edges, x, 'right'), the last edge
+// belongs to the last bin, everything outside is dropped) -- threeBodyCalc(output2D=True), orderParam_lib.py:1385-1393
+__device__ __forceinline__ int edge_bin(const double *edges, int n_edges, double x) {
+    int lo = 0, hi = n_edges;  // number of edges <= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (edges[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    if (x == edges[n_edges - 1]) lo -= 1;
+    return lo - 1;  // valid bins: 0 .. n_edges - 2
+}
+
+__global__ void __launch_bounds__(256) histogram2d_kernel(const double *__restrict__ x, const double *__restrict__ y, long long n,
+                                                          const double *__restrict__ xedges, int nxe, const double *__restrict__ yedges,
+                                                          int nye, unsigned long long *out) {
+    extern __shared__ double s_edges[];
+    double *sx = s_edges, *sy = s_edges + nxe;
+    for (int i = threadIdx.x; i < nxe; i += blockDim.x) sx[i] = xedges[i];
+    for (int i = threadIdx.x; i < nye; i += blockDim.x) sy[i] = yedges[i];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int bx = edge_bin(sx, nxe, x[i]), by = edge_bin(sy, nye, y[i]);
+        if (bx >= 0 && bx < nxe - 1 && by >= 0 && by < nye - 1) atomicAdd(out + (size_t)bx * (nye - 1) + by, 1ull);
+    }
+}
+
 extern "C" {
 
 int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t n_outer, const double *box, int32_t n_inner,
@@ -315,6 +421,51 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_pair_hist", e);
+    return WOL_OK;
+}
+
+int wol_radial_dist_plane(const double *pos1, const double *pos2, int32_t n_pos2, const double *box, double binwidth, int32_t totbins,
+                          double bulkdens, int64_t *counts, int32_t *n_out_of_bounds, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!pos1 || !box || !counts || !n_out_of_bounds || (!pos2 && n_pos2 > 0))
+        return set_error(WOL_ERR_INVALID, "wol_radial_dist_plane: null argument");
+    if (totbins < 1 || !(binwidth > 0.0) || n_pos2 < 0 || bulkdens == 0.0)
+        return set_error(WOL_ERR_INVALID, "wol_radial_dist_plane: need totbins >= 1, binwidth > 0, a non-zero BulkDens");
+    PlaneParams P;
+    P.pos1 = pos1;
+    P.pos2 = pos2;
+    P.box = box;
+    P.binwidth = binwidth;
+    P.bulkdens = bulkdens;
+    P.totbins = totbins;
+    P.n = n_pos2;
+    P.counts = reinterpret_cast<unsigned long long *>(counts);
+    P.n_bad = reinterpret_cast<unsigned *>(n_out_of_bounds);
+    if (n_pos2 > 0) {
+        const int blocks = (n_pos2 + 127) / 128 < sm_count() * 8 ? (n_pos2 + 127) / 128 : sm_count() * 8;
+        radial_dist_plane_kernel<<<blocks, 128, 0, stream>>>(P);
+        add_launches(1);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_radial_dist_plane", e);
+    return WOL_OK;
+}
+
+int wol_histogram2d(const double *x, const double *y, int64_t n, const double *xedges, int32_t n_xedges, const double *yedges,
+                    int32_t n_yedges, int64_t *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || n_xedges < 2 || n_yedges < 2 || !xedges || !yedges || !out || ((!x || !y) && n > 0))
+        return set_error(WOL_ERR_INVALID, "wol_histogram2d: bad argument");
+    if ((size_t)(n_xedges + n_yedges) * sizeof(double) > 40000) return set_error(WOL_ERR_RANGE, "wol_histogram2d: more than 5000 edges");
+    if (n > 0) {
+        long long blocks = (n + 255) / 256;
+        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+        histogram2d_kernel<<<(unsigned)blocks, 256, (size_t)(n_xedges + n_yedges) * sizeof(double), stream>>>(
+            x, y, n, xedges, n_xedges, yedges, n_yedges, reinterpret_cast<unsigned long long *>(out));
+        add_launches(1);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_histogram2d", e);
     return WOL_OK;
 }
 

@@ -506,6 +506,39 @@ def pair_hist(mode, pos1, pos2, box, binwidth, totbins, device=None):
     return counts
 
 
+def radial_dist_plane(pos1, pos2, box, binwidth, totbins, bulkdens, device=None):
+    """RadialDistPlane (fortran/waterlib.f90:237-314) -> (counts int64 CUDA tensor (totbins, totbins), number of slab atoms
+    whose bin index is <= 0 -- an out-of-bounds write in the Fortran, skipped here)."""
+    device = _device(device, pos2, pos1)
+    p1 = _f64(pos1, device, (3,)).reshape(-1, 3)
+    if p1.shape[0] != 3:
+        raise ValueError("pos1 must hold the three points that span the plane, shape (3, 3)")
+    p2 = _f64(pos2, device, (3,)).reshape(-1, 3)
+    b = _box3(box, device)
+    counts = torch.zeros((int(totbins), int(totbins)), dtype=torch.int64, device=device)
+    bad = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_radial_dist_plane(_vp(p1.data_ptr()), _vp(p2.data_ptr()), int(p2.shape[0]), _vp(b.data_ptr()), float(binwidth),
+                                          int(totbins), float(bulkdens), _vp(counts.data_ptr()), _vp(bad.data_ptr()), _stream()),
+              "wol_radial_dist_plane")
+    return counts, int(bad.item())
+
+
+def histogram2d(x, y, xedges, yedges, out=None, device=None):
+    """np.histogram2d(x, y, bins=(xedges, yedges))[0] as an int64 CUDA tensor (accumulated into `out` when given)."""
+    device = _device(device, x, y)
+    xd, yd = _f64(x, device).reshape(-1), _f64(y, device).reshape(-1)
+    if xd.numel() != yd.numel():
+        raise ValueError("x and y must have the same length")
+    xe, ye = _f64(np.asarray(xedges, dtype=np.float64), device).reshape(-1), _f64(np.asarray(yedges, dtype=np.float64), device).reshape(-1)
+    if out is None:
+        out = torch.zeros((xe.numel() - 1, ye.numel() - 1), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        check(lib().wol_histogram2d(_vp(xd.data_ptr()), _vp(yd.data_ptr()), int(xd.numel()), _vp(xe.data_ptr()), int(xe.numel()),
+                                    _vp(ye.data_ptr()), int(ye.numel()), _vp(out.data_ptr()), _stream()), "wol_histogram2d")
+    return out
+
+
 def rdf_normalise(counts, n_norm, binwidth, bulkdens):
     """counts(k) / (N * BulkDens * (4./3.) * pi * binwidth**3 * (k**3 - (k-1)**3)) in the Fortran's order of
     operations (waterlib.f90:227-229); O(totbins) on the host."""

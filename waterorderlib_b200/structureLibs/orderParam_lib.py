@@ -317,10 +317,11 @@ def threeBodyCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)'
                   output2D=False):
     """Three-body angle distribution statistics for all waters and nPops sub-populations (reference
     orderParam_lib.py:1269-1424).  Returns (pTet, avgCos, varCos, entropy, nWats), each [means, CIs], and writes
-    3bDistribution_<j>.txt.  output2D (a matplotlib figure in the reference) is not part of the hot path."""
-    if output2D:
-        raise NotImplementedError("output2D draws a matplotlib figure in the reference (orderParam_lib.py:1384-1422); "
-                                  "it is outside the hot path this backend replaces")
+    3bDistribution_<j>.txt.  output2D=True also accumulates the (N_c, theta) histogram the reference builds with
+    np.histogram2d (:1329-1335, :1385-1393: water-water coordination number minus one against the angle, edges
+    arange(-1.5, 13.5, 1) x linspace(0, 180, 500), normalised to 1): it is written to 3bDistribution_2D.txt and kept
+    in threeBodyCalc.last_2d = (H, xedges, yedges); the matplotlib figure the reference draws from it is not
+    produced."""
     obj = TrajObject(topFile, trajFile, stride, solResName, watResName)
     if subInds is None:
         nPops = 0
@@ -352,8 +353,44 @@ def threeBodyCalc(topFile, trajFile, subInds=None, nPops=0, solResName='(!:WAT)'
                 np.savetxt('3bDistribution_' + str(j) + '.txt',
                            np.stack([0.5 * (bins[:-1] + bins[1:]), hist[:, j].sum(axis=0)], axis=1),
                            header='3-body angle (deg)    frequency', fmt="%.3e")
+    if output2D:
+        threeBodyCalc.last_2d = _theta_nc_histogram(obj)
     pTet, avgCos, varCos, entropy, nWats = out
     return pTet, avgCos, varCos, entropy, nWats
+
+
+def _theta_nc_histogram(obj):
+    """The 2-D histogram of threeBodyCalc(output2D=True): for every three-body angle of every water, (number of
+    neighbours of its central water - 1, angle) -- reference orderParam_lib.py:1329-1335 builds the first coordinate by
+    repeating n - 1 once per angle, :1385-1393 bins the pairs.  Angles are materialised in the reference's order by the
+    getCosAngs path and binned on the device with numpy's histogramdd rule; frames are sharded over ranks."""
+    traj = obj.traj
+    watInds, _, _ = obj.getWatInds()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xedges, yedges = np.arange(-1.5, 13.5, 1), np.linspace(0, 180, 500)
+    H = torch.zeros((len(xedges) - 1, len(yedges) - 1), dtype=torch.int64, device=dev)
+    wat_d = torch.from_numpy(np.ascontiguousarray(np.asarray(watInds, dtype=np.int64))).to(dev)
+    begin, end = wdist.shard_frames(len(traj))
+    stager = _FrameStager(dev)
+    for t in range(begin, end):
+        xyz, box = _frame_arrays(traj, t, t + 1)
+        xyz_d, ready = stager.put(xyz)
+        torch.cuda.current_stream(dev).wait_event(ready)
+        xyz_d.record_stream(torch.cuda.current_stream(dev))
+        watPos = xyz_d.index_select(1, wat_d).to(torch.float64)
+        angles, n3, _ = routines.three_body_angles(None, watPos, box)
+        k = n3.reshape(-1).to(torch.int64)
+        numbers = torch.repeat_interleave((k - 1).to(torch.float64), k * (k - 1) // 2)
+        routines.histogram2d(numbers, angles, xedges, yedges, out=H)
+    wdist.reduce_histograms(H)
+    Hn = H.cpu().numpy().astype(np.float64)
+    tot = Hn.sum()
+    if tot > 0:
+        Hn = Hn / tot
+    if wdist.world()[0] == 0:
+        np.savetxt('3bDistribution_2D.txt', Hn, fmt="%.3e",
+                   header='rows: N_c - 1 bins, edges arange(-1.5, 13.5, 1); columns: angle bins, edges linspace(0, 180, 500); sum = 1')
+    return Hn, xedges, yedges
 
 
 def _hb_sums(acc, don, donh, box, dist, ang, cells=None):

@@ -100,6 +100,19 @@ def radialdist(pos1, pos2, binwidth, totbins, bulkdens, boxl):
     return routines.rdf_normalise(counts, p1.shape[0], binwidth, bulkdens)
 
 
+def radialdistplane(pos1, pos2, binwidth, totbins, bulkdens, boxl):
+    """rdf = radialdistplane(pos1,pos2,binwidth,totbins,bulkdens,boxl)   (fortran/waterlib.f90:237-314): counts of the atoms
+    of pos2 within 5 A of the plane through the three points pos1, on a totbins x totbins grid of in-plane coordinates.
+    The Fortran indexes bin <= 0 (an out-of-bounds write) for atoms with a non-positive in-plane coordinate; that raises
+    ValueError here instead of corrupting memory."""
+    counts, bad = routines.radial_dist_plane(np.asarray(pos1, dtype=np.float64), _check_pos(pos2, "pos2"), boxl, binwidth, totbins,
+                                             bulkdens)
+    if bad:
+        raise ValueError("radialdistplane: %d atoms of the slab have a non-positive in-plane coordinate (bin <= 0, out of "
+                         "bounds in the reference)" % bad)
+    return np.asfortranarray(counts.cpu().numpy().astype(np.float64))
+
+
 def radialdistsame(pos, binwidth, totbins, bulkdens, boxl):
     """rdf = radialdistsame(pos,binwidth,totbins,bulkdens,boxl)   (fortran/waterlib.f90:316-353)"""
     p = _check_pos(pos, "pos")

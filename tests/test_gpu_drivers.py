@@ -122,8 +122,6 @@ def test_threeBodyCalc_matches_reference_loop(in_tmp):
         want = port.histogram(np.concatenate(pooled[j]), 500, 0.0, 180.0)
         assert np.array_equal(got[:, 1], np.array([float("%.3e" % v) for v in want]))
     assert nWats[0][0] == 216 and nWats[0][1] == 40
-    with pytest.raises(NotImplementedError):
-        opl.threeBodyCalc(top, traj, output2D=True)
 
 
 def ref_hbcalc(top, traj, obj):

@@ -114,3 +114,32 @@ def test_few_neighbours_padding_and_empty():
     assert np.array_equal(r.nn_idx.cpu().numpy()[0], nn4)
     assert_q_close(r.q.cpu().numpy()[0], q)
     assert r.q[0, 5].item() == 0.0 and abs(r.q[0, 0].item()) < 1e-12
+
+
+def test_graphed_call_replays_and_matches_the_plain_call():
+    """engine.q3b_frames_graphed: one captured launch sequence per signature, replayed on new inputs of the same shape;
+    every output equals the plain call's, histograms start from zero on every replay."""
+    from waterorderlib_b200 import engine, synth
+    box = None
+    frames = []
+    for seed in (1, 2, 3):
+        p, box = synth.water_box(4, sigma=0.3 + 0.1 * seed, seed=seed)
+        frames.append(p)
+    n0 = len(engine._GRAPHS)
+    for rep in range(2):
+        for p in frames:
+            g = engine.q3b_frames_graphed(p, box)
+            r = engine.q3b_frames(p, box)
+            assert g["graph"] and g["launches"] == r["launches"]
+            for k in ("q", "nn_idx", "n3", "ang_hist", "q_hist"):
+                assert torch.equal(g[k], r[k]), k
+            assert torch.allclose(g["frame_stats"], r["frame_stats"], rtol=1e-13, atol=0)
+            assert g["n_widened"] == r["n_widened"] and g["n_overflow"] == r["n_overflow"]
+    assert len(engine._GRAPHS) == n0 + 1  # same signature: captured once
+    sub = frames[0][:37] + 0.05
+    g = engine.q3b_frames_graphed(frames[1], box, sub, do_q=False, want=("n3", "ang_hist"))
+    r = engine.q3b_frames(frames[1], box, sub, do_q=False, want=("n3", "ang_hist"))
+    assert torch.equal(g["n3"], r["n3"]) and torch.equal(g["ang_hist"], r["ang_hist"])
+    # another box = another signature (cutoff margins derived from the box are baked into the captured kernels)
+    g2 = engine.q3b_frames_graphed(frames[0] * 1.01, box * 1.01, want=("q",))
+    assert torch.equal(g2["q"], engine.q3b_frames(frames[0] * 1.01, box * 1.01, want=("q",))["q"])

@@ -112,6 +112,81 @@ class Workspace:
         return self.buf.data_ptr() + off, self.buf.numel() - off
 
 
+_GRAPHS = {}          # signature -> captured call (see q3b_frames_graphed)
+_GRAPH_CACHE_MAX = 16
+GRAPH_MAX_ATOMS = 1 << 18  # below this many atoms per call the ~10 launches of a call cost more than its kernels
+
+
+def q3b_frames_graphed(pos, box, centres=None, *, want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), device=None,
+                       check_status=True, **opts):
+    """q3b_frames for small, repeated calls (a driver looping over frames of a few thousand waters): the whole launch
+    sequence -- cell build, sweep, queued passes -- is captured ONCE into a CUDA graph per call signature (shapes, dtypes,
+    options and the exact box: cutoffs and rounding margins derived from the box are baked into the kernels' arguments)
+    and replayed afterwards, which replaces ~10 launches by one.  Inputs are copied into the graph's own buffers; the
+    returned tensors ARE the graph's output buffers and are overwritten by the next call with the same signature --
+    copy what must survive (the numpy-returning wrappers do).  Histograms and frame_stats start from zero each call."""
+    if device is None:
+        device = pos.device if isinstance(pos, torch.Tensor) and pos.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    pos_t = pos if isinstance(pos, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(pos)))
+    if pos_t.dtype not in (torch.float32, torch.float64):
+        pos_t = pos_t.to(torch.float64)
+    if pos_t.dim() == 2:
+        pos_t = pos_t.unsqueeze(0)
+    cen_t = None
+    if centres is not None:
+        cen_t = centres if isinstance(centres, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(centres)))
+        if cen_t.dtype not in (torch.float32, torch.float64):
+            cen_t = cen_t.to(torch.float64)
+        if cen_t.dim() == 2:
+            cen_t = cen_t.unsqueeze(0)
+    F = int(pos_t.shape[0])
+    box_h = as_host_boxes(box, F)
+    key = (str(device), tuple(pos_t.shape), pos_t.dtype, None if cen_t is None else (tuple(cen_t.shape), cen_t.dtype),
+           tuple(want), tuple(sorted((k, repr(v)) for k, v in opts.items())), box_h.tobytes())
+    g = _GRAPHS.get(key)
+    if g is None:
+        if len(_GRAPHS) >= _GRAPH_CACHE_MAX:
+            _GRAPHS.pop(next(iter(_GRAPHS)))
+        g = {"pos": torch.empty(pos_t.shape, dtype=pos_t.dtype, device=device),
+             "cen": None if cen_t is None else torch.empty(cen_t.shape, dtype=cen_t.dtype, device=device),
+             "box": torch.from_numpy(box_h.copy()).to(device), "ws": Workspace(device)}
+        g["pos"].copy_(pos_t)
+        if cen_t is not None:
+            g["cen"].copy_(cen_t)
+        # eager once: loads the kernels, sizes the workspace, builds the bin table, creates the output buffers
+        r0 = q3b_frames(g["pos"], box_h, g["cen"], want=want, workspace=g["ws"], device=device, check_status=False,
+                        box_device=g["box"], **opts)
+        g["out"] = {k: r0[k] for k in want if k in r0}
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for k in ("ang_hist", "q_hist", "frame_stats"):
+                if k in g["out"]:
+                    g["out"][k].zero_()
+            rg = q3b_frames(g["pos"], box_h, g["cen"], want=tuple(g["out"].keys()), out=g["out"], workspace=g["ws"], device=device,
+                            check_status=False, box_device=g["box"], **opts)
+        g["graph"], g["meta"] = graph, {k: rg[k] for k in ("launches", "nc", "edge_min")}
+        _GRAPHS[key] = g
+    with torch.cuda.device(device):
+        g["pos"].copy_(pos_t, non_blocking=True)
+        if cen_t is not None:
+            g["cen"].copy_(cen_t, non_blocking=True)
+        g["graph"].replay()
+        res = Q3bResult(g["out"])
+        res.update(g["meta"])
+        res["graph"] = True
+        if check_status:
+            M = int(cen_t.shape[1]) if cen_t is not None else int(pos_t.shape[1])
+            ws_ptr, _ = g["ws"].get(0)
+            st = (ctypes.c_int32 * 4)()
+            nc = _I3(*g["meta"]["nc"])
+            check(lib().wol_status(ctypes.c_void_p(ws_ptr), F, int(pos_t.shape[1]), M, ctypes.byref(nc), _stream_ptr(device),
+                                   ctypes.byref(st)), "wol_status")
+            res["n_widened"], res["n_overflow"], res["n_slow_pairs"] = int(st[0]), int(st[1]), int(st[3])
+    return res
+
+
 def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, high3=3.413, lowq=0.0, highq=10.0,
                nbins=500, bin_range=(0.0, 180.0), q_nbins=500, precision="fp64", hist_per_frame=False, r_cell=None,
                want=("q", "nn_idx", "n3", "ang_hist", "q_hist", "frame_stats"), out=None, workspace=None,

@@ -65,9 +65,13 @@ def getOrderParamq(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
         return torch.zeros(0, dtype=torch.float64) if tor else np.zeros(0)
     if len(Pos) == 0:
         return _out(torch.zeros(len(subPos), dtype=torch.float64), tor)
-    r = engine.q3b_frames(Pos, BoxDims, None if _same(subPos, Pos) else subPos, do_q=True, do_3body=False,
-                          lowq=lowCut, highq=highCut, want=("q",))
-    return _out(r["q"][0], tor)
+    # a loop over frames of a few thousand waters is launch-bound: replay the captured launch sequence (the result is
+    # copied out of the graph's buffer either way)
+    call = engine.q3b_frames_graphed if len(Pos) <= engine.GRAPH_MAX_ATOMS else engine.q3b_frames
+    r = call(Pos, BoxDims, None if _same(subPos, Pos) else subPos, do_q=True, do_3body=False, lowq=lowCut, highq=highCut,
+             want=("q",))
+    q = r["q"][0]
+    return q.clone() if tor else _out(q, tor)
 
 
 def getCosAngs(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413):

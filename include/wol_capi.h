@@ -196,7 +196,8 @@ int wol_status(const void *workspace, int32_t n_frames, int32_t n_pos, int32_t n
  * Offsets of each centre's block inside the flat angle array getCosAngs returns
  * (structureLibs/water_properties.py:247: np.hstack of the triu entries, centre by centre):
  *   offsets[i] = sum_{k<i} n3[k] (n3[k] - 1) / 2,   i = 0..n   (offsets[n] = number of angles)
- * n3 as written by wol_q3b_frames.  scratch: at least (n / 2048 + 2) uint32.
+ * n3 as written by wol_q3b_frames.  scratch: at least (n / 2048 + 8) uint32, 8-byte aligned.  The offsets are 32-bit: when the
+ * total does not fit (> 2^32 - 2 angles) offsets[n] is set to 0xFFFFFFFF -- split the batch.
  */
 int wol_angle_offsets(const int32_t *n3, int64_t n, uint32_t *offsets, uint32_t *scratch, void *stream);
 
@@ -219,7 +220,8 @@ int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box
  * boolean-mask gathers, structureLibs/water_properties.py:243,372).
  *   workspace : cell list of wol_cell_build(FP64) over pos with r_cell >= highcut
  *   offsets   : [n_frames * n_centres + 1] uint32; offsets[last] = number of pairs
- *   scratch   : at least (n_frames * n_centres / 2048 + 2) uint32
+ *   scratch   : at least (n_frames * n_centres / 2048 + 8) uint32, 8-byte aligned; offsets[last] = 0xFFFFFFFF when the total
+ *               number of pairs does not fit 32 bits (split the batch)
  *   indices   : [capacity] int32; a centre whose segment ends beyond capacity is not written (call with capacity 0
  *               and indices NULL to get the offsets only, read offsets[last], allocate, call again)
  */

@@ -128,6 +128,38 @@ __global__ void pair_counts_kernel(const int32_t *__restrict__ n3, size_t n, uin
     }
 }
 
+// The offsets are 32-bit: 2^26 centres with a hundred neighbours each would wrap them silently.  The counts are summed
+// in 64 bits before the scan; a total beyond 2^32 - 2 turns the last offset (the total the caller sizes its output
+// by) into the sentinel 0xFFFFFFFF = "does not fit, use smaller batches".
+constexpr uint32_t kOffsetsOverflow = 0xFFFFFFFFu;
+
+__global__ void count_total_kernel(const uint32_t *__restrict__ counts, size_t n, unsigned long long *total) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += counts[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+__global__ void mark_overflow_kernel(uint32_t *last_offset, const unsigned long long *total) {
+    if (*total > 0xFFFFFFFEull) *last_offset = kOffsetsOverflow;
+}
+
+// exclusive scan of n + 1 counts (the last one 0) into offsets, with the 64-bit check; scratch: n / 2048 + 8 values
+static int scan_offsets_checked(uint32_t *offsets, size_t n_plus_1, uint32_t *scratch, cudaStream_t stream) {
+    // the scan uses n_plus_1 / kScanTile + 2 values of scratch; an aligned 8-byte slot behind them holds the total
+    size_t slot = n_plus_1 / kScanTile + 3;
+    slot += slot & 1;
+    unsigned long long *total = reinterpret_cast<unsigned long long *>(scratch + slot);
+    cudaError_t e = cudaMemsetAsync(total, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync(offset total)", e);
+    const unsigned blocks = (unsigned)((n_plus_1 + 1023) / 1024 < 1184 ? (n_plus_1 + 1023) / 1024 : 1184);
+    count_total_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(offsets, n_plus_1, total);
+    exclusive_scan_u32(offsets, n_plus_1, scratch, stream);
+    mark_overflow_kernel<<<1, 1, 0, stream>>>(offsets + (n_plus_1 - 1), total);
+    add_launches(2);
+    return WOL_OK;
+}
+
 // ---- materialised three-body angles in the reference's order ---------------------------------------
 
 constexpr int kMatCap = 64;
@@ -686,7 +718,8 @@ int wol_angle_offsets(const int32_t *n3, int64_t n, uint32_t *offsets, uint32_t 
     const size_t cnt = (size_t)n + 1;
     pair_counts_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(n3, (size_t)n, offsets);
     add_launches(1);
-    exclusive_scan_u32(offsets, cnt, scratch, stream);
+    const int rc = scan_offsets_checked(offsets, cnt, scratch, stream);
+    if (rc != WOL_OK) return rc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_angle_offsets", e);
     return WOL_OK;
@@ -755,7 +788,8 @@ int wol_neighbors_csr(const void *centres, int32_t centre_dtype, const double *b
     P.capacity = capacity;
     const unsigned blocks = (unsigned)((total + 1 + kPrefThreads - 1) / kPrefThreads);
     neighbors_csr_kernel<false><<<blocks, kPrefThreads, 0, stream>>>(P);
-    exclusive_scan_u32(offsets, total + 1, scratch, stream);
+    const int rc = scan_offsets_checked(offsets, total + 1, scratch, stream);
+    if (rc != WOL_OK) return rc;
     add_launches(1);
     if (capacity > 0 && total > 0) {
         neighbors_csr_kernel<true><<<blocks, kPrefThreads, 0, stream>>>(P);

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import engine
-from ._capi import WOL_F64, WOL_PREC_FP64, HbondArgs, check, lib
+from ._capi import WOL_F64, WOL_PREC_FP64, HbondArgs, WolError, check, lib
 
 _vp = ctypes.c_void_p
 
@@ -81,6 +81,14 @@ class CellList:
         return tuple(st)
 
 
+def _total_from_offsets(offsets, what):
+    """Last entry of a 32-bit offsets array as a python int; the library marks a total beyond 32 bits with 0xFFFFFFFF."""
+    total = int(offsets[-1].item()) & 0xFFFFFFFF
+    if total == 0xFFFFFFFF:
+        raise WolError("more than 2^32 - 2 %s in one call: materialise the frames in smaller batches" % what)
+    return total
+
+
 def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
     """getCosAngs (structureLibs/water_properties.py:210-250) for one or several frames.
     Returns (angles f64 (n_angles,), n3 int32 (F, M), offsets uint32-as-int64 (F*M+1,)): the flat angle
@@ -109,7 +117,7 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
     with torch.cuda.device(device):
         check(L.wol_angle_offsets(_vp(n3.data_ptr()), total, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()), _stream()),
               "wol_angle_offsets")
-        n_angles = int(offsets[-1].item()) & 0xFFFFFFFF
+        n_angles = _total_from_offsets(offsets, "three-body angles")
         angles = torch.empty(n_angles, dtype=torch.float64, device=device)
         if n_angles > 0:
             check(L.wol_angles_fill(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(box_d.data_ptr()), F, N, M,
@@ -143,7 +151,7 @@ def neighbors_csr(sub, pos, box, low=0.0, high=3.413, device=None):
                                           cells.ws_bytes, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()),
                                           _vp(indices.data_ptr()) if indices is not None else None, cap, _stream()), "wol_neighbors_csr")
         run(None, 0)
-        n_pairs = int(offsets[-1].item()) & 0xFFFFFFFF  # sizes the output: one host read
+        n_pairs = _total_from_offsets(offsets, "neighbour pairs")  # sizes the output: one host read
         indices = torch.empty(n_pairs, dtype=torch.int32, device=device)
         if n_pairs:
             run(indices, n_pairs)

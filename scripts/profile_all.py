@@ -1,0 +1,38 @@
+"""One pass over the kernels north_star asks evidence for, for ncu (no oracle, product calls only):
+K1 cell build, K2 brick sweep (fp64), K2f (fp32 mode), queued-centre passes, K3 H-bond counts, K5 Willard-Chandler field and
+interface search.
+
+    python scripts/profile_all.py
+"""
+import numpy as np
+import torch
+
+from waterorderlib_b200 import engine, routines, synth
+
+dev = torch.device("cuda", 0)
+pos, box = synth.device_frames(50, 0, 2, sigma=0.25, device=dev)
+for prec in ("fp64", "fp32"):
+    for _ in range(2):
+        r = engine.q3b_frames(pos, box, precision=prec)
+    torch.cuda.synchronize()
+    print(prec, "angles", int(r["ang_hist"].sum()), "widened", r["n_widened"], "overflow", r["n_overflow"], flush=True)
+# K3: H-bond counts of a 1M-water frame (acceptors = O, donors = O listed twice, their hydrogens)
+o = pos[0].cpu().numpy()
+h = synth.add_hydrogens(o, seed=3)
+o_d, h_d = pos[:1], torch.from_numpy(h[None]).to(dev)
+d_d = o_d.repeat_interleave(2, dim=1).contiguous()
+for _ in range(2):
+    hb = routines.hbond_counts(o_d, d_d, h_d, box, 3.5, 120.0)
+torch.cuda.synchronize()
+print("hbonds per water", float(hb["acc_count"].sum()) / o.shape[0], flush=True)
+del pos, o_d, h_d, d_d
+# K5: 65536-water slab, 80^3 Willard-Chandler field, interface search against the ideal faces
+sp, sbox, z_lo, z_hi = synth.slab_box(32, 32, 8, sigma=0.3, seed=11)
+gp, gn = synth.plane_interface(sbox, z_lo, z_hi, spacing=2.0)
+sp_d, gp_d, gn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(gp).to(dev), torch.from_numpy(gn).to(dev)
+grid = [(np.arange(80) + 0.5) * (sbox[d] / 80) for d in range(3)]
+for _ in range(2):
+    dens, _ = routines.willard_density(sp_d, sbox, 2.4, grid=grid, want_normals=True)
+    iw = routines.interface_water(sp_d, gp_d, gn_d, 0.0, sbox)
+torch.cuda.synchronize()
+print("field max", float(dens.max()), "interface points", gp.shape[0], flush=True)

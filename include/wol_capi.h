@@ -364,6 +364,23 @@ int wol_iso_points(const double *densvals, const double *gridx, const double *gr
                    int32_t *n_total, void *stream);
 
 /*
+ * Triangles of the same iso-surface (structureLibs/surface_library.py:202 takes verts, faces, normals, values from
+ * skimage.measure.marching_cubes; skimage is not vendored, so the triangulation rule is this library's own, generated by
+ * scripts/make_mc_table.py: PARITY UNPINNED, the surface is pinned by its properties -- watertight, consistently oriented
+ * towards lower values, vertices = wol_iso_points').  Call after wol_iso_points has filled `vertex_scratch` for the same
+ * field and level (its per-node vertex offsets are reused).
+ *   faces[capacity][3]  int32 vertex indices into wol_iso_points' output, ordered by cube index; capacity 0: count only
+ *   areas[capacity]     optional, needs `points`: the reference's triangleArea of each face (fortran/imagelib.f90:254-267,
+ *                       which returns |v1 x v2|, twice the geometric area)
+ *   n_total             device int32, number of faces
+ *   face_scratch        wol_iso_face_scratch_bytes(nx, ny, nz) bytes of device memory, 16-byte aligned
+ */
+size_t wol_iso_face_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);
+int wol_iso_faces(const double *densvals, int32_t nx, int32_t ny, int32_t nz, double level, const uint32_t *vertex_scratch,
+                  uint32_t *face_scratch, size_t face_scratch_bytes, int32_t *faces, int64_t capacity, const double *points,
+                  double *areas, int32_t *n_total, void *stream);
+
+/*
  * InterfaceWater (fortran/waterlib.f90:1414-1469): for every water the nearest interface point (0-based,
  * first index on ties, -1 if none within distance^2 < 1000 -- the Fortran leaves that entry unwritten) and
  * its signed depth allwatdists = (water - point) . normal; for every interface point the nearest water;

@@ -213,3 +213,56 @@ def test_instantaneous_interface_slab_end_to_end():
     flat = sl.depthBinnedQ(pos, box, gp0, gn0, binWidth=1.0, depthRange=(-12.0, 4.0))
     assert np.abs(np.median(out["depth"].cpu().numpy() - flat["depth"].cpu().numpy())) < 3.0
     assert out["count"].sum() > 0.9 * len(pos)
+
+
+def test_iso_surface_faces_are_a_closed_oriented_mesh_over_the_iso_points():
+    """wol_iso_faces (parity unpinned: skimage is not vendored) pinned by properties on fields with known surfaces: same
+    vertices as iso_points; every mesh edge is shared by exactly two faces with opposite directions (watertight, consistently
+    oriented); Euler characteristic 2 per closed component; area and enclosed volume of a sphere; normals towards lower
+    values; the area rule of fortran/imagelib.f90:254-267."""
+    g = np.linspace(-1.0, 1.0, 41)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    r = np.sqrt(X * X + Y * Y + Z * Z)
+    field = 1.0 - r                      # above the level inside the sphere
+    R = 0.6
+    verts, faces, areas = routines.iso_surface(field, (g, g, g), 1.0 - R)
+    v, f, a = verts.cpu().numpy(), faces.cpu().numpy(), areas.cpu().numpy()
+    assert np.array_equal(v, routines.iso_points(field, (g, g, g), 1.0 - R).cpu().numpy())
+    assert f.min() >= 0 and f.max() < len(v) and len(np.unique(f)) == len(v)
+    # directed edges: each appears once, and its reverse appears once
+    de = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    key = de[:, 0].astype(np.int64) * len(v) + de[:, 1]
+    rev = de[:, 1].astype(np.int64) * len(v) + de[:, 0]
+    assert len(np.unique(key)) == len(key) and np.array_equal(np.sort(key), np.sort(rev))
+    assert len(v) - len(key) // 2 + len(f) == 2                                          # V - E + F of a sphere
+    p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    cr = np.cross(p1 - p0, p2 - p0)
+    assert np.allclose(a, np.linalg.norm(cr, axis=1), rtol=1e-6, atol=1e-12)          # |v1 x v2| (imagelib.f90:254-267)
+    assert abs(0.5 * a.sum() - 4.0 * np.pi * R * R) < 0.01 * 4.0 * np.pi * R * R
+    vol = np.einsum("ij,ij->i", p0, cr).sum() / 6.0
+    assert abs(vol - 4.0 / 3.0 * np.pi * R ** 3) < 0.01 * 4.0 / 3.0 * np.pi * R ** 3      # positive: normals point outwards = to lower values
+    # two separate blobs and an ambiguous saddle: still closed and oriented, Euler characteristic 2 per component
+    blobs = np.maximum(1.0 - np.sqrt((X - 0.45) ** 2 + Y * Y + Z * Z), 1.0 - np.sqrt((X + 0.45) ** 2 + Y * Y + Z * Z))
+    for fld, lvl, chi in ((blobs, 0.7, 4), (blobs, 0.56, None), (np.sin(3 * X) * np.sin(3 * Y) * np.sin(3 * Z), 0.3, None)):
+        vv, ff, _ = routines.iso_surface(fld, (g, g, g), lvl, want_areas=False)
+        ff = ff.cpu().numpy()
+        n = vv.shape[0]
+        de = np.concatenate([ff[:, [0, 1]], ff[:, [1, 2]], ff[:, [2, 0]]]).astype(np.int64)
+        key, rev = de[:, 0] * n + de[:, 1], de[:, 1] * n + de[:, 0]
+        inner = ~np.isin(key, rev)  # edges on the grid boundary have no partner; everything else is matched exactly once
+        pts = vv.cpu().numpy()
+        on_border = lambda idx: np.any(np.isclose(np.abs(pts[idx]), 1.0), axis=1)  # noqa: E731
+        assert len(np.unique(key)) == len(key) and np.all(on_border(de[inner, 0]) & on_border(de[inner, 1]))
+        if chi is not None:
+            assert n - len(key) // 2 + len(ff) == chi
+    e = routines.iso_surface(field, (g, g, g), 5.0)
+    assert e[0].shape == (0, 3) and e[1].shape == (0, 3)
+
+
+def test_interfaceMesh_of_a_slab():
+    pos, box, z_lo, z_hi = synth.slab_box(6, 6, 3, sigma=0.3, seed=2)
+    verts, faces, norms, values, areas = sl.interfaceMesh(pos, box, spacing=1.5)
+    assert verts.shape[0] > 100 and faces.shape[1] == 3 and norms.shape == verts.shape and np.all(values == 0.016)
+    # two sheets near the ideal faces; the triangulated area is about twice the box cross-section (0.5 * the imagelib rule)
+    assert np.all((np.abs(verts[:, 2] - z_lo) < 3.0) | (np.abs(verts[:, 2] - z_hi) < 3.0))
+    assert 0.9 < 0.5 * areas.sum() / (2.0 * box[0] * box[1]) < 1.6

@@ -79,6 +79,8 @@ SIGNATURES = {
     "wol_bin_on_grid": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp]),
     "wol_hist_allreduce": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_i32, c_vp]),
     "wol_fma_probe": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "wol_iso_face_scratch_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
+    "wol_iso_faces": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp, ctypes.c_size_t, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "wol_radial_dist_plane": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_f64, c_i32, c_f64, c_vp, c_vp, c_vp]),
     "wol_histogram2d": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
     "wol_iso_scratch_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),

@@ -7,6 +7,7 @@
 //   profile_kernel        depth-binned profile of a per-water observable (the cfg-4 composition; the reference
 //                         has the ingredients, structureLibs/surface_library.py:170-210, but no such function)
 //   histrr3b_kernel       histrr3b                                        fortran/waterlib.f90:1550-1593
+#include "wol_mc_table.h"
 #include <math.h>
 
 #include "wol_q3b_common.cuh"
@@ -355,6 +356,88 @@ __global__ void __launch_bounds__(256) iso_kernel(const IsoParams P) {
     if (!FILL) P.offs[g] = n;
 }
 
+// ---- iso-surface faces ------------------------------------------------------------------------------------------
+// Triangles over the vertices above: one thread per grid cube, corner configuration -> kMcTri (wol_mc_table.h, generated
+// from first principles by scripts/make_mc_table.py: faces joined so that inside regions never connect across a face
+// diagonal, which makes the surface watertight; normals point towards lower values).  A triangle corner is the vertex of a
+// cube edge = (lower node of the edge, axis) = voffs[node] + the number of crossed edges of that node along lower axes.
+// Same count / scan / fill scheme, so faces come out ordered by cube index.  Optional per-face area with the reference's
+// rule (fortran/imagelib.f90:254-267: (v1.v1 v2.v2)^0.5 (1 - cos^2)^0.5, i.e. |v1 x v2| -- twice the geometric area).
+
+struct IsoFaceParams {
+    const double *dens;
+    int nx, ny, nz;
+    long long n_cubes;
+    double level;
+    const uint32_t *voffs;  // [n_nodes + 1] vertex offsets (the scratch wol_iso_points filled)
+    uint32_t *foffs;        // [n_cubes + 1]
+    long long capacity;
+    int32_t *faces;         // [capacity][3]
+    const double *points;   // vertices, for the areas (may be null)
+    double *areas;          // [capacity] (may be null)
+    int32_t *n_total;
+};
+
+__device__ __forceinline__ int iso_vertex_id(const IsoFaceParams &P, int i, int j, int k, int axis) {
+    const long long g = ((long long)i * P.ny + j) * P.nz + k;
+    const bool a = iso_above(P.dens[g], P.level);
+    int id = (int)P.voffs[g];
+    if (axis > 0 && i + 1 < P.nx && iso_above(P.dens[g + (long long)P.ny * P.nz], P.level) != a) ++id;
+    if (axis > 1 && j + 1 < P.ny && iso_above(P.dens[g + P.nz], P.level) != a) ++id;
+    return id;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) iso_face_kernel(const IsoFaceParams P) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > P.n_cubes) return;
+    if (c == P.n_cubes) {
+        if (!FILL) P.foffs[c] = 0u;
+        else *P.n_total = (int32_t)P.foffs[c];
+        return;
+    }
+    const int cz = P.nz - 1, cy = P.ny - 1;
+    const int k = (int)(c % cz), j = (int)((c / cz) % cy), i = (int)(c / ((long long)cz * cy));
+    int cfg = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const long long g = ((long long)(i + (q & 1)) * P.ny + (j + ((q >> 1) & 1))) * P.nz + (k + (q >> 2));
+        if (iso_above(P.dens[g], P.level)) cfg |= 1 << q;
+    }
+    int n = 0;
+    while (n < 5 && kMcTri[cfg][3 * n] >= 0) ++n;
+    if (!FILL) {
+        P.foffs[c] = (uint32_t)n;
+        return;
+    }
+    long long o = (long long)P.foffs[c];
+    for (int t = 0; t < n; ++t, ++o) {
+        if (o >= P.capacity) break;
+        int v[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int e = kMcTri[cfg][3 * t + m];
+            const int a = kMcEdge[e][0], ax = kMcEdge[e][2];
+            v[m] = iso_vertex_id(P, i + (a & 1), j + ((a >> 1) & 1), k + (a >> 2), ax);
+        }
+        P.faces[3 * o + 0] = v[0];
+        P.faces[3 * o + 1] = v[1];
+        P.faces[3 * o + 2] = v[2];
+        if (P.areas && P.points) {
+            double v1[3], v2[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                v1[d] = __dsub_rn(P.points[3 * (size_t)v[1] + d], P.points[3 * (size_t)v[0] + d]);
+                v2[d] = __dsub_rn(P.points[3 * (size_t)v[2] + d], P.points[3 * (size_t)v[0] + d]);
+            }
+            const double s1 = sumsq3<double>(v1[0], v1[1], v1[2]), s2 = sumsq3<double>(v2[0], v2[1], v2[2]);
+            const double root = __dsqrt_rn(__dmul_rn(s1, s2));
+            const double cth = __ddiv_rn(dot3<double>(v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]), root);
+            P.areas[o] = __dmul_rn(root, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cth, cth))));
+        }
+    }
+}
+
 // ---- histrr3b ---------------------------------------------------------------------------------------------
 // One warp per centre.  The lanes walk the candidates of the 27-cell stencil (cell edge >= dNum * distWidth),
 // keep those whose distance bin is inside the histogram in a shared list, then spread the list's pairs over
@@ -585,6 +668,42 @@ int wol_iso_points(const double *densvals, const double *gridx, const double *gr
     add_launches(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("wol_iso_points", e);
+    return WOL_OK;
+}
+
+size_t wol_iso_face_scratch_bytes(int32_t nx, int32_t ny, int32_t nz) {
+    if (nx < 2 || ny < 2 || nz < 2) return 16;
+    const size_t n = (size_t)(nx - 1) * (ny - 1) * (nz - 1) + 1;
+    return sizeof(uint32_t) * (((n + 3) & ~(size_t)3) + n / kScanTile + 2);
+}
+
+int wol_iso_faces(const double *densvals, int32_t nx, int32_t ny, int32_t nz, double level, const uint32_t *vertex_scratch,
+                  uint32_t *face_scratch, size_t face_scratch_bytes, int32_t *faces, int64_t capacity, const double *points,
+                  double *areas, int32_t *n_total, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!densvals || !vertex_scratch || !face_scratch || !n_total) return set_error(WOL_ERR_INVALID, "wol_iso_faces: null argument");
+    if (nx < 1 || ny < 1 || nz < 1 || capacity < 0 || (capacity > 0 && !faces)) return set_error(WOL_ERR_INVALID, "wol_iso_faces: bad size");
+    if (face_scratch_bytes < wol_iso_face_scratch_bytes(nx, ny, nz))
+        return set_error(WOL_ERR_WORKSPACE, "face scratch holds %zu bytes, %zu needed", face_scratch_bytes, wol_iso_face_scratch_bytes(nx, ny, nz));
+    IsoFaceParams P;
+    P.dens = densvals;
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.n_cubes = (nx < 2 || ny < 2 || nz < 2) ? 0 : (long long)(nx - 1) * (ny - 1) * (nz - 1);
+    P.level = level;
+    P.voffs = vertex_scratch;
+    P.foffs = face_scratch;
+    P.capacity = capacity;
+    P.faces = faces;
+    P.points = points;
+    P.areas = areas;
+    P.n_total = n_total;
+    const unsigned blocks = (unsigned)((P.n_cubes + 1 + 127) / 128);
+    iso_face_kernel<false><<<blocks, 128, 0, stream>>>(P);
+    exclusive_scan_u32(face_scratch, (size_t)P.n_cubes + 1, face_scratch + (((size_t)P.n_cubes + 1 + 3) & ~(size_t)3), stream);
+    iso_face_kernel<true><<<blocks, 128, 0, stream>>>(P);
+    add_launches(2);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("wol_iso_faces", e);
     return WOL_OK;
 }
 

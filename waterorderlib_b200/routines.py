@@ -399,6 +399,53 @@ def iso_points(dens, grid, level, device=None):
     return pts
 
 
+def iso_surface(dens, grid, level, want_areas=True, device=None):
+    """Triangulated iso-surface dens == level: (verts (n, 3) f64, faces (m, 3) int32 into verts, areas (m,) f64 or None), all
+    CUDA tensors.  Vertices are iso_points' (same order); faces come from the library's own marching-cubes table
+    (scripts/make_mc_table.py: watertight, normals towards lower values; PARITY UNPINNED against skimage, which the
+    reference calls at structureLibs/surface_library.py:202 and which is not vendored); areas follow the reference's
+    triangleArea (fortran/imagelib.f90:254-267 = |v1 x v2|, twice the geometric area)."""
+    device = _device(device, dens)
+    gx, gy, gz = (_f64(np.asarray(g, dtype=np.float64).reshape(-1) if not isinstance(g, torch.Tensor) else g.reshape(-1), device)
+                  for g in grid)
+    nx, ny, nz = int(gx.numel()), int(gy.numel()), int(gz.numel())
+    d = _f64(dens, device).reshape(-1)
+    if int(d.numel()) != nx * ny * nz:
+        raise ValueError("dens has %d values, the grid %d x %d x %d nodes" % (d.numel(), nx, ny, nz))
+    empty = (torch.zeros((0, 3), dtype=torch.float64, device=device), torch.zeros((0, 3), dtype=torch.int32, device=device),
+             torch.zeros(0, dtype=torch.float64, device=device) if want_areas else None)
+    if nx * ny * nz == 0:
+        return empty
+    L = lib()
+    vbytes, fbytes = int(L.wol_iso_scratch_bytes(nx, ny, nz)), int(L.wol_iso_face_scratch_bytes(nx, ny, nz))
+    vscr = torch.empty(vbytes // 4 + 4, dtype=torch.int32, device=device)
+    fscr = torch.empty(fbytes // 4 + 4, dtype=torch.int32, device=device)
+    n_total = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        def verts(points, cap):
+            check(L.wol_iso_points(_vp(d.data_ptr()), _vp(gx.data_ptr()), _vp(gy.data_ptr()), _vp(gz.data_ptr()), nx, ny, nz, float(level),
+                                   _vp(vscr.data_ptr()), vbytes, _vp(points.data_ptr()) if points is not None else None, cap,
+                                   _vp(n_total.data_ptr()), _stream()), "wol_iso_points")
+
+        def tris(faces, cap, pts, areas):
+            check(L.wol_iso_faces(_vp(d.data_ptr()), nx, ny, nz, float(level), _vp(vscr.data_ptr()), _vp(fscr.data_ptr()), fbytes,
+                                  _vp(faces.data_ptr()) if faces is not None else None, cap, _vp(pts.data_ptr()) if pts is not None else None,
+                                  _vp(areas.data_ptr()) if areas is not None else None, _vp(n_total.data_ptr()), _stream()), "wol_iso_faces")
+        verts(None, 0)
+        n = int(n_total.item())
+        if n == 0:
+            return empty
+        pts = torch.empty((n, 3), dtype=torch.float64, device=device)
+        verts(pts, n)
+        tris(None, 0, None, None)
+        m = int(n_total.item())
+        faces = torch.empty((m, 3), dtype=torch.int32, device=device)
+        areas = torch.empty(m, dtype=torch.float64, device=device) if want_areas else None
+        if m:
+            tris(faces, m, pts, areas)
+    return pts, faces, areas
+
+
 def interface_water(pos, gridpos, gridnorm, cutoff, box, want_surfclose=True, device=None):
     """InterfaceWater (fortran/waterlib.f90:1414-1469) -> dict(watclose int32 (n,) 0-based / -1, surfclose int32
     (ng,), numwater int, allwatdists f64 (n,))."""

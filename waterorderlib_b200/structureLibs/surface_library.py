@@ -39,6 +39,28 @@ def densityGrid(heavyPos, watPos, thisbox, level=0.016, minFrac=0.7):
     return verts, faces
 
 
+def interfaceMesh(watPos, thisbox, grid=None, spacing=2.0, level=0.016, smoothlen=2.4):
+    """The triangulated Willard-Chandler interface of one frame -- what densityGrid gets from
+    skimage.measure.marching_cubes (structureLibs/surface_library.py:197-202): (verts (n,3), faces (m,3) int32,
+    normals (n,3), values (n,), areas (m,)).  verts / normals as instantaneousInterface (normals = the density gradient
+    at the vertices, pointing to HIGHER density as skimage's gradient direction does for this field), values = the level;
+    faces from the library's own marching-cubes table, oriented towards lower density (parity unpinned: skimage is not
+    vendored); areas by the reference's triangleArea rule (fortran/imagelib.f90:254-267).  CUDA tensors for tensor
+    input, numpy arrays otherwise."""
+    box = np.asarray(thisbox.detach().cpu() if isinstance(thisbox, torch.Tensor) else thisbox, dtype=np.float64).reshape(-1)[:3]
+    if grid is None:
+        grid = []
+        for d in range(3):
+            n = max(int(np.ceil(box[d] / float(spacing))), 1)
+            grid.append((np.arange(n) + 0.5) * (box[d] / n))
+    dens, _ = routines.willard_density(watPos, box, smoothlen, grid=grid, want_normals=False)
+    verts, faces, areas = routines.iso_surface(dens, grid, level)
+    norms = routines.willard_density(watPos, box, smoothlen, points=verts)[1] if verts.shape[0] else torch.zeros_like(verts)
+    values = torch.full((verts.shape[0],), float(level), dtype=torch.float64, device=verts.device)
+    out = (verts, faces, norms, values, areas)
+    return out if isinstance(watPos, torch.Tensor) else tuple(t.cpu().numpy() for t in out)
+
+
 def instantaneousInterface(watPos, thisbox, grid=None, spacing=2.0, level=0.016, smoothlen=2.4, outward=True):
     """Willard-Chandler instantaneous interface of one frame as the point set InterfaceWater consumes
     (fortran/waterlib.f90:1414-1469): density field on `grid` (default: the whole box at about `spacing` Angstrom,

@@ -96,8 +96,18 @@ def case_triangles(case):
             e = nxt[e]
         assert len(loop) >= 3
         for k in range(1, len(loop) - 1):
-            tris.append((loop[0], loop[k], loop[k + 1]))
+            tris.append((loop[0], loop[k + 1], loop[k]))  # this order makes the normal (right-hand rule) point to the OUTSIDE
     return tris
+
+
+def check_orientation(rows):
+    """Case 1 (only corner 0 inside): the triangle's normal must point away from corner 0."""
+    import numpy as np
+    mid = [0.5 * (np.array([(a >> k) & 1 for k in range(3)], float) + np.array([(b >> k) & 1 for k in range(3)], float)) for a, b, _ in EDGES]
+    t = rows[1][:3]
+    p0, p1, p2 = (mid[e] for e in t)
+    n = np.cross(p1 - p0, p2 - p0)
+    assert np.dot(n, (p0 + p1 + p2) / 3.0) > 0, "normals must point towards lower values"
 
 
 def main():
@@ -114,6 +124,7 @@ def main():
         crossed = {i for i, (a, b, _) in enumerate(EDGES) if ((case >> a) & 1) != ((case >> b) & 1)}
         used = {e for e in rows[case] if e >= 0}
         assert used == crossed, (case, used, crossed)
+    check_orientation(rows)
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "waterorderlib_b200", "csrc", "wol_mc_table.h")
     with open(path, "w") as f:
         f.write("// GENERATED by scripts/make_mc_table.py (derivation and conventions there) -- do not edit.\n")

@@ -237,7 +237,7 @@ def test_iso_surface_faces_are_a_closed_oriented_mesh_over_the_iso_points():
     assert len(v) - len(key) // 2 + len(f) == 2                                          # V - E + F of a sphere
     p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
     cr = np.cross(p1 - p0, p2 - p0)
-    assert np.allclose(a, np.linalg.norm(cr, axis=1), rtol=1e-6, atol=1e-12)          # |v1 x v2| (imagelib.f90:254-267)
+    assert np.allclose(a, np.linalg.norm(cr, axis=1), rtol=1e-5, atol=1e-9)            # |v1 x v2| (imagelib.f90:254-267; 1 - cos^2 cancels for slivers)
     assert abs(0.5 * a.sum() - 4.0 * np.pi * R * R) < 0.01 * 4.0 * np.pi * R * R
     vol = np.einsum("ij,ij->i", p0, cr).sum() / 6.0
     assert abs(vol - 4.0 / 3.0 * np.pi * R ** 3) < 0.01 * 4.0 / 3.0 * np.pi * R ** 3      # positive: normals point outwards = to lower values

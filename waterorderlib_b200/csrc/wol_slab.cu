@@ -432,8 +432,10 @@ __global__ void __launch_bounds__(128) iso_face_kernel(const IsoFaceParams P) {
             }
             const double s1 = sumsq3<double>(v1[0], v1[1], v1[2]), s2 = sumsq3<double>(v2[0], v2[1], v2[2]);
             const double root = __dsqrt_rn(__dmul_rn(s1, s2));
-            const double cth = __ddiv_rn(dot3<double>(v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]), root);
-            P.areas[o] = __dmul_rn(root, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cth, cth))));
+            // (a degenerate face -- two vertices on the same grid node -- is 0 / 0 = NaN in the Fortran rule: 0 here; rounding
+            // can push 1 - cos^2 of a sliver below zero: clamped)
+            const double cth = root > 0.0 ? __ddiv_rn(dot3<double>(v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]), root) : 1.0;
+            P.areas[o] = __dmul_rn(root, __dsqrt_rn(fmax(__dsub_rn(1.0, __dmul_rn(cth, cth)), 0.0)));
         }
     }
 }

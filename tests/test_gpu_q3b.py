@@ -143,3 +143,32 @@ def test_graphed_call_replays_and_matches_the_plain_call():
     # another box = another signature (cutoff margins derived from the box are baked into the captured kernels)
     g2 = engine.q3b_frames_graphed(frames[0] * 1.01, box * 1.01, want=("q",))
     assert torch.equal(g2["q"], engine.q3b_frames(frames[0] * 1.01, box * 1.01, want=("q",))["q"])
+
+
+@pytest.mark.parametrize("sigma,kw", [(0.25, {}), (0.6, {}), (0.45, {"do_q": False}), (0.45, {"do_3body": False}),
+                                      (0.45, {"highq": 3.0, "lowq": 1.0, "low3": 2.5})])
+def test_brick_kernels_agree_with_the_thread_per_centre_path(monkeypatch, sigma, kw):
+    """The three fp64 kernels of K2 on the same frames: thread-per-centre (WOL_BRICK=0), brick (1) and the opt-in
+    warp-specialised brick kernel (3) -- indices, counts and histogram bins identical, q to the last bits; frame 0
+    against the oracle."""
+    pos, box = synth.trajectory(12, 3, sigma=sigma, seed0=31)  # 3 x 13 824 waters
+    out = {}
+    for mode in ("0", "1", "3"):
+        monkeypatch.setenv("WOL_BRICK", mode)
+        out[mode] = run(None, pos, box, True, **kw)
+    a = out["0"]
+    for mode in ("1", "3"):
+        b = out[mode]
+        for k in ("nn_idx", "n3", "ang_hist", "q_hist"):
+            if k in a and a[k] is not None:
+                assert torch.equal(a[k], b[k]), (mode, k)
+        if "q" in a and a["q"] is not None:
+            assert float((a["q"] - b["q"]).abs().max()) < 1e-12
+        assert torch.allclose(a["frame_stats"], b["frame_stats"], rtol=1e-12, atol=1e-9)
+    if kw.get("do_3body", True):
+        tb = port.three_body(pos[0], pos[0], box[0], kw.get("low3", 0.0), kw.get("high3", 3.413), materialize=False)
+        assert np.array_equal(out["3"].n3.cpu().numpy()[0], tb["numAngs"])
+    if kw.get("do_q", True):
+        q, nn4, _ = port.order_param_q(pos[0], pos[0], box[0], kw.get("lowq", 0.0), kw.get("highq", 10.0))
+        assert np.array_equal(out["3"].nn_idx.cpu().numpy()[0], nn4)
+        assert_q_close(out["3"].q.cpu().numpy()[0], q)

@@ -1,7 +1,8 @@
 """Brick path (wol_q3b_brick.cu) against the thread-per-centre path on the same inputs, output by output,
 plus kernel timings.  Run on a GPU box:  python tests/tools/brick_check.py [--big]
 
-The WOL_BRICK environment switch is read per call: 0 = never, 1 = whenever the shape allows.
+The WOL_BRICK environment switch is read per call: 0 = never, 1 = the brick kernel whenever the shape allows, 3 = the
+warp-specialised brick kernel (wol_q3b_brick_ws.cu) where it applies, else as 1.
 """
 import json
 import os
@@ -16,39 +17,46 @@ from waterorderlib_b200 import engine, synth  # noqa: E402
 
 
 def run(pos, box, brick, **kw):
-    os.environ["WOL_BRICK"] = "1" if brick else "0"
+    os.environ["WOL_BRICK"] = str(int(brick))
     r = engine.q3b_frames(pos, box, **kw)
     torch.cuda.synchronize()
     return r
 
 
 def compare(name, pos, box, **kw):
-    a = run(pos, box, False, **kw)
-    b = run(pos, box, True, **kw)
+    a = run(pos, box, 0, **kw)
     ok = True
     msgs = []
-    for k in ("nn_idx", "n3", "ang_hist", "q_hist"):
-        if k in a and a[k] is not None and k in b:
-            same = torch.equal(a[k], b[k])
-            if not same:
-                ok = False
-                msgs.append("%s differs in %d entries" % (k, int((a[k] != b[k]).sum())))
-    if "q" in a:
-        d = (a["q"] - b["q"]).abs().max().item()
-        if not d < 1e-12:
-            ok = False
-            msgs.append("max |dq| = %g" % d)
-    fs = torch.allclose(a["frame_stats"], b["frame_stats"], rtol=1e-12, atol=1e-9)
-    if not fs:
-        ok = False
-        msgs.append("frame_stats differ: %s vs %s" % (a["frame_stats"][0].tolist(), b["frame_stats"][0].tolist()))
+    for mode in (1, 3):
+        b = run(pos, box, mode, **kw)
+        ok &= _same(a, b, msgs, "mode %d: " % mode)
     print("%-34s %s  widened %d/%d overflow %d/%d %s" % (name, "ok" if ok else "MISMATCH", a["n_widened"], b["n_widened"],
                                                         a["n_overflow"], b["n_overflow"], "; ".join(msgs)), flush=True)
     return ok
 
 
+def _same(a, b, msgs, tag):
+    ok = True
+    for k in ("nn_idx", "n3", "ang_hist", "q_hist"):
+        if k in a and a[k] is not None and k in b:
+            same = torch.equal(a[k], b[k])
+            if not same:
+                ok = False
+                msgs.append(tag + "%s differs in %d entries" % (k, int((a[k] != b[k]).sum())))
+    if "q" in a:
+        d = (a["q"] - b["q"]).abs().max().item()
+        if not d < 1e-12:
+            ok = False
+            msgs.append(tag + "max |dq| = %g" % d)
+    fs = torch.allclose(a["frame_stats"], b["frame_stats"], rtol=1e-12, atol=1e-9)
+    if not fs:
+        ok = False
+        msgs.append(tag + "frame_stats differ: %s vs %s" % (a["frame_stats"][0].tolist(), b["frame_stats"][0].tolist()))
+    return ok
+
+
 def timed(pos_d, box, brick, reps=5, **kw):
-    os.environ["WOL_BRICK"] = "1" if brick else "0"
+    os.environ["WOL_BRICK"] = str(int(brick))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for e in ev:
         e.record()
@@ -100,12 +108,14 @@ def main():
         pd = torch.from_numpy(np.stack([pos] * F)).to(dev)
         pd6 = torch.from_numpy(np.stack([pos6] * F)).to(dev)
         for label, p in (("ice", pd), ("liquid", pd6)):
-            t_old = timed(p, box, False)
-            t_new = timed(p, box, True)
+            t_old = timed(p, box, 0)
+            t_one = timed(p, box, 1)
+            t_new = timed(p, box, 3)
             res["ms_%s_tpc" % label] = t_old
-            res["ms_%s_brick" % label] = t_new
-            print("%s: %d x 1M waters  tpc %.3f ms  brick %.3f ms" % (label, F, t_old, t_new), flush=True)
-        r = run(pd, box, True)
+            res["ms_%s_brick" % label] = t_one
+            res["ms_%s_brick_ws" % label] = t_new
+            print("%s: %d x 1M waters  tpc %.3f ms  brick %.3f ms  brick_ws %.3f ms" % (label, F, t_old, t_one, t_new), flush=True)
+        r = run(pd, box, 1)
         st = engine.workspace_status  # noqa: F841
         res["slow_pairs_note"] = "see wol_status[3]"
     print(json.dumps(res))

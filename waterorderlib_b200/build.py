@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwol.so")
-SOURCES = ["wol_capi.cu", "wol_cells.cu", "wol_q3b.cu", "wol_q3b_tpc.cu", "wol_q3b_brick.cu", "wol_q3b_tpc32.cu", "wol_aux.cu", "wol_slab.cu", "wol_pairs.cu"]
+SOURCES = ["wol_capi.cu", "wol_cells.cu", "wol_q3b.cu", "wol_q3b_tpc.cu", "wol_q3b_brick.cu", "wol_q3b_brick_ws.cu", "wol_q3b_tpc32.cu", "wol_aux.cu", "wol_slab.cu", "wol_pairs.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "--threads", "4", "-ldl"]
 
@@ -32,7 +32,8 @@ def build_lib(force=False, verbose=True):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + _sources()
+    extra = os.environ.get("WOL_NVCC_EXTRA", "").split()  # development switches, e.g. -DWOL_WS_PROF
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + _sources()
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -1,7 +1,8 @@
 // K1: cell-list build for a batch of frames (sm_100a).
 //
-//   count pass  : one thread per atom; positions are staged through shared memory with 16-byte
-//                 vector loads and binned; one atomicAdd per atom counts its cell.
+//   count pass  : a block per tile of 1024 atoms, four atoms per thread; positions are staged through shared memory
+//                 with 16-byte streaming loads (the whole 24 KB tile in flight before the first store) and binned;
+//                 one atomicAdd per atom counts its cell.
 //   scan_*      : exclusive prefix sum over all F*ncell counters (reduce / scan-of-sums / apply, the
 //                 in-block part is a warp shuffle scan).
 //   scatter pass: each atom is binned again and takes the next free place of its cell with an atomicAdd on
@@ -18,21 +19,36 @@
 namespace wol {
 
 constexpr int kBuildThreads = 256;
+constexpr int kBuildPerThread = 4;                                // atoms per thread
+constexpr int kBuildTile = kBuildThreads * kBuildPerThread;      // atoms per block: 24 KB of fp64 positions in flight
 
-// Stage `n_elems` consecutive position components (3 per atom) of a tile into shared memory.
-// 16-byte vector loads when the tile base is 16-byte aligned, scalar (still coalesced) otherwise.
+// Stage `n_elems` consecutive position components (3 per atom) of a tile into shared memory.  16-byte vector loads
+// when the tile base is 16-byte aligned (every load of the thread issued before the first store, so a block keeps its
+// whole tile in flight), scalar (still coalesced) otherwise.
 template <typename T>
 __device__ __forceinline__ void stage_tile(const T *__restrict__ src, int n_elems, T *smem) {
     constexpr int kVec = 16 / sizeof(T);
+    constexpr int kMaxVec = kBuildTile * 3 / kVec;                         // 16-byte words of a full tile
+    constexpr int kPer = (kMaxVec + kBuildThreads - 1) / kBuildThreads;   // per thread
     const int tid = threadIdx.x;
     if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
         const int n_vec = n_elems / kVec;
         const int4 *src4 = reinterpret_cast<const int4 *>(src);
         int4 *dst4 = reinterpret_cast<int4 *>(smem);
-        for (int i = tid; i < n_vec; i += blockDim.x) dst4[i] = __ldg(src4 + i);
-        for (int i = n_vec * kVec + tid; i < n_elems; i += blockDim.x) smem[i] = src[i];
+        int4 v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kBuildThreads;
+            if (i < n_vec) v[k] = __ldcs(src4 + i);  // streamed: read once per pass
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kBuildThreads;
+            if (i < n_vec) dst4[i] = v[k];
+        }
+        for (int i = n_vec * kVec + tid; i < n_elems; i += kBuildThreads) smem[i] = src[i];
     } else {
-        for (int i = tid; i < n_elems; i += blockDim.x) smem[i] = src[i];
+        for (int i = tid; i < n_elems; i += kBuildThreads) smem[i] = src[i];
     }
 }
 
@@ -54,15 +70,17 @@ struct BuildParams {
 // SCATTER = true : bin again (same arithmetic, same cell) and take the next free place of the cell with an atomicAdd on
 //                  entry c + 1, which thereby ends up as the cell's END = the start of cell c + 1: afterwards entry c is
 //                  the start of cell c for every c, with no per-atom scratch (cell id, rank) written or re-read.
+// A block owns a tile of kBuildTile consecutive atoms of one frame; a thread handles atoms t, t + 256, ... of it, all
+// their atomics issued before the first record is written.
 template <typename T, typename R, bool SCATTER>
 __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p) {
-    __shared__ __align__(16) T s_pos[kBuildThreads * 3];
+    __shared__ __align__(16) T s_pos[kBuildTile * 3];
     __shared__ double s_iL[3];
     __shared__ double s_L[3];
     const int f = blockIdx.x / p.tiles_per_frame;
     const int tile = blockIdx.x - f * p.tiles_per_frame;
-    const int a0 = tile * kBuildThreads;
-    const int n_here = min(kBuildThreads, p.n_pos - a0);
+    const int a0 = tile * kBuildTile;
+    const int n_here = min(kBuildTile, p.n_pos - a0);
     const size_t frame_atom0 = (size_t)f * p.n_pos;
     if (threadIdx.x < 3) {
         const double L = p.box[(size_t)f * 3 + threadIdx.x];
@@ -71,61 +89,76 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     }
     stage_tile(reinterpret_cast<const T *>(p.pos) + (frame_atom0 + a0) * 3, n_here * 3, s_pos);
     __syncthreads();
-    const int t = threadIdx.x;
-    if (t >= n_here) return;
-    const T x = s_pos[3 * t + 0], y = s_pos[3 * t + 1], z = s_pos[3 * t + 2];
     const size_t ncell = (size_t)p.nc0 * p.nc1 * p.nc2;
-    double xd = (double)x, yd = (double)y, zd = (double)z;
-    if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
-        xd = (double)(float)x;
-        yd = (double)(float)y;
-        zd = (double)(float)z;
+    uint32_t *const frame_counters = p.cell_start + (size_t)f * ncell + 1;
+    const double iL0 = s_iL[0], iL1 = s_iL[1], iL2 = s_iL[2];
+    T x[kBuildPerThread], y[kBuildPerThread], z[kBuildPerThread];
+    int cellpack[kBuildPerThread];
+    uint32_t dst[kBuildPerThread];
+#pragma unroll
+    for (int k = 0; k < kBuildPerThread; ++k) {
+        const int t = threadIdx.x + k * kBuildThreads;
+        cellpack[k] = -1;
+        if (t < n_here) {
+            x[k] = s_pos[3 * t + 0];
+            y[k] = s_pos[3 * t + 1];
+            z[k] = s_pos[3 * t + 2];
+            double xd = (double)x[k], yd = (double)y[k], zd = (double)z[k];
+            if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
+                xd = (double)(float)x[k];
+                yd = (double)(float)y[k];
+                zd = (double)(float)z[k];
+            }
+            const int cx = cell_coord(xd, iL0, p.nc0);
+            const int cy = cell_coord(yd, iL1, p.nc1);
+            const int cz = cell_coord(zd, iL2, p.nc2);
+            cellpack[k] = cx | (cy << 10) | (cz << 20);
+            uint32_t *counter = frame_counters + (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx);
+            if (!SCATTER) atomicAdd(counter, 1u);
+            else dst[k] = atomicAdd(counter, 1u);
+        }
     }
-    const int cx = cell_coord(xd, s_iL[0], p.nc0);
-    const int cy = cell_coord(yd, s_iL[1], p.nc1);
-    const int cz = cell_coord(zd, s_iL[2], p.nc2);
-    uint32_t *counter = p.cell_start + (size_t)f * ncell + (uint32_t)((cz * p.nc1 + cy) * p.nc0 + cx) + 1;
-    if (!SCATTER) {
-        atomicAdd(counter, 1u);
-    } else {
-        const uint32_t dst = atomicAdd(counter, 1u);
-        const int cellpack = cx | (cy << 10) | (cz << 20);
+    if (!SCATTER) return;
+#pragma unroll
+    for (int k = 0; k < kBuildPerThread; ++k) {
+        if (cellpack[k] < 0) continue;
+        const int t = threadIdx.x + k * kBuildThreads;
         if (sizeof(R) == sizeof(RecD)) {
             RecD r;
-            r.x = (double)x;
-            r.y = (double)y;
-            r.z = (double)z;
+            r.x = (double)x[k];
+            r.y = (double)y[k];
+            r.z = (double)z[k];
             r.idx = a0 + t;
-            r.cell = cellpack;
-            int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst);
+            r.cell = cellpack[k];
+            int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst[k]);
             const int4 *s4 = reinterpret_cast<const int4 *>(&r);
             d4[0] = s4[0];
             d4[1] = s4[1];
             if (p.wrapped) {
                 // box-wrapped coordinates for the float prefilter of the sweep: frac(x / L) * L
                 float4 w;
-                w.x = wrapped_coord((double)x, s_L[0], s_iL[0]);
-                w.y = wrapped_coord((double)y, s_L[1], s_iL[1]);
-                w.z = wrapped_coord((double)z, s_L[2], s_iL[2]);
-                w.w = __int_as_float((int)dst);  // fp64 records: the atom's place in the cell-sorted arrays (brick sweep)
-                p.wrapped[dst] = w;
+                w.x = wrapped_coord((double)x[k], s_L[0], iL0);
+                w.y = wrapped_coord((double)y[k], s_L[1], iL1);
+                w.z = wrapped_coord((double)z[k], s_L[2], iL2);
+                w.w = __int_as_float((int)dst[k]);  // fp64 records: the atom's place in the cell-sorted arrays (brick sweep)
+                p.wrapped[dst[k]] = w;
             }
         } else {
             RecF r;
-            r.x = (float)x;
-            r.y = (float)y;
-            r.z = (float)z;
+            r.x = (float)x[k];
+            r.y = (float)y[k];
+            r.z = (float)z[k];
             r.idx = a0 + t;
-            *reinterpret_cast<int4 *>(reinterpret_cast<RecF *>(p.recs) + dst) = *reinterpret_cast<const int4 *>(&r);
+            *reinterpret_cast<int4 *>(reinterpret_cast<RecF *>(p.recs) + dst[k]) = *reinterpret_cast<const int4 *>(&r);
             if (p.wrapped) {
                 // the FP32 sweep works on box-wrapped coordinates throughout (same binning input as the count pass)
                 float4 w;
-                w.x = wrapped_coord((double)r.x, s_L[0], s_iL[0]);
-                w.y = wrapped_coord((double)r.y, s_L[1], s_iL[1]);
-                w.z = wrapped_coord((double)r.z, s_L[2], s_iL[2]);
+                w.x = wrapped_coord((double)r.x, s_L[0], iL0);
+                w.y = wrapped_coord((double)r.y, s_L[1], iL1);
+                w.z = wrapped_coord((double)r.z, s_L[2], iL2);
                 w.w = __int_as_float(a0 + t);
-                p.wrapped[dst] = w;
-                p.cellpack[dst] = (uint32_t)cellpack;
+                p.wrapped[dst[k]] = w;
+                p.cellpack[dst[k]] = (uint32_t)cellpack[k];
             }
         }
     }
@@ -272,7 +305,7 @@ int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_f
     p.nc0 = nc[0];
     p.nc1 = nc[1];
     p.nc2 = nc[2];
-    p.tiles_per_frame = (n_pos + kBuildThreads - 1) / kBuildThreads;
+    p.tiles_per_frame = (n_pos + kBuildTile - 1) / kBuildTile;
     p.cell_start = reinterpret_cast<uint32_t *>(ws + lay.off_cell_start);
     p.recs = ws + lay.off_recs;
     p.wrapped = reinterpret_cast<float4 *>(ws + lay.off_wrapped);

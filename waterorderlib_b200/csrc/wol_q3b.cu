@@ -635,7 +635,8 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc, d
     add_launches(1);
     if (P.ev_begin) cudaEventRecord((cudaEvent_t)P.ev_begin, stream);
     if (brick_box_max > 0.0) {
-        int rc = q3b_brick_launch(P, brick_box_max, stream);
+        // warp-specialised kernel where its shapes allow (batch-wide histograms), the single-role one otherwise
+        int rc = q3b_brick_ws_supported(P, false) ? q3b_brick_ws_launch(P, brick_box_max, stream) : q3b_brick_launch(P, brick_box_max, stream);
         if (rc != WOL_OK) return rc;
     } else if (use_tpc) {
         int rc = (sizeof(T) == 8) ? q3b_tpc_launch(P, stream, EXACT) : q3b_tpc32_launch(P, stream);
@@ -777,7 +778,7 @@ int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t s
     const bool use_tpc = q3b_tpc_supported(P) && a.box_max > 0.0 && getenv("WOL_NO_TPC") == nullptr;
     if (a.precision == WOL_PREC_FP64) {
         // large batches where every atom is a centre: brick path (wol_q3b_brick.cu); it feeds the same queues
-        if (use_tpc && q3b_brick_supported(P, exact)) return launch_typed<double, false>(P, stream, true, a.box_max);
+        if (use_tpc && (q3b_brick_ws_supported(P, exact) || q3b_brick_supported(P, exact))) return launch_typed<double, false>(P, stream, true, a.box_max);
         return exact ? launch_typed<double, true>(P, stream, use_tpc) : launch_typed<double, false>(P, stream, use_tpc);
     }
     const bool use_tpc32 = use_tpc && getenv("WOL_NO_TPC32") == nullptr;

@@ -35,10 +35,7 @@
 // otherwise the pair is re-evaluated in the reference's exact arithmetic (bk_exact_pair), or the centre's
 // q is handed to the exact widened-search kernel.  Outputs are therefore bit-identical to the exact path;
 // the slow paths fire for ~1e-8 of the angles (counted in counters[kCntSlowPair]).
-#include <math.h>
-#include <stdlib.h>
-
-#include "wol_q3b_common.cuh"
+#include "wol_q3b_brick.cuh"
 
 namespace wol {
 
@@ -46,45 +43,11 @@ constexpr int kBkWarps = 15;                    // consumer warps (16 warps with
                                                 // a 17th warp would be charged as 20 -- warps are allocated in fours)
 constexpr int kBkConsumers = kBkWarps * 32;
 constexpr int kBkThreads = kBkConsumers + 32;   // + one producer warp
-constexpr int kBkStages = 3;
 constexpr int kBkAtomCap = 1536;                // atoms of brick + halo per stage (slot fits 11 bits)
-constexpr int kBkRowCap = 49;                   // (y, z) rows of brick + halo: (nby + 2) (nbz + 2), nby, nbz <= 5
-constexpr int kBkCsW = 32;                      // cell starts per row: nbx + 3 <= 32
-constexpr int kBkMaxBx = kBkCsW - 3;
-constexpr int kBkMaxByz = 5;
-constexpr int kBkCRowCap = kBkMaxByz * kBkMaxByz;
-constexpr int kBkListCap = 16;                  // prefilter survivors per centre (self included)
-constexpr int kBkEntCap = 8;                    // unit vectors per centre (three-body neighbours from the front,
-                                                // q-only candidates from the back)
-constexpr int kBkMaxPairs = kBkEntCap * (kBkEntCap - 1) / 2;
-constexpr unsigned kBkSlotMask = 2047u;         // list entry = float bits of distance^2 with the low 11 bits = slot
 static_assert(kBkAtomCap <= 2048, "slot must fit 11 bits");
 
-struct BrickPlan {
-    int nb0, nb1, nb2;        // bricks per axis; brick i covers cells [i nc / nb, (i + 1) nc / nb)
-    int bricks_per_frame;
-    unsigned total;           // bricks in the batch
-    float pre_thr3;           // prefilter threshold of the three-body cutoff (< 0: no three-body)
-    float pre_cst1;           // slack added to the running 4th-smallest float distance^2
-    double eps_a, eps_b;      // eps_c = eps_a * (max |coordinate|) + eps_b
-    double floor2;            // neighbours closer than this (squared) send the centre to the exact path
-};
-
-struct BkItem {
-    int done, frame, n_centres, n_chunks;
-    int nbx, nby, n_crows, next;             // next: chunk counter
-    double L[3], iL[3];
-    int crow_off[kBkCRowCap + 1];            // centres before centre row r
-    unsigned short crow_slot[kBkCRowCap];    // stage slot of the first centre of row r
-    unsigned short crow_hrow[kBkCRowCap];    // its row among brick + halo rows
-};
-
-struct BkRowInfo {    // one (y, z) row of brick + halo (producer scratch)
-    int base;         // cell_start index of the row's cell x = 0
-    int delta;        // stage slot - cell-sorted index, for the atoms of the main run
-};
-
 struct BkSmem {
+    static constexpr int kAtomCap = kBkAtomCap;
     float4 loc[kBkStages][kBkAtomCap];
     double ent[kBkEntCap][3][kBkConsumers];
     unsigned char ent_k[kBkEntCap][kBkConsumers];  // which kept survivor the entry is (its list entry says where the record is)
@@ -93,345 +56,15 @@ struct BkSmem {
     int cgj[kBkConsumers];                       // where the centre's fp64 record is
     int woff[kBkWarps][33];
     BkItem item[kBkStages];
-    BkRowInfo rows[kBkRowCap];
+    BkRow prow[kBkRowCap];
+    double pbox[6];                              // producer scratch: box edges of the frame being staged and their reciprocals
     unsigned long long bar_full[kBkStages], bar_raw[kBkStages], bar_empty[kBkStages];
     unsigned char pair_ab[kBkMaxPairs + 4];
+    __device__ __forceinline__ BkRow *prow_of(int) { return prow; }
+    __device__ __forceinline__ double *pbox_of(int) { return pbox; }
 };
 
-// ---- mbarrier / bulk-copy primitives (PTX) -------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t a, unsigned parity) {
-    unsigned done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    return done != 0u;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    const uint32_t a = smem_addr(bar);
-    if (mbar_try(a, parity)) return;
-    unsigned polls = 0;
-    while (!mbar_try(a, parity)) {
-        __nanosleep(40);  // leave the issue slots to the warps that have work (the producer shares a scheduler with three consumers)
-        // a wait that never completes becomes a launch failure the host sees, not a hung device
-        if (++polls > (1u << 24)) __trap();
-    }
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kBkConsumers) : "memory"); }
-
-// ---- producer ------------------------------------------------------------------------------------------------------
-
-struct BkRow {        // as the lane that measures the row sees it
-    int gA, gM, gB, cA, cM, cB;
-    int cc, gc;       // centres of the row (0 for halo rows), cell_start index of the first centre cell
-    int base;
-    float sy, sz;
-    int off;
-};
-
-__device__ __forceinline__ void bk_measure_row(const Q3bParams &P, int f, int rr, int nby, int nbz, int by0, int bz0, int xa, int w,
-                                               float Lyf, float Lzf, BkRow &R) {
-    const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
-    const int hz = rr / (nby + 2), hy = rr - hz * (nby + 2);
-    int y = by0 - 1 + hy, z = bz0 - 1 + hz;
-    R.sy = 0.f;
-    R.sz = 0.f;
-    if (y < 0) { y += nc1; R.sy = -Lyf; } else if (y >= nc1) { y -= nc1; R.sy = Lyf; }
-    if (z < 0) { z += nc2; R.sz = -Lzf; } else if (z >= nc2) { z -= nc2; R.sz = Lzf; }
-    const uint32_t *cs = P.cell_start;
-    const int base = (int)(((size_t)f * nc2 + z) * nc1 + y) * nc0;  // < 2^31 (checked on the host)
-    R.base = base;
-    const int x0 = xa - 1, x1 = xa + w;  // inclusive cell range of the row, may leave [0, nc0)
-    R.cA = R.cB = 0;
-    R.gA = R.gB = 0;
-    if (x0 < 0) {
-        R.gA = (int)__ldg(cs + base + nc0 + x0);
-        R.cA = (int)__ldg(cs + base + nc0) - R.gA;
-    }
-    const int m0 = max(x0, 0), m1 = min(x1, nc0 - 1);
-    R.gM = (int)__ldg(cs + base + m0);
-    R.cM = (int)__ldg(cs + base + m1 + 1) - R.gM;
-    if (x1 >= nc0) {
-        R.gB = (int)__ldg(cs + base);
-        R.cB = (int)__ldg(cs + base + x1 - nc0 + 1) - R.gB;
-    }
-    R.cc = 0;
-    R.gc = base + xa;
-    if (hy >= 1 && hy <= nby && hz >= 1 && hz <= nbz) R.cc = (int)__ldg(cs + base + xa + w) - (int)__ldg(cs + base + xa);
-}
-
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(kFullMask, inc, o);
-        if (lane >= o) inc += n;
-    }
-    total = __shfl_sync(kFullMask, inc, 31);
-    return inc - v;
-}
-
-// centres of a sub-brick that cannot be staged even one cell wide: hand them to the large-capacity pass
-__device__ void bk_route_to_fallback(const Q3bParams &P, const BkRow &R) {
-    const uint32_t flags = (P.do_3b ? kFbNeed3b : 0u) | (P.do_q ? kFbNeedQ : 0u);
-    const int g0 = (int)__ldg(P.cell_start + R.gc);
-    for (int k = 0; k < R.cc; ++k) {
-        const uint32_t at = atomicAdd(P.counters + kCntFallback, 1u);
-        P.fb_list[at] = (uint32_t)(g0 + k) | flags;
-        atomicAdd(P.counters + kCntOverflow, 1u);
-    }
-}
-
-__device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, BkSmem &S, int lane) {
-    const int nc0 = P.nc0, nc1 = P.nc1, nc2 = P.nc2;
-    unsigned it = 0;
-    int xa = 0, xb = 0, w = 0, f = 0, by0 = 0, nby = 0, bz0 = 0, nbz = 0;
-    double Lx = 1, Ly = 1, Lz = 1;
-    int box_f = -1;
-    unsigned next_id = 0;  // the next brick id is fetched one brick ahead: the atomic's round trip is off the critical path
-    if (lane == 0) next_id = atomicAdd(P.counters + kCntBrick, 1u);
-    for (;;) {
-        if (xa >= xb) {  // next brick
-            const unsigned id = __shfl_sync(kFullMask, next_id, 0);
-            if (id >= B.total) break;
-            if (lane == 0) next_id = atomicAdd(P.counters + kCntBrick, 1u);
-            f = (int)(id / (unsigned)B.bricks_per_frame);
-            const int r = (int)(id - (unsigned)f * (unsigned)B.bricks_per_frame);
-            const int ibx = r % B.nb0, iby = (r / B.nb0) % B.nb1, ibz = r / (B.nb0 * B.nb1);
-            xa = ibx * nc0 / B.nb0;  // nc <= 1024
-            xb = (ibx + 1) * nc0 / B.nb0;
-            by0 = iby * nc1 / B.nb1;
-            nby = (iby + 1) * nc1 / B.nb1 - by0;
-            bz0 = ibz * nc2 / B.nb2;
-            nbz = (ibz + 1) * nc2 / B.nb2 - bz0;
-            w = xb - xa;
-            if (f != box_f) {
-                Lx = P.box[(size_t)f * 3 + 0];
-                Ly = P.box[(size_t)f * 3 + 1];
-                Lz = P.box[(size_t)f * 3 + 2];
-                box_f = f;
-            }
-            if (w <= 0 || nby <= 0 || nbz <= 0) { xa = xb; continue; }
-        }
-        const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
-        const int nrows = (nby + 2) * (nbz + 2);
-        // ---- measure the sub-brick [xa, xa + w): atoms per row, centres per row (lane <-> rows lane, lane + 32) -----
-        BkRow R0, R1;
-        R0.cA = R0.cM = R0.cB = R0.cc = 0;
-        R1.cA = R1.cM = R1.cB = R1.cc = 0;
-        if (lane < nrows) bk_measure_row(P, f, lane, nby, nbz, by0, bz0, xa, w, Lyf, Lzf, R0);
-        if (lane + 32 < nrows) bk_measure_row(P, f, lane + 32, nby, nbz, by0, bz0, xa, w, Lyf, Lzf, R1);
-        int tot0, tot1, ctot0, ctot1;
-        R0.off = warp_excl_scan(R0.cA + R0.cM + R0.cB, lane, tot0);
-        R1.off = tot0 + warp_excl_scan(R1.cA + R1.cM + R1.cB, lane, tot1);
-        const int coff0 = warp_excl_scan(R0.cc, lane, ctot0);
-        const int coff1 = ctot0 + warp_excl_scan(R1.cc, lane, ctot1);
-        const int n_atoms = tot0 + tot1, n_centres = ctot0 + ctot1;
-        if (n_centres == 0) { xa += w; w = min(w, xb - xa); continue; }
-        if (n_atoms > kBkAtomCap - 1) {
-            if (w > 1) { w = (w + 1) / 2; continue; }
-            if (R0.cc > 0) bk_route_to_fallback(P, R0);
-            if (R1.cc > 0) bk_route_to_fallback(P, R1);
-            if (lane == 0) atomicAdd(P.counters + kCntBrickFb, 1u);
-            xa += 1;
-            w = min(w, xb - xa);
-            continue;
-        }
-        // ---- stage it ---------------------------------------------------------------------------------------
-        const int s = (int)(it % kBkStages);
-        const unsigned round = it / kBkStages;
-        if (round >= 1) mbar_wait(&S.bar_empty[s], (round + 1u) & 1u);
-        BkItem &I = S.item[s];
-        unsigned short *cst = S.cs[s];
-        float4 *stage = S.loc[s];
-        if (lane == 0) {
-            I.done = 0;
-            I.frame = f;
-            I.n_centres = n_centres;
-            I.n_chunks = (n_centres + 31) >> 5;
-            I.nbx = w;
-            I.nby = nby;
-            I.n_crows = nby * nbz;
-            I.next = 0;
-            I.L[0] = Lx; I.L[1] = Ly; I.L[2] = Lz;
-            I.iL[0] = __ddiv_rn(1.0, Lx);
-            I.iL[1] = __ddiv_rn(1.0, Ly);
-            I.iL[2] = __ddiv_rn(1.0, Lz);
-            I.crow_off[nby * nbz] = n_centres;
-            mbar_arrive_expect_tx(&S.bar_raw[s], (unsigned)n_atoms * 16u);
-        }
-        __syncwarp();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const BkRow &R = h ? R1 : R0;
-            const int rr = lane + 32 * h;
-            if (rr >= nrows) continue;
-            if (R.cA > 0) bulk_g2s(stage + R.off, P.wrapped + R.gA, (unsigned)R.cA * 16u, &S.bar_raw[s]);
-            if (R.cM > 0) bulk_g2s(stage + R.off + R.cA, P.wrapped + R.gM, (unsigned)R.cM * 16u, &S.bar_raw[s]);
-            if (R.cB > 0) bulk_g2s(stage + R.off + R.cA + R.cM, P.wrapped + R.gB, (unsigned)R.cB * 16u, &S.bar_raw[s]);
-            S.rows[rr].base = R.base;
-            S.rows[rr].delta = R.off + R.cA - R.gM;
-            const int hz = rr / (nby + 2), hy = rr - hz * (nby + 2);
-            if (hy >= 1 && hy <= nby && hz >= 1 && hz <= nbz) {
-                const int r = (hz - 1) * nby + (hy - 1);
-                I.crow_off[r] = h ? coff1 : coff0;
-                I.crow_slot[r] = (unsigned short)(R.off + R.cA + (int)__ldg(P.cell_start + R.gc) - R.gM);
-                I.crow_hrow[r] = (unsigned short)rr;
-            }
-        }
-        __syncwarp();
-        // ---- while the copies fly: stage slot of every cell start.  Entry i of a row <-> cell xa - 1 + i, entry
-        // w + 2 = end of the row.  Lane <-> cell, one coalesced load per row, eight rows in flight; the entries of
-        // the image cells and the row ends are patched afterwards by the lane that measured the row.
-        {
-            const int gx = min(max(xa - 1 + lane, 0), nc0 - 1);
-            const bool act = lane <= w + 1;
-            for (int r0 = 0; r0 < nrows; r0 += 8) {
-                int v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (r0 + u < nrows && act) v[u] = (int)__ldg(P.cell_start + S.rows[r0 + u].base + gx);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (r0 + u < nrows && act) cst[(r0 + u) * kBkCsW + lane] = (unsigned short)(v[u] + S.rows[r0 + u].delta);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const BkRow &R = h ? R1 : R0;
-                const int rr = lane + 32 * h;
-                if (rr >= nrows) continue;
-                unsigned short *row = cst + rr * kBkCsW;
-                row[w + 2] = (unsigned short)(R.off + R.cA + R.cM + R.cB);
-                if (xa - 1 < 0) row[0] = (unsigned short)R.off;                          // the single cell at x - L
-                if (xa + w >= nc0) row[w + 1] = (unsigned short)(R.off + R.cA + R.cM);   // the single cell at x + L
-            }
-        }
-        mbar_wait(&S.bar_raw[s], round & 1u);
-        // ---- periodic images: rows (or row ends) that come from the other side of the box are shifted in place, so
-        // the sweep has no image logic.  Interior bricks have none.
-        {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const BkRow &R = h ? R1 : R0;
-                const bool mine = (lane + 32 * h < nrows) && (R.sy != 0.f || R.sz != 0.f || R.cA > 0 || R.cB > 0);
-                unsigned todo = __ballot_sync(kFullMask, mine);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int off = __shfl_sync(kFullMask, R.off, src), cA = __shfl_sync(kFullMask, R.cA, src);
-                    const int cM = __shfl_sync(kFullMask, R.cM, src), cB = __shfl_sync(kFullMask, R.cB, src);
-                    const float sy = __shfl_sync(kFullMask, R.sy, src), sz = __shfl_sync(kFullMask, R.sz, src);
-                    const int n = cA + cM + cB;
-                    for (int k = lane; k < n; k += 32) {
-                        float4 v = stage[off + k];
-                        v.x += k < cA ? -Lxf : (k >= cA + cM ? Lxf : 0.f);
-                        v.y += sy;
-                        v.z += sz;
-                        stage[off + k] = v;
-                    }
-                }
-            }
-        }
-        mbar_arrive(&S.bar_full[s]);  // 32 arrivals: every lane's metadata and rewritten rows are published
-        ++it;
-        xa += w;
-        w = min(w, xb - xa);
-    }
-    // no more bricks: publish the end marker in the next stage
-    const int s = (int)(it % kBkStages);
-    const unsigned round = it / kBkStages;
-    if (round >= 1) mbar_wait(&S.bar_empty[s], (round + 1u) & 1u);
-    if (lane == 0) S.item[s].done = 1;
-    mbar_arrive(&S.bar_full[s]);
-}
-
-// ---- consumers -----------------------------------------------------------------------------------------------------
-
-// Sorted four smallest squared distances with the column entry each belongs to.
-struct Top4S {
-    double d[4];
-    int p[4];
-    __device__ __forceinline__ void reset() {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            d[k] = Ops<double>::inf();
-            p[k] = 0;
-        }
-    }
-    // strict <: equal keys keep their arrival order; ties are caught by the gap test afterwards
-    __device__ __forceinline__ void insert(double dd, int pp) {
-        d[3] = dd;
-        p[3] = pp;
-#pragma unroll
-        for (int k = 3; k > 0; --k) {
-            if (d[k] < d[k - 1]) {
-                const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td;
-                const int tp = p[k]; p[k] = p[k - 1]; p[k - 1] = tp;
-            }
-        }
-    }
-};
-
-// The reference's clamped cosine for one pair, from the fp64 records, every operation as the Fortran
-// performs it (waterlib.f90:880-883 second reimage is the identity here: |v| < L / 2).
-static __device__ __noinline__ double bk_exact_pair(const RecD *recs, int gc, int ga, int gb, const double *L, const double *iL) {
-    const RecD c = recs[gc], a = recs[ga], b = recs[gb];
-    double va[3], vb[3];
-    const double r[3] = {c.x, c.y, c.z}, pa[3] = {a.x, a.y, a.z}, pb[3] = {b.x, b.y, b.z};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double da = min_image_1<double, false>(pa[k], r[k], L[k], iL[k]);
-        const double db = min_image_1<double, false>(pb[k], r[k], L[k], iL[k]);
-        va[k] = __dsub_rn(__dadd_rn(r[k], da), r[k]);
-        vb[k] = __dsub_rn(__dadd_rn(r[k], db), r[k]);
-    }
-    const double wa = sumsq3<double>(va[0], va[1], va[2]), wb = sumsq3<double>(vb[0], vb[1], vb[2]);
-    if (wa == 0.0 || wb == 0.0) return 1.0;  // (cannot happen: such centres never reach the pair phase)
-    return clamped_cos<double>(dot3<double>(va[0], va[1], va[2], vb[0], vb[1], vb[2]), wa, wb);
-}
-
-// (the statistics stay in registers: the out-of-line flush gets a copy)
-static __device__ __noinline__ void bk_flush_stats_copy(const Q3bParams &P, int f, LaneStats st) { flush_stats(P, f, st); }
-__device__ __forceinline__ void bk_flush_stats(const Q3bParams &P, int f, LaneStats &st) {
-    bk_flush_stats_copy(P, f, st);
-    st.reset();
-}
-static __device__ __noinline__ int bk_exact_position(double c, const double *tab, int nbins, float lo_f, float invw_f) {
-    return angle_position(c, tab, nbins, lo_f, invw_f);
-}
-
-// float seed of the bin of cosine c, always a valid bin index (see angle_position, which it mirrors)
-__device__ __forceinline__ int bk_seed_position(double c, int nbins, float lo, float inv_width) {
-    const float x = (float)c, ax = fabsf(x);
-    const float t = fmaxf(1.0f - ax, 1e-30f);
-    float r = fmaf(fmaf(fmaf(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f) * (t * rsqrtf(t));
-    r = x < 0.f ? 3.14159265f - r : r;
-    const int k = (int)((r * 57.29577951f - lo) * inv_width);
-    return min(max(k, 0), nbins - 1);
-}
 
 __device__ __forceinline__ void bk_flush_bins(unsigned *s_bins, unsigned long long *g_bins, int nbins, bool clear, int tid) {
     for (int i = tid; i < nbins; i += kBkConsumers) {
@@ -439,21 +72,6 @@ __device__ __forceinline__ void bk_flush_bins(unsigned *s_bins, unsigned long lo
         if (v) atomicAdd(g_bins + i, (unsigned long long)v);
         if (clear) s_bins[i] = 0u;
     }
-}
-
-__device__ __forceinline__ void bk_push_q(const Q3bParams &P, uint32_t fb_id) {
-    const uint32_t at = atomicAdd(P.counters + kCntFallback, 1u);
-    P.fb_list[at] = fb_id | kFbNeedQ;
-    atomicAdd(P.counters + kCntWidened, 1u);
-}
-
-__device__ __forceinline__ void bk_load_rec(const void *recs, int g, double &x, double &y, double &z, int &idx) {
-    const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + g);
-    const int4 a = __ldg(p), b = __ldg(p + 1);
-    x = __hiloint2double(a.y, a.x);
-    y = __hiloint2double(a.w, a.z);
-    z = __hiloint2double(b.y, b.x);
-    idx = b.z;
 }
 
 __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_constant__ Q3bParams P, const __grid_constant__ BrickPlan B) {
@@ -487,7 +105,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
     }
     __syncthreads();
     if (warp == kBkWarps) {
-        bk_producer(P, B, S, lane);
+        bk_producer<BkSmem, 1>(P, B, S, lane, 0);
         return;
     }
 
@@ -660,9 +278,12 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                             overflow = true;
                         } else {
                             const double rs = rsqrt(sq);
-                            S.ent[e][0][tid] = dx * rs;
-                            S.ent[e][1][tid] = dy * rs;
-                            S.ent[e][2][tid] = dz * rs;
+                            // column rotated by 3 e inside the warp's 32: the lanes of phase 3a that work on one centre's
+                            // pairs read different entries of it, and a plain [e][k][t] layout puts those in one bank
+                            const int te = (tid & ~31) | ((tid + 3 * e) & 31);
+                            S.ent[e][0][te] = dx * rs;
+                            S.ent[e][1][te] = dy * rs;
+                            S.ent[e][2][te] = dz * rs;
                             S.ent_k[e][tid] = (unsigned char)k;
                             if (want_q) {
                                 if (sq < top.d[3]) {
@@ -731,8 +352,9 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     }
                     const int ab = S.pair_ab[w - base];
                     const int col = warp * 32 + t, ea = ab & 15, eb = ab >> 4;
-                    double c = fma(S.ent[ea][0][col], S.ent[eb][0][col],
-                                   fma(S.ent[ea][1][col], S.ent[eb][1][col], S.ent[ea][2][col] * S.ent[eb][2][col]));
+                    const int ca = warp * 32 + ((t + 3 * ea) & 31), cb = warp * 32 + ((t + 3 * eb) & 31);
+                    double c = fma(S.ent[ea][0][ca], S.ent[eb][0][cb],
+                                   fma(S.ent[ea][1][ca], S.ent[eb][1][cb], S.ent[ea][2][ca] * S.ent[eb][2][cb]));
                     // Bin of the fast value with its certificate: the reference's (clamped) cosine lies within eps_c of c, so
                     // the bin is settled when [c - eps_c, c + eps_c] sits inside one bin's cosine interval and away from -1
                     // (whose angle the reference turns into -180 degrees).  No clamp: a |c| beyond 1 fails the certificate.
@@ -780,9 +402,10 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int e = top.p[k];
-                    ux[k] = S.ent[e][0][tid];
-                    uy[k] = S.ent[e][1][tid];
-                    uz[k] = S.ent[e][2][tid];
+                    const int te = (tid & ~31) | ((tid + 3 * e) & 31);
+                    ux[k] = S.ent[e][0][te];
+                    uy[k] = S.ent[e][1][te];
+                    uz[k] = S.ent[e][2][te];
                 }
                 double acc = 0.0;
                 int n_real = 0;
@@ -857,49 +480,23 @@ static size_t brick_smem_bytes(const Q3bParams &P) {
     return smem;
 }
 
-// Bricks per axis: the largest bricks (<= 29 x 5 x 5 cells) whose expected brick + halo population fits the stage
-// with some head-room and whose centres about fill the consumer warps.  A brick that turns out denser than
-// expected is split by the producer, so this is a throughput choice, not a correctness one.
-static void brick_dims(const Q3bParams &P, int nb[3]) {
-    const double occ = (double)P.n_pos / ((double)P.nc0 * P.nc1 * P.nc2);  // atoms per cell
-    int by = P.nc1 < 4 ? P.nc1 : 4, bz = P.nc2 < 4 ? P.nc2 : 4;
-    const double want_cells = 0.97 * kBkConsumers / (occ > 1e-9 ? occ : 1e-9);
-    int bx = (int)(want_cells / (by * bz));
-    if (bx > kBkMaxBx) bx = kBkMaxBx;
-    if (bx > P.nc0) bx = P.nc0;
-    if (bx < 1) bx = 1;
-    auto halo = [&](int x, int y, int z) { return (double)(x + 2) * (y + 2) * (z + 2) * occ; };
-    const double room = 0.92 * (kBkAtomCap - 1);
-    while (bx > 1 && halo(bx, by, bz) > room) --bx;
-    while (by > 1 && halo(bx, by, bz) > room) --by;
-    while (bz > 1 && halo(bx, by, bz) > room) --bz;
-    // even split: nb bricks of floor / ceil (nc / nb) cells, none larger than the limits above
-    auto count = [](int nc, int b, int bmax) {
-        int n = (nc + b - 1) / b;
-        while ((nc + n - 1) / n > bmax) ++n;
-        return n;
-    };
-    nb[0] = count(P.nc0, bx, kBkMaxBx);
-    nb[1] = count(P.nc1, by, kBkMaxByz);
-    nb[2] = count(P.nc2, bz, kBkMaxByz);
-}
-
 bool q3b_brick_supported(const Q3bParams &P, bool exact) {
     if (P.centres != nullptr || P.n_valid != nullptr || P.wrapped == nullptr || exact) return false;
     if (P.nc0 < 4 || P.nc1 < 4 || P.nc2 < 4) return false;
     if (brick_smem_bytes(P) > 227u * 1024u) return false;
-    const char *env = getenv("WOL_BRICK");  // test switch: 1 = also for small batches, 0 = never
+    const char *env = getenv("WOL_BRICK");  // test switch: 1 = also for small batches, 0 = never, 3 = also, and the
+                                            // warp-specialised kernel where it applies (wol_q3b_brick_ws.cu)
     if (env && env[0] == '0') return false;
-    if (env && env[0] == '1') return true;
+    if (env && (env[0] == '1' || env[0] == '3')) return true;
     int nb[3];
-    brick_dims(P, nb);
+    brick_dims(P, nb, kBkConsumers, kBkAtomCap);
     return (long long)nb[0] * nb[1] * nb[2] * P.n_frames >= 2LL * sm_count();
 }
 
 int q3b_brick_launch(const Q3bParams &P, double box_max, cudaStream_t stream) {
     BrickPlan B;
     int nb[3];
-    brick_dims(P, nb);
+    brick_dims(P, nb, kBkConsumers, kBkAtomCap);
     B.nb0 = nb[0];
     B.nb1 = nb[1];
     B.nb2 = nb[2];
@@ -907,23 +504,11 @@ int q3b_brick_launch(const Q3bParams &P, double box_max, cudaStream_t stream) {
     const long long total = (long long)B.bricks_per_frame * P.n_frames;
     if (total >= (1LL << 31)) return set_error(WOL_ERR_RANGE, "too many bricks");
     B.total = (unsigned)total;
-    // float thresholds, same rounding margin as the thread-per-centre path (see q3b_launch)
-    const double margin = 16.0 * ldexp(1.0, -24) * box_max;
-    const bool last1 = P.wq_max <= 1;
-    const double high3 = sqrt(P.high3sq);
-    const double rsel = P.do_q ? (last1 ? P.highq : fmin(P.highq, P.rc1)) : 0.0;
-    const double rthr = fmax(P.do_3b ? high3 : 0.0, rsel);
-    B.pre_thr3 = P.do_3b ? nextafterf((float)((high3 + margin) * (high3 + margin) * (1.0 + 1e-6)), INFINITY) : -1.0f;
-    const double cst = (4.0 * margin * (rthr + margin) + 4.0 * margin * margin) * (1.0 + 1e-6) + 1e-6 * rthr * rthr;
-    // + what dropping 11 mantissa bits of a survivor's distance^2 can hide (phase 1b)
-    B.pre_cst1 = nextafterf((float)(cst + 2.0 * ldexp(1.0, -12) * (rthr + margin) * (rthr + margin) * (1.0 + 1e-6)), INFINITY);
-    // eps_c (bk header): the reference's vectors (r + d) - r differ from d by at most delta = 2^-51 (|r| + reach) per
-    // component; two such vectors of length >= r_floor turn the cosine by at most 2 sqrt(3) delta / r_floor; the
-    // roundings of either evaluation add less than 2^-48.  Factor 4 of safety on the first term.
-    const double r_floor = 0.25, reach = rthr + margin + 1.0;
-    B.floor2 = r_floor * r_floor;
-    B.eps_a = 4.0 * 2.0 * sqrt(3.0) * ldexp(1.0, -51) / r_floor;
-    B.eps_b = B.eps_a * reach + ldexp(1.0, -46);  // eps_c = eps_a (max |coordinate| + reach) + 2^-46
+    B.m_bpf = bk_div_magic((unsigned)B.bricks_per_frame);
+    B.m_nb0 = bk_div_magic((unsigned)nb[0]);
+    B.m_nb1 = bk_div_magic((unsigned)nb[1]);
+    B.m_nb2 = bk_div_magic((unsigned)nb[2]);
+    brick_plan_bounds(P, box_max, B);
     const size_t smem = brick_smem_bytes(P);
     cudaError_t e = cudaFuncSetAttribute(q3b_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(brick)", e);

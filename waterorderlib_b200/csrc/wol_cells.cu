@@ -130,10 +130,15 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
             r.z = (double)z[k];
             r.idx = a0 + t;
             r.cell = cellpack[k];
-            int4 *d4 = reinterpret_cast<int4 *>(reinterpret_cast<RecD *>(p.recs) + dst[k]);
-            const int4 *s4 = reinterpret_cast<const int4 *>(&r);
-            d4[0] = s4[0];
-            d4[1] = s4[1];
+            // one 256-bit store (STG.256) per record: the 32-byte record is exactly one sector of L2, and the scatter
+            // pass is bound by the number of L2 transactions, not by bytes
+            {
+                RecD *d = reinterpret_cast<RecD *>(p.recs) + dst[k];
+                const long long tail = (long long)(unsigned)r.idx | ((long long)r.cell << 32);
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(d), "l"(__double_as_longlong(r.x)),
+                             "l"(__double_as_longlong(r.y)), "l"(__double_as_longlong(r.z)), "l"(tail)
+                             : "memory");
+            }
             if (p.wrapped) {
                 // box-wrapped coordinates for the float prefilter of the sweep: frac(x / L) * L
                 float4 w;

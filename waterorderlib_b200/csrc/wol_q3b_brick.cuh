@@ -452,13 +452,15 @@ __device__ __forceinline__ void bk_push_q(const Q3bParams &P, uint32_t fb_id) {
     atomicAdd(P.counters + kCntWidened, 1u);
 }
 
+// one 256-bit load (LDG.256) per 32-byte record
 __device__ __forceinline__ void bk_load_rec(const void *recs, int g, double &x, double &y, double &z, int &idx) {
-    const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + g);
-    const int4 a = __ldg(p), b = __ldg(p + 1);
-    x = __hiloint2double(a.y, a.x);
-    y = __hiloint2double(a.w, a.z);
-    z = __hiloint2double(b.y, b.x);
-    idx = b.z;
+    const RecD *p = reinterpret_cast<const RecD *>(recs) + g;
+    long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    x = __longlong_as_double(a);
+    y = __longlong_as_double(b);
+    z = __longlong_as_double(c);
+    idx = (int)d;
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------

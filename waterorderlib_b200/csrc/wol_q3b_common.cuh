@@ -66,12 +66,15 @@ template <>
 struct RecTraits<double> {
     typedef RecD Rec;
     static __device__ __forceinline__ void load(const void *recs, size_t j, double &x, double &y, double &z, int &idx) {
-        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const RecD *>(recs) + j);
-        const int4 a = __ldg(p), b = __ldg(p + 1);
-        x = __hiloint2double(a.y, a.x);
-        y = __hiloint2double(a.w, a.z);
-        z = __hiloint2double(b.y, b.x);
-        idx = b.z;
+        // the 32-byte record is one sector: one 256-bit load (LDG.256) instead of two 128-bit ones -- the load / store
+        // unit's transaction rate, not bytes, is what the sweeps over the records run into
+        const RecD *p = reinterpret_cast<const RecD *>(recs) + j;
+        long long a, b, c, d;
+        asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        x = __longlong_as_double(a);
+        y = __longlong_as_double(b);
+        z = __longlong_as_double(c);
+        idx = (int)d;
     }
     static __device__ __forceinline__ int cell(const void *recs, size_t j) {
         return reinterpret_cast<const RecD *>(recs)[j].cell;

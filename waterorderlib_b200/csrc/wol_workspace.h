@@ -14,8 +14,8 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 // Sorted per-atom records, grouped by (frame, cell).
 // FP64 mode: original coordinates (bit-identical to the input, the reference arithmetic needs them),
 // original atom index and the cell coordinates packed 10 bits per axis (cx | cy << 10 | cz << 20).
-// 32 bytes = two 16-byte loads.
-struct alignas(16) RecD {
+// 32 bytes = one sector: one 256-bit store / load (two 16-byte loads where a kernel prefers them).
+struct alignas(32) RecD {
     double x, y, z;
     int32_t idx;
     int32_t cell;

@@ -219,7 +219,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=N_CELLS_1M, help="diamond-cubic cells per edge (50 -> 1M waters)")
     ap.add_argument("--frames-per-step", type=int, default=16, help="frames per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=1, help="frames per pipeline batch of the end-to-end legs")
+    ap.add_argument("--e2e-batch", type=int, default=2, help="frames per pipeline batch of the end-to-end legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cells", type=int, default=8, help="reference sample box: 8 -> 4096 waters")
     args = ap.parse_args()

@@ -36,7 +36,7 @@ extern "C" {
 enum {
     WOL_OK = 0,
     WOL_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown enum)          */
-    WOL_ERR_UNSUPPORTED = -2, /* valid in the reference but not implemented here (e.g. BoxL <= 0)  */
+    WOL_ERR_UNSUPPORTED = -2, /* valid in the reference but not implemented by this entry point     */
     WOL_ERR_WORKSPACE = -3,   /* workspace too small                                                */
     WOL_ERR_CUDA = -4,        /* a CUDA runtime call failed; message holds cudaGetErrorString       */
     WOL_ERR_RANGE = -5,       /* sizes overflow the 32-bit indexing of the kernels                  */
@@ -76,6 +76,25 @@ int wol_abi_version(void);
  */
 int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32_t nc_out[3],
                   double *edge_min_out, double *box_max_out);
+
+/*
+ * Non-periodic axes.  The reference marks an axis as not periodic with a NEGATIVE box edge (fortran/waterlib.f90:41,
+ * :840: iBoxL = merge(1/BoxL, 0, BoxL >= 0), so the minimum-image step leaves that component untouched).  The cell-list
+ * entry points need a positive period on every axis; this call replaces every negative edge by an equivalent period
+ *     L' = 2 (extent + reach) + 1,   extent = max - min of that coordinate over the frame's atoms (and centres),
+ * for which the kernels' arithmetic is bit-identical to "no wrap" (every difference d has |d| < L'/2, so
+ * d - L' anint(d / L') = d) and no periodic image comes within `reach` of any atom.  Pass the result to wol_plan_grid,
+ * wol_cell_build and the evaluation calls in place of the original box.
+ *   box_host      [n_frames][3] as the reference takes it (negative = open axis)
+ *   reach         the largest cutoff / search radius any later call on these frames uses
+ *   scratch_dev   n_frames * 48 bytes of device memory (only touched when some edge is negative; may be NULL otherwise)
+ *   box_out_host  [n_frames][3], all positive
+ * Positive edges are copied unchanged and nothing is launched when no edge is negative; otherwise one small reduction
+ * kernel per array runs on `stream` and the call synchronises it.  Zero, NaN or infinite edges: WOL_ERR_INVALID.
+ */
+int wol_effective_box(const void *pos, int32_t pos_dtype, int32_t n_frames, int32_t n_pos, const void *centres,
+                      int32_t centre_dtype, int32_t n_centres, const double *box_host, double reach, void *scratch_dev,
+                      double *box_out_host, void *stream);
 
 /* Bytes of scratch needed by wol_cell_build + the evaluation kernels for this batch shape.
  * n_centres_max = the largest number of centres per frame any later call on this workspace passes. */

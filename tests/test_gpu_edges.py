@@ -109,7 +109,7 @@ def test_ragged_subpopulations_same_workspace():
 def test_error_paths():
     pos, box = synth.water_box(3, sigma=0.3, seed=1)
     with pytest.raises(ValueError):
-        engine.q3b_frames(pos, np.array([18.0, -1.0, 18.0]))     # non-periodic axis: not supported by the cell list
+        engine.q3b_frames(pos, np.array([18.0, 0.0, 18.0]))      # an empty axis (negative = non-periodic is supported, see below)
     with pytest.raises(ValueError):
         engine.q3b_frames(pos, box, r_cell=2.0)                  # three-body cutoff beyond the planned cell edge
     with pytest.raises(ValueError):
@@ -250,3 +250,69 @@ def test_generic_kernels_agree_with_the_fast_path_at_size(monkeypatch):
                 assert same.double().mean().item() > 0.999 and (a.n3 == b.n3).double().mean().item() > 0.999
                 assert torch.allclose(a.q[same], b.q[same], rtol=0, atol=1e-4)
                 assert (a.ang_hist - b.ang_hist).abs().sum().item() < 2e-3 * a.ang_hist.sum().item()
+
+
+# ---- non-periodic axes: the reference's negative box edges (fortran/waterlib.f90:41, :840) -------------------------
+
+def _slab(seed=3):
+    pos, box, _, _ = synth.slab_box(6, 6, 3, sigma=0.4, seed=seed)  # 864 waters, vacuum above and below in z
+    return pos, box
+
+
+@pytest.mark.parametrize("open_axes", [(2,), (0, 2), (0, 1, 2)])
+def test_open_axes_fused_path_vs_oracle(open_axes):
+    """q, 4-NN, neighbour counts and angle bins with negative edges = the oracle's (and the reference Fortran's, which
+    the oracle is pinned on) with the same negative edges; shifted far from the origin and in float32 storage too."""
+    pos, box = _slab()
+    b = box.copy()
+    for k in open_axes:
+        b[k] = -1.0
+    check(pos, b)
+    check(pos + np.array([1000.0, -250.0, 3000.0]), b)
+    r32 = engine.q3b_frames(pos.astype(np.float32), b)
+    q, nn4, _ = port.order_param_q(pos.astype(np.float32).astype(np.float64), pos.astype(np.float32).astype(np.float64), b)
+    assert np.array_equal(r32.nn_idx.cpu().numpy()[0], nn4)
+    # an open axis is not a periodic one: the atoms at the two faces of the slab must not see each other
+    per = engine.q3b_frames(pos, np.array([box[0], box[1], pos[:, 2].max() - pos[:, 2].min() + 1.5]))
+    opn = engine.q3b_frames(pos, np.array([box[0], box[1], -1.0]))
+    assert int(per.n3.sum()) > int(opn.n3.sum())
+
+
+def test_open_axes_sub_population_outside_the_atoms_extent():
+    pos, box = _slab(seed=5)
+    b = np.array([box[0], -box[1], -1.0])
+    rng = np.random.default_rng(2)
+    sub = np.concatenate([pos[rng.choice(pos.shape[0], 40, replace=False)] + rng.normal(0, 0.3, (40, 3)),
+                          pos[:5] + np.array([0.0, 0.0, 60.0]),          # far above the slab: no neighbours at all
+                          pos[:5] + np.array([0.0, -45.0, 0.0])])        # outside along the other open axis
+    check(pos, b, sub=sub, highq=8.0)
+    ang, num = wp.getCosAngs(sub, pos, b)
+    ang_o, num_o = port.getCosAngs(sub, pos, b)
+    assert np.array_equal(num, num_o) and np.allclose(ang, ang_o, rtol=1e-12, atol=1e-9)
+
+
+def test_open_axes_neighbour_lists_hbonds_and_shell():
+    pos, box = _slab(seed=7)
+    b = np.array([box[0], box[1], -box[2]])
+    off, idx = routines.neighbors_csr(None, pos, b, 0.0, 3.5)
+    mat = port.neighbor_matrix(pos, pos, b, 0.0, 3.5)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    for i in range(0, pos.shape[0], 37):
+        assert np.array_equal(idx[off[i]:off[i + 1]], np.nonzero(mat[i])[0])
+    assert off[-1] == mat.sum()
+    H = synth.add_hydrogens(pos, seed=7)
+    r = routines.hbond_counts(pos, np.repeat(pos, 2, axis=0), H, b, 3.5, 120.0)
+    a, d = port.hbonds(pos, np.repeat(pos, 2, axis=0), H, b, 3.5, 120.0)
+    assert np.array_equal(r["acc_count"].cpu().numpy()[0], a) and np.array_equal(r["don_count"].cpu().numpy()[0], d)
+    sol = np.array([[5.0, 5.0, pos[:, 2].min() - 2.0], [20.0, 12.0, pos[:, 2].max() + 1.0], [9.0, 30.0, pos[:, 2].mean()]])
+    m = routines.shell_mask(sol, pos, b, 4.0).cpu().numpy()[0]
+    assert np.array_equal(m.astype(bool), port.shell_mask(sol, pos, b, 4.0).astype(bool))
+
+
+def test_open_axes_limits_are_reported():
+    pos, box = _slab()
+    b = np.array([box[0], box[1], -1.0])
+    with pytest.raises(ValueError):
+        routines.lsi(None, pos, b)          # not one of the routines that take non-periodic axes
+    with pytest.raises((ValueError, WolError)):
+        engine.q3b_frames(pos, np.array([box[0], 0.0, box[2]]))  # an empty axis is an error, not "open"

@@ -55,6 +55,7 @@ SIGNATURES = {
     "wol_plan_grid": (ctypes.c_int, [c_vp, c_i32, ctypes.c_double, ctypes.POINTER(c_i32 * 3), ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(ctypes.c_double)]),
     "wol_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, ctypes.POINTER(c_i32 * 3)]),
+    "wol_effective_box": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, ctypes.c_double, c_vp, c_vp, c_vp]),
     "wol_cell_build": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, ctypes.POINTER(c_i32 * 3), c_i32, c_vp, ctypes.c_size_t, c_vp]),
     "wol_angle_table": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, c_i32, ctypes.c_double, ctypes.c_double, c_vp]),
     "wol_q3b_frames": (ctypes.c_int, [ctypes.POINTER(Q3bArgs), c_vp]),

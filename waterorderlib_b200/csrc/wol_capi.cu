@@ -185,7 +185,7 @@ int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32
             const double L = box_host[(size_t)f * 3 + k];
             if (!(L > 0.0) || !isfinite(L))
                 return set_error(WOL_ERR_UNSUPPORTED,
-                                 "frame %d: box edge %d is %g; non-periodic (negative) or empty axes are not supported", f, k, L);
+                                 "frame %d: box edge %d is %g; for non-periodic (negative) axes pass the box through wol_effective_box first", f, k, L);
             if (L < lmin[k]) lmin[k] = L;
             if (L > lmax) lmax = L;
         }
@@ -201,6 +201,18 @@ int wol_plan_grid(const double *box_host, int32_t n_frames, double r_cell, int32
     if (edge_min_out) *edge_min_out = emin;
     if (box_max_out) *box_max_out = lmax;
     return WOL_OK;
+}
+
+int wol_effective_box(const void *pos, int32_t pos_dtype, int32_t n_frames, int32_t n_pos, const void *centres, int32_t centre_dtype,
+                      int32_t n_centres, const double *box_host, double reach, void *scratch_dev, double *box_out_host, void *stream) {
+    if (!box_host || !box_out_host || n_frames < 1) return set_error(WOL_ERR_INVALID, "wol_effective_box: null argument or no frames");
+    if (n_pos < 0 || n_centres < 0 || (n_pos > 0 && !pos)) return set_error(WOL_ERR_INVALID, "wol_effective_box: bad positions");
+    if ((pos_dtype != WOL_F64 && pos_dtype != WOL_F32) || (centres && centre_dtype != WOL_F64 && centre_dtype != WOL_F32))
+        return set_error(WOL_ERR_INVALID, "wol_effective_box: unknown dtype");
+    if (!(reach >= 0.0) || isinf(reach)) return set_error(WOL_ERR_INVALID, "wol_effective_box: reach must be a finite distance");
+    g_launches = 0;
+    return effective_box(pos, pos_dtype, n_frames, n_pos, centres, centre_dtype, n_centres, box_host, reach, scratch_dev, box_out_host,
+                         (cudaStream_t)stream);
 }
 
 size_t wol_workspace_bytes(int32_t n_frames, int32_t n_pos, int32_t n_centres_max, const int32_t nc[3]) {

@@ -12,6 +12,10 @@
 //
 // The reference has no counterpart: its neighbour search is the O(N^2) double loop of
 // fortran/waterlib.f90:846-861 writing an N x N logical matrix.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "wol_device.cuh"
 #include "wol_internal.h"
 #include "wol_workspace.h"
@@ -167,6 +171,107 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
             }
         }
     }
+}
+
+// ---- open (non-periodic) axes --------------------------------------------------------------------------------------
+// The reference marks an axis as not periodic with a negative box edge (fortran/waterlib.f90:41: iBoxL = 0 there, so
+// distvec - BoxL * anint(distvec * iBoxL) leaves the component untouched).  The cell-list kernels want a positive
+// period on every axis, so an open axis gets an EQUIVALENT period L' = 2 (extent + reach) + 1: every difference
+// between two atoms is below L' / 2, so anint(d / L') = 0 and d - L' * 0 = d bit for bit, and no periodic image comes
+// closer than extent + 2 reach + 1 > reach.  extent = max - min of the coordinate over the frame's atoms (and centres).
+
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);  // monotone in v
+}
+static double key_to_double(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+    memcpy(&v, &b, sizeof v);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) extent_kernel(const T *__restrict__ pos, int n_pos, unsigned long long *__restrict__ keys) {
+    const int f = blockIdx.y;
+    const T *p = pos + (size_t)f * n_pos * 3;
+    double lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = Ops<double>::inf();
+        hi[k] = -Ops<double>::inf();
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pos; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double v = (double)p[(size_t)i * 3 + k];
+            lo[k] = fmin(lo[k], v);
+            hi[k] = fmax(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(keys + (size_t)f * 6 + k, ordered_key(lo[k]));
+            atomicMax(keys + (size_t)f * 6 + 3 + k, ordered_key(hi[k]));
+        }
+    }
+}
+
+static void launch_extent(const void *pos, int dtype, int n_frames, int n_pos, unsigned long long *keys, cudaStream_t stream) {
+    if (n_pos < 1) return;
+    int bx = (n_pos + 255) / 256;
+    if (bx > 4 * sm_count()) bx = 4 * sm_count();
+    const dim3 grid((unsigned)bx, (unsigned)n_frames);
+    if (dtype == WOL_F64) extent_kernel<double><<<grid, 256, 0, stream>>>(reinterpret_cast<const double *>(pos), n_pos, keys);
+    else extent_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float *>(pos), n_pos, keys);
+    add_launches(1);
+}
+
+int effective_box(const void *pos, int pos_dtype, int n_frames, int n_pos, const void *centres, int centre_dtype, int n_centres,
+                  const double *box_host, double reach, void *scratch_dev, double *box_out_host, cudaStream_t stream) {
+    bool open = false;
+    for (size_t i = 0; i < (size_t)n_frames * 3; ++i) {
+        const double L = box_host[i];
+        if (!(L == L) || L == 0.0 || isinf(L)) return set_error(WOL_ERR_INVALID, "box edge %zu is %g", i, L);
+        box_out_host[i] = L;
+        open |= L < 0.0;
+    }
+    if (!open) return WOL_OK;
+    if (!scratch_dev) return set_error(WOL_ERR_INVALID, "wol_effective_box: open axes need %d bytes of device scratch", n_frames * 48);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(scratch_dev);
+    // min slots start at the largest key, max slots at the smallest: two strided memsets
+    cudaError_t e = cudaMemset2DAsync(keys, 48, 0xff, 24, (size_t)n_frames, stream);
+    if (e == cudaSuccess) e = cudaMemset2DAsync(keys + 3, 48, 0x00, 24, (size_t)n_frames, stream);
+    if (e != cudaSuccess) return set_cuda_error("wol_effective_box: memset", e);
+    launch_extent(pos, pos_dtype, n_frames, n_pos, keys, stream);
+    if (centres && n_centres > 0) launch_extent(centres, centre_dtype, n_frames, n_centres, keys, stream);
+    unsigned long long *host = (unsigned long long *)malloc((size_t)n_frames * 48);
+    if (!host) return set_error(WOL_ERR_INVALID, "wol_effective_box: out of host memory");
+    e = cudaMemcpyAsync(host, keys, (size_t)n_frames * 48, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        free(host);
+        return set_cuda_error("wol_effective_box: extent", e);
+    }
+    for (int f = 0; f < n_frames; ++f)
+        for (int k = 0; k < 3; ++k) {
+            if (!(box_host[(size_t)f * 3 + k] < 0.0)) continue;
+            const double lo = key_to_double(host[(size_t)f * 6 + k]), hi = key_to_double(host[(size_t)f * 6 + 3 + k]);
+            const double extent = (hi >= lo) ? hi - lo : 0.0;  // no atoms: any period will do
+            if (!(extent == extent) || isinf(extent)) {
+                free(host);
+                return set_error(WOL_ERR_INVALID, "frame %d: coordinates along open axis %d are not finite", f, k);
+            }
+            box_out_host[(size_t)f * 3 + k] = 2.0 * (extent + reach) + 1.0;
+        }
+    free(host);
+    return WOL_OK;
 }
 
 // ---- exclusive scan over n uint32 values, in place ------------------------------------------

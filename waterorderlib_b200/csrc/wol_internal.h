@@ -15,6 +15,9 @@ void add_launches(int n);
 int cell_build_launch(const void *pos, int pos_dtype, const double *box, int n_frames, int n_pos, const int32_t nc[3],
                       int precision, void *workspace, const WorkspaceLayout &lay, cudaStream_t stream);
 
+int effective_box(const void *pos, int pos_dtype, int n_frames, int n_pos, const void *centres, int centre_dtype, int n_centres,
+                  const double *box_host, double reach, void *scratch_dev, double *box_out_host, cudaStream_t stream);
+
 int q3b_launch(const wol_q3b_args &a, const WorkspaceLayout &lay, cudaStream_t stream);
 
 int sm_count();

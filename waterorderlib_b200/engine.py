@@ -78,6 +78,24 @@ def angle_table(hist_lo, hist_hi, nbins, device, tet_lo=100.0, tet_hi=120.0):
     return t
 
 
+def effective_boxes(box_host, pos_d, cen_d, reach, device):
+    """The reference's "negative edge = axis not periodic" (fortran/waterlib.f90:41) for the cell-list paths: every
+    negative edge becomes an equivalent period (wol_effective_box: bit-identical arithmetic, no image within `reach`).
+    Boxes without a negative edge come back unchanged, without touching the device."""
+    if not (box_host < 0.0).any():
+        return box_host
+    F = int(box_host.shape[0])
+    out = np.empty_like(box_host)
+    with torch.cuda.device(device):
+        scratch = torch.empty(F * 6, dtype=torch.int64, device=device)
+        check(lib().wol_effective_box(_ptr(pos_d), _dtype_code(pos_d), F, int(pos_d.shape[1]),
+                                      _ptr(cen_d) if cen_d is not None else None, _dtype_code(cen_d) if cen_d is not None else 0,
+                                      int(cen_d.shape[1]) if cen_d is not None else 0,
+                                      box_host.ctypes.data_as(ctypes.c_void_p), float(reach), _ptr(scratch),
+                                      out.ctypes.data_as(ctypes.c_void_p), _stream_ptr(device)), "wol_effective_box")
+    return out
+
+
 def plan_grid(box_host, r_cell):
     nc = _I3()
     edge = ctypes.c_double(0.0)
@@ -208,9 +226,6 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     pos_d = as_device_positions(pos, device)
     F, N = int(pos_d.shape[0]), int(pos_d.shape[1])
     box_h = as_host_boxes(box, F)
-    # a pageable host->device copy blocks the host behind everything queued on the stream: callers that pipeline
-    # batches upload all boxes once and pass the slice (box_device)
-    box_d = box_device if box_device is not None else torch.from_numpy(box_h.copy()).to(device)
     cen_d = None
     M = N
     if centres is not None:
@@ -221,6 +236,13 @@ def q3b_frames(pos, box, centres=None, *, do_q=True, do_3body=True, low3=0.0, hi
     prec = {"fp64": WOL_PREC_FP64, "fp32": WOL_PREC_FP32}[precision]
     if r_cell is None:
         r_cell = default_r_cell(do_q, do_3body, high3, highq)
+    if (box_h < 0.0).any():  # open axes (the reference's negative edges): equivalent periods, see effective_boxes
+        if box_device is not None:
+            raise ValueError("box_device cannot be combined with non-periodic (negative) box edges")
+        box_h = effective_boxes(box_h, pos_d, cen_d, max(high3 if do_3body else 0.0, highq if do_q else 0.0, r_cell), device)
+    # a pageable host->device copy blocks the host behind everything queued on the stream: callers that pipeline
+    # batches upload all boxes once and pass the slice (box_device)
+    box_d = box_device if box_device is not None else torch.from_numpy(box_h.copy()).to(device)
     nc, edge_min, box_max = plan_grid(box_h, r_cell)
     ws = workspace if workspace is not None else Workspace(device)
     need = L.wol_workspace_bytes(F, N, M, ctypes.byref(nc))

@@ -56,11 +56,25 @@ def _stream():
 class CellList:
     """A built cell list over one batch of frames (FP64 records), reusable by several queries."""
 
-    def __init__(self, pos, box, r_cell, device=None, workspace=None, n_centres_max=0):
+    def __init__(self, pos, box, r_cell, device=None, workspace=None, n_centres_max=0, others=None, reach=None):
+        """others: the further position arrays (centres, hydrogens ...) the queries on this list measure distances
+        to; reach: the largest distance any of them uses (default r_cell).  Both only matter for non-periodic
+        (negative) box edges, which become equivalent periods (engine.effective_boxes); box_h / box_d hold those.
+        A routine that has not declared its `others` does not take non-periodic axes."""
         self.device = _device(device, pos)
         self.pos = engine.as_device_positions(pos, self.device)
         self.F, self.N = int(self.pos.shape[0]), int(self.pos.shape[1])
         self.box_h = engine.as_host_boxes(box, self.F)
+        if (self.box_h < 0.0).any():
+            if others is None:
+                raise ValueError("non-periodic (negative) box edges are taken by the q / three-body, neighbour-list, "
+                                 "hydrogen-bond and shell-selection routines only")
+            extra = [engine.as_device_positions(o, self.device) for o in others if o is not None]
+            extra = [o for o in extra if o.shape[1] > 0]
+            cen = None
+            if extra:
+                cen = torch.cat([o.to(torch.float64) for o in extra], dim=1).contiguous()
+            self.box_h = engine.effective_boxes(self.box_h, self.pos, cen, float(reach if reach is not None else r_cell), self.device)
         self.box_d = torch.from_numpy(self.box_h.copy()).to(self.device)
         self.nc, self.edge_min, self.box_max = engine.plan_grid(self.box_h, r_cell)
         self.n_centres_max = max(int(n_centres_max), self.N)
@@ -103,14 +117,15 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
         return (torch.zeros(0, dtype=torch.float64, device=device), torch.zeros((F, M), dtype=torch.int32, device=device),
                 torch.zeros(F * M + 1, dtype=torch.int64, device=device))
     ws = engine.Workspace(device)
-    r = engine.q3b_frames(pos_d, box, cen_d, do_q=False, do_3body=True, low3=low, high3=high, want=("n3",),
+    # (non-periodic axes become equivalent periods here, once, so that both passes see the same grid)
+    box_h = engine.effective_boxes(engine.as_host_boxes(box, F), pos_d, None if sub is None else cen_d, max(float(high), 1e-3), device)
+    r = engine.q3b_frames(pos_d, box_h, cen_d, do_q=False, do_3body=True, low3=low, high3=high, want=("n3",),
                           workspace=ws, device=device, r_cell=max(float(high), 1e-3))
     n3 = r["n3"]
     L = lib()
     total = F * M
     offsets = torch.empty(total + 1, dtype=torch.int32, device=device)
     scratch = torch.empty(total // 2048 + 8, dtype=torch.int32, device=device)
-    box_h = engine.as_host_boxes(box, F)
     box_d = torch.from_numpy(box_h.copy()).to(device)
     nc, edge_min, _ = engine.plan_grid(box_h, max(float(high), 1e-3))
     ws_ptr, ws_bytes = ws.get(L.wol_workspace_bytes(F, N, M, ctypes.byref(nc)))
@@ -134,7 +149,7 @@ def neighbors_csr(sub, pos, box, low=0.0, high=3.413, device=None):
     of centre i of frame f are indices[offsets[f*M+i]:offsets[f*M+i+1]], frame-local atom indices, ascending."""
     device = _device(device, pos, sub)
     cells = CellList(pos, box, max(float(high), 1e-3), device=device,
-                     n_centres_max=0 if sub is None else int(np.shape(sub)[-2]))
+                     n_centres_max=0 if sub is None else int(np.shape(sub)[-2]), others=(sub,))
     cen_d = cells.pos if sub is None else engine.as_device_positions(sub, device)
     if cen_d.shape[0] != cells.F:
         raise ValueError("sub and pos must hold the same number of frames")
@@ -258,7 +273,7 @@ def hbond_counts(acc, don, donh, box, dist_cut=3.5, ang_cut=150.0, dense=False, 
             res["pairs"] = torch.zeros((0, 2), dtype=torch.int32, device=device)
         return res
     if cells is None:
-        cells = CellList(don_d, box, max(float(dist_cut), 1e-3), device=device)
+        cells = CellList(don_d, box, max(float(dist_cut), 1e-3), device=device, others=(acc_d, donh_d))
     a = HbondArgs()
     a.struct_size = ctypes.sizeof(HbondArgs)
     a.n_frames, a.n_acc, a.n_don = F, Na, Nd
@@ -307,7 +322,7 @@ def shell_mask(sol, wat, box, cutoff=4.0, low=0.0, device=None, cells=None):
     if Ns == 0 or Nw == 0:
         return mask
     if cells is None:
-        cells = CellList(wat_d, box, max(float(cutoff), 1e-3), device=device)
+        cells = CellList(wat_d, box, max(float(cutoff), 1e-3), device=device, others=(sol_d,))
     with torch.cuda.device(device):
         check(lib().wol_shell_mask(_vp(sol_d.data_ptr()), engine._dtype_code(sol_d), Ns, _vp(cells.box_d.data_ptr()), F, Nw,
                                    ctypes.byref(cells.nc), cells.edge_min, float(low), float(cutoff), _vp(cells.ws_ptr),

@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     const int jend = row[3];
                     row += (r9 == 2 || r9 == 5) ? (rstride - 2) * kBkCsW : kBkCsW;
                     float4 w = loc[j];
+                    // (left to itself the compiler unrolls by four with a remainder loop; the lanes of a warp have different
+                    // trip counts, so every step of unrolling is lanes idling: by two measured best, -3.5 %)
+#pragma unroll 2
                     while (j < jend) {
                         const float4 wn = loc[j + 1];  // a stage holds one spare entry
                         const float dx = w.x - me.x, dy = w.y - me.y, dz = w.z - me.z;
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
             int nk = 0;
             if (valid && !overflow) {
                 float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
+#pragma unroll 2
                 for (int k = 0; k < nl; ++k) {
                     const unsigned e = my_list[k * kBkConsumers];
                     const float r2 = __uint_as_float(e & ~kBkSlotMask);
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) q3b_brick_kernel(const __grid_c
                     }
                 }
                 const float thr_q = doq ? a3 + pre_cst1 : -1.f, thr_keep = fmaxf(pre_thr3, thr_q);
+#pragma unroll 2
                 for (int k = 0; k < nl; ++k) {
                     const unsigned e = my_list[k * kBkConsumers];
                     const int j = (int)(e & kBkSlotMask);

@@ -171,6 +171,9 @@ __device__ void ws_sweep(const Q3bParams &P, const BrickPlan &B, WsSmem &S, int 
                     const int jend = row[3];
                     row += (r9 == 2 || r9 == 5) ? (rstride - 2) * kBkCsW : kBkCsW;
                     float4 w = loc[j];
+                    // (left to itself the compiler unrolls by four with a remainder loop; the lanes of a warp have different
+                    // trip counts, so every step of unrolling is lanes idling: by two measured best, -3.5 %)
+#pragma unroll 2
                     while (j < jend) {
                         const float4 wn = loc[j + 1];  // a stage holds one spare entry
                         const float dx = w.x - me.x, dy = w.y - me.y, dz = w.z - me.z;
@@ -190,6 +193,7 @@ __device__ void ws_sweep(const Q3bParams &P, const BrickPlan &B, WsSmem &S, int 
             int nk = 0;
             if (valid && !overflow) {
                 float a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf;
+#pragma unroll 2
                 for (int k = 0; k < nl; ++k) {
                     const unsigned e = my_list[k * 32];
                     const float r2 = __uint_as_float(e & ~kBkSlotMask);
@@ -202,6 +206,7 @@ __device__ void ws_sweep(const Q3bParams &P, const BrickPlan &B, WsSmem &S, int 
                     }
                 }
                 const float thr_q = doq ? a3 + pre_cst1 : -1.f, thr_keep = fmaxf(pre_thr3, thr_q);
+#pragma unroll 2
                 for (int k = 0; k < nl; ++k) {
                     const unsigned e = my_list[k * 32];
                     const int j = (int)(e & kBkSlotMask);

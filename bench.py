@@ -219,7 +219,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=N_CELLS_1M, help="diamond-cubic cells per edge (50 -> 1M waters)")
     ap.add_argument("--frames-per-step", type=int, default=16, help="frames per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=2, help="frames per pipeline batch of the end-to-end legs")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="frames per pipeline batch of the end-to-end legs (0: 1 for the per-water legs, 2 for the driver leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cells", type=int, default=8, help="reference sample box: 8 -> 4096 waters")
     args = ap.parse_args()
@@ -400,9 +400,10 @@ def main():
     del out32, ws32
 
     # ---- end-to-end legs (host buffers in, host results out; copies inside the timed region) ----------------------
-    eb = max(1, min(B, args.e2e_batch))
-
     def e2e_leg(dtype, per_water):
+        # the per-water legs are bound by the host link, where a one-frame first batch starts the kernels soonest; the
+        # driver leg is bound by the kernels, which like two frames per batch better (scripts/e2e_batch_sweep.py)
+        eb = max(1, min(B, args.e2e_batch if args.e2e_batch > 0 else (1 if per_water else 2)))
         pipe = FramePipeline(n_waters, eb, dtype=dtype, device=dev, want_q=per_water, want_n3=per_water)
         src = pos_h if dtype == np.float64 else pos_h32
         qh = torch.empty((B, n_waters), dtype=torch.float64, pin_memory=True) if per_water else None

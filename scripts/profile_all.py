@@ -11,8 +11,10 @@ from waterorderlib_b200 import engine, routines, synth
 
 dev = torch.device("cuda", 0)
 pos, box = synth.device_frames(50, 0, 2, sigma=0.25, device=dev)
+import os
+REPS = int(os.environ.get("WOL_PROFILE_REPS", "2"))  # 1 under ncu --set full (the report must stay below 64 MB)
 for prec in ("fp64", "fp32"):
-    for _ in range(2):
+    for _ in range(REPS):
         r = engine.q3b_frames(pos, box, precision=prec)
     torch.cuda.synchronize()
     print(prec, "angles", int(r["ang_hist"].sum()), "widened", r["n_widened"], "overflow", r["n_overflow"], flush=True)
@@ -21,7 +23,7 @@ o = pos[0].cpu().numpy()
 h = synth.add_hydrogens(o, seed=3)
 o_d, h_d = pos[:1], torch.from_numpy(h[None]).to(dev)
 d_d = o_d.repeat_interleave(2, dim=1).contiguous()
-for _ in range(2):
+for _ in range(REPS):
     hb = routines.hbond_counts(o_d, d_d, h_d, box, 3.5, 120.0)
 torch.cuda.synchronize()
 print("hbonds per water", float(hb["acc_count"].sum()) / o.shape[0], flush=True)
@@ -31,7 +33,7 @@ sp, sbox, z_lo, z_hi = synth.slab_box(32, 32, 8, sigma=0.3, seed=11)
 gp, gn = synth.plane_interface(sbox, z_lo, z_hi, spacing=2.0)
 sp_d, gp_d, gn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(gp).to(dev), torch.from_numpy(gn).to(dev)
 grid = [(np.arange(80) + 0.5) * (sbox[d] / 80) for d in range(3)]
-for _ in range(2):
+for _ in range(REPS):
     dens, _ = routines.willard_density(sp_d, sbox, 2.4, grid=grid, want_normals=True)
     iw = routines.interface_water(sp_d, gp_d, gn_d, 0.0, sbox)
 torch.cuda.synchronize()

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     const size_t ncell = (size_t)p.nc0 * p.nc1 * p.nc2;
     uint32_t *const frame_counters = p.cell_start + (size_t)f * ncell + 1;
     const double iL0 = s_iL[0], iL1 = s_iL[1], iL2 = s_iL[2];
-    T x[kBuildPerThread], y[kBuildPerThread], z[kBuildPerThread];
+    // (the positions stay in shared memory and are read again after the atomics have returned: holding four atoms'
+    // coordinates in registers across that wait costs the scatter pass half of its resident warps)
     int cellpack[kBuildPerThread];
     uint32_t dst[kBuildPerThread];
 #pragma unroll
@@ -104,14 +105,12 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
         const int t = threadIdx.x + k * kBuildThreads;
         cellpack[k] = -1;
         if (t < n_here) {
-            x[k] = s_pos[3 * t + 0];
-            y[k] = s_pos[3 * t + 1];
-            z[k] = s_pos[3 * t + 2];
-            double xd = (double)x[k], yd = (double)y[k], zd = (double)z[k];
+            const T x = s_pos[3 * t + 0], y = s_pos[3 * t + 1], z = s_pos[3 * t + 2];
+            double xd = (double)x, yd = (double)y, zd = (double)z;
             if (sizeof(R) == sizeof(RecF)) {  // FP32 records: bin the value the sweep will see
-                xd = (double)(float)x[k];
-                yd = (double)(float)y[k];
-                zd = (double)(float)z[k];
+                xd = (double)(float)x;
+                yd = (double)(float)y;
+                zd = (double)(float)z;
             }
             const int cx = cell_coord(xd, iL0, p.nc0);
             const int cy = cell_coord(yd, iL1, p.nc1);
@@ -127,11 +126,12 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
     for (int k = 0; k < kBuildPerThread; ++k) {
         if (cellpack[k] < 0) continue;
         const int t = threadIdx.x + k * kBuildThreads;
+        const T x = s_pos[3 * t + 0], y = s_pos[3 * t + 1], z = s_pos[3 * t + 2];
         if (sizeof(R) == sizeof(RecD)) {
             RecD r;
-            r.x = (double)x[k];
-            r.y = (double)y[k];
-            r.z = (double)z[k];
+            r.x = (double)x;
+            r.y = (double)y;
+            r.z = (double)z;
             r.idx = a0 + t;
             r.cell = cellpack[k];
             // one 256-bit store (STG.256) per record: the 32-byte record is exactly one sector of L2, and the scatter
@@ -146,17 +146,17 @@ __global__ void __launch_bounds__(kBuildThreads) cell_pass_kernel(BuildParams p)
             if (p.wrapped) {
                 // box-wrapped coordinates for the float prefilter of the sweep: frac(x / L) * L
                 float4 w;
-                w.x = wrapped_coord((double)x[k], s_L[0], iL0);
-                w.y = wrapped_coord((double)y[k], s_L[1], iL1);
-                w.z = wrapped_coord((double)z[k], s_L[2], iL2);
+                w.x = wrapped_coord((double)x, s_L[0], iL0);
+                w.y = wrapped_coord((double)y, s_L[1], iL1);
+                w.z = wrapped_coord((double)z, s_L[2], iL2);
                 w.w = __int_as_float((int)dst[k]);  // fp64 records: the atom's place in the cell-sorted arrays (brick sweep)
                 p.wrapped[dst[k]] = w;
             }
         } else {
             RecF r;
-            r.x = (float)x[k];
-            r.y = (float)y[k];
-            r.z = (float)z[k];
+            r.x = (float)x;
+            r.y = (float)y;
+            r.z = (float)z;
             r.idx = a0 + t;
             *reinterpret_cast<int4 *>(reinterpret_cast<RecF *>(p.recs) + dst[k]) = *reinterpret_cast<const int4 *>(&r);
             if (p.wrapped) {

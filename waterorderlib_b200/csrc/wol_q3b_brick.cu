@@ -48,6 +48,7 @@ static_assert(kBkAtomCap <= 2048, "slot must fit 11 bits");
 
 struct BkSmem {
     static constexpr int kAtomCap = kBkAtomCap;
+    static constexpr int kProducerRegs = 124;      // registers the producer warp may use
     float4 loc[kBkStages][kBkAtomCap];
     double ent[kBkEntCap][3][kBkConsumers];
     unsigned char ent_k[kBkEntCap][kBkConsumers];  // which kept survivor the entry is (its list entry says where the record is)

@@ -218,7 +218,7 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, SM &S, int l
         // ---- measure the sub-brick [xa, xa + w): atoms per row, centres per row ------------------------------------
         int n0 = 0, n1 = 0, c0 = 0, c1 = 0;
         __syncwarp();
-#pragma unroll 1
+#pragma unroll (SM::kProducerRegs >= 96 ? 2 : 1)  // both rows' loads in flight where the producer has the registers
         for (int h = 0; h < 2; ++h) {
             const int rr = lane + 32 * h;
             if (rr < nrows) {
@@ -297,18 +297,19 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, SM &S, int l
         }
         __syncwarp();
         // ---- while the copies fly: stage slot of every cell start.  Entry i of a row <-> cell xa - 1 + i, entry
-        // w + 2 = end of the row.  Lane <-> cell, one coalesced load per row, twelve rows in flight; the entries of
+        // w + 2 = end of the row.  Lane <-> cell, one coalesced load per row, 12 or 18 rows in flight; the entries of
         // the image cells and the row ends are patched afterwards by the lane that measured the row.
         {
             const int gx = min(max(xa - 1 + lane, 0), nc0 - 1);
             const bool act = lane <= w + 1;
-            for (int r0 = 0; r0 < nrows; r0 += 12) {
-                int v[12];
+            constexpr int kBatch = SM::kProducerRegs >= 96 ? 18 : 12;  // rows in flight
+            for (int r0 = 0; r0 < nrows; r0 += kBatch) {
+                int v[kBatch];
 #pragma unroll
-                for (int u = 0; u < 12; ++u)
+                for (int u = 0; u < kBatch; ++u)
                     if (r0 + u < nrows && act) v[u] = (int)__ldg(P.cell_start + prow[r0 + u].base + gx);
 #pragma unroll
-                for (int u = 0; u < 12; ++u)
+                for (int u = 0; u < kBatch; ++u)
                     if (r0 + u < nrows && act) cst[(r0 + u) * kBkCsW + lane] = (unsigned short)(v[u] + prow[r0 + u].delta);
             }
             __syncwarp();

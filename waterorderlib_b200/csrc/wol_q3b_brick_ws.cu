@@ -60,6 +60,7 @@ struct alignas(16) WsExact {           // private to one exact warp
 
 struct WsSmem {
     static constexpr int kAtomCap = kWsAtomCap;
+    static constexpr int kProducerRegs = kWsRegsS;      // registers the producer warp may use
     float4 loc[kBkStages][kWsAtomCap];
     WsSlot ring[kWsRing];
     WsExact ex[kWsEWarps];

@@ -309,10 +309,29 @@ def test_open_axes_neighbour_lists_hbonds_and_shell():
     assert np.array_equal(m.astype(bool), port.shell_mask(sol, pos, b, 4.0).astype(bool))
 
 
+def test_open_axes_lsi_psi_rdf_histrr3b():
+    pos, box = _slab(seed=9)
+    b = np.array([box[0], box[1], -1.0])
+    rng = np.random.default_rng(4)
+    sub = pos[rng.choice(pos.shape[0], 60, replace=False)]
+    for c in (pos, sub):
+        vals, num = wp.getLSI(c, pos, b)
+        ref_vals, ref_num = port.getLSI(c, pos, b)
+        assert np.array_equal(num, ref_num) and np.allclose(vals, ref_vals, rtol=1e-10, atol=1e-12)
+    psi = wp.getOrderParamPsi(sub, pos, b, 0.0, 7.0)
+    assert np.allclose(psi, port.getOrderParamPsi(sub, pos, b, 0.0, 7.0), rtol=1e-9, atol=1e-12, equal_nan=True)
+    g = routines.pair_hist(1, pos, None, b, 0.1, 80).cpu().numpy()
+    assert np.array_equal(g, port._pair_hist(1, pos, pos, b, 0.1, 80))
+    g2 = routines.pair_hist(0, sub, pos, b, 0.1, 80).cpu().numpy()
+    assert np.array_equal(g2, port._pair_hist(0, sub, pos, b, 0.1, 80))
+    h = routines.histrr3b(pos[:300], b, 0.25, 16, 5.0, 36).cpu().numpy()
+    assert np.array_equal(h, port.histrr3b(pos[:300], b, 0.25, 16, 5.0, 36))
+
+
 def test_open_axes_limits_are_reported():
     pos, box = _slab()
     b = np.array([box[0], box[1], -1.0])
     with pytest.raises(ValueError):
-        routines.lsi(None, pos, b)          # not one of the routines that take non-periodic axes
+        routines.willard_density(pos, b, 2.4, points=pos[:10])   # needs a periodic (or explicitly bounded) grid
     with pytest.raises((ValueError, WolError)):
         engine.q3b_frames(pos, np.array([box[0], 0.0, box[2]]))  # an empty axis is an error, not "open"

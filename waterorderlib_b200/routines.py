@@ -67,8 +67,8 @@ class CellList:
         self.box_h = engine.as_host_boxes(box, self.F)
         if (self.box_h < 0.0).any():
             if others is None:
-                raise ValueError("non-periodic (negative) box edges are taken by the q / three-body, neighbour-list, "
-                                 "hydrogen-bond and shell-selection routines only")
+                raise ValueError("non-periodic (negative) box edges are not taken by this routine (Willard-Chandler "
+                                 "density and binOnGrid need a periodic or explicitly bounded grid)")
             extra = [engine.as_device_positions(o, self.device) for o in others if o is not None]
             extra = [o for o in extra if o.shape[1] > 0]
             cen = None
@@ -133,6 +133,11 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
         check(L.wol_angle_offsets(_vp(n3.data_ptr()), total, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()), _stream()),
               "wol_angle_offsets")
         n_angles = _total_from_offsets(offsets, "three-body angles")
+        n3_max = int(n3.max().item()) if n3.numel() else 0
+        if n3_max > 64:  # kMatCap of angles_fill_kernel (csrc/wol_aux.cu)
+            raise WolError("getCosAngs materialises at most 64 neighbours per centre; a centre has %d inside the cutoff "
+                           "(%g A).  The histogram path (tetOrderCalc / threeBodyCalc / q3b_frames) has no such limit."
+                           % (n3_max, float(high)))
         angles = torch.empty(n_angles, dtype=torch.float64, device=device)
         if n_angles > 0:
             check(L.wol_angles_fill(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(box_d.data_ptr()), F, N, M,
@@ -517,7 +522,7 @@ def histrr3b(pos, box, dist_width, d_num, ang_width, a_num, device=None):
         check(lib().wol_angle_table_ceil(float(ang_width), int(a_num), host.ctypes.data_as(_vp)), "wol_angle_table_ceil")
         table = torch.from_numpy(host).to(device)
         _CEIL_TABLES[key] = table
-    cells = CellList(pos, box, float(dist_width) * int(d_num) * (1.0 + 1e-9), device=device)
+    cells = CellList(pos, box, float(dist_width) * int(d_num) * (1.0 + 1e-9), device=device, others=())
     if cells.F != 1:
         raise ValueError("histrr3b takes one frame")
     hist = torch.zeros((d_num, d_num, a_num), dtype=torch.int64, device=device)
@@ -542,7 +547,8 @@ def lsi(sub, pos, box, low=0.0, high=3.7, device=None):
     num = torch.zeros((F, M), dtype=torch.int32, device=device)
     if M == 0 or N == 0:
         return out, num
-    cells = CellList(pos_d, box, (float(high) + 3.7) * (1.0 + 1e-9), device=device, n_centres_max=M)
+    cells = CellList(pos_d, box, (float(high) + 3.7) * (1.0 + 1e-9), device=device, n_centres_max=M,
+                     others=() if sub is None else (cen_d,))
     with torch.cuda.device(device):
         check(lib().wol_lsi(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
                             ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr), cells.ws_bytes,
@@ -567,7 +573,7 @@ def pair_hist(mode, pos1, pos2, box, binwidth, totbins, device=None):
     counts = torch.zeros(int(totbins), dtype=torch.int64, device=device)
     if outer.shape[0] == 0 or inner.shape[0] == 0:
         return counts
-    cells = CellList(inner, box, float(binwidth) * int(totbins) * (1.0 + 1e-9), device=device)
+    cells = CellList(inner, box, float(binwidth) * int(totbins) * (1.0 + 1e-9), device=device, others=(outer,))
     with torch.cuda.device(device):
         check(lib().wol_pair_hist(int(mode), _vp(outer.data_ptr()), WOL_F64, int(outer.shape[0]), _vp(cells.box_d.data_ptr()), cells.N,
                                   ctypes.byref(cells.nc), cells.edge_min, float(binwidth), int(totbins), _vp(cells.ws_ptr),
@@ -630,7 +636,8 @@ def psi(sub, pos, box, low=0.0, high=10.0, device=None):
     out = torch.zeros((F, M), dtype=torch.float64, device=device)
     if M == 0 or N == 0:
         return out
-    cells = CellList(pos_d, box, max(float(high), 1e-3) * (1.0 + 1e-9), device=device, n_centres_max=M)
+    cells = CellList(pos_d, box, max(float(high), 1e-3) * (1.0 + 1e-9), device=device, n_centres_max=M,
+                     others=() if sub is None else (cen_d,))
     with torch.cuda.device(device):
         check(lib().wol_psi(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
                             ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr), cells.ws_bytes,

@@ -77,7 +77,8 @@ def getOrderParamq(subPos, Pos, BoxDims, lowCut=0.0, highCut=10.0):
 def getCosAngs(subPos, Pos, BoxDims, lowCut=0.0, highCut=3.413):
     """All three-body angles (degrees, despite the name) about each position of subPos among its neighbours in
     Pos within (lowCut, highCut], in the reference's order, and the neighbour count per centre as float64
-    (reference water_properties.py:210-250)."""
+    (reference water_properties.py:210-250).  Limit: at most 64 neighbours per centre inside the cutoff (about 7.5 A in
+    liquid water) -- beyond that WolError names the count; the fused histogram path has no such limit."""
     tor = _is_torch(subPos, Pos)
     subPos = subPos if tor else np.asarray(subPos)
     Pos = Pos if tor else np.asarray(Pos)

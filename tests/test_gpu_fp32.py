@@ -69,3 +69,24 @@ def test_fp32_mode_small_box_generic_path():
     torch.cuda.synchronize()
     assert r.nc[0] < 4
     compare(r, 0, pos, box, highq=5.5)
+
+
+def test_fp32_brick_kernel_agrees_with_the_thread_per_centre_kernel(monkeypatch):
+    """The two fp32 kernels of K2f on the same frames (WOL_BRICK=0: thread per centre, 1: brick): both are float
+    arithmetic on the same wrapped coordinates and may differ only in last-ulp distances (the periodic shift is applied
+    to the other operand); each stays inside the mode's bar against the fp64 oracle."""
+    pos, box = synth.trajectory(12, 3, sigma=0.45, seed0=41)  # 3 x 13 824 waters
+    pos32 = pos.astype(np.float32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("WOL_BRICK", mode)
+        out[mode] = engine.q3b_frames(pos32, box, precision="fp32", hist_per_frame=True)
+        torch.cuda.synchronize()
+    a, b = out["0"], out["1"]
+    same = (a.nn_idx == b.nn_idx).all(dim=-1)
+    assert float(same.float().mean()) > 0.9995
+    assert float((a.q - b.q).abs()[same].max()) < Q_ATOL
+    assert float((a.n3 == b.n3).float().mean()) > 0.9995
+    assert float((a.ang_hist - b.ang_hist).abs().sum()) <= 1e-3 * float(a.ang_hist.sum())
+    for f in range(3):
+        compare(b, f, pos32[f].astype(np.float64), box[f])

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwol.so")
 STAMP = LIB + ".srchash"  # hash of the sources and flags the library was built from
-SOURCES = ["wol_capi.cu", "wol_cells.cu", "wol_q3b.cu", "wol_q3b_tpc.cu", "wol_q3b_brick.cu", "wol_q3b_brick_ws.cu", "wol_q3b_tpc32.cu", "wol_aux.cu", "wol_slab.cu", "wol_pairs.cu"]
+SOURCES = ["wol_capi.cu", "wol_cells.cu", "wol_q3b.cu", "wol_q3b_tpc.cu", "wol_q3b_brick.cu", "wol_q3b_brick_ws.cu", "wol_q3b_brick32.cu", "wol_q3b_tpc32.cu", "wol_aux.cu", "wol_slab.cu", "wol_pairs.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "--threads", "4", "-ldl"]
 

@@ -639,7 +639,9 @@ static int launch_typed(const Q3bParams &P, cudaStream_t stream, bool use_tpc, d
         int rc = q3b_brick_ws_supported(P, false) ? q3b_brick_ws_launch(P, brick_box_max, stream) : q3b_brick_launch(P, brick_box_max, stream);
         if (rc != WOL_OK) return rc;
     } else if (use_tpc) {
-        int rc = (sizeof(T) == 8) ? q3b_tpc_launch(P, stream, EXACT) : q3b_tpc32_launch(P, stream);
+        // fp32 mode: the brick kernel for large batches where every atom is a centre, else thread per centre
+        int rc = (sizeof(T) == 8) ? q3b_tpc_launch(P, stream, EXACT)
+                                  : (!EXACT && q3b_brick32_supported(P) ? q3b_brick32_launch(P, stream) : q3b_tpc32_launch(P, stream));
         if (rc != WOL_OK) return rc;
     } else {
         const int tab_len = P.do_3b ? P.nbins + 1 + WOL_TABLE_EXTRA : 0;

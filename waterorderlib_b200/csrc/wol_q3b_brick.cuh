@@ -39,6 +39,7 @@ struct BkItem {
     int nbx, nby, n_crows, next;             // next: chunk counter
     double L[3], iL[3];
     int crow_off[kBkCRowCap + 1];            // centres before centre row r
+    int crow_g0[kBkCRowCap];                 // place in the cell-sorted arrays of the first centre of row r
     unsigned short crow_slot[kBkCRowCap];    // stage slot of the first centre of row r
     unsigned short crow_hrow[kBkCRowCap];    // its row among brick + halo rows
 };
@@ -291,7 +292,9 @@ __device__ void bk_producer(const Q3bParams &P, const BrickPlan &B, SM &S, int l
             if (hy >= 1 && hy <= nby && hz >= 1 && hz <= nbz) {
                 const int r = (hz - 1) * nby + (hy - 1);
                 I.crow_off[r] = h ? coff1 : coff0;
-                I.crow_slot[r] = (unsigned short)(off + cA + (int)__ldg(P.cell_start + R.base + xa) - gM);
+                const int g0 = (int)__ldg(P.cell_start + R.base + xa);
+                I.crow_g0[r] = g0;
+                I.crow_slot[r] = (unsigned short)(off + cA + g0 - gM);
                 I.crow_hrow[r] = (unsigned short)rr;
             }
         }

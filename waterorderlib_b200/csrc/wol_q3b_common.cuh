@@ -311,6 +311,8 @@ bool q3b_tpc_supported(const Q3bParams &P);
 bool q3b_brick_supported(const Q3bParams &P, bool exact);
 int q3b_brick_launch(const Q3bParams &P, double box_max, cudaStream_t stream);
 bool q3b_brick_ws_supported(const Q3bParams &P, bool exact);
+bool q3b_brick32_supported(const Q3bParams &P);
+int q3b_brick32_launch(const Q3bParams &P, cudaStream_t stream);
 int q3b_brick_ws_launch(const Q3bParams &P, double box_max, cudaStream_t stream);
 
 }  // namespace wol

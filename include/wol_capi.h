@@ -19,6 +19,15 @@
  *   - return value: WOL_OK or a negative WOL_ERR_* code; wol_last_error() describes the failure.
  *     Nothing aborts the process (the reference's Fortran `stop`s do, waterlib.f90:1171-1174).
  *   - indices are 0-based int32; "no neighbour" is -1.
+ *   - the library never synchronises the host except in wol_status and wol_effective_box (open axes only).
+ *
+ * Limits (reported, never silent)
+ *   - n_frames * max(n_pos, n_centres) < 2^30 per call (WOL_ERR_RANGE): batch longer trajectories.
+ *   - at most 1024 cells per axis (wol_plan_grid coarsens the grid beyond that).
+ *   - more than 1024 neighbours of one centre inside a cutoff: WOL_ERR_CAPACITY from wol_status.
+ *   - wol_angles_fill materialises at most 64 neighbours per centre (the histogram path has no such limit).
+ *   - materialising calls address at most 2^32 - 2 angles / pairs (WOL_ERR_RANGE; offsets[last] = 0xFFFFFFFF).
+ *   - box edges must be finite and non-zero; negative (= non-periodic) edges go through wol_effective_box first.
  */
 #ifndef WOL_CAPI_H
 #define WOL_CAPI_H

@@ -26,6 +26,8 @@ drivers push BATCHES of frames through the fused cell-list kernels of libwol.so 
 per-frame sums on the device; under ``torch.distributed`` (one process per GPU) frames are sharded across
 ranks and combined with one all-reduce + one all-gather (waterorderlib_b200.distributed).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -135,6 +137,27 @@ def _frame_arrays(traj, begin, end):
     return np.stack(xyz), np.stack(box)
 
 
+_COPY_POOL = None
+_COPY_THREADS = max(1, int(os.environ.get("WOL_STAGE_THREADS", "4")))
+
+
+def _host_copy(dst, src):
+    """dst[:] = src for 1-D uint8 numpy arrays, large copies split over a few threads (numpy releases the GIL for a
+    contiguous copy; one core moves ~10 GB/s, which would be the slowest stage of the frame drivers)."""
+    global _COPY_POOL
+    n = src.size
+    if n < (8 << 20):
+        np.copyto(dst, src)
+        return
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="wol-stage")
+    step = ((n + _COPY_THREADS - 1) // _COPY_THREADS + 4095) // 4096 * 4096
+    jobs = [_COPY_POOL.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
+    for j in jobs:
+        j.result()
+
+
 class _FrameStager:
     """Moves batches of whole frames to the device.  numpy frames live in pageable memory: each batch is copied into one
     of two page-locked buffers (a plain, multi-threaded host memcpy) and sent from there on a side stream, so the host copy
@@ -168,7 +191,7 @@ class _FrameStager:
             if self.bufs[i] is None or self.bufs[i].numel() < raw.size:
                 self.bufs[i] = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
             src = self.bufs[i][:raw.size]
-            src.copy_(torch.from_numpy(raw))
+            _host_copy(src.numpy(), raw)
             self.sent[i] = done
             with torch.cuda.stream(self.stream):
                 up = src.to(self.dev, non_blocking=True)
@@ -231,6 +254,8 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
     # whole frames go to the device as they are and the water oxygens are gathered THERE: a host-side fancy-index
     # gather of 10^6 waters costs 40-90 ms per frame, a hundred times the kernels.  One batch is staged ahead.
     ahead = None
+    last_shape = None
+    box_pin = torch.empty((max(Tl, 1), 3), dtype=torch.float64, pin_memory=True)
     for n, (b0, b1) in enumerate(batches):
         if ahead is None:
             xyz, box = _frame_arrays(traj, b0, b1)
@@ -241,7 +266,15 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
         watPos = xyz_d.index_select(1, wat_d)
         l0, l1 = b0 - begin, b1 - begin
         o = outputs(0, l0, l1)
-        engine.q3b_frames(watPos, box, None, out=o, want=tuple(o.keys()), workspace=ws, **kw)
+        # the boxes go up from page-locked memory: a pageable copy would block the host until the previous batch's kernels
+        # are done, and the staging of the next batch could no longer overlap them
+        box_h = engine.as_host_boxes(box, b1 - b0)
+        bkw = {}
+        if (box_h > 0.0).all():
+            box_pin[l0:l1] = torch.from_numpy(box_h)  # (every batch has its own rows: nothing in flight is overwritten)
+            bkw["box_device"] = box_pin[l0:l1].to(dev, non_blocking=True)
+        engine.q3b_frames(watPos, box_h, None, out=o, want=tuple(o.keys()), workspace=ws, check_status=False, **bkw, **kw)
+        last_shape = (b1 - b0, box_h)
         members[l0:l1, 0] = float(len(watInds))
         # sub-populations: their centres change from frame to frame, so each population is padded to the batch's
         # largest member count and evaluated in ONE call against the cell list population 0 just built
@@ -257,12 +290,17 @@ def _run_populations(obj, subInds, nPops, do_q, do_3body, nBins):
                 pad[k, :len(i)] = i
             cen = torch.gather(xyz_d, 1, torch.from_numpy(pad).to(dev)[:, :, None].expand(-1, -1, 3))
             o = outputs(j, l0, l1)
-            engine.q3b_frames(watPos, box, cen, out=o, want=tuple(o.keys()), workspace=ws, n_valid=counts, reuse_cells=True,
-                              **kw)
+            engine.q3b_frames(watPos, box_h, cen, out=o, want=tuple(o.keys()), workspace=ws, n_valid=counts, reuse_cells=True,
+                              check_status=False, **bkw, **kw)
         ahead = None
         if n + 1 < len(batches):   # the kernels of this batch are queued: stage the next one while they run
             nxt, nbox = _frame_arrays(traj, *batches[n + 1])
             ahead = (stager.put(nxt), nbox)
+    # no batch synchronised the host (that is what lets the staging of batch k+1 overlap the kernels of batch k): the
+    # sticky list-capacity flag of the workspace is read once, here
+    if last_shape is not None:
+        engine.workspace_status(ws, last_shape[0], len(watInds), len(watInds), engine.default_r_cell(do_q, do_3body, 3.413, 10.0),
+                                last_shape[1])
     # ---- combine ranks: one all-reduce of the integer histograms, one all-gather of the per-frame rows ----
     rows = [stats.permute(1, 0, 2).reshape(Tl, P * NS), members]
     if do_3body:

@@ -261,3 +261,14 @@ def test_vectorised_getHBInds_equals_the_per_atom_loop():
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
     assert len(fast[1][1]) == 2 * n_sol and len(fast[0][1]) == n_sol + 2 * n_w
+
+
+def test_threaded_staging_copy_is_a_plain_copy():
+    """The frame drivers' host staging copy (orderParam_lib._host_copy) over several threads = np.copyto."""
+    from waterorderlib_b200.structureLibs import orderParam_lib as opl
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 4097, (8 << 20) - 1, (8 << 20) + 12345, 3 * (8 << 20) + 7):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        dst = np.zeros(n, dtype=np.uint8)
+        opl._host_copy(dst, src)
+        assert np.array_equal(dst, src)

@@ -335,3 +335,22 @@ def test_open_axes_limits_are_reported():
         routines.willard_density(pos, b, 2.4, points=pos[:10])   # needs a periodic (or explicitly bounded) grid
     with pytest.raises((ValueError, WolError)):
         engine.q3b_frames(pos, np.array([box[0], 0.0, box[2]]))  # an empty axis is an error, not "open"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_odd_atom_counts_over_several_frames(dtype):
+    """Frames whose first atom is not 16-byte aligned in the batch (odd atom counts: the cell build's scalar staging path)
+    and tiles that end in the middle of a 1024-atom block."""
+    rng = np.random.default_rng(11)
+    box = np.array([31.0, 29.5, 33.0])
+    n = 1027
+    pos = (rng.random((3, n, 3)) * box).astype(np.float32).astype(np.float64)
+    r = engine.q3b_frames(pos.astype(dtype), box, hist_per_frame=True, highq=8.0)
+    torch.cuda.synchronize()
+    for f in range(3):
+        q, nn4, _ = port.order_param_q(pos[f], pos[f], box, 0.0, 8.0)
+        tb = port.three_body(pos[f], pos[f], box, materialize=False)
+        assert np.array_equal(r.nn_idx.cpu().numpy()[f], nn4)
+        assert np.array_equal(r.n3.cpu().numpy()[f], tb["numAngs"])
+        assert np.array_equal(r.ang_hist.cpu().numpy()[f], tb["hist"])
+        assert np.allclose(r.q.cpu().numpy()[f], q, rtol=1e-6, atol=1e-9)

@@ -354,3 +354,36 @@ def test_odd_atom_counts_over_several_frames(dtype):
         assert np.array_equal(r.n3.cpu().numpy()[f], tb["numAngs"])
         assert np.array_equal(r.ang_hist.cpu().numpy()[f], tb["hist"])
         assert np.allclose(r.q.cpu().numpy()[f], q, rtol=1e-6, atol=1e-9)
+
+
+def test_effective_box_through_the_c_abi():
+    """wol_effective_box called as a C host would: positive edges copied, negative edges replaced by
+    2 (extent + reach) + 1 with the extent taken over atoms AND centres of each frame; bad arguments refused."""
+    import ctypes
+    from waterorderlib_b200._capi import lib
+    L = lib()
+    rng = np.random.default_rng(3)
+    F, N, M = 3, 500, 40
+    pos = rng.normal(0.0, 7.0, (F, N, 3))
+    cen = rng.normal(50.0, 1.0, (F, M, 3))
+    box = np.array([[30.0, -1.0, 25.0], [-2.0, -2.0, -2.0], [30.0, 31.0, 32.0]])
+    out = np.zeros_like(box)
+    pos_d, cen_d = torch.from_numpy(pos).cuda(), torch.from_numpy(cen.astype(np.float32)).cuda()
+    scratch = torch.empty(F * 6, dtype=torch.int64, device="cuda")
+    vp = ctypes.c_void_p
+    rc = L.wol_effective_box(vp(pos_d.data_ptr()), 0, F, N, vp(cen_d.data_ptr()), 1, M, box.ctypes.data_as(vp), 10.0,
+                             vp(scratch.data_ptr()), out.ctypes.data_as(vp), None)
+    assert rc == 0, L.wol_last_error()
+    allp = np.concatenate([pos, cen.astype(np.float32).astype(np.float64)], axis=1)
+    ext = allp.max(axis=1) - allp.min(axis=1)
+    want = np.where(box > 0, box, 2.0 * (ext + 10.0) + 1.0)
+    assert np.array_equal(out, want)
+    # nothing open: no device work, no scratch needed
+    rc = L.wol_effective_box(vp(pos_d.data_ptr()), 0, 1, N, None, 0, 0, box[2:].ctypes.data_as(vp), 10.0, None,
+                             out[2:].ctypes.data_as(vp), None)
+    assert rc == 0 and np.array_equal(out[2], box[2])
+    bad = np.array([[30.0, 0.0, 25.0]])
+    assert L.wol_effective_box(vp(pos_d.data_ptr()), 0, 1, N, None, 0, 0, bad.ctypes.data_as(vp), 10.0, vp(scratch.data_ptr()),
+                               out[:1].ctypes.data_as(vp), None) < 0
+    assert L.wol_effective_box(vp(pos_d.data_ptr()), 0, 1, N, None, 0, 0, box[:1].ctypes.data_as(vp), 10.0, None,
+                               out[:1].ctypes.data_as(vp), None) < 0  # open axis without scratch

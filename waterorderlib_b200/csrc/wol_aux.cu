@@ -25,26 +25,69 @@ struct CellGrid {
 };
 
 // Visits every record of the half-width-1 stencil around cell (cx, cy, cz) of frame f exactly once
-// (axes with <= 3 cells are enumerated completely).
-template <typename F>
-__device__ __forceinline__ void sweep_stencil1(const CellGrid &g, int f, int cx, int cy, int cz, F &&fn) {
-    const int cntx = min(3, g.nc0), cnty = min(3, g.nc1), cntz = min(3, g.nc2);
-    const int xs = (g.nc0 <= 3) ? 0 : (cx - 1 + g.nc0) % g.nc0;
-    const int ys = (g.nc1 <= 3) ? 0 : (cy - 1 + g.nc1) % g.nc1;
-    const int zs = (g.nc2 <= 3) ? 0 : (cz - 1 + g.nc2) % g.nc2;
+// (axes with <= 3 cells are enumerated completely), as RUNS of records: cells are ordered x-fastest, so the
+// (up to) three cells of a stencil row are one contiguous run of the cell-sorted arrays -- two runs where the row wraps
+// around the box.  run(j0, j1, sx, sy, sz) gets the records [j0, j1) and, per axis, the periodic image the run's cells
+// are adjacent through: -1 / 0 / +1 box edges to ADD to a record's box-wrapped coordinate (only meaningful on an axis
+// with more than 3 cells; with fewer the adjacency is ambiguous and the caller must take the minimum image itself).
+// Cells are visited in the same order as a cell-by-cell enumeration starting at (cx - 1, cy - 1, cz - 1).
+template <typename R>
+__device__ __forceinline__ void sweep_stencil1_runs(const CellGrid &g, int f, int cx, int cy, int cz, R &&run) {
+    const int cnty = min(3, g.nc1), cntz = min(3, g.nc2);
+    const int ys = (g.nc1 <= 3) ? 0 : cy - 1, zs = (g.nc2 <= 3) ? 0 : cz - 1;
+    // x: [xa, xb] and, when the row wraps, [xc, xd] after it
+    int xa, xb, xc = 0, xd = -1, sxa = 0, sxc = 0;
+    if (g.nc0 <= 3) {
+        xa = 0;
+        xb = g.nc0 - 1;
+    } else if (cx == 0) {
+        xa = xb = g.nc0 - 1;
+        sxa = -1;
+        xc = 0;
+        xd = 1;
+    } else if (cx == g.nc0 - 1) {
+        xa = cx - 1;
+        xb = cx;
+        xc = xd = 0;
+        sxc = 1;
+    } else {
+        xa = cx - 1;
+        xb = cx + 1;
+    }
     const size_t base = (size_t)f * g.nc0 * g.nc1 * g.nc2;
     for (int iz = 0; iz < cntz; ++iz) {
-        const int z = (zs + iz) % g.nc2;
+        int z = zs + iz, sz = 0;
+        if (z < 0) {
+            z += g.nc2;
+            sz = -1;
+        } else if (z >= g.nc2) {
+            z -= g.nc2;
+            sz = 1;
+        }
         for (int iy = 0; iy < cnty; ++iy) {
-            const int y = (ys + iy) % g.nc1;
-            for (int ix = 0; ix < cntx; ++ix) {
-                const int x = (xs + ix) % g.nc0;
-                const size_t c = base + ((size_t)z * g.nc1 + y) * g.nc0 + x;
-                const int j1 = (int)__ldg(g.cell_start + c + 1);
-                for (int j = (int)__ldg(g.cell_start + c); j < j1; ++j) fn(j);
+            int y = ys + iy, sy = 0;
+            if (y < 0) {
+                y += g.nc1;
+                sy = -1;
+            } else if (y >= g.nc1) {
+                y -= g.nc1;
+                sy = 1;
+            }
+            const uint32_t *row = g.cell_start + base + ((size_t)z * g.nc1 + y) * g.nc0;
+            const int nrun = (xd >= xc) ? 2 : 1;
+            for (int r = 0; r < nrun; ++r) {  // one body for both runs: the caller's code is inlined here once
+                const int a = r ? xc : xa, e = r ? xd : xb;
+                run((int)__ldg(row + a), (int)__ldg(row + e + 1), r ? sxc : sxa, sy, sz);
             }
         }
     }
+}
+
+template <typename F>
+__device__ __forceinline__ void sweep_stencil1(const CellGrid &g, int f, int cx, int cy, int cz, F &&fn) {
+    sweep_stencil1_runs(g, f, cx, cy, cz, [&](int j0, int j1, int, int, int) {
+        for (int j = j0; j < j1; ++j) fn(j);
+    });
 }
 
 // The same sweep behind a float prefilter: fn(j) runs only for records whose float minimum-image distance^2 from the
@@ -60,7 +103,8 @@ __device__ __forceinline__ FloatBox float_box(double Lx, double Ly, double Lz) {
     return b;
 }
 // squared float acceptance threshold for an exact cutoff `cut` in a box whose largest edge is lmax: wrapped
-// coordinates carry an absolute error below 2^-24 lmax each, the float arithmetic a few more roundings of that size
+// coordinates carry an absolute error below 2^-24 lmax each, the float arithmetic (incl. the rounding of a centre
+// shifted by a box edge, below) a few more roundings of that size
 __device__ __forceinline__ float float_margin_thr2(double cut, double lmax) {
     const double m = cut + 16.0 * 5.9604644775390625e-8 * lmax;
     return __double2float_ru(m * m * (1.0 + 1e-6));
@@ -68,24 +112,35 @@ __device__ __forceinline__ float float_margin_thr2(double cut, double lmax) {
 // Two steps, because the exact work is heavy and only a few records per thread pass: the sweep appends the survivors
 // to the thread's column of a shared list (a few instructions inside the divergent loop), fn runs over the list in a
 // dense loop -- when the list fills up and once more at the end, so there is no capacity limit.
+//
+// With more than 3 cells on every axis the periodic image of a whole run is known from the cells' adjacency (every
+// record within a cutoff <= the cell edge is met through that image, and it is the nearest one because the box has at
+// least 4 cells), so the centre is shifted once per run and a candidate costs a 16-byte load, 3 FADD, FMUL, 2 FFMA
+// and the compare; the next candidate's load is in flight meanwhile.  On a grid with <= 3 cells on some axis (boxes
+// of a few cutoffs: tiny systems) the adjacency image is ambiguous, so there every record goes to fn, which decides
+// exactly anyway.
 constexpr int kPrefThreads = 128;
 constexpr int kPrefCap = 16;
 template <typename F>
 __device__ __forceinline__ void sweep_stencil1_pref(const CellGrid &g, int f, int cx, int cy, int cz, float wx, float wy, float wz,
                                                     const FloatBox &fb, float thr2, int *list, F &&fn) {
     int nl = 0;
-    sweep_stencil1(g, f, cx, cy, cz, [&](int j) {
-        const float4 w = __ldg(g.wrapped + j);
-        float dx = w.x - wx, dy = w.y - wy, dz = w.z - wz;
-        dx -= fb.Lx * rintf(dx * fb.iLx);
-        dy -= fb.Ly * rintf(dy * fb.iLy);
-        dz -= fb.Lz * rintf(dz * fb.iLz);
-        if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr2) {
-            list[nl * kPrefThreads] = j;
-            if (++nl == kPrefCap) {
-                for (int k = 0; k < kPrefCap; ++k) fn(list[k * kPrefThreads]);
-                nl = 0;
+    const bool small = !(g.nc0 > 3 && g.nc1 > 3 && g.nc2 > 3);  // uniform over the grid
+    sweep_stencil1_runs(g, f, cx, cy, cz, [&](int j0, int j1, int sx, int sy, int sz) {
+        if (j0 >= j1) return;
+        const float mx = wx - (float)sx * fb.Lx, my = wy - (float)sy * fb.Ly, mz = wz - (float)sz * fb.Lz;
+        float4 w = __ldg(g.wrapped + j0);
+        for (int j = j0; j < j1; ++j) {
+            const float4 wn = __ldg(g.wrapped + min(j + 1, j1 - 1));
+            const float dx = w.x - mx, dy = w.y - my, dz = w.z - mz;
+            if (small || fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr2) {
+                list[nl * kPrefThreads] = j;
+                if (++nl == kPrefCap) {
+                    for (int k = 0; k < kPrefCap; ++k) fn(list[k * kPrefThreads]);
+                    nl = 0;
+                }
             }
+            w = wn;
         }
     });
     for (int k = 0; k < nl; ++k) fn(list[k * kPrefThreads]);
@@ -104,6 +159,7 @@ __device__ __forceinline__ void load3(const void *p, int dtype, size_t i, T &x, 
 
 struct BoxD {
     double Lx, Ly, Lz, iLx, iLy, iLz;
+    double near;  // 0.49 x the smallest edge when all three are periodic, else 0 (min_image_3's short cut never taken)
 };
 // iBoxL = merge(1/BoxL, 0, BoxL >= 0)  (waterlib.f90:41); the dense / small-array routines keep the
 // reference's "negative edge = not periodic" rule because they need no cell grid
@@ -113,7 +169,24 @@ __device__ __forceinline__ BoxD load_box(const double *b) {
     o.iLx = (o.Lx >= 0.0) ? __ddiv_rn(1.0, o.Lx) : 0.0;
     o.iLy = (o.Ly >= 0.0) ? __ddiv_rn(1.0, o.Ly) : 0.0;
     o.iLz = (o.Lz >= 0.0) ? __ddiv_rn(1.0, o.Lz) : 0.0;
+    o.near = (o.Lx > 0.0 && o.Ly > 0.0 && o.Lz > 0.0) ? 0.49 * fmin(o.Lx, fmin(o.Ly, o.Lz)) : 0.0;
     return o;
+}
+
+// distvec = p - r ; distvec = distvec - BoxL * anint(distvec * iBoxL) on the three axes (waterlib.f90:43-44), with
+// the common case short-cut: when every |p - r| is below 0.49 of the smallest edge, distvec * iBoxL rounds to a
+// magnitude below 0.5 on every axis, anint gives 0, and distvec - BoxL * 0 is distvec bit for bit -- so the two
+// products and the rounding are skipped (11 of the 12 fp64 instructions of an axis).
+__device__ __forceinline__ void min_image_3(double px, double py, double pz, double rx, double ry, double rz, const BoxD &b,
+                                            double &dx, double &dy, double &dz) {
+    dx = __dsub_rn(px, rx);
+    dy = __dsub_rn(py, ry);
+    dz = __dsub_rn(pz, rz);
+    if (!(fabs(dx) < b.near && fabs(dy) < b.near && fabs(dz) < b.near)) {
+        dx = __dsub_rn(dx, __dmul_rn(b.Lx, anint_exact<double>(__dmul_rn(dx, b.iLx))));
+        dy = __dsub_rn(dy, __dmul_rn(b.Ly, anint_exact<double>(__dmul_rn(dy, b.iLy))));
+        dz = __dsub_rn(dz, __dmul_rn(b.Lz, anint_exact<double>(__dmul_rn(dz, b.iLz))));
+    }
 }
 
 // ---- exclusive scan of pair counts (n3 -> angle offsets) -----------------------------------------
@@ -199,9 +272,8 @@ __global__ void __launch_bounds__(kPrefThreads) angles_fill_kernel(const MatPara
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-        const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
-        const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
-        const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+        double dx, dy, dz;
+        min_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
         const double s = sumsq3<double>(dx, dy, dz);
         if (s > P.lowsq && s <= P.highsq) {
             if (K >= kMatCap) {
@@ -284,9 +356,8 @@ __global__ void __launch_bounds__(kPrefThreads) neighbors_csr_kernel(const CsrPa
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-        const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
-        const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
-        const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+        double dx, dy, dz;
+        min_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
         const double s = sumsq3<double>(dx, dy, dz);
         if (s > P.lowsq && s <= P.highsq) {
             if (fits) {  // insertion by atom index into this thread's own segment
@@ -413,9 +484,8 @@ __global__ void neighbor_matrix_kernel(const void *sub, int sub_dtype, int m, co
     double rx, ry, rz, px, py, pz;
     load3<double>(sub, sub_dtype, i, rx, ry, rz);
     load3<double>(pos, pos_dtype, j, px, py, pz);
-    const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
-    const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
-    const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+    double dx, dy, dz;
+    min_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
     const double s = sumsq3<double>(dx, dy, dz);
     out[g] = (s > lowsq && s <= highsq) ? 1 : 0;
 }
@@ -506,22 +576,19 @@ __global__ void __launch_bounds__(kPrefThreads) hbond_kernel(const HbParams P) {
         int jd;
         RecTraits<double>::load(P.grid.recs, (size_t)j, dxp, dyp, dzp, jd);
         // distvec = donor - acceptor, reimaged; reject distSq > distCut^2 or distSq <= 1.0E-2 (:1184-1188)
-        const double ddx = min_image_1<double, true>(dxp, ax, b.Lx, b.iLx);
-        const double ddy = min_image_1<double, true>(dyp, ay, b.Ly, b.iLy);
-        const double ddz = min_image_1<double, true>(dzp, az, b.Lz, b.iLz);
+        double ddx, ddy, ddz;
+        min_image_3(dxp, dyp, dzp, ax, ay, az, b, ddx, ddy, ddz);
         const double s = sumsq3<double>(ddx, ddy, ddz);
         if (!(s > P.tiny && s <= P.cutsq)) return;
         double hx, hy, hz;
         load3<double>(P.donh, P.donh_dtype, (size_t)f * P.n_don + jd, hx, hy, hz);
         // unit vectors from the hydrogen to the acceptor and to the donor, each reimaged (:1190-1198)
-        double v1x = min_image_1<double, true>(ax, hx, b.Lx, b.iLx);
-        double v1y = min_image_1<double, true>(ay, hy, b.Ly, b.iLy);
-        double v1z = min_image_1<double, true>(az, hz, b.Lz, b.iLz);
+        double v1x, v1y, v1z;
+        min_image_3(ax, ay, az, hx, hy, hz, b, v1x, v1y, v1z);
         const double n1 = __dsqrt_rn(sumsq3<double>(v1x, v1y, v1z));
         v1x = __ddiv_rn(v1x, n1); v1y = __ddiv_rn(v1y, n1); v1z = __ddiv_rn(v1z, n1);
-        double v2x = min_image_1<double, true>(dxp, hx, b.Lx, b.iLx);
-        double v2y = min_image_1<double, true>(dyp, hy, b.Ly, b.iLy);
-        double v2z = min_image_1<double, true>(dzp, hz, b.Lz, b.iLz);
+        double v2x, v2y, v2z;
+        min_image_3(dxp, dyp, dzp, hx, hy, hz, b, v2x, v2y, v2z);
         const double n2 = __dsqrt_rn(sumsq3<double>(v2x, v2y, v2z));
         v2x = __ddiv_rn(v2x, n2); v2y = __ddiv_rn(v2y, n2); v2z = __ddiv_rn(v2z, n2);
         const double c = fmin(1.0, fmax(-1.0, dot3<double>(v1x, v1y, v1z, v2x, v2y, v2z)));
@@ -587,9 +654,8 @@ __global__ void __launch_bounds__(kPrefThreads) shell_kernel(const ShellParams P
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-        const double dx = min_image_1<double, true>(px, sx, b.Lx, b.iLx);
-        const double dy = min_image_1<double, true>(py, sy, b.Ly, b.iLy);
-        const double dz = min_image_1<double, true>(pz, sz, b.Lz, b.iLz);
+        double dx, dy, dz;
+        min_image_3(px, py, pz, sx, sy, sz, b, dx, dy, dz);
         const double s = sumsq3<double>(dx, dy, dz);
         if (s > P.lowsq && s <= P.highsq) P.mask[(size_t)f * P.n_pos + id] = 1;
     });
@@ -636,9 +702,8 @@ __global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
         double px, py, pz;
         int id;
         RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-        const double dx = min_image_1<double, true>(px, rx, b.Lx, b.iLx);
-        const double dy = min_image_1<double, true>(py, ry, b.Ly, b.iLy);
-        const double dz = min_image_1<double, true>(pz, rz, b.Lz, b.iLz);
+        double dx, dy, dz;
+        min_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
         const double s = sumsq3<double>(dx, dy, dz);
         if (s > P.lowsq && s <= P.highsq) {
             if (k >= kLsiCap - 1) {

@@ -233,7 +233,9 @@ int wol_angle_offsets(const int32_t *n3, int64_t n, uint32_t *offsets, uint32_t 
  * The angle VALUES (degrees) of getCosAngs in the reference's order: centres ascending, neighbours in
  * ascending atom index, pairs in np.triu_indices(k=1) order (water_properties.py:241-247; CosAngle3
  * fortran/waterlib.f90:683-703 incl. the -180 it returns for an exactly antiparallel pair).
- * `centres` is required here (pass pos itself for the subPos == Pos branch).  Needs the cell list of
+ * centres == NULL: every atom of pos is a centre (the subPos == Pos branch; n_centres must equal n_pos): the
+ * kernel then walks the atoms in cell order, which is faster than passing pos itself when the atoms are not
+ * spatially ordered -- same results, written at each atom's own index.  Needs the cell list of
  * wol_cell_build(FP64) over pos; at most 64 neighbours per centre (more -> wol_status reports it).
  */
 int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos,
@@ -246,6 +248,7 @@ int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box
  * For centre g = f * n_centres + i its neighbours j with lowcut^2 < r^2 <= highcut^2 (minimum image) are
  * indices[offsets[g] .. offsets[g + 1]), frame-local atom indices in ASCENDING order (the order of the reference's
  * boolean-mask gathers, structureLibs/water_properties.py:243,372).
+ *   centres   : NULL = every atom of pos is a centre (allNearNeighbors; n_centres must equal n_pos), walked in cell order
  *   workspace : cell list of wol_cell_build(FP64) over pos with r_cell >= highcut
  *   offsets   : [n_frames * n_centres + 1] uint32; offsets[last] = number of pairs
  *   scratch   : at least (n_frames * n_centres / 2048 + 8) uint32, 8-byte aligned; offsets[last] = 0xFFFFFFFF when the total
@@ -292,7 +295,8 @@ int wol_tetracosang(const double *ref, const double *neigh, int32_t k, const dou
  * least one in the next shell (highcut, highcut + 3.7]: the population variance of the gaps between the sorted
  * minimum-image distances of those neighbours plus the next-shell atom with the smallest NON-periodic distance
  * (the reference's choice, :289).  num[f][i] = number of gaps (0: the centre has no value, lsi = 0).
- * workspace: cell list over pos with r_cell >= highcut + 3.7.  `centres` is required.  At most 47 neighbours
+ * workspace: cell list over pos with r_cell >= highcut + 3.7.  centres == NULL: every atom of pos is a centre
+ * (n_centres must equal n_pos), walked in cell order.  At most 47 neighbours
  * inside highcut (more -> wol_status reports it).
  */
 int wol_lsi(const void *centres, int32_t centre_dtype, const double *box, int32_t n_frames, int32_t n_pos, int32_t n_centres,

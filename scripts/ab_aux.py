@@ -45,6 +45,8 @@ for order in ("lattice", "shuffled"):
     print("%-9s lsi 1M waters: %.3f ms" % (order, ms))
     ms, r = timeit(lambda: routines.neighbors_csr(None, O_d[0], box, 0.0, 3.5))
     print("%-9s neighbors_csr 1M waters, 3.5 A: %.3f ms (%d pairs)" % (order, ms, int(r[1].numel())))
+    ms, r = timeit(lambda: routines.three_body_angles(None, O_d, box))
+    print("%-9s getCosAngs values 1M waters: %.3f ms (%d angles)" % (order, ms, int(r[0].numel())))
     sol = O_d[0, :4096].contiguous()
     ms, r = timeit(lambda: routines.shell_mask(sol, O_d[0], box, 4.0))
     print("%-9s shell of 4096 solute atoms in 1M waters: %.3f ms" % (order, ms))

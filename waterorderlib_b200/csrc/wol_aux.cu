@@ -189,6 +189,40 @@ __device__ __forceinline__ void min_image_3(double px, double py, double pz, dou
     }
 }
 
+// A kernel's centre.  From the caller's array (thread g <-> centre g), or -- centres == NULL: every atom of the cell
+// list is a centre, as in wol_q3b_frames -- the g-th record of the cell-sorted arrays: the threads of a warp then work
+// on atoms of the same or adjacent cells whatever order the caller's atoms are in (overlapping stencils: the same cache
+// lines, similar trip counts), and results still go to the atom's own index.
+struct CentreRef {
+    double x, y, z;
+    int cx, cy, cz;
+    size_t out;  // frame * n_centres + centre index
+};
+__device__ __forceinline__ CentreRef get_centre(const CellGrid &g, const void *centres, int dtype, size_t gid, int f, int n_centres,
+                                                const BoxD &b) {
+    CentreRef c;
+    if (centres) {
+        load3<double>(centres, dtype, gid, c.x, c.y, c.z);
+        c.cx = cell_coord(c.x, b.iLx, g.nc0);
+        c.cy = cell_coord(c.y, b.iLy, g.nc1);
+        c.cz = cell_coord(c.z, b.iLz, g.nc2);
+        c.out = gid;
+    } else {
+        const RecD *p = reinterpret_cast<const RecD *>(g.recs) + gid;
+        long long a, bb, cc, d;
+        asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(bb), "=l"(cc), "=l"(d) : "l"(p));
+        c.x = __longlong_as_double(a);
+        c.y = __longlong_as_double(bb);
+        c.z = __longlong_as_double(cc);
+        const int cell = (int)(d >> 32);
+        c.cx = cell & 1023;
+        c.cy = (cell >> 10) & 1023;
+        c.cz = (cell >> 20) & 1023;
+        c.out = (size_t)f * n_centres + (size_t)(int)(d & 0xffffffffLL);
+    }
+    return c;
+}
+
 // ---- exclusive scan of pair counts (n3 -> angle offsets) -----------------------------------------
 
 __global__ void pair_counts_kernel(const int32_t *__restrict__ n3, size_t n, uint32_t *__restrict__ out) {
@@ -256,10 +290,10 @@ __global__ void __launch_bounds__(kPrefThreads) angles_fill_kernel(const MatPara
     if (g >= total) return;
     const int f = (int)(g / P.n_centres);
     const BoxD b = load_box(P.box + (size_t)f * 3);
-    double rx, ry, rz;
-    load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);  // centres are always given (checked by the launcher)
-    const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
-              cz = cell_coord(rz, b.iLz, P.grid.nc2);
+    const CentreRef ctr = get_centre(P.grid, P.centres, P.centre_dtype, g, f, P.n_centres, b);
+    const double rx = ctr.x, ry = ctr.y, rz = ctr.z;
+    const int cx = ctr.cx, cy = ctr.cy, cz = ctr.cz;
+    const size_t og = ctr.out;  // where this centre's results go
     int idx[kMatCap];
     idx[0] = 0;
     double ex[kMatCap], ey[kMatCap], ez[kMatCap], en[kMatCap];
@@ -299,8 +333,8 @@ __global__ void __launch_bounds__(kPrefThreads) angles_fill_kernel(const MatPara
         atomicAdd(P.counters + kCntFatal, 1u);
         return;
     }
-    size_t o = P.offsets[g];
-    if ((size_t)P.offsets[g + 1] - o != (size_t)K * (K - 1) / 2) {  // counts and fill disagree: never expected
+    size_t o = P.offsets[og];
+    if ((size_t)P.offsets[og + 1] - o != (size_t)K * (K - 1) / 2) {  // counts and fill disagree: never expected
         atomicAdd(P.counters + kCntFatal, 1u);
         return;
     }
@@ -342,14 +376,14 @@ __global__ void __launch_bounds__(kPrefThreads) neighbors_csr_kernel(const CsrPa
     }
     const int f = (int)(g / P.n_centres);
     const BoxD b = load_box(P.box + (size_t)f * 3);
-    double rx, ry, rz;
-    load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);
-    const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
-              cz = cell_coord(rz, b.iLz, P.grid.nc2);
+    const CentreRef ctr = get_centre(P.grid, P.centres, P.centre_dtype, g, f, P.n_centres, b);
+    const double rx = ctr.x, ry = ctr.y, rz = ctr.z;
+    const int cx = ctr.cx, cy = ctr.cy, cz = ctr.cz;
+    const size_t og = ctr.out;  // where this centre's results go
     const FloatBox fb = float_box(b.Lx, b.Ly, b.Lz);
     const float thr2 = float_margin_thr2(sqrt(P.highsq), fmax(b.Lx, fmax(b.Ly, b.Lz)));
-    const size_t o = FILL ? (size_t)P.offsets[g] : 0;
-    const bool fits = FILL && (long long)P.offsets[g + 1] <= P.capacity;
+    const size_t o = FILL ? (size_t)P.offsets[og] : 0;
+    const bool fits = FILL && (long long)P.offsets[og + 1] <= P.capacity;
     uint32_t K = 0;
     sweep_stencil1_pref(P.grid, f, cx, cy, cz, wrapped_coord(rx, b.Lx, b.iLx), wrapped_coord(ry, b.Ly, b.iLy),
                         wrapped_coord(rz, b.Lz, b.iLz), fb, thr2, s_list + threadIdx.x, [&](int j) {
@@ -372,7 +406,7 @@ __global__ void __launch_bounds__(kPrefThreads) neighbors_csr_kernel(const CsrPa
             ++K;
         }
     });
-    if (!FILL) P.offsets[g] = K;
+    if (!FILL) P.offsets[og] = K;
 }
 
 // ---- water orientation (watOrient) and cube/sphere occupancy (binOnGrid) ---------------------------------------------------
@@ -687,10 +721,10 @@ __global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
     if (g >= (size_t)P.n_frames * P.n_centres) return;
     const int f = (int)(g / P.n_centres);
     const BoxD b = load_box(P.box + (size_t)f * 3);
-    double rx, ry, rz;
-    load3<double>(P.centres, P.centre_dtype, g, rx, ry, rz);
-    const int cx = cell_coord(rx, b.iLx, P.grid.nc0), cy = cell_coord(ry, b.iLy, P.grid.nc1),
-              cz = cell_coord(rz, b.iLz, P.grid.nc2);
+    const CentreRef ctr = get_centre(P.grid, P.centres, P.centre_dtype, g, f, P.n_centres, b);
+    const double rx = ctr.x, ry = ctr.y, rz = ctr.z;
+    const int cx = ctr.cx, cy = ctr.cy, cz = ctr.cz;
+    const size_t og = ctr.out;  // where this centre's results go
     double dist[kLsiCap];
     dist[0] = 0.0;
     int k = 0, n_next = 0, next_idx = 0;
@@ -754,8 +788,8 @@ __global__ void __launch_bounds__(128) lsi_kernel(const LsiParams P) {
         }
         val /= (double)nd;
     }
-    P.lsi[g] = val;
-    P.num[g] = nd;
+    P.lsi[og] = val;
+    P.num[og] = nd;
 }
 
 static CellGrid make_grid(void *workspace, const WorkspaceLayout &lay, const int32_t nc[3]) {
@@ -794,7 +828,8 @@ int wol_angles_fill(const void *centres, int32_t centre_dtype, const double *box
                     int32_t n_centres, const int32_t nc[3], double edge_min, double low3, double high3, void *workspace,
                     size_t workspace_bytes, const uint32_t *offsets, double *angles, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!centres || !box || !nc || !workspace || !offsets || (!angles)) return set_error(WOL_ERR_INVALID, "wol_angles_fill: null argument");
+    if (!box || !nc || !workspace || !offsets || (!angles)) return set_error(WOL_ERR_INVALID, "wol_angles_fill: null argument");
+    if (!centres && n_centres != n_pos) return set_error(WOL_ERR_INVALID, "wol_angles_fill: centres == NULL means every atom is a centre (n_centres == n_pos)");
     for (int k = 0; k < 3; ++k)
         if (nc[k] > 3 && high3 * (1.0 + 1e-9) > edge_min)
             return set_error(WOL_ERR_INVALID, "cutoff %.6g exceeds the planned cell edge %.6g", high3, edge_min);
@@ -828,8 +863,9 @@ int wol_neighbors_csr(const void *centres, int32_t centre_dtype, const double *b
                       size_t workspace_bytes, uint32_t *offsets, uint32_t *scratch, int32_t *indices, int64_t capacity,
                       void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!centres || !box || !nc || !workspace || !offsets || !scratch || capacity < 0 || (capacity > 0 && !indices))
+    if (!box || !nc || !workspace || !offsets || !scratch || capacity < 0 || (capacity > 0 && !indices))
         return set_error(WOL_ERR_INVALID, "wol_neighbors_csr: bad argument");
+    if (!centres && n_centres != n_pos) return set_error(WOL_ERR_INVALID, "wol_neighbors_csr: centres == NULL means every atom is a centre (n_centres == n_pos)");
     if (n_frames < 1 || n_pos < 0 || n_centres < 0) return set_error(WOL_ERR_INVALID, "wol_neighbors_csr: negative size");
     for (int k = 0; k < 3; ++k)
         if (nc[k] > 3 && highcut * (1.0 + 1e-9) > edge_min)
@@ -961,7 +997,8 @@ int wol_lsi(const void *centres, int32_t centre_dtype, const double *box, int32_
             const int32_t nc[3], double edge_min, double lowcut, double highcut, void *workspace, size_t workspace_bytes,
             double *lsi, int32_t *num, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!centres || !box || !nc || !workspace || !lsi || !num) return set_error(WOL_ERR_INVALID, "wol_lsi: null argument");
+    if (!box || !nc || !workspace || !lsi || !num) return set_error(WOL_ERR_INVALID, "wol_lsi: null argument");
+    if (!centres && n_centres != n_pos) return set_error(WOL_ERR_INVALID, "wol_lsi: centres == NULL means every atom is a centre (n_centres == n_pos)");
     const double reach = highcut + 3.7;  // width of the next-neighbour shell, hard-coded in the reference (:269, :274)
     for (int k = 0; k < 3; ++k)
         if (nc[k] > 3 && reach * (1.0 + 1e-9) > edge_min)

@@ -119,7 +119,7 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
     ws = engine.Workspace(device)
     # (non-periodic axes become equivalent periods here, once, so that both passes see the same grid)
     box_h = engine.effective_boxes(engine.as_host_boxes(box, F), pos_d, None if sub is None else cen_d, max(float(high), 1e-3), device)
-    r = engine.q3b_frames(pos_d, box_h, cen_d, do_q=False, do_3body=True, low3=low, high3=high, want=("n3",),
+    r = engine.q3b_frames(pos_d, box_h, None if sub is None else cen_d, do_q=False, do_3body=True, low3=low, high3=high, want=("n3",),
                           workspace=ws, device=device, r_cell=max(float(high), 1e-3))
     n3 = r["n3"]
     L = lib()
@@ -140,7 +140,8 @@ def three_body_angles(sub, pos, box, low=0.0, high=3.413, device=None):
                            % (n3_max, float(high)))
         angles = torch.empty(n_angles, dtype=torch.float64, device=device)
         if n_angles > 0:
-            check(L.wol_angles_fill(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(box_d.data_ptr()), F, N, M,
+            # (sub is None: NULL centres = every atom, walked in cell order)
+            check(L.wol_angles_fill(None if sub is None else _vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(box_d.data_ptr()), F, N, M,
                                     ctypes.byref(nc), edge_min, float(low), float(high), _vp(ws_ptr), ws_bytes,
                                     _vp(offsets.data_ptr()), _vp(angles.data_ptr()), _stream()), "wol_angles_fill")
             st = (ctypes.c_int32 * 4)()
@@ -166,7 +167,7 @@ def neighbors_csr(sub, pos, box, low=0.0, high=3.413, device=None):
     scratch = torch.empty(total // 2048 + 8, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         def run(indices, cap):
-            check(lib().wol_neighbors_csr(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
+            check(lib().wol_neighbors_csr(None if sub is None else _vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
                                           ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr),
                                           cells.ws_bytes, _vp(offsets.data_ptr()), _vp(scratch.data_ptr()),
                                           _vp(indices.data_ptr()) if indices is not None else None, cap, _stream()), "wol_neighbors_csr")
@@ -550,7 +551,7 @@ def lsi(sub, pos, box, low=0.0, high=3.7, device=None):
     cells = CellList(pos_d, box, (float(high) + 3.7) * (1.0 + 1e-9), device=device, n_centres_max=M,
                      others=() if sub is None else (cen_d,))
     with torch.cuda.device(device):
-        check(lib().wol_lsi(_vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
+        check(lib().wol_lsi(None if sub is None else _vp(cen_d.data_ptr()), engine._dtype_code(cen_d), _vp(cells.box_d.data_ptr()), F, N, M,
                             ctypes.byref(cells.nc), cells.edge_min, float(low), float(high), _vp(cells.ws_ptr), cells.ws_bytes,
                             _vp(out.data_ptr()), _vp(num.data_ptr()), _stream()), "wol_lsi")
         cells.status()

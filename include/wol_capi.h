@@ -455,8 +455,10 @@ int wol_histrr3b(const double *box, int32_t n_pos, const int32_t nc[3], double e
 /*
  * Pair-distance histograms with the Fortran binning nbin = ceiling(dist / binwidth):
  *   mode 0  RadialDist            (fortran/waterlib.f90:193-231)  outer = Pos2, cell list over Pos1, every pair
- *   mode 1  RadialDistSame        (fortran/waterlib.f90:316-353)  outer = Pos (input order), cell list over the same Pos,
- *                                                                 each pair once (inner index > outer index)
+ *   mode 1  RadialDistSame        (fortran/waterlib.f90:316-353)  cell list over Pos, each unordered pair once (the i < j
+ *                                                                 loops); the atoms are taken from the cell list, in cell
+ *                                                                 order: `outer` must be that same Pos (n_outer == n_inner)
+ *                                                                 and is not read
  *   mode 2  PairDistanceHistogram (fortran/waterlib.f90:358-389)  outer = Pos1, cell list over Pos2, 3-D
  * counts[totbins] int64, ACCUMULATED (the g(r) normalisation of the first two, O(totbins), is left to the caller:
  * counts(k) / (N * BulkDens * (4./3.) * pi * binwidth**3 * (k**3 - (k-1)**3)) with the Fortran's single-precision

@@ -47,6 +47,8 @@ for order in ("lattice", "shuffled"):
     print("%-9s neighbors_csr 1M waters, 3.5 A: %.3f ms (%d pairs)" % (order, ms, int(r[1].numel())))
     ms, r = timeit(lambda: routines.three_body_angles(None, O_d, box))
     print("%-9s getCosAngs values 1M waters: %.3f ms (%d angles)" % (order, ms, int(r[0].numel())))
+    ms, r = timeit(lambda: routines.pair_hist(1, O_d[0], None, box, 0.1, 150), reps=2)
+    print("%-9s radialdistsame 1M waters, 150 bins of 0.1 A: %.3f ms (%d pairs)" % (order, ms, int(r.sum().item())))
     sol = O_d[0, :4096].contiguous()
     ms, r = timeit(lambda: routines.shell_mask(sol, O_d[0], box, 4.0))
     print("%-9s shell of 4096 solute atoms in 1M waters: %.3f ms" % (order, ms))

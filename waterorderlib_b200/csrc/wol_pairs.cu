@@ -10,6 +10,7 @@ namespace wol {
 
 struct PBox {
     double L[3], iL[3];
+    double near;  // 0.49 x the smallest edge when all three are periodic, else 0 (pmin_image_3's short cut never taken)
 };
 __device__ __forceinline__ PBox load_pbox(const double *b) {
     PBox o;
@@ -18,7 +19,23 @@ __device__ __forceinline__ PBox load_pbox(const double *b) {
         o.L[k] = b[k];
         o.iL[k] = (b[k] >= 0.0) ? __ddiv_rn(1.0, b[k]) : 0.0;
     }
+    o.near = (b[0] > 0.0 && b[1] > 0.0 && b[2] > 0.0) ? 0.49 * fmin(b[0], fmin(b[1], b[2])) : 0.0;
     return o;
+}
+
+// distVec = p - r, minimum image (waterlib.f90:43-44) on the three axes with the common case short-cut: when every
+// |p - r| is below 0.49 of the smallest edge, anint(distVec * iBoxL) is 0 on every axis and distVec - BoxL * 0 is
+// distVec bit for bit, so the two products and the rounding are skipped (11 of the 12 fp64 instructions of an axis).
+__device__ __forceinline__ void pmin_image_3(double px, double py, double pz, double rx, double ry, double rz, const PBox &b,
+                                             double &dx, double &dy, double &dz) {
+    dx = __dsub_rn(px, rx);
+    dy = __dsub_rn(py, ry);
+    dz = __dsub_rn(pz, rz);
+    if (!(fabs(dx) < b.near && fabs(dy) < b.near && fabs(dz) < b.near)) {
+        dx = __dsub_rn(dx, __dmul_rn(b.L[0], anint_exact<double>(__dmul_rn(dx, b.iL[0]))));
+        dy = __dsub_rn(dy, __dmul_rn(b.L[1], anint_exact<double>(__dmul_rn(dy, b.iL[1]))));
+        dz = __dsub_rn(dz, __dmul_rn(b.L[2], anint_exact<double>(__dmul_rn(dz, b.iL[2]))));
+    }
 }
 
 struct PGrid {
@@ -81,6 +98,7 @@ struct PairHistParams {
     int mode;
     double binwidth;
     int totbins;
+    double far_sq;  // distances^2 above this are beyond the last bin whatever the roundings: (totbins binwidth)^2 (1 + 1e-9)
     unsigned long long *counts;
 };
 
@@ -95,9 +113,30 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
     if (g < P.n_outer) {
         const PBox b = load_pbox(P.box);
         double rx, ry, rz;
-        pload3<double>(P.outer, P.outer_dtype, (size_t)g, rx, ry, rz);
         const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
-        const int cx = cell_coord(rx, b.iL[0], nc0), cy = cell_coord(ry, b.iL[1], nc1), cz = cell_coord(rz, b.iL[2], nc2);
+        int cx, cy, cz;
+        if (P.mode == 1) {
+            // outer = inner: thread g takes the g-th atom of the CELL-SORTED list, so the threads of a warp sweep the same
+            // cells (their record loads coalesce into broadcasts) whatever order the caller's atoms are in, and a pair is
+            // counted once by its place in that list (j > g) instead of by atom index: the same set of unordered pairs,
+            // and dist(i, j) = dist(j, i) bit for bit (p - r and r - p are exact negations, anint is odd)
+            const RecD *rp = reinterpret_cast<const RecD *>(P.grid.recs) + g;
+            long long qa, qb, qc, qd;
+            asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(qa), "=l"(qb), "=l"(qc), "=l"(qd) : "l"(rp));
+            rx = __longlong_as_double(qa);
+            ry = __longlong_as_double(qb);
+            rz = __longlong_as_double(qc);
+            const int cell = (int)(qd >> 32);
+            cx = cell & 1023;
+            cy = (cell >> 10) & 1023;
+            cz = (cell >> 20) & 1023;
+        } else {
+            pload3<double>(P.outer, P.outer_dtype, (size_t)g, rx, ry, rz);
+            cx = cell_coord(rx, b.iL[0], nc0);
+            cy = cell_coord(ry, b.iL[1], nc1);
+            cz = cell_coord(rz, b.iL[2], nc2);
+        }
+        const int j_min = (P.mode == 1) ? g + 1 : 0;
         const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
         const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
                   zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
@@ -107,12 +146,12 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
             double px, py, pz;
             int id;
             RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-            if (P.mode == 1 && id <= g) return;  // do j = i + 1, NPos
             // distVec = jPos - iPos, minimum image (:213-214)
-            const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
-            const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
-            const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
-            const double dist = __dsqrt_rn(sumsq3<double>(dx, dy, dz));
+            double dx, dy, dz;
+            pmin_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
+            const double s = sumsq3<double>(dx, dy, dz);
+            if (s > P.far_sq) return;  // certainly beyond the last bin (5/6 of the stencil): no sqrt, no division
+            const double dist = __dsqrt_rn(s);
             const double nb = ceil(__ddiv_rn(dist, P.binwidth));
             if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) return;  // bin 0 (dist == 0) is out of bounds in the Fortran
             if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
@@ -127,7 +166,7 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
                     const int x = (xs + ix) % nc0;
                     const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
                     const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
-                    for (int j = (int)__ldg(P.grid.cell_start + c); j < j1; ++j) exact(j);
+                    for (int j = max((int)__ldg(P.grid.cell_start + c), j_min); j < j1; ++j) exact(j);  // (mode 1: do j = i + 1, NPos)
                 }
             }
         }
@@ -197,9 +236,8 @@ __global__ void __launch_bounds__(kPsiThreads) psi_kernel(const PsiParams P) {
                 double px, py, pz;
                 int id;
                 RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-                const double dx = min_image_1<double, true>(px, rx, b.L[0], b.iL[0]);
-                const double dy = min_image_1<double, true>(py, ry, b.L[1], b.iL[1]);
-                const double dz = min_image_1<double, true>(pz, rz, b.L[2], b.iL[2]);
+                double dx, dy, dz;
+                pmin_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
                 const double s = sumsq3<double>(dx, dy, dz);
                 if (!(s > P.lowsq && s <= P.highsq)) continue;
                 // reimage: ref + d; tetraCosAng: ref + minimg((ref + d) - ref); CosAngle3: that - ref
@@ -398,6 +436,7 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     if (mode < 0 || mode > 2 || !outer || !box || !nc || !workspace || !counts) return set_error(WOL_ERR_INVALID, "wol_pair_hist: bad argument");
     if (totbins < 1 || !(binwidth > 0.0) || n_outer < 0 || n_inner < 0) return set_error(WOL_ERR_INVALID, "wol_pair_hist: bad bin spec or size");
+    if (mode == 1 && n_outer != n_inner) return set_error(WOL_ERR_INVALID, "wol_pair_hist: mode 1 pairs a set with itself (n_outer == n_inner)");
     const double reach = binwidth * totbins;
     for (int k = 0; k < 3; ++k)
         if (nc[k] > 3 && reach * (1.0 + 1e-9) > edge_min)
@@ -413,6 +452,9 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     P.mode = mode;
     P.binwidth = binwidth;
     P.totbins = totbins;
+    // dist^2 > r^2 (1 + 1e-9), r = totbins binwidth  =>  sqrt rounds to more than r (1 + 4e-10), the quotient by
+    // binwidth to more than totbins, and ceiling() lands beyond the last bin
+    P.far_sq = ((double)totbins * binwidth) * ((double)totbins * binwidth) * (1.0 + 1e-9);
     P.counts = reinterpret_cast<unsigned long long *>(counts);
     if (n_outer > 0 && n_inner > 0) {
         const size_t smem = totbins <= kMaxSmemBins ? sizeof(unsigned) * totbins : 0;

@@ -102,19 +102,25 @@ struct PairHistParams {
     unsigned long long *counts;
 };
 
-__global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) {
+constexpr int kPhThreads = 128;
+constexpr int kPhCap = 16;  // in-range distances^2 a thread collects before the warp bins them
+constexpr int kPhUnroll = 4;
+
+__global__ void __launch_bounds__(kPhThreads, 5) pair_hist_kernel(const PairHistParams P) {
     extern __shared__ unsigned s_cnt[];
+    __shared__ double s_list[kPhCap * kPhThreads];
     const bool smem = P.totbins <= kMaxSmemBins;
     if (smem) {
         for (int i = threadIdx.x; i < P.totbins; i += blockDim.x) s_cnt[i] = 0u;
         __syncthreads();
     }
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < P.n_outer) {
-        const PBox b = load_pbox(P.box);
-        double rx, ry, rz;
-        const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
-        int cx, cy, cz;
+    const bool live = g < P.n_outer;  // (every thread runs the loops: they hold warp-wide votes)
+    const PBox b = load_pbox(P.box);
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
+    int cx = 0, cy = 0, cz = 0;
+    if (live) {
         if (P.mode == 1) {
             // outer = inner: thread g takes the g-th atom of the CELL-SORTED list, so the threads of a warp sweep the same
             // cells (their record loads coalesce into broadcasts) whatever order the caller's atoms are in, and a pair is
@@ -136,41 +142,80 @@ __global__ void __launch_bounds__(128) pair_hist_kernel(const PairHistParams P) 
             cy = cell_coord(ry, b.iL[1], nc1);
             cz = cell_coord(rz, b.iL[2], nc2);
         }
-        const int j_min = (P.mode == 1) ? g + 1 : 0;
-        const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
-        const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
-                  zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
-        // (no float prefilter: a sixth of the stencil lies inside the histogram range, so a uniform exact sweep beats a
-        // divergent two-step one -- measured 12 ms vs 110 ms per 1M waters at 15 A)
-        auto exact = [&](int j) {
-            double px, py, pz;
-            int id;
-            RecTraits<double>::load(P.grid.recs, (size_t)j, px, py, pz, id);
-            // distVec = jPos - iPos, minimum image (:213-214)
-            double dx, dy, dz;
-            pmin_image_3(px, py, pz, rx, ry, rz, b, dx, dy, dz);
-            const double s = sumsq3<double>(dx, dy, dz);
-            if (s > P.far_sq) return;  // certainly beyond the last bin (5/6 of the stencil): no sqrt, no division
-            const double dist = __dsqrt_rn(s);
+    }
+    const int j_min = (P.mode == 1) ? g + 1 : 0;
+    const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
+    const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
+              zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
+    // Two steps.  Only a sixth of the stencil lies inside the histogram range, and binning a distance (sqrt, division,
+    // ceiling, atomic) costs five times what rejecting one does: binned where they are found, a few lanes of the warp
+    // would do that work in nearly every iteration while the others wait.  So the sweep only collects the in-range
+    // distances^2 in the thread's column of a shared list, in a loop whose trip count is the warp's (a vote is legal in
+    // it), and the WARP bins its lists together whenever one of them is full: dense work, every operation the Fortran's.
+    double *const my_list = s_list + threadIdx.x;
+    int nl = 0;
+    auto bin_lists = [&]() {
+        for (int k = 0; k < nl; ++k) {
+            const double dist = __dsqrt_rn(my_list[k * kPhThreads]);
             const double nb = ceil(__ddiv_rn(dist, P.binwidth));
-            if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) return;  // bin 0 (dist == 0) is out of bounds in the Fortran
+            if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) continue;  // bin 0 (dist == 0) is out of bounds in the Fortran
             if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
             else atomicAdd(P.counts + (int)nb - 1, 1ull);
-        };
-        for (int iz = 0; iz < cntz; ++iz) {
-            const int z = (zs + iz) % nc2;
-            for (int iy = 0; iy < cnty; ++iy) {
-                const int y = (ys + iy) % nc1;
-                // the x cells of a row are contiguous in memory: one run, or two when the row wraps
-                for (int ix = 0; ix < cntx; ++ix) {
-                    const int x = (xs + ix) % nc0;
-                    const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
-                    const int j1 = (int)__ldg(P.grid.cell_start + c + 1);
-                    for (int j = max((int)__ldg(P.grid.cell_start + c), j_min); j < j1; ++j) exact(j);  // (mode 1: do j = i + 1, NPos)
+        }
+        nl = 0;
+    };
+    for (int iz = 0; iz < cntz; ++iz) {
+        const int z = (zs + iz) % nc2;
+        for (int iy = 0; iy < cnty; ++iy) {
+            const int y = (ys + iy) % nc1;
+            for (int ix = 0; ix < cntx; ++ix) {
+                const int x = (xs + ix) % nc0;
+                const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
+                int j0 = 0, len = 0;
+                if (live) {
+                    j0 = max((int)__ldg(P.grid.cell_start + c), j_min);  // (mode 1: do j = i + 1, NPos)
+                    len = max((int)__ldg(P.grid.cell_start + c + 1) - j0, 0);
+                }
+                const int len_warp = __reduce_max_sync(kFullMask, len);
+                // four candidates per step, their loads and arithmetic independent of one another (the loop is bound by
+                // the latency of load -> subtract -> compare -> multiply -> add chains, not by any unit's throughput)
+                for (int it = 0; it < len_warp; it += kPhUnroll) {
+                    double tx[kPhUnroll], ty[kPhUnroll], tz[kPhUnroll];
+                    bool all_near = true;
+#pragma unroll
+                    for (int u = 0; u < kPhUnroll; ++u) {
+                        double px, py, pz;
+                        int id;
+                        // (lanes past their own run re-read its last record, or record 0 when the run is empty, and drop it)
+                        RecTraits<double>::load(P.grid.recs, (size_t)(j0 + max(min(it + u, len - 1), 0)), px, py, pz, id);
+                        // distVec = jPos - iPos (:213)
+                        tx[u] = __dsub_rn(px, rx);
+                        ty[u] = __dsub_rn(py, ry);
+                        tz[u] = __dsub_rn(pz, rz);
+                        all_near &= fabs(tx[u]) < b.near && fabs(ty[u]) < b.near && fabs(tz[u]) < b.near;
+                    }
+                    if (!all_near) {
+                        // minimum image (:214); for a difference below 0.49 of the smallest edge it is the identity (anint
+                        // gives 0), which is why the common case skips it
+#pragma unroll
+                        for (int u = 0; u < kPhUnroll; ++u) {
+                            tx[u] = __dsub_rn(tx[u], __dmul_rn(b.L[0], anint_exact<double>(__dmul_rn(tx[u], b.iL[0]))));
+                            ty[u] = __dsub_rn(ty[u], __dmul_rn(b.L[1], anint_exact<double>(__dmul_rn(ty[u], b.iL[1]))));
+                            tz[u] = __dsub_rn(tz[u], __dmul_rn(b.L[2], anint_exact<double>(__dmul_rn(tz[u], b.iL[2]))));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPhUnroll; ++u) {
+                        const double s = sumsq3<double>(tx[u], ty[u], tz[u]);
+                        // beyond far_sq: certainly past the last bin, whatever the roundings of sqrt and division
+                        if (it + u < len && s <= P.far_sq) my_list[nl++ * kPhThreads] = s;
+                    }
+                    if (__any_sync(kFullMask, nl > kPhCap - kPhUnroll)) bin_lists();
                 }
             }
         }
     }
+    bin_lists();
     if (smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < P.totbins; i += blockDim.x)

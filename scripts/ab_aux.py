@@ -52,3 +52,10 @@ for order in ("lattice", "shuffled"):
     sol = O_d[0, :4096].contiguous()
     ms, r = timeit(lambda: routines.shell_mask(sol, O_d[0], box, 4.0))
     print("%-9s shell of 4096 solute atoms in 1M waters: %.3f ms" % (order, ms))
+
+sp, sbox, z_lo, z_hi = synth.slab_box(32, 32, 8, sigma=0.3, seed=11)
+gp, gn = synth.plane_interface(sbox, z_lo, z_hi, spacing=2.0)
+sp_d, gp_d, gn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(gp).to(dev), torch.from_numpy(gn).to(dev)
+for surf in (False, True):
+    ms, r = timeit(lambda: routines.interface_water(sp_d, gp_d, gn_d, 0.0, sbox, want_surfclose=surf))
+    print("interface_water %d waters x %d surface points, surfclose %s: %.3f ms" % (sp.shape[0], gp.shape[0], surf, ms))

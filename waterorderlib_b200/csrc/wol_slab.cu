@@ -173,13 +173,14 @@ struct NearestScan {
 
 // row = the entity that owns the search (rx, ry, rz fp64 + float copy); columns come from `col` (fp64, global)
 // through the float tile.  ROW_IS_WATER selects the operand order of distvec = watpos - gpos (:1440).
+// A row's columns may be shared out among `step` threads (thread `first` of them takes columns first, first + step, ...).
 template <bool ROW_IS_WATER>
 __device__ __forceinline__ void nearest_tile(NearestScan &S, const float *__restrict__ s_t, int nt, int t0,
                                              const double *__restrict__ col, double rx, double ry, double rz, float fx, float fy,
                                              float fz, const Box3 &b, float Lxf, float Lyf, float Lzf, float iLxf, float iLyf,
-                                             float iLzf) {
+                                             float iLzf, int first, int step) {
 #pragma unroll 4
-    for (int t = 0; t < nt; ++t) {
+    for (int t = first; t < nt; t += step) {
         float dx = s_t[3 * t + 0] - fx, dy = s_t[3 * t + 1] - fy, dz = s_t[3 * t + 2] - fz;
         dx -= Lxf * rintf(dx * iLxf);
         dy -= Lyf * rintf(dy * iLyf);
@@ -207,7 +208,11 @@ __device__ __forceinline__ void nearest_tile(NearestScan &S, const float *__rest
     }
 }
 
-template <bool ROW_IS_WATER>
+// SPLIT threads (adjacent lanes) share one row entity: each scans every SPLIT-th column and the partial results are
+// merged at the end -- smallest exact distance^2, smallest index among equals, which is what the Fortran's strict '<' over
+// ascending indices keeps.  SPLIT > 1 is for searches with few rows (19 602 surface points are 154 blocks of 128 threads:
+// one block per SM, four warps each).
+template <bool ROW_IS_WATER, int SPLIT>
 __global__ void __launch_bounds__(kIfaceThreads) iface_nearest_kernel(const double *__restrict__ row, int n_row,
                                                                       const double *__restrict__ col, int n_col,
                                                                       const double *__restrict__ gridnorm,
@@ -215,7 +220,8 @@ __global__ void __launch_bounds__(kIfaceThreads) iface_nearest_kernel(const doub
                                                                       int32_t *__restrict__ closest, double *__restrict__ dists,
                                                                       int32_t *__restrict__ numwater) {
     __shared__ float s_t[kIfaceTile * 3];
-    const int i = blockIdx.x * kIfaceThreads + threadIdx.x;
+    const int i = blockIdx.x * (kIfaceThreads / SPLIT) + threadIdx.x / SPLIT;
+    const int part = threadIdx.x % SPLIT;
     const bool valid = i < n_row;
     const Box3 b = load_box3(box);
     // a non-periodic axis (negative edge, iBoxL = 0) simply never wraps in the float pass either
@@ -233,7 +239,19 @@ __global__ void __launch_bounds__(kIfaceThreads) iface_nearest_kernel(const doub
         __syncthreads();
         for (int k = threadIdx.x; k < nt * 3; k += kIfaceThreads) s_t[k] = (float)col[3 * (size_t)t0 + k];
         __syncthreads();
-        if (valid) nearest_tile<ROW_IS_WATER>(S, s_t, nt, t0, col, rx, ry, rz, fx, fy, fz, b, Lxf, Lyf, Lzf, iLxf, iLyf, iLzf);
+        if (valid) nearest_tile<ROW_IS_WATER>(S, s_t, nt, t0, col, rx, ry, rz, fx, fy, fz, b, Lxf, Lyf, Lzf, iLxf, iLyf, iLzf, part, SPLIT);
+    }
+    if (SPLIT > 1) {
+#pragma unroll
+        for (int o = 1; o < SPLIT; o <<= 1) {
+            const double ob = __shfl_xor_sync(kFullMask, S.best, o);
+            const int oc = __shfl_xor_sync(kFullMask, S.close, o);
+            if (oc >= 0 && (ob < S.best || (ob == S.best && (S.close < 0 || oc < S.close)))) {
+                S.best = ob;
+                S.close = oc;
+            }
+        }
+        if (part != 0) return;  // (SPLIT > 1 is only instantiated for the search that needs no warp vote below)
     }
     if (!ROW_IS_WATER) {
         if (valid) closest[i] = S.close;
@@ -629,13 +647,19 @@ int wol_interface_water(const double *pos, int32_t n_pos, const double *gridpos,
     if (n_pos < 0 || n_grid < 0 || !box || (!pos && n_pos > 0) || ((!gridpos || !gridnorm) && n_grid > 0) || !watclose || !allwatdists)
         return set_error(WOL_ERR_INVALID, "wol_interface_water: bad argument");
     if (n_pos > 0) {
-        iface_nearest_kernel<true><<<(n_pos + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
+        iface_nearest_kernel<true, 1><<<(n_pos + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
             pos, n_pos, gridpos, n_grid, gridnorm, box, cutoff, watclose, allwatdists, numwater);
         add_launches(1);
     }
     if (surfclose && n_grid > 0) {
-        iface_nearest_kernel<false><<<(n_grid + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
-            gridpos, n_grid, pos, n_pos, nullptr, box, cutoff, surfclose, nullptr, nullptr);
+        // few surface points: eight threads per point, so that the grid fills the SMs
+        constexpr int kSplit = 8;
+        if ((n_grid + kIfaceThreads - 1) / kIfaceThreads < 8 * sm_count())
+            iface_nearest_kernel<false, kSplit><<<(n_grid + kIfaceThreads / kSplit - 1) / (kIfaceThreads / kSplit), kIfaceThreads, 0, stream>>>(
+                gridpos, n_grid, pos, n_pos, nullptr, box, cutoff, surfclose, nullptr, nullptr);
+        else
+            iface_nearest_kernel<false, 1><<<(n_grid + kIfaceThreads - 1) / kIfaceThreads, kIfaceThreads, 0, stream>>>(
+                gridpos, n_grid, pos, n_pos, nullptr, box, cutoff, surfclose, nullptr, nullptr);
         add_launches(1);
     }
     cudaError_t e = cudaGetLastError();

@@ -27,7 +27,15 @@ for _ in range(REPS):
     hb = routines.hbond_counts(o_d, d_d, h_d, box, 3.5, 120.0)
 torch.cuda.synchronize()
 print("hbonds per water", float(hb["acc_count"].sum()) / o.shape[0], flush=True)
-del pos, o_d, h_d, d_d
+# same-sweep observables of the same frame: LSI, CSR neighbour list, materialised three-body angles, RadialDistSame
+for _ in range(REPS):
+    lsi = routines.lsi(None, o_d, box)
+    csr = routines.neighbors_csr(None, o_d[0], box, 0.0, 3.5)
+    ang = routines.three_body_angles(None, o_d, box)
+    rdf = routines.pair_hist(1, o_d[0], None, box, 0.1, 150)
+torch.cuda.synchronize()
+print("lsi mean", float(lsi[0].mean()), "csr pairs", int(csr[1].numel()), "angles", int(ang[0].numel()), "rdf pairs", int(rdf.sum()), flush=True)
+del pos, o_d, h_d, d_d, lsi, csr, ang, rdf
 # K5: 65536-water slab, 80^3 Willard-Chandler field, interface search against the ideal faces
 sp, sbox, z_lo, z_hi = synth.slab_box(32, 32, 8, sigma=0.3, seed=11)
 gp, gn = synth.plane_interface(sbox, z_lo, z_hi, spacing=2.0)
@@ -35,6 +43,6 @@ sp_d, gp_d, gn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(gp).to(dev), t
 grid = [(np.arange(80) + 0.5) * (sbox[d] / 80) for d in range(3)]
 for _ in range(REPS):
     dens, _ = routines.willard_density(sp_d, sbox, 2.4, grid=grid, want_normals=True)
-    iw = routines.interface_water(sp_d, gp_d, gn_d, 0.0, sbox)
+    iw = routines.interface_water(sp_d, gp_d, gn_d, 0.0, sbox, want_surfclose=True)
 torch.cuda.synchronize()
 print("field max", float(dens.max()), "interface points", gp.shape[0], flush=True)

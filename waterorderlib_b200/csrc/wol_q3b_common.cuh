@@ -51,6 +51,7 @@ struct Q3bParams {
     const uint32_t *list;     // entries
     int list_counter;         // index into counters[] of its length
     int list_w_start;         // half-width at which a q-only entry resumes its search
+    uint32_t widen_lo, widen_hi;  // a widened-search launch works only when widen_lo <= counters[kCntWidened] < widen_hi
     uint32_t *list2;          // second-level queue (appended to by the thread-per-centre widened pass)
     float lowq_hi2;           // (lowq + margin)^2: float distances above this are certainly beyond lowCut
     float pre_thr2_w2;        // prefilter threshold of the half-width-2 pass

@@ -428,7 +428,10 @@ __global__ void __launch_bounds__(kWidenThreads) q3b_tpc_widen_kernel(const __gr
     __shared__ int s_list[kWidenListCap * kWidenThreads];
     extern __shared__ unsigned s_qhist_dyn[];
     const uint32_t n_items = P.counters[P.list_counter];
-    if (P.counters[kCntWidened] == 0u) return;
+    {
+        const uint32_t n_widened = P.counters[kCntWidened];
+        if (n_widened == 0u || n_widened < P.widen_lo || n_widened >= P.widen_hi) return;
+    }
     // one shared row only: the queue mixes frames, so per-frame histograms go straight to global memory
     unsigned *s_qhist = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? s_qhist_dyn : nullptr;
     if (s_qhist) {
@@ -646,7 +649,10 @@ __global__ void __launch_bounds__(kWidenWarps * 32) q3b_widen_warp_kernel(const 
     __shared__ int s_count[kWidenWarps];
     extern __shared__ unsigned s_qhist_dyn[];
     const uint32_t n_items = P.counters[P.list_counter];
-    if (P.counters[kCntWidened] == 0u) return;
+    {
+        const uint32_t n_widened = P.counters[kCntWidened];
+        if (n_widened == 0u || n_widened < P.widen_lo || n_widened >= P.widen_hi) return;
+    }
     unsigned *s_qhist = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? s_qhist_dyn : nullptr;
     if (s_qhist) {
         for (int i = threadIdx.x; i < P.q_nbins; i += kWidenWarps * 32) s_qhist[i] = 0u;
@@ -852,18 +858,40 @@ bool q3b_tpc_widen_supported(const Q3bParams &P) {
     return P.wrapped != nullptr && P.nc0 >= 7 && P.nc1 >= 7 && P.nc2 >= 7;
 }
 
-int q3b_tpc_widen_launch(const Q3bParams &P, cudaStream_t stream, bool exact, bool f32) {
+// How many widened centres make the thread-per-centre kernel the faster one (fp64 records).  One warp per centre has short
+// dependent chains -- 39 us for 6 000 centres, where a thread per centre has a ~100 us floor -- but costs 4.2 us per 1000
+// centres against 0.5: a liquid-like 8 x 1M-water batch queues 160 000 (678 us against 181 us).
+constexpr uint32_t kWidenPerThreadFrom = 24576;
+
+int q3b_tpc_widen_launch(const Q3bParams &P0, cudaStream_t stream, bool exact, bool f32) {
+    Q3bParams P = P0;
+    P.widen_lo = 0u;
+    P.widen_hi = 0xffffffffu;
     const int grid = sm_count() * 8;
     const size_t smem = (P.q_hist && !P.hist_per_frame && P.q_nbins <= kMaxSmemBins) ? sizeof(unsigned) * P.q_nbins : 0;
-    // fp64 records: one warp per queued centre (short dependent chains: the pass is a latency floor, not a throughput
-    // problem); WOL_WIDEN_THREAD=1 keeps the thread-per-centre version for comparison
-    const bool per_warp = !f32 && getenv("WOL_WIDEN_THREAD") == nullptr;
-    if (f32) q3b_tpc_widen_kernel<false, true><<<grid, kWidenThreads, smem, stream>>>(P);
-    else if (per_warp && exact) q3b_widen_warp_kernel<true><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
-    else if (per_warp) q3b_widen_warp_kernel<false><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
-    else if (exact) q3b_tpc_widen_kernel<true, false><<<grid, kWidenThreads, smem, stream>>>(P);
-    else q3b_tpc_widen_kernel<false, false><<<grid, kWidenThreads, smem, stream>>>(P);
-    add_launches(1);
+    if (f32) {
+        q3b_tpc_widen_kernel<false, true><<<grid, kWidenThreads, smem, stream>>>(P);
+        add_launches(1);
+        return WOL_OK;
+    }
+    // fp64 records: BOTH kernels are launched and the device-side count picks the one that works (the host does not know
+    // the count without a synchronisation; the other launch returns at once).  WOL_WIDEN_THREAD=1 / =0 force one of them.
+    const char *env = getenv("WOL_WIDEN_THREAD");
+    const bool only_thread = env && env[0] == '1', only_warp = env && env[0] == '0';
+    if (!only_thread) {
+        P.widen_lo = 0u;
+        P.widen_hi = only_warp ? 0xffffffffu : kWidenPerThreadFrom;
+        if (exact) q3b_widen_warp_kernel<true><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
+        else q3b_widen_warp_kernel<false><<<sm_count() * 16, kWidenWarps * 32, smem, stream>>>(P);
+        add_launches(1);
+    }
+    if (!only_warp) {
+        P.widen_lo = only_thread ? 0u : kWidenPerThreadFrom;
+        P.widen_hi = 0xffffffffu;
+        if (exact) q3b_tpc_widen_kernel<true, false><<<grid, kWidenThreads, smem, stream>>>(P);
+        else q3b_tpc_widen_kernel<false, false><<<grid, kWidenThreads, smem, stream>>>(P);
+        add_launches(1);
+    }
     return WOL_OK;
 }
 

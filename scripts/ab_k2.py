@@ -37,4 +37,6 @@ for sigma in (0.25, 0.6):
             ts.append(ev[2].elapsed_time(ev[3]))
     print("sigma %.2f  %d frames: kernel best %.4f median %.4f ms | call best %.4f median %.4f ms | angles %d  q sum %.9f  n3 sum %d" % (
         sigma, F, min(ks), float(np.median(ks)), min(ts), float(np.median(ts)), int(r["ang_hist"].sum()), float(r["q"].sum()), int(r["n3"].sum())), flush=True)
+    r = engine.q3b_frames(pos, box, workspace=ws, want=("q",))
+    print("           widened %d  overflow %d  (of %d centres)" % (r["n_widened"], r["n_overflow"], F * pos.shape[1]), flush=True)
     del pos, ws, r

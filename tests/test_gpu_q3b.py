@@ -172,3 +172,29 @@ def test_brick_kernels_agree_with_the_thread_per_centre_path(monkeypatch, sigma,
         q, nn4, _ = port.order_param_q(pos[0], pos[0], box[0], kw.get("lowq", 0.0), kw.get("highq", 10.0))
         assert np.array_equal(out["3"].nn_idx.cpu().numpy()[0], nn4)
         assert_q_close(out["3"].q.cpu().numpy()[0], q)
+
+
+@pytest.mark.parametrize("sigma", [0.6, 0.9])
+def test_widened_search_kernels_agree(monkeypatch, sigma):
+    """The widened 4-NN search has a warp-per-centre and a thread-per-centre kernel, and the device-side count of queued
+    centres picks one (wol_q3b_tpc.cu: q3b_tpc_widen_launch).  Forced either way (WOL_WIDEN_THREAD=0 / 1) and left to
+    the count, the results are the same -- and frame 0 is the oracle's."""
+    pos, box = synth.trajectory(12, 2, sigma=sigma, seed0=77)  # 2 x 13 824 waters, hundreds of widened centres each
+    out = {}
+    for mode in ("0", "1", None):
+        if mode is None:
+            monkeypatch.delenv("WOL_WIDEN_THREAD", raising=False)
+        else:
+            monkeypatch.setenv("WOL_WIDEN_THREAD", mode)
+        out[mode] = run(None, pos, box, True)
+    a = out["0"]
+    assert a["n_widened"] > 50
+    for mode in ("1", None):
+        b = out[mode]
+        for k in ("nn_idx", "n3", "ang_hist", "q_hist"):
+            assert torch.equal(a[k], b[k]), (mode, k)
+        assert torch.equal(a["q"], b["q"])
+        assert a["n_widened"] == b["n_widened"]
+    q, nn4, _ = port.order_param_q(pos[0], pos[0], box[0])
+    assert np.array_equal(out["1"].nn_idx.cpu().numpy()[0], nn4)
+    assert_q_close(out["1"].q.cpu().numpy()[0], q)

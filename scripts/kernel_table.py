@@ -29,8 +29,10 @@ for r in rows[2:]:
     name = d["Kernel Name"]
     name = re.sub(r"^void ", "", name)
     name = name.split("(")[0].replace("wol::", "")
-    if name not in last or float(d["gpu__time_duration.sum"]) * tscale0[u["gpu__time_duration.sum"]] > float(last[name]["gpu__time_duration.sum"]) * tscale0[u["gpu__time_duration.sum"]]:
-        last[name] = d  # the largest launch of each kernel (the same kernel also runs on small inputs)
+    def size(x):  # the largest launch of each kernel (the same kernel also runs on small inputs): grid first, then duration
+        return (int(x["launch__grid_size"]), float(x["gpu__time_duration.sum"]) * tscale0[u["gpu__time_duration.sum"]])
+    if name not in last or size(d) > size(last[name]):
+        last[name] = d
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 tscale = {"s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6}
 lines = ["| kernel | grid x block | regs | time (ms) | DRAM read + write (MB) | DRAM GB/s | of measured HBM (%.1f GB/s) | FP64 pipe %% | FP32 FMA pipe %% | issue slots busy %% | lanes / instr | warps / SM |" % peak,

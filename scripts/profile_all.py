@@ -4,10 +4,14 @@ interface search.
 
     python scripts/profile_all.py
 """
+import os
+import sys
+
 import numpy as np
 import torch
 
-from waterorderlib_b200 import engine, routines, synth
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from waterorderlib_b200 import engine, routines, synth  # noqa: E402
 
 dev = torch.device("cuda", 0)
 pos, box = synth.device_frames(50, 0, 2, sigma=0.25, device=dev)

@@ -94,12 +94,11 @@ __device__ __forceinline__ void sweep_stencil1(const CellGrid &g, int f, int cx,
 // (box-wrapped) point (wx, wy, wz) is within thr2 -- a bound the caller widens by float_margin() so that no record
 // inside the exact cutoff can be rejected; everything that decides a result is then recomputed exactly by fn.
 struct FloatBox {
-    float Lx, Ly, Lz, iLx, iLy, iLz;
+    float Lx, Ly, Lz;
 };
 __device__ __forceinline__ FloatBox float_box(double Lx, double Ly, double Lz) {
     FloatBox b;
     b.Lx = (float)Lx; b.Ly = (float)Ly; b.Lz = (float)Lz;
-    b.iLx = 1.0f / b.Lx; b.iLy = 1.0f / b.Ly; b.iLz = 1.0f / b.Lz;
     return b;
 }
 // squared float acceptance threshold for an exact cutoff `cut` in a box whose largest edge is lmax: wrapped

@@ -400,3 +400,23 @@ def test_histogram2d_is_numpy_histogram2d():
     assert np.array_equal(got.cpu().numpy(), want.astype(np.int64))
     routines.histogram2d(x, y, xe, ye, out=got)
     assert np.array_equal(got.cpu().numpy(), 2 * want.astype(np.int64))
+
+
+def test_pair_histograms_on_a_grid_with_many_cells():
+    """Pair-distance histograms where every axis has more than 3 cells -- the path with the float pass, the periodic
+    image taken from cell adjacency, the warp's queue and the bin edges in distance^2 (csrc/wol_pairs.cu) -- against
+    the oracle: shuffled atoms, a non-cubic box, atoms left outside the box by whole periods, all three modes."""
+    pos, box = synth.water_box(12, sigma=0.3, seed=21)  # 13 824 waters, L = 74.5 A
+    rng = np.random.default_rng(3)
+    pos = pos[rng.permutation(pos.shape[0])]
+    box = box * np.array([1.0, 1.07, 0.93])
+    pos = pos * np.array([1.0, 1.07, 0.93])
+    pos[::7] += box * rng.integers(-2, 3, size=(pos[::7].shape[0], 3))
+    sub = rng.uniform(-0.5, 1.5, size=(300, 3)) * box
+    for bw, nb in ((0.1, 120), (0.25, 60), (0.37, 9)):
+        g = routines.pair_hist(1, pos, None, box, bw, nb).cpu().numpy()
+        assert np.array_equal(g, port._pair_hist(1, pos, pos, box, bw, nb)), (bw, nb)
+        g0 = routines.pair_hist(0, sub, pos, box, bw, nb).cpu().numpy()
+        assert np.array_equal(g0, port._pair_hist(0, sub, pos, box, bw, nb)), (bw, nb)
+        g2 = routines.pair_hist(2, sub, pos, box, bw, nb).cpu().numpy()
+        assert np.array_equal(g2, port._pair_hist(2, sub, pos, box, bw, nb)), (bw, nb)

@@ -94,7 +94,7 @@ struct PairHistParams {
     const double *box;
     const void *outer;
     int outer_dtype;
-    int n_outer;
+    int n_outer, n_inner;
     int mode;
     double binwidth;
     int totbins;
@@ -103,29 +103,72 @@ struct PairHistParams {
 };
 
 constexpr int kPhThreads = 128;
-constexpr int kPhCap = 16;  // in-range distances^2 a thread collects before the warp bins them
+constexpr int kPhQueue = 512;  // (owner lane, record) pairs a warp collects before it evaluates them
 constexpr int kPhUnroll = 4;
 
+// Three ideas, in the order they were measured (1M waters, 150 bins of 0.1 A: 12.1 ms at the start of this file's history):
+//   * Cell order (mode 1): thread g takes the g-th atom of the cell-sorted list, so a warp sweeps the same cells and its
+//     loads are broadcasts; a pair is counted once by its place in that list.
+//   * A float pass decides which records can be in range at all (a sixth of the stencil); the periodic image of a whole
+//     cell is known from its adjacency when every axis has more than 3 cells, so a candidate costs a 16-byte load, 3 FADD,
+//     FMUL, 2 FFMA and a compare.
+//   * What passes goes to a queue of the WARP (owner lane, record), appended with a ballot, and is evaluated by all 32 lanes
+//     together when the queue fills: an atom near a face of its cell takes most of its pairs from the cell behind that face,
+//     so per-lane lists fill at very different rates and a lane-owned exact pass runs at a third of its lanes.  Only the
+//     fp64 value -- the reference's operations in the reference's order -- decides a bin.
+//   * Bin edges in distance^2: the Fortran's bin, nb(s) = ceiling(RN(RN(sqrt(s)) / binwidth)), is a monotone step function
+//     of s = distance^2, so with s_edge[k] = the LARGEST double s with nb(s) <= k it is settled by comparisons: bin k <=>
+//     s_edge[k - 1] < s <= s_edge[k], no sqrt and no division per pair.  Every block finds the edges itself, a thread per
+//     edge: from the estimate (k binwidth)^2, a few ulps away, it walks neighbouring doubles with the very operations it
+//     replaces.  If a walk does not end within 64 steps the block keeps the per-pair arithmetic.
 __global__ void __launch_bounds__(kPhThreads, 5) pair_hist_kernel(const PairHistParams P) {
     extern __shared__ unsigned s_cnt[];
-    __shared__ double s_list[kPhCap * kPhThreads];
+    __shared__ uint2 s_queue[kPhThreads / 32][kPhQueue];
+    __shared__ double s_ctr[3][kPhThreads];
+    __shared__ int s_tab_bad;
     const bool smem = P.totbins <= kMaxSmemBins;
+    double *const s_edge = reinterpret_cast<double *>(s_cnt + ((P.totbins + 1) & ~1));
     if (smem) {
+        if (threadIdx.x == 0) s_tab_bad = 0;
         for (int i = threadIdx.x; i < P.totbins; i += blockDim.x) s_cnt[i] = 0u;
         __syncthreads();
+        for (int k = threadIdx.x; k <= P.totbins; k += blockDim.x) {
+            double t = 0.0;  // nb(0) = 0, nb(s) >= 1 for every s > 0
+            if (k > 0) {
+                const double e = __dmul_rn((double)k, P.binwidth);
+                t = __dmul_rn(e, e);
+                int steps = 0;
+                while (ceil(__ddiv_rn(__dsqrt_rn(t), P.binwidth)) <= (double)k && steps < 64) {
+                    t = __longlong_as_double(__double_as_longlong(t) + 1);
+                    ++steps;
+                }
+                if (steps >= 64) s_tab_bad = 1;
+                steps = 0;
+                while (ceil(__ddiv_rn(__dsqrt_rn(t), P.binwidth)) > (double)k && steps < 64) {
+                    t = __longlong_as_double(__double_as_longlong(t) - 1);
+                    ++steps;
+                }
+                if (steps >= 64) s_tab_bad = 1;
+            }
+            s_edge[k] = t;
+        }
+        __syncthreads();
     }
+    const bool use_edges = smem && s_tab_bad == 0;
+    const float inv_bw_f = (float)(1.0 / P.binwidth);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lanes_below = (1u << lane) - 1u;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = g < P.n_outer;  // (every thread runs the loops: they hold warp-wide votes)
     const PBox b = load_pbox(P.box);
     double rx = 0.0, ry = 0.0, rz = 0.0;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
     const int nc0 = P.grid.nc0, nc1 = P.grid.nc1, nc2 = P.grid.nc2;
     int cx = 0, cy = 0, cz = 0;
     if (live) {
         if (P.mode == 1) {
-            // outer = inner: thread g takes the g-th atom of the CELL-SORTED list, so the threads of a warp sweep the same
-            // cells (their record loads coalesce into broadcasts) whatever order the caller's atoms are in, and a pair is
-            // counted once by its place in that list (j > g) instead of by atom index: the same set of unordered pairs,
-            // and dist(i, j) = dist(j, i) bit for bit (p - r and r - p are exact negations, anint is odd)
+            // outer = inner: the g-th atom of the cell-sorted list; dist(i, j) = dist(j, i) bit for bit (p - r and r - p are
+            // exact negations, anint is odd), so counting a pair by list position (j > g) gives the i < j loops' counts
             const RecD *rp = reinterpret_cast<const RecD *>(P.grid.recs) + g;
             long long qa, qb, qc, qd;
             asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(qa), "=l"(qb), "=l"(qc), "=l"(qd) : "l"(rp));
@@ -142,80 +185,97 @@ __global__ void __launch_bounds__(kPhThreads, 5) pair_hist_kernel(const PairHist
             cy = cell_coord(ry, b.iL[1], nc1);
             cz = cell_coord(rz, b.iL[2], nc2);
         }
+        wx = wrapped_coord(rx, b.L[0], b.iL[0]);
+        wy = wrapped_coord(ry, b.L[1], b.iL[1]);
+        wz = wrapped_coord(rz, b.L[2], b.iL[2]);
     }
+    s_ctr[0][threadIdx.x] = rx;
+    s_ctr[1][threadIdx.x] = ry;
+    s_ctr[2][threadIdx.x] = rz;
+    __syncwarp();
     const int j_min = (P.mode == 1) ? g + 1 : 0;
+    const int j_last = P.n_inner - 1;  // last record of the cell-sorted arrays
     const int cntx = min(3, nc0), cnty = min(3, nc1), cntz = min(3, nc2);
-    const int xs = (nc0 <= 3) ? 0 : (cx - 1 + nc0) % nc0, ys = (nc1 <= 3) ? 0 : (cy - 1 + nc1) % nc1,
-              zs = (nc2 <= 3) ? 0 : (cz - 1 + nc2) % nc2;
-    // Two steps.  Only a sixth of the stencil lies inside the histogram range, and binning a distance (sqrt, division,
-    // ceiling, atomic) costs five times what rejecting one does: binned where they are found, a few lanes of the warp
-    // would do that work in nearly every iteration while the others wait.  So the sweep only collects the in-range
-    // distances^2 in the thread's column of a shared list, in a loop whose trip count is the warp's (a vote is legal in
-    // it), and the WARP bins its lists together whenever one of them is full: dense work, every operation the Fortran's.
-    double *const my_list = s_list + threadIdx.x;
-    int nl = 0;
-    auto bin_lists = [&]() {
-        for (int k = 0; k < nl; ++k) {
-            const double dist = __dsqrt_rn(my_list[k * kPhThreads]);
+    // Grids with <= 3 cells on some axis: adjacency does not determine the image, so the float pass lets everything through.
+    const bool small = !(nc0 > 3 && nc1 > 3 && nc2 > 3);
+    const float Lxf = (float)b.L[0], Lyf = (float)b.L[1], Lzf = (float)b.L[2];
+    // float acceptance threshold for an exact far_sq: wrapped coordinates carry an absolute error below 2^-24 lmax each,
+    // the shifted centre and the float arithmetic a few more roundings of that size
+    const double reach_m = sqrt(P.far_sq) + 16.0 * 5.9604644775390625e-8 * fmax(b.L[0], fmax(b.L[1], b.L[2]));
+    const float thr2 = small ? __int_as_float(0x7f800000) : __double2float_ru(reach_m * reach_m * (1.0 + 1e-6));
+    uint2 *const queue = s_queue[warp];
+    int qn = 0;  // the same in every lane of the warp
+    auto drain = [&]() {
+        __syncwarp();
+        for (int i = lane; i < qn; i += 32) {
+            const uint2 e = queue[i];
+            const int o = warp * 32 + (int)e.x;
+            double px, py, pz;
+            int id;
+            RecTraits<double>::load(P.grid.recs, (size_t)e.y, px, py, pz, id);
+            // distVec = jPos - iPos, minimum image (:213-214)
+            double dx, dy, dz;
+            pmin_image_3(px, py, pz, s_ctr[0][o], s_ctr[1][o], s_ctr[2][o], b, dx, dy, dz);
+            const double s = sumsq3<double>(dx, dy, dz);
+            if (use_edges) {
+                if (!(s <= s_edge[P.totbins])) continue;  // past the last bin (or NaN)
+                int kb = min(max((int)(sqrtf((float)s) * inv_bw_f) + 1, 0), P.totbins);  // float seed, then the exact edges
+                while (s > s_edge[kb]) ++kb;
+                while (kb > 0 && s <= s_edge[kb - 1]) --kb;
+                if (kb > 0) atomicAdd(s_cnt + kb - 1, 1u);  // bin 0 (dist == 0) is out of bounds in the Fortran
+                continue;
+            }
+            if (!(s <= P.far_sq)) continue;  // certainly past the last bin, whatever the roundings of sqrt and division
+            const double dist = __dsqrt_rn(s);
             const double nb = ceil(__ddiv_rn(dist, P.binwidth));
-            if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) continue;  // bin 0 (dist == 0) is out of bounds in the Fortran
+            if (!(nb >= 1.0) || !(nb <= (double)P.totbins)) continue;
             if (smem) atomicAdd(s_cnt + (int)nb - 1, 1u);
             else atomicAdd(P.counts + (int)nb - 1, 1ull);
         }
-        nl = 0;
+        __syncwarp();
+        qn = 0;
     };
     for (int iz = 0; iz < cntz; ++iz) {
-        const int z = (zs + iz) % nc2;
+        int z = (nc2 <= 3) ? iz : cz - 1 + iz;
+        float mz = wz;
+        if (z < 0) { z += nc2; mz += Lzf; } else if (z >= nc2) { z -= nc2; mz -= Lzf; }
         for (int iy = 0; iy < cnty; ++iy) {
-            const int y = (ys + iy) % nc1;
+            int y = (nc1 <= 3) ? iy : cy - 1 + iy;
+            float my = wy;
+            if (y < 0) { y += nc1; my += Lyf; } else if (y >= nc1) { y -= nc1; my -= Lyf; }
             for (int ix = 0; ix < cntx; ++ix) {
-                const int x = (xs + ix) % nc0;
+                int x = (nc0 <= 3) ? ix : cx - 1 + ix;
+                float mx = wx;
+                if (x < 0) { x += nc0; mx += Lxf; } else if (x >= nc0) { x -= nc0; mx -= Lxf; }
                 const size_t c = ((size_t)z * nc1 + y) * nc0 + x;
                 int j0 = 0, len = 0;
                 if (live) {
                     j0 = max((int)__ldg(P.grid.cell_start + c), j_min);  // (mode 1: do j = i + 1, NPos)
                     len = max((int)__ldg(P.grid.cell_start + c + 1) - j0, 0);
+                    j0 = min(j0, j_last);  // (an empty run at the very end: keeps the loads below inside the array)
                 }
                 const int len_warp = __reduce_max_sync(kFullMask, len);
-                // four candidates per step, their loads and arithmetic independent of one another (the loop is bound by
-                // the latency of load -> subtract -> compare -> multiply -> add chains, not by any unit's throughput)
                 for (int it = 0; it < len_warp; it += kPhUnroll) {
-                    double tx[kPhUnroll], ty[kPhUnroll], tz[kPhUnroll];
-                    bool all_near = true;
+                    float4 w[kPhUnroll];
+                    const float4 *wp = P.grid.wrapped + (j0 + it);
+#pragma unroll
+                    for (int u = 0; u < kPhUnroll; ++u)  // (lanes past their own run read on into the next cell, or the last atom, and drop it)
+                        w[u] = __ldg(wp + min(u, j_last - (j0 + it)));
 #pragma unroll
                     for (int u = 0; u < kPhUnroll; ++u) {
-                        double px, py, pz;
-                        int id;
-                        // (lanes past their own run re-read its last record, or record 0 when the run is empty, and drop it)
-                        RecTraits<double>::load(P.grid.recs, (size_t)(j0 + max(min(it + u, len - 1), 0)), px, py, pz, id);
-                        // distVec = jPos - iPos (:213)
-                        tx[u] = __dsub_rn(px, rx);
-                        ty[u] = __dsub_rn(py, ry);
-                        tz[u] = __dsub_rn(pz, rz);
-                        all_near &= fabs(tx[u]) < b.near && fabs(ty[u]) < b.near && fabs(tz[u]) < b.near;
+                        const float dx = w[u].x - mx, dy = w[u].y - my, dz = w[u].z - mz;
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const bool take = it + u < len && r2 <= thr2;
+                        const unsigned m = __ballot_sync(kFullMask, take);
+                        if (take) queue[qn + __popc(m & lanes_below)] = make_uint2((unsigned)lane, (unsigned)(j0 + it + u));
+                        qn += __popc(m);
                     }
-                    if (!all_near) {
-                        // minimum image (:214); for a difference below 0.49 of the smallest edge it is the identity (anint
-                        // gives 0), which is why the common case skips it
-#pragma unroll
-                        for (int u = 0; u < kPhUnroll; ++u) {
-                            tx[u] = __dsub_rn(tx[u], __dmul_rn(b.L[0], anint_exact<double>(__dmul_rn(tx[u], b.iL[0]))));
-                            ty[u] = __dsub_rn(ty[u], __dmul_rn(b.L[1], anint_exact<double>(__dmul_rn(ty[u], b.iL[1]))));
-                            tz[u] = __dsub_rn(tz[u], __dmul_rn(b.L[2], anint_exact<double>(__dmul_rn(tz[u], b.iL[2]))));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kPhUnroll; ++u) {
-                        const double s = sumsq3<double>(tx[u], ty[u], tz[u]);
-                        // beyond far_sq: certainly past the last bin, whatever the roundings of sqrt and division
-                        if (it + u < len && s <= P.far_sq) my_list[nl++ * kPhThreads] = s;
-                    }
-                    if (__any_sync(kFullMask, nl > kPhCap - kPhUnroll)) bin_lists();
+                    if (qn > kPhQueue - 32 * kPhUnroll) drain();
                 }
             }
         }
     }
-    bin_lists();
+    drain();
     if (smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < P.totbins; i += blockDim.x)
@@ -494,6 +554,7 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     P.outer = outer;
     P.outer_dtype = outer_dtype;
     P.n_outer = n_outer;
+    P.n_inner = n_inner;
     P.mode = mode;
     P.binwidth = binwidth;
     P.totbins = totbins;
@@ -502,7 +563,12 @@ int wol_pair_hist(int32_t mode, const void *outer, int32_t outer_dtype, int32_t 
     P.far_sq = ((double)totbins * binwidth) * ((double)totbins * binwidth) * (1.0 + 1e-9);
     P.counts = reinterpret_cast<unsigned long long *>(counts);
     if (n_outer > 0 && n_inner > 0) {
-        const size_t smem = totbins <= kMaxSmemBins ? sizeof(unsigned) * totbins : 0;
+        // shared bins + the table of bin edges in distance^2 (8-byte aligned behind the bins)
+        const size_t smem = totbins <= kMaxSmemBins ? sizeof(unsigned) * ((totbins + 1) & ~1) + sizeof(double) * (totbins + 1) : 0;
+        if (smem > 16 * 1024) {
+            cudaError_t ea = cudaFuncSetAttribute(pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(pair_hist)", ea);
+        }
         pair_hist_kernel<<<(n_outer + 127) / 128, 128, smem, stream>>>(P);
         add_launches(1);
     }

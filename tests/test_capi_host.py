@@ -104,3 +104,18 @@ def test_argument_validation_without_gpu(L):
     nc = (ctypes.c_int32 * 3)(4, 4, 4)
     assert L.wol_workspace_bytes(2, 1000, 1000, ctypes.byref(nc)) > 2 * 1000 * 32
     assert L.wol_cell_build(None, 0, None, 1, 10, ctypes.byref(nc), 0, None, 0, None) == -1
+
+
+def test_all_atoms_convention_is_validated_without_gpu(L):
+    """centres == NULL means "every atom of the cell list is a centre" (walked in cell order) and needs n_centres == n_pos;
+    mode 1 of wol_pair_hist pairs a set with itself.  Both are rejected before anything is launched."""
+    nc = (ctypes.c_int32 * 3)(8, 8, 8)
+    p = ctypes.c_void_p(4096)  # never dereferenced: the calls fail in their argument checks
+    rc = L.wol_lsi(None, 0, p, 1, 100, 99, ctypes.byref(nc), 8.0, 0.0, 3.7, p, 1 << 20, p, p, None)
+    assert rc == -1 and b"every atom is a centre" in L.wol_last_error()
+    rc = L.wol_neighbors_csr(None, 0, p, 1, 100, 99, ctypes.byref(nc), 8.0, 0.0, 3.5, p, 1 << 20, p, p, None, 0, None)
+    assert rc == -1 and b"every atom is a centre" in L.wol_last_error()
+    rc = L.wol_angles_fill(None, 0, p, 1, 100, 99, ctypes.byref(nc), 8.0, 0.0, 3.4, p, 1 << 20, p, p, None)
+    assert rc == -1 and b"every atom is a centre" in L.wol_last_error()
+    rc = L.wol_pair_hist(1, p, 0, 100, p, 99, ctypes.byref(nc), 8.0, 0.1, 50, p, 1 << 20, p, None)
+    assert rc == -1 and b"pairs a set with itself" in L.wol_last_error()

@@ -1,6 +1,6 @@
 """RadialDistSame of one 1M-water frame (development aid; run it under ncu for the kernel's own time).
 
-    python scripts/rdf_time.py [path/to/other/libwol.so]
+    python scripts/rdf_time.py [path/to/other/libwol.so | -] [shuffle]
 
 Prints the routine time and a checksum of the counts, so that two builds of the library can be compared bin for bin.
 """
@@ -11,12 +11,15 @@ import torch
 sys.path.insert(0, ".")
 from waterorderlib_b200 import _capi
 
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] != "-":
     _capi.LIB_PATH = sys.argv[1]
 from waterorderlib_b200 import routines, synth  # noqa: E402
 
 dev = torch.device("cuda")
 O, box = synth.water_box(50, sigma=0.25, seed=1)
+if "shuffle" in sys.argv[2:]:  # a real topology: atom order unrelated to position
+    import numpy as np
+    O = O[np.random.default_rng(5).permutation(O.shape[0])]
 O_d = torch.from_numpy(O).to(dev)
 for _ in range(2):
     r = routines.pair_hist(1, O_d, None, box, 0.1, 150)
